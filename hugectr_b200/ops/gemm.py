@@ -1,0 +1,113 @@
+"""bf16 tensor-core GEMM with fused epilogues (tcgen05/TMEM/TMA kernel in csrc/gemm_tc.cu).
+
+``gemm_bf16`` is the single entry point used by the MLP / InnerProduct / MultiCross layers for
+fprop, dgrad and wgrad.  On CPU (or for shapes TMA cannot address) it falls back to an fp32
+PyTorch reference that implements exactly the same epilogue math; the same function is the
+numerics oracle in the tests.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _native
+
+EPI_RELU = 1
+EPI_OUT_F32 = 2
+EPI_ATOMIC = 4
+EPI_ACCUM = 8
+EPI_CROSS = 16
+EPI_MASK = 32
+EPI_SIGMOID = 64
+
+_c = ctypes
+_sig_set = False
+
+
+def _lib():
+    global _sig_set
+    lib = _native.cuda_lib()
+    if not _sig_set:
+        lib.hctr_gemm_bf16.restype = _c.c_int
+        lib.hctr_gemm_bf16.argtypes = [
+            _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+            _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_int,
+            _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_void_p, _c.c_longlong,
+            _c.c_void_p, _c.c_longlong, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+        _sig_set = True
+    return lib
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def tc_eligible(a: torch.Tensor, b: torch.Tensor, a_mn: bool, b_mn: bool) -> bool:
+    """TMA needs 16-byte aligned bases and row pitches; tcgen05 path is bf16 only."""
+    if not (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16):
+        return False
+    for t in (a, b):
+        if t.dim() != 2 or t.stride(1) != 1 or (t.stride(0) * 2) % 16 or t.data_ptr() % 16:
+            return False
+    return True
+
+
+def gemm_reference(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
+                   alpha=1.0, flags=0, out=None, aux=None):
+    """fp32 PyTorch oracle with the same epilogue semantics as the kernel."""
+    A = a.float().t() if a_mn else a.float()          # [M, K]
+    B = b.float() if b_mn else b.float().t()          # [K, N]
+    v = (A @ B) * alpha
+    if bias is not None:
+        v = v + bias.float()
+    if flags & EPI_CROSS:
+        if aux is not None:
+            aux.copy_(v.to(aux.dtype))
+        v = x0.float() * v + xl.float()
+    if flags & EPI_MASK:
+        v = v * (mask.float() > 0)
+    if flags & EPI_RELU:
+        v = torch.relu(v)
+    if flags & EPI_SIGMOID:
+        v = torch.sigmoid(v)
+    if flags & (EPI_ATOMIC | EPI_ACCUM):
+        out.add_(v.to(out.dtype))
+        return out
+    odt = torch.float32 if (flags & EPI_OUT_F32) else a.dtype
+    if out is None:
+        return v.to(odt)
+    out.copy_(v.to(out.dtype))
+    return out
+
+
+def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
+              aux=None, alpha=1.0, flags=0, splits=1, block_n=0):
+    """out[M,N] = epilogue(alpha * op(a) @ op(b)).
+
+    a: ``[M,K]`` (K-major) or ``[K,M]`` when ``a_mn``;  b: ``[N,K]`` or ``[K,N]`` when ``b_mn``.
+    """
+    M = a.shape[1] if a_mn else a.shape[0]
+    K = a.shape[0] if a_mn else a.shape[1]
+    N = b.shape[1] if b_mn else b.shape[0]
+    f32_out = bool(flags & (EPI_OUT_F32 | EPI_ATOMIC | EPI_ACCUM))
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else a.dtype)
+    if not tc_eligible(a, b, a_mn, b_mn) or out.stride(1) != 1:
+        return gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux)
+    if splits > 1:
+        flags |= EPI_ATOMIC
+    if block_n == 0:
+        block_n = 256 if (N % 256 == 0 and (M // 128) * (N // 256) >= 120) else 128
+        if N <= 64:
+            block_n = 64
+    stream = torch.cuda.current_stream(a.device).cuda_stream
+    rc = _lib().hctr_gemm_bf16(
+        a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+        out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(mask),
+        0 if mask is None else mask.stride(0), _ptr(x0), _ptr(xl),
+        0 if x0 is None else x0.stride(0), _ptr(aux), 0 if aux is None else aux.stride(0),
+        float(alpha), int(flags), int(splits), int(block_n), stream)
+    if rc != 0:
+        raise RuntimeError(f"hctr_gemm_bf16 failed rc={rc} M={M} N={N} K={K}")
+    return out
