@@ -1,0 +1,29 @@
+"""hugectr_b200 -- a Blackwell (sm_100a) native CTR training framework with HugeCTR's API.
+
+``import hugectr`` resolves to this package (see the top-level ``hugectr`` shim): CreateSolver,
+DataReaderParams, CreateOptimizer, Model, Input, SparseEmbedding, DenseLayer,
+EmbeddingTableConfig, EmbeddingCollectionConfig, tools.DataGenerator, data.DataSourceParams,
+TrainingCallback (HugeCTR/src/pybind/module_main.cpp:36-48).
+"""
+from .enums import *  # noqa: F401,F403
+from .enums import (Activation_t, Alignment_t, AllReduceAlgo, Check_t, CommunicationStrategy,
+                    CompressionStrategy, DataReaderType_t, DeviceLayout, Distribution_t,
+                    Embedding_t, Error_t, FcPosition_t, FileSystemType_t, Initializer_t, Layer_t,
+                    LrPolicy_t, MetricsRawType, MetricsType, Optimizer_t, PowerLaw_t,
+                    Regularizer_t, SourceType_t, Tensor_t, TrainPSType_t, Update_t)
+from .solver import (AsyncParam, CreateOptimizer, CreateSolver, DataReaderParams,
+                     DataReaderSparseParam, DataSourceParams, DenseLayer, DenseLayerComputeConfig,
+                     Input, OptParamsPy, Solver, SparseEmbedding)
+from .embedding.collection import (EmbeddingCollectionConfig, EmbeddingTableConfig, InitParams)
+from .lr_scheduler import LearningRateScheduler
+from .model import Model, TrainingCallback
+
+__version__ = "25.03.b200.1"
+
+
+def __getattr__(name):
+    # lazy sub-namespaces: hugectr.tools / hugectr.data / hugectr.sok / hugectr.inference
+    import importlib
+    if name in ("tools", "data", "sok", "onnx", "cache", "io", "parallel", "utils", "models"):
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

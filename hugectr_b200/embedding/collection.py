@@ -1,0 +1,488 @@
+"""EmbeddingCollection ("3G" embedding): configs, sharding resolution and the per-rank runtime.
+
+API parity: HugeCTR/include/pybind/embedding_collection_wrapper.hpp:29-65,
+HugeCTR/include/embeddings/embedding_collection.hpp:55-90 (shard_matrix / shard_strategy),
+key->shard rule  owner = shard_gpus[key % num_shards], row = key // num_shards
+(HugeCTR/embedding/data_distributor/key_filtering_operators.cu:88, operators/keys_to_indices.cu:39),
+column-wise split (HugeCTR/src/embeddings/embedding_collection.cpp:25-150).
+
+Runtime design (differs from the reference on purpose): one process per GPU; every rank keeps its
+keys / EBC outputs / EBC top-grads in *slabs* with identical layout on all ranks.  In ``fused`` mode
+the slabs live in a peer-mapped symmetric heap and the owner-side kernels read the requesters' keys
+and write their outputs (and read their gradients) directly over NVLink, so no NCCL all-to-all runs
+on the forward or backward path.  In ``collective`` mode (CPU/gloo tests and the NCCL baseline the
+fused path is measured against) the same local kernels run on all-gathered keys and the pooled
+vectors travel through ``all_to_all_single``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from ..enums import CommunicationStrategy, CompressionStrategy, Optimizer_t
+from ..solver import OptParamsPy
+from . import ops as E
+
+
+def _stable_seed(*parts) -> int:
+    import zlib
+    return zlib.crc32(repr(parts).encode()) & 0x7FFFFFFF
+
+
+# ------------------------------------------------------------------------- configs
+@dataclass
+class InitParams:
+    """embedding_storage/common.hpp:43-77: Uniform(up_bound) or Sinusoidal(max_sequence_len, ev)."""
+    initializer_type: str = "Default"
+    up_bound: float = -1.0
+    max_sequence_len: int = 0
+    ev_size: int = 0
+
+
+class EmbeddingTableConfig:
+    def __init__(self, name: str, max_vocabulary_size: int, ev_size: int,
+                 opt_params_or_empty: Optional[OptParamsPy] = None,
+                 init_param_or_empty: Optional[InitParams] = None, **kw):
+        self.name = str(name)
+        self.max_vocabulary_size = int(max_vocabulary_size)
+        self.ev_size = int(ev_size)
+        self.opt_params = kw.get("opt_params", opt_params_or_empty)
+        self.init_param = kw.get("init_param", init_param_or_empty)
+
+
+class EmbeddingCollectionConfig:
+    def __init__(self, use_exclusive_keys: bool = False,
+                 comm_strategy: CommunicationStrategy = CommunicationStrategy.Uniform):
+        self.use_exclusive_keys = use_exclusive_keys
+        self.comm_strategy = comm_strategy
+        self.lookups: List[dict] = []       # one entry per embedding_lookup call
+        self.shard_matrix: Optional[List[List[int]]] = None
+        self.shard_strategy: Optional[list] = None
+        self.compression_strategy: dict = {}
+
+    def embedding_lookup(self, table_config, bottom_name, top_name: str, combiner):
+        if isinstance(table_config, (list, tuple)):
+            assert len(table_config) == len(bottom_name) == len(combiner)
+            self.lookups.append({"tables": list(table_config), "bottoms": list(bottom_name),
+                                 "top": top_name, "combiners": list(combiner), "batch_major": True})
+        else:
+            self.lookups.append({"tables": [table_config], "bottoms": [bottom_name],
+                                 "top": top_name, "combiners": [combiner], "batch_major": False})
+
+    def shard(self, shard_matrix, shard_strategy, compression_strategy=None):
+        self.shard_matrix = [list(r) for r in shard_matrix]
+        self.shard_strategy = list(shard_strategy)
+        self.compression_strategy = dict(compression_strategy or {})
+
+    def tables(self) -> List[EmbeddingTableConfig]:
+        seen, res = set(), []
+        for lk in self.lookups:
+            for t in lk["tables"]:
+                if t.name not in seen:
+                    seen.add(t.name)
+                    res.append(t)
+        return res
+
+
+# ------------------------------------------------------------------------- placement
+@dataclass
+class TablePlacement:
+    kind: str                  # "mp" | "dp"
+    shard_gpus: List[int]      # GPUs holding a row shard (mp) ; all GPUs (dp)
+    col_factor: int = 1        # column-wise split factor
+
+
+def resolve_placement(cfg: EmbeddingCollectionConfig, num_gpus: int) -> Dict[str, TablePlacement]:
+    tables = cfg.tables()
+    names = [t.name for t in tables]
+    place: Dict[str, TablePlacement] = {}
+    if cfg.shard_matrix is None:
+        # default plan: every table model-parallel, table-wise round robin (sample round_robin plan)
+        for i, n in enumerate(names):
+            place[n] = TablePlacement("mp", [i % num_gpus])
+        return place
+    sm = cfg.shard_matrix
+    assert len(sm) == num_gpus, "shard_matrix must have one row per GPU"
+    for n in names:
+        place[n] = None
+    for kind, items in cfg.shard_strategy:
+        for it in items:
+            if isinstance(it, (tuple, list)):
+                tn, factor = str(it[0]), int(it[1])
+            else:
+                tn, factor = str(it), 1
+            ti = names.index(tn)
+            gpus = [g for g in range(num_gpus) if sm[g][ti]]
+            if kind == "dp":
+                place[tn] = TablePlacement("dp", list(range(num_gpus)))
+            else:
+                assert gpus, f"table {tn} is not placed on any GPU"
+                assert len(gpus) % factor == 0, "column-wise factor must divide the shard count"
+                place[tn] = TablePlacement("mp", gpus, factor)
+    for n in names:
+        if place[n] is None:
+            ti = names.index(n)
+            gpus = [g for g in range(num_gpus) if sm[g][ti]]
+            place[n] = TablePlacement("mp", gpus or [ti % num_gpus])
+    return place
+
+
+def shard_rows(vocab: int, k: int, s: int) -> int:
+    """number of keys in [0, vocab) with key % k == s"""
+    return (vocab - s + k - 1) // k if vocab > s else 0
+
+
+# ------------------------------------------------------------------------- runtime
+class _Group:
+    """Local tables of one (kind, ev pitch) group: one fp32 arena + optimizer state."""
+
+    def __init__(self, kind, pitch):
+        self.kind, self.pitch = kind, pitch
+        self.rows = 0
+        self.table_slices = []   # (table name, col part, row_off, rows, num_shards, shard_idx, col0)
+        self.lookups: List[E.LookupDesc] = []
+        self.opt: Optional[OptParamsPy] = None
+
+
+class EmbeddingCollection:
+    def __init__(self, cfg: EmbeddingCollectionConfig, batch_per_gpu: int, hotness: Dict[str, int],
+                 device, act_dtype, comm, default_opt: OptParamsPy, key_dtype=torch.int32,
+                 scaler: float = 1.0, state_dtype=torch.float32, seed: int = 0,
+                 fused: Optional[bool] = None, is_train: bool = True):
+        self.cfg, self.b, self.device, self.act_dtype = cfg, batch_per_gpu, device, act_dtype
+        self.comm = comm
+        self.rank, self.world = comm.rank, comm.world_size
+        self.key_dtype = key_dtype
+        self.scaler = scaler
+        self.state_dtype = state_dtype
+        self.default_opt = default_opt
+        self.tables = cfg.tables()
+        self.tmap = {t.name: t for t in self.tables}
+        self.placement = resolve_placement(cfg, self.world)
+        self.native = device.type == "cuda"
+        self.fused = (self.native and self.world > 1 and comm.p2p_available) if fused is None else fused
+        self.is_train = is_train
+        self.hotness = dict(hotness)
+        self.seed = seed
+        self._build_layout(hotness)
+        self._build_storage(seed)
+        self._alloc_buffers()
+
+    def eval_clone(self, batch_per_gpu: int) -> "EmbeddingCollection":
+        """Second plan (different batch, no grads) over the SAME tables -- the eval graph."""
+        import copy
+        c = copy.copy(self)
+        c.b = batch_per_gpu
+        c.is_train = False
+        c._shared = self
+        c._build_layout(self.hotness)
+        c._build_storage(self.seed, share_from=self)
+        c._alloc_buffers()
+        return c
+
+    # ---- layout of key / output / grad slabs (identical on every rank)
+    def _build_layout(self, hotness):
+        b = self.b
+        self.glookups = []          # global lookup list
+        self.tops = []              # (top name, width, batch_major, [global lookup ids])
+        koff = 0
+        ooff = 0
+        for lk in self.cfg.lookups:
+            ids, col = [], 0
+            width = 0
+            for t, bot, comb in zip(lk["tables"], lk["bottoms"], lk["combiners"]):
+                H = int(hotness[bot])
+                w = t.ev_size * (H if comb == "concat" else 1)
+                width += w
+            for t, bot, comb in zip(lk["tables"], lk["bottoms"], lk["combiners"]):
+                H = int(hotness[bot])
+                gl = {"table": t.name, "bottom": bot, "combiner": comb, "hotness": H,
+                      "key_off": koff, "top": len(self.tops), "col": col, "ev": t.ev_size,
+                      "out_off": ooff + col, "out_stride": width}
+                koff += b * H
+                col += t.ev_size * (H if comb == "concat" else 1)
+                ids.append(len(self.glookups))
+                self.glookups.append(gl)
+            self.tops.append({"name": lk["top"], "width": width, "batch_major": lk["batch_major"],
+                              "lookups": ids, "off": ooff})
+            ooff += b * width
+        self.key_slab_elems = koff
+        self.top_slab_elems = ooff
+        # partial blocks for row-sharded lookups (k > 1 on the mp side)
+        poff = ooff
+        for gl in self.glookups:
+            pl = self.placement[gl["table"]]
+            k = len(pl.shard_gpus) // pl.col_factor if pl.kind == "mp" else 1
+            gl["k"] = k
+            if pl.kind == "mp" and k > 1:
+                gl["partial_off"] = poff
+                gl["partial_w"] = k * gl["ev"] * (gl["hotness"] if gl["combiner"] == "concat" else 1)
+                poff += b * gl["partial_w"]
+        self.out_slab_elems = poff
+
+    # ---- local storage + owner-side lookup descriptors
+    def _build_storage(self, seed, share_from=None):
+        groups: Dict[Tuple[str, int], _Group] = {}
+        b = self.b
+        for t in self.tables:
+            pl = self.placement[t.name]
+            cf = pl.col_factor
+            ev_part = t.ev_size // cf
+            assert ev_part * cf == t.ev_size, "ev_size must be divisible by the column factor"
+            if pl.kind == "dp":
+                parts = [(0, 1, 0)]
+            else:
+                parts = []
+                kk = len(pl.shard_gpus) // cf
+                for idx, g in enumerate(pl.shard_gpus):
+                    if g == self.rank:
+                        parts.append((idx // kk, kk, idx % kk))   # (col part, num row shards, shard)
+            for (cpart, k, s) in parts:
+                key = (pl.kind, ev_part)
+                grp = groups.setdefault(key, _Group(pl.kind, ev_part))
+                rows = shard_rows(t.max_vocabulary_size, k, s)
+                grp.table_slices.append({"table": t.name, "cpart": cpart, "row_off": grp.rows,
+                                         "rows": rows, "k": k, "s": s, "col0": cpart * ev_part,
+                                         "ev": ev_part})
+                grp.rows += rows
+                o = t.opt_params or self.default_opt
+                if grp.opt is None:
+                    grp.opt = o
+        # lookups per group
+        for gi, gl in enumerate(self.glookups):
+            t = self.tmap[gl["table"]]
+            pl = self.placement[t.name]
+            for (kind, pitch), grp in groups.items():
+                for sl in grp.table_slices:
+                    if sl["table"] != t.name:
+                        continue
+                    H = gl["hotness"]
+                    concat = gl["combiner"] == "concat"
+                    nsub = H if concat else 1
+                    for sub in range(nsub):
+                        if pl.kind == "mp" and sl["k"] > 1:
+                            base = gl["partial_off"]
+                            ostride = gl["partial_w"]
+                            ocol = sl["s"] * gl["ev"] * nsub + sub * gl["ev"] + sl["col0"]
+                        else:
+                            base = gl["out_off"]
+                            ostride = gl["out_stride"]
+                            ocol = sub * gl["ev"] + sl["col0"]
+                        grp.lookups.append(E.LookupDesc(
+                            table_row_off=sl["row_off"], key_off=gl["key_off"] + sub,
+                            out_off=base + ocol, grad_off=gl["out_off"] + sub * gl["ev"] + sl["col0"],
+                            hotness=1 if concat else H, key_stride=H, num_shards=sl["k"],
+                            shard_idx=sl["s"], out_stride=ostride, grad_stride=gl["out_stride"],
+                            combiner=1 if gl["combiner"] in ("mean", "average") else 0,
+                            ev_size=sl["ev"], rows=sl["rows"]))
+        self.groups = list(groups.values())
+        dev = self.device
+        gen = torch.Generator(device="cpu")
+        if share_from is not None:
+            for grp, src in zip(self.groups, share_from.groups):
+                assert (grp.kind, grp.pitch, grp.rows) == (src.kind, src.pitch, src.rows)
+                grp.table, grp.s0, grp.s1, grp.opt = src.table, src.s0, src.s1, src.opt
+                grp.lookups_dev = E.lookups_to_device(grp.lookups, dev)
+                grp.ws = None
+            return
+        for grp in self.groups:
+            n = max(grp.rows, 1) * grp.pitch
+            grp.table = torch.empty(n, dtype=torch.float32, device=dev)
+            self._init_group(grp, gen, seed)
+            ns = grp.opt.num_states if grp.opt is not None else 0
+            if grp.opt.optimizer_type == Optimizer_t.Adam:
+                ns = 2
+            sdt = self.state_dtype if grp.kind == "mp" else torch.float32
+            grp.s0 = torch.zeros(n, dtype=sdt, device=dev) if ns >= 1 and self.is_train else None
+            grp.s1 = torch.zeros(n, dtype=sdt, device=dev) if ns >= 2 and self.is_train else None
+            if grp.s0 is not None and grp.opt.optimizer_type == Optimizer_t.AdaGrad \
+                    and grp.opt.initial_accu_value != 0.0:
+                grp.s0.fill_(grp.opt.initial_accu_value)
+            grp.lookups_dev = E.lookups_to_device(grp.lookups, dev)
+            pairs = (self.world if grp.kind == "mp" else 1) * self.b * \
+                sum(l.hotness for l in grp.lookups)
+            if self.is_train:
+                if grp.kind == "mp":
+                    grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev)
+                else:
+                    grp.dense_wgrad = torch.zeros(n, dtype=torch.float32, device=dev)
+                    grp.ws = None
+
+    def _init_group(self, grp, gen, seed):
+        """default U(+-sqrt(1/max_vocabulary_size)) (ragged_static_embedding.cu:501-530)."""
+        for sl in grp.table_slices:
+            t = self.tmap[sl["table"]]
+            bound = math.sqrt(1.0 / max(t.max_vocabulary_size, 1))
+            ip = t.init_param
+            if ip is not None and ip.up_bound > 0:
+                bound = ip.up_bound
+            view = grp.table[sl["row_off"] * grp.pitch:(sl["row_off"] + sl["rows"]) * grp.pitch]
+            if view.numel() == 0:
+                continue
+            if grp.kind == "dp" or self.device.type == "cpu":
+                # identical on every replica: generate by global row on host
+                gen.manual_seed(_stable_seed(seed, sl["table"], sl["cpart"]))
+                full_rows = t.max_vocabulary_size
+                if full_rows * grp.pitch <= (1 << 26):
+                    full = (torch.rand(full_rows, grp.pitch, generator=gen) * 2 - 1) * bound
+                    view.copy_(full[sl["s"]::sl["k"]].reshape(-1).to(view.device))
+                    continue
+            g2 = torch.Generator(device=self.device)
+            g2.manual_seed(_stable_seed(seed, sl["table"], sl["cpart"], sl["s"]))
+            view.uniform_(-bound, bound, generator=g2)
+
+    def _alloc_buffers(self):
+        dev, b = self.device, self.b
+        alloc = self.comm.symm_alloc if self.fused else \
+            (lambda n, dt: torch.zeros(n, dtype=dt, device=dev))
+        self.key_slab = alloc(max(self.key_slab_elems, 1), self.key_dtype)
+        self.out_slab = alloc(max(self.out_slab_elems, 1), self.act_dtype)
+        self.grad_slab = alloc(max(self.top_slab_elems, 1), self.act_dtype) if self.is_train else None
+        if self.fused:
+            self.peer_keys = self.comm.peer_ptrs(self.key_slab)
+            self.peer_out = self.comm.peer_ptrs(self.out_slab)
+            self.peer_grad = self.comm.peer_ptrs(self.grad_slab) if self.is_train else None
+        elif self.world > 1:
+            self.keys_all = torch.zeros(self.world, max(self.key_slab_elems, 1),
+                                        dtype=self.key_dtype, device=dev)
+            self.send_out = torch.zeros(self.world, max(self.out_slab_elems, 1),
+                                        dtype=self.act_dtype, device=dev)
+            self.recv_out = torch.zeros_like(self.send_out)
+            if self.is_train:
+                self.grads_all = torch.zeros(self.world, max(self.top_slab_elems, 1),
+                                             dtype=self.act_dtype, device=dev)
+        # named views
+        self.key_views = {}
+        for gl in self.glookups:
+            self.key_views[gl["bottom"]] = self.key_slab[gl["key_off"]:gl["key_off"] + b * gl["hotness"]] \
+                .view(b, gl["hotness"])
+        self.top_data, self.top_grad = {}, {}
+        for tp in self.tops:
+            w = tp["width"]
+            shp = (b, w) if tp["batch_major"] else (b, 1, w)
+            self.top_data[tp["name"]] = self.out_slab[tp["off"]:tp["off"] + b * w].view(shp)
+            if self.is_train:
+                self.top_grad[tp["name"]] = self.grad_slab[tp["off"]:tp["off"] + b * w].view(shp)
+
+    # ------------------------------------------------------------------ API
+    def top_shapes(self):
+        return {tp["name"]: ((self.b, tp["width"]) if tp["batch_major"] else (self.b, 1, tp["width"]))
+                for tp in self.tops}
+
+    def set_keys(self, feature_major_keys: torch.Tensor):
+        """Copy a whole feature-major key batch into the key slab (H2D lands here directly)."""
+        self.key_slab[:feature_major_keys.numel()].copy_(feature_major_keys.reshape(-1), non_blocking=True)
+
+    def forward(self, is_train: bool = True):
+        b = self.b
+        if self.world == 1:
+            for grp in self.groups:
+                E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
+                          [self.out_slab], b)
+        elif self.fused:
+            self.comm.barrier_device()           # every rank's keys are in place
+            for grp in self.groups:
+                if grp.kind == "mp":
+                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
+                              self.peer_out, b, self.rank)
+                else:
+                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
+                              [self.out_slab], b)
+            self.comm.barrier_device()           # every owner finished writing my outputs
+        else:
+            self.comm.all_gather(self.keys_all, self.key_slab)
+            self.send_out.zero_()
+            for grp in self.groups:
+                if grp.kind == "mp":
+                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch,
+                              list(self.keys_all.unbind(0)), list(self.send_out.unbind(0)), b, self.rank)
+            self.comm.all_to_all(self.recv_out, self.send_out)
+            # each (rank, lookup) region of my slab is written by exactly one owner -> sum == place
+            self.out_slab.copy_(self.recv_out.sum(0))
+            for grp in self.groups:
+                if grp.kind == "dp":
+                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
+                              [self.out_slab], b)
+        self._reduce_partials()
+
+    def _reduce_partials(self):
+        b = self.b
+        for gl in self.glookups:
+            if gl.get("k", 1) > 1 and "partial_off" in gl:
+                w = gl["partial_w"] // gl["k"]
+                part = self.out_slab[gl["partial_off"]:gl["partial_off"] + b * gl["partial_w"]] \
+                    .view(b, gl["k"], w)
+                tp = self.tops[gl["top"]]
+                full = self.out_slab[tp["off"]:tp["off"] + b * tp["width"]].view(b, tp["width"])
+                full[:, gl["col"]:gl["col"] + w] = part.float().sum(1).to(full.dtype)
+
+    def backward(self, lr_t, step_t):
+        """Consumes top grads (grad slab), updates local tables. grads are already / global batch."""
+        b = self.b
+        if self.world == 1:
+            kb, gb = [self.key_slab], [self.grad_slab]
+            for grp in self.groups:
+                self._accum_update(grp, kb, gb, lr_t, step_t)
+            return
+        if self.fused:
+            self.comm.barrier_device()           # all top-grads are final
+            for grp in self.groups:
+                if grp.kind == "mp":
+                    self._accum_update(grp, self.peer_keys, self.peer_grad, lr_t, step_t)
+                else:
+                    self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
+            self.comm.barrier_device()           # keys / grads may now be overwritten
+            return
+        self.comm.all_gather(self.grads_all, self.grad_slab)
+        for grp in self.groups:
+            if grp.kind == "mp":
+                self._accum_update(grp, list(self.keys_all.unbind(0)), list(self.grads_all.unbind(0)),
+                                   lr_t, step_t)
+            else:
+                self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
+
+    def _hp(self, o: OptParamsPy):
+        return {"scaler": self.scaler, "beta1": o.beta1, "beta2": o.beta2, "epsilon": o.epsilon,
+                "lambda1": o.lambda1, "lambda2": o.lambda2, "ftrl_beta": o.beta,
+                "momentum": o.momentum_factor, "initial_accu_value": o.initial_accu_value}
+
+    def _accum_update(self, grp, key_bufs, grad_bufs, lr_t, step_t):
+        o = grp.opt
+        if grp.kind == "mp":
+            E.backward_accum(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, grad_bufs,
+                             self.b, grp.ws, 1.0, self.rank)
+            E.update(o.optimizer_type, grp.table, grp.s0, grp.s1, grp.pitch, grp.ws, self._hp(o),
+                     lr_t, step_t)
+        else:
+            from ..ops import dense as D
+            E.backward_accum(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, grad_bufs,
+                             self.b, None, 1.0, self.rank, dense_wgrad=grp.dense_wgrad)
+            if self.world > 1:
+                self.comm.all_reduce(grp.dense_wgrad)
+            dcode = {Optimizer_t.SGD: D.D_SGD, Optimizer_t.AdaGrad: D.D_ADAGRAD,
+                     Optimizer_t.Adam: D.D_ADAM, Optimizer_t.Ftrl: D.D_FTRL,
+                     Optimizer_t.MomentumSGD: D.D_MOMENTUM, Optimizer_t.Nesterov: D.D_NESTEROV,
+                     Optimizer_t.RMSProp: D.D_RMSPROP}[o.optimizer_type]
+            D.dense_opt_step(dcode, grp.table, grp.dense_wgrad, None, grp.s0, grp.s1, lr_t, step_t,
+                             self._hp(o), zero_grad=True)
+
+    # ------------------------------------------------------------------ checkpoint helpers
+    def local_table_items(self):
+        """yield (table name, column part, global keys tensor, weight view [rows, ev], group, slice)"""
+        for grp in self.groups:
+            for sl in grp.table_slices:
+                w = grp.table[sl["row_off"] * grp.pitch:(sl["row_off"] + sl["rows"]) * grp.pitch] \
+                    .view(sl["rows"], grp.pitch)
+                keys = torch.arange(sl["rows"], dtype=torch.int64) * sl["k"] + sl["s"]
+                yield sl["table"], sl, keys, w, grp
+
+    def memory_bytes(self) -> int:
+        tot = 0
+        for grp in self.groups:
+            for t in (grp.table, grp.s0, grp.s1):
+                if t is not None:
+                    tot += t.numel() * t.element_size()
+        return tot

@@ -1,0 +1,352 @@
+"""Embedding kernels: ctypes bindings for csrc/embedding.cu + PyTorch reference implementations.
+
+The reference implementations define the semantics (they are the CPU path and the test oracle):
+  forward   pooled[src, lookup, sample] = combiner( table[row_off + key // k] for owned keys )
+  backward  per unique arena row: g = sum of bucket gradients (scaled 1/nnz for mean);
+            then the sparse optimizer of Appendix A.3 on that row.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from .. import _native
+from ..enums import Optimizer_t
+from ..ops import dense as D
+
+MAX_RANKS = 16
+OPT_CODE = {Optimizer_t.SGD: 0, Optimizer_t.AdaGrad: 1, Optimizer_t.Adam: 2, Optimizer_t.Ftrl: 3,
+            Optimizer_t.MomentumSGD: 4, Optimizer_t.Nesterov: 5, Optimizer_t.RMSProp: 6}
+
+
+class CEmbLookup(C.Structure):
+    _fields_ = [("table_row_off", C.c_longlong), ("key_off", C.c_longlong),
+                ("nnz_off", C.c_longlong), ("out_off", C.c_longlong), ("grad_off", C.c_longlong),
+                ("hotness", C.c_int), ("key_stride", C.c_int), ("num_shards", C.c_int),
+                ("shard_idx", C.c_int), ("out_stride", C.c_int), ("grad_stride", C.c_int),
+                ("combiner", C.c_int), ("ev_size", C.c_int), ("rows", C.c_int), ("pad_", C.c_int)]
+
+
+class CEmbParams(C.Structure):
+    _fields_ = [("num_ranks", C.c_int), ("my_rank", C.c_int), ("batch", C.c_int),
+                ("num_lookups", C.c_int), ("keys", C.c_void_p * MAX_RANKS),
+                ("nnz", C.c_void_p * MAX_RANKS), ("out", C.c_void_p * MAX_RANKS),
+                ("grad", C.c_void_p * MAX_RANKS), ("lookups", C.c_void_p), ("table", C.c_void_p),
+                ("ev_size", C.c_int)]
+
+
+class CUniqueTable(C.Structure):
+    _fields_ = [("keys", C.c_void_p), ("vals", C.c_void_p), ("counter", C.c_void_p),
+                ("rows", C.c_void_p), ("slots", C.c_void_p), ("mask", C.c_uint),
+                ("max_unique", C.c_uint)]
+
+
+class COptHyper(C.Structure):
+    _fields_ = [("lr_ptr", C.c_void_p), ("lr_scale", C.c_float), ("scaler", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("lambda1", C.c_float), ("lambda2", C.c_float), ("ftrl_beta", C.c_float),
+                ("momentum", C.c_float), ("initial_accu", C.c_float), ("step_ptr", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        l = _native.cuda_lib()
+        vp, i, f, ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+        l.hctr_emb_forward.argtypes = [C.POINTER(CEmbParams), i, i, i, vp]
+        l.hctr_emb_backward_accum.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable), vp, f,
+                                              i, i, i, vp]
+        l.hctr_emb_update.argtypes = [vp, vp, vp, vp, C.POINTER(CUniqueTable), i, i, i,
+                                      C.POINTER(COptHyper), vp, i, vp]
+        l.hctr_emb_gather_rows.argtypes = [vp, vp, vp, ll, i, i, vp]
+        for n in ("hctr_emb_forward", "hctr_emb_backward_accum", "hctr_emb_update",
+                  "hctr_emb_gather_rows"):
+            getattr(l, n).restype = i
+        _lib = l
+    return _lib
+
+
+@dataclass
+class LookupDesc:
+    """Python mirror of EmbLookup (one owner-side lookup)."""
+    table_row_off: int
+    key_off: int
+    out_off: int
+    grad_off: int
+    hotness: int
+    key_stride: int
+    num_shards: int
+    shard_idx: int
+    out_stride: int
+    grad_stride: int
+    combiner: int
+    ev_size: int
+    rows: int
+    nnz_off: int = -1
+
+    def to_c(self) -> CEmbLookup:
+        return CEmbLookup(self.table_row_off, self.key_off, self.nnz_off, self.out_off,
+                          self.grad_off, self.hotness, self.key_stride, self.num_shards,
+                          self.shard_idx, self.out_stride, self.grad_stride, self.combiner,
+                          self.ev_size, self.rows, 0)
+
+
+def lookups_to_device(lookups: List[LookupDesc], device) -> torch.Tensor:
+    arr = (CEmbLookup * max(1, len(lookups)))()
+    for i, l in enumerate(lookups):
+        arr[i] = l.to_c()
+    raw = bytes(arr)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    return t.to(device)
+
+
+def _st(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+# ----------------------------------------------------------------------------- forward
+def forward(lookups, lookups_dev, table, ev_pitch, key_bufs, out_bufs, batch, my_rank=0,
+            nnz_bufs=None):
+    """key_bufs / out_bufs: one entry per source rank (tensor, or int device pointer for peers)."""
+    R = len(key_bufs)
+    if table.is_cuda:
+        p = CEmbParams()
+        p.num_ranks, p.my_rank, p.batch, p.num_lookups = R, my_rank, batch, len(lookups)
+        kb = 4
+        out_bf16 = 1
+        for r in range(R):
+            k, o = key_bufs[r], out_bufs[r]
+            p.keys[r] = k if isinstance(k, int) else k.data_ptr()
+            p.out[r] = o if isinstance(o, int) else o.data_ptr()
+            if nnz_bufs is not None:
+                n = nnz_bufs[r]
+                p.nnz[r] = n if isinstance(n, int) else n.data_ptr()
+            if not isinstance(k, int):
+                kb = k.element_size()
+            if not isinstance(o, int):
+                out_bf16 = int(o.dtype == torch.bfloat16)
+        p.lookups = lookups_dev.data_ptr()
+        p.table = table.data_ptr()
+        p.ev_size = ev_pitch
+        max_ev = max((l.ev_size for l in lookups), default=ev_pitch)
+        rc = lib().hctr_emb_forward(C.byref(p), max_ev, kb, out_bf16, _st(table.device))
+        if rc:
+            raise RuntimeError("hctr_emb_forward failed")
+        D._count()
+        return
+    forward_reference(lookups, table, ev_pitch, key_bufs, out_bufs, batch, nnz_bufs)
+
+
+def _owned(lk: LookupDesc, keys):
+    keys = keys.long()
+    own = keys >= 0
+    if lk.num_shards > 1:
+        own &= (keys % lk.num_shards) == lk.shard_idx
+    r = torch.div(keys, lk.num_shards, rounding_mode="floor")
+    own &= r < lk.rows
+    return own, lk.table_row_off + torch.where(own, r, torch.zeros_like(r))
+
+
+def forward_reference(lookups, table, ev_pitch, key_bufs, out_bufs, batch, nnz_bufs=None):
+    tab = table.view(-1, ev_pitch)
+    for src in range(len(key_bufs)):
+        kbuf, obuf = key_bufs[src].reshape(-1), out_bufs[src].reshape(-1)
+        for lk in lookups:
+            keys = kbuf[lk.key_off:lk.key_off + batch * lk.key_stride].view(batch, lk.key_stride)
+            keys = keys[:, :lk.hotness]
+            own, rows = _owned(lk, keys)
+            nnz = torch.full((batch,), lk.hotness, device=keys.device)
+            if lk.nnz_off >= 0 and nnz_bufs is not None:
+                nnz = nnz_bufs[src].reshape(-1)[lk.nnz_off:lk.nnz_off + batch].long().clamp(max=lk.hotness)
+                own &= torch.arange(lk.hotness, device=keys.device).view(1, -1) < nnz.view(-1, 1)
+            v = tab[rows][..., :lk.ev_size].float() * own.unsqueeze(-1)
+            pooled = v.sum(1)
+            if lk.combiner == 1:
+                pooled = pooled / nnz.clamp(min=1).view(-1, 1).float()
+            o = torch.as_strided(obuf, (batch, lk.ev_size), (lk.out_stride, 1), lk.out_off)
+            o.copy_(pooled.to(o.dtype))
+
+
+# ----------------------------------------------------------------------------- backward
+class UniqueWorkspace:
+    """Transient hash + fp32 per-unique-row gradient accumulator (device)."""
+
+    def __init__(self, max_pairs: int, ev_pitch: int, device, unique_ratio: float = 1.0):
+        self.device = device
+        self.ev = ev_pitch
+        self.max_unique = max(16, int(max_pairs * unique_ratio))
+        cap = 1
+        while cap < 2 * self.max_unique:
+            cap <<= 1
+        self.capacity = cap
+        if device.type == "cuda":
+            self.keys = torch.full((cap,), -1, dtype=torch.int64, device=device)
+            self.vals = torch.full((cap,), -1, dtype=torch.int32, device=device)
+            self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+            self.rows = torch.zeros(self.max_unique, dtype=torch.int64, device=device)
+            self.slots = torch.zeros(self.max_unique, dtype=torch.int32, device=device)
+            self.wgrad = torch.zeros(self.max_unique, ev_pitch, dtype=torch.float32, device=device)
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+            self.c = CUniqueTable(self.keys.data_ptr(), self.vals.data_ptr(),
+                                  self.counter.data_ptr(), self.rows.data_ptr(),
+                                  self.slots.data_ptr(), cap - 1, self.max_unique)
+        else:
+            self.ref_rows = None
+            self.ref_grads = None
+
+
+def backward_accum(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, batch, ws, grad_scale=1.0,
+                   my_rank=0, nnz_bufs=None, dense_wgrad=None):
+    """Accumulate bucket gradients per unique row (or into a dense wgrad for DP tables)."""
+    R = len(key_bufs)
+    if table.is_cuda:
+        p = CEmbParams()
+        p.num_ranks, p.my_rank, p.batch, p.num_lookups = R, my_rank, batch, len(lookups)
+        kb, gbf = 4, 1
+        for r in range(R):
+            k, g = key_bufs[r], grad_bufs[r]
+            p.keys[r] = k if isinstance(k, int) else k.data_ptr()
+            p.grad[r] = g if isinstance(g, int) else g.data_ptr()
+            if nnz_bufs is not None:
+                n = nnz_bufs[r]
+                p.nnz[r] = n if isinstance(n, int) else n.data_ptr()
+            if not isinstance(k, int):
+                kb = k.element_size()
+            if not isinstance(g, int):
+                gbf = int(g.dtype == torch.bfloat16)
+        p.lookups = lookups_dev.data_ptr()
+        p.table = table.data_ptr()
+        p.ev_size = ev_pitch
+        max_ev = max((l.ev_size for l in lookups), default=ev_pitch)
+        if dense_wgrad is not None:
+            ut = CUniqueTable(0, 0, 0, 0, 0, 0, 0xFFFFFFFF)
+            dst = dense_wgrad.data_ptr()
+        else:
+            ut, dst = ws.c, ws.wgrad.data_ptr()
+        rc = lib().hctr_emb_backward_accum(C.byref(p), C.byref(ut), dst, float(grad_scale), max_ev,
+                                           kb, gbf, _st(table.device))
+        if rc:
+            raise RuntimeError("hctr_emb_backward_accum failed")
+        D._count()
+        return
+    rows_all, grads_all = [], []
+    for src in range(R):
+        kbuf, gbuf = key_bufs[src].reshape(-1), grad_bufs[src].reshape(-1)
+        for lk in lookups:
+            keys = kbuf[lk.key_off:lk.key_off + batch * lk.key_stride].view(batch, lk.key_stride)
+            keys = keys[:, :lk.hotness]
+            own, rows = _owned(lk, keys)
+            nnz = torch.full((batch,), lk.hotness, device=keys.device)
+            if lk.nnz_off >= 0 and nnz_bufs is not None:
+                nnz = nnz_bufs[src].reshape(-1)[lk.nnz_off:lk.nnz_off + batch].long().clamp(max=lk.hotness)
+                own &= torch.arange(lk.hotness, device=keys.device).view(1, -1) < nnz.view(-1, 1)
+            g = torch.as_strided(gbuf, (batch, lk.ev_size), (lk.grad_stride, 1), lk.grad_off)
+            g = g.float() * grad_scale
+            if lk.combiner == 1:
+                g = g / nnz.clamp(min=1).view(-1, 1).float()
+            gg = g.unsqueeze(1).expand(batch, lk.hotness, lk.ev_size)[own]
+            if lk.ev_size < ev_pitch:
+                gg = torch.nn.functional.pad(gg, (0, ev_pitch - lk.ev_size))
+            rows_all.append(rows[own])
+            grads_all.append(gg)
+    rows = torch.cat(rows_all) if rows_all else torch.zeros(0, dtype=torch.long)
+    grads = torch.cat(grads_all) if grads_all else torch.zeros(0, ev_pitch)
+    if dense_wgrad is not None:
+        dense_wgrad.view(-1, ev_pitch).index_add_(0, rows, grads)
+        return
+    if ws.ref_rows is not None:
+        rows = torch.cat([ws.ref_rows, rows])
+        grads = torch.cat([ws.ref_grads, grads])
+    ws.ref_rows, ws.ref_grads = rows, grads
+
+
+def sparse_opt_reference(opt: Optimizer_t, w, s0, s1, g, hp, lr, step):
+    """Row-block update (w, s0, s1, g all [n, ev] fp32). Returns nothing, updates in place."""
+    g = g / hp.get("scaler", 1.0)
+    eps = hp.get("epsilon", 1e-7)
+    if opt == Optimizer_t.SGD:
+        w -= lr * g
+    elif opt == Optimizer_t.AdaGrad:
+        s0 += g * g
+        w -= lr * g / (s0.sqrt() + eps)
+    elif opt == Optimizer_t.Adam:
+        b1, b2 = hp.get("beta1", 0.9), hp.get("beta2", 0.999)
+        s0.mul_(b1).add_((1 - b1) * g)
+        s1.mul_(b2).add_((1 - b2) * g * g)
+        alpha = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+        w -= alpha * s0 / (s1.sqrt() + eps)
+    elif opt == Optimizer_t.Ftrl:
+        fb, l1, l2 = hp.get("ftrl_beta", 0.0), hp.get("lambda1", 0.0), hp.get("lambda2", 0.0)
+        n_new = s1 + g * g
+        s0 += g + ((s1 + fb).sqrt() - (n_new + fb).sqrt()) * w / lr
+        s1.copy_(n_new)
+        p = torch.where(s0 > 0, l1 - s0, -l1 - s0)
+        q = (n_new + fb).sqrt() / lr + l2
+        w.copy_(torch.where(s0.abs() > l1, p / q, torch.zeros_like(w)))
+    elif opt == Optimizer_t.MomentumSGD:
+        s0.mul_(hp.get("momentum", 0.0)).sub_(lr * g)
+        w += s0
+    elif opt == Optimizer_t.Nesterov:
+        mu = hp.get("momentum", 0.0)
+        an = mu * s0 - lr * g
+        w += -mu * s0 + (1 + mu) * an
+        s0.copy_(an)
+    elif opt == Optimizer_t.RMSProp:
+        b2 = hp.get("beta2", 0.999)
+        s0.mul_(b2).add_((1 - b2) * g * g)
+        w -= lr * g / (s0.sqrt() + eps)
+
+
+def update(opt: Optimizer_t, table, s0, s1, ev_pitch, ws: UniqueWorkspace, hp: dict, lr_t, step_t,
+           num_sms: int = 148):
+    """Fused per-unique-row optimizer; consumes and clears the workspace."""
+    if table.is_cuda:
+        h = COptHyper(lr_t.data_ptr(), 1.0, hp.get("scaler", 1.0), hp.get("beta1", 0.9),
+                      hp.get("beta2", 0.999), hp.get("epsilon", 1e-7), hp.get("lambda1", 0.0),
+                      hp.get("lambda2", 0.0), hp.get("ftrl_beta", 0.0), hp.get("momentum", 0.0),
+                      hp.get("initial_accu_value", 0.0), step_t.data_ptr())
+        sbf = int(s0 is not None and s0.dtype == torch.bfloat16)
+        rc = lib().hctr_emb_update(table.data_ptr(), 0 if s0 is None else s0.data_ptr(),
+                                   0 if s1 is None else s1.data_ptr(), ws.wgrad.data_ptr(),
+                                   C.byref(ws.c), ev_pitch, OPT_CODE[opt], sbf, C.byref(h),
+                                   ws.overflow.data_ptr(), num_sms, _st(table.device))
+        if rc:
+            raise RuntimeError("hctr_emb_update failed")
+        D._count(2)
+        return
+    if ws.ref_rows is None or ws.ref_rows.numel() == 0:
+        ws.ref_rows = ws.ref_grads = None
+        return
+    uniq, inv = torch.unique(ws.ref_rows, return_inverse=True)
+    g = torch.zeros(uniq.numel(), ev_pitch).index_add_(0, inv, ws.ref_grads)
+    tab = table.view(-1, ev_pitch)
+    w = tab[uniq].clone()
+    a = None if s0 is None else s0.view(-1, ev_pitch)[uniq].float().clone()
+    b = None if s1 is None else s1.view(-1, ev_pitch)[uniq].float().clone()
+    sparse_opt_reference(opt, w, a, b, g, hp, float(lr_t.item()), int(step_t.item()))
+    tab[uniq] = w
+    if a is not None:
+        s0.view(-1, ev_pitch)[uniq] = a.to(s0.dtype)
+    if b is not None:
+        s1.view(-1, ev_pitch)[uniq] = b.to(s1.dtype)
+    ws.ref_rows = ws.ref_grads = None
+
+
+def gather_rows(table, ev_pitch, rows, out):
+    """out[i] = table[rows[i]] (rows < 0 -> zeros)."""
+    if table.is_cuda and rows.dtype == torch.int64:
+        rc = lib().hctr_emb_gather_rows(table.data_ptr(), rows.data_ptr(), out.data_ptr(),
+                                        rows.numel(), ev_pitch, int(out.dtype == torch.bfloat16),
+                                        _st(table.device))
+        if rc:
+            raise RuntimeError("hctr_emb_gather_rows failed")
+        D._count()
+        return
+    v = table.view(-1, ev_pitch)[rows.clamp(min=0)] * (rows >= 0).unsqueeze(-1)
+    out.copy_(v.to(out.dtype))

@@ -1,0 +1,611 @@
+"""The remaining dense layer inventory: shape ops, elementwise, reductions,
+normalisation, attention, GRU.  Views are zero-copy where the reference copies; elementwise hot
+ones (ReLU/Sigmoid/Concat) call the sm_100a kernels, the rest derive backward from autograd.
+File references are given per class.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ..enums import Initializer_t
+from ..ops import dense as D
+from .base import Layer, TorchLayer, make_init
+
+
+# ------------------------------------------------------------------------- activations
+class ReLULayer(Layer):
+    """HugeCTR/src/layers/relu_layer.cu:35"""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def fprop(self, is_train):
+        D.elementwise(D.EW_RELU, self.inputs[0].data, None, self.outputs[0].data)
+
+    def bprop(self):
+        if self.inputs[0].grad is not None:
+            D.elementwise(D.EW_RELU_BWD, self.outputs[0].grad, self.outputs[0].data,
+                          self.inputs[0].grad)
+
+
+class SigmoidLayer(Layer):
+    """HugeCTR/src/layers/sigmoid_layer.cu"""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def fprop(self, is_train):
+        D.elementwise(D.EW_SIGMOID, self.inputs[0].data, None, self.outputs[0].data)
+
+    def bprop(self):
+        if self.inputs[0].grad is not None:
+            D.elementwise(D.EW_SIGMOID_BWD, self.outputs[0].grad, self.outputs[0].data,
+                          self.inputs[0].grad)
+
+
+class ELULayer(TorchLayer):
+    """HugeCTR/src/layers/elu_layer.cu"""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, x):
+        return F.elu(x, alpha=self.cfg.elu_alpha)
+
+
+class PReLUDiceLayer(TorchLayer):
+    """HugeCTR/src/layers/prelu_dice_layer.cu:45-86 (batch statistics per feature)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, x):
+        x2 = x.reshape(-1, x.shape[-1]).float()
+        ex = x2.mean(0, keepdim=True)
+        var = (x2 * x2).mean(0, keepdim=True) - ex * ex
+        ps = torch.sigmoid((x2 - ex) / torch.sqrt(var + self.cfg.eps))
+        y = ps * x2 + (1 - ps) * self.cfg.elu_alpha * x2
+        return y.reshape(x.shape).to(x.dtype)
+
+
+class DropoutLayer(Layer):
+    """HugeCTR/src/layers/dropout_layer.cu:91-104 (inverted dropout, identity in eval)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self.rate = float(cfg.dropout_rate)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def allocate(self):
+        super().allocate()
+        if self.ctx.is_train:
+            self.mask = torch.ones(self.inputs[0].shape, dtype=self.inputs[0].dtype,
+                                   device=self.ctx.device)
+
+    def fprop(self, is_train):
+        x = self.inputs[0].data
+        if is_train and self.rate > 0:
+            keep = 1.0 - self.rate
+            self.mask.bernoulli_(keep).mul_(1.0 / keep)
+            torch.mul(x, self.mask, out=self.outputs[0].data)
+        else:
+            self.outputs[0].data.copy_(x)
+
+    def bprop(self):
+        if self.inputs[0].grad is not None:
+            if self.rate > 0:
+                torch.mul(self.outputs[0].grad, self.mask, out=self.inputs[0].grad)
+            else:
+                self.inputs[0].grad.copy_(self.outputs[0].grad)
+
+
+class CastLayer(Layer):
+    """HugeCTR/src/layers/cast_layer.cu:26-40 (fp32 <-> compute dtype)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        src = inputs[0].dtype
+        dst = ctx.act_dtype if src == torch.float32 else torch.float32
+        self._out(0, inputs[0].shape, dst)
+
+    def fprop(self, is_train):
+        self.outputs[0].data.copy_(self.inputs[0].data)
+
+    def bprop(self):
+        if self.inputs[0].grad is not None:
+            self.inputs[0].grad.copy_(self.outputs[0].grad)
+
+
+# ------------------------------------------------------------------------- shape ops
+class ReshapeLayer(Layer):
+    """reshape_layer.cu / reshape_layer_v2.cu: leading_dim, (time_step, leading_dim), selected
+    slots, or explicit ``shape``.  Zero-copy view unless slots are selected."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        x = inputs[0]
+        n = math.prod(x.shape)
+        self.sel = list(cfg.selected_slots) if cfg.selected else None
+        if cfg.shape:
+            shp = list(cfg.shape)
+            if -1 in shp:
+                known = -math.prod(shp)
+                shp[shp.index(-1)] = n // known
+            out = tuple(shp)
+        elif self.sel is not None:
+            assert len(x.shape) == 3
+            out = (x.shape[0], len(self.sel) * x.shape[2])
+        elif cfg.time_step > 0:
+            out = (n // (cfg.time_step * cfg.leading_dim), cfg.time_step, cfg.leading_dim)
+        else:
+            ld = cfg.leading_dim if cfg.leading_dim > 0 else math.prod(x.shape[1:])
+            out = (n // ld, ld)
+        assert math.prod(out) == (n if self.sel is None else out[0] * out[1]), "Reshape size mismatch"
+        self._out(0, out, x.dtype)
+
+    def allocate(self):
+        if self.sel is not None:
+            return super().allocate()
+        o, x = self.outputs[0], self.inputs[0]
+        o.data = x.data.view(o.shape)
+        if self.ctx.is_train:
+            o.grad = x.grad.view(o.shape) if x.grad is not None else None
+            if o.grad is None and o.dtype.is_floating_point and x.needs_grad is False:
+                o.needs_grad = False
+
+    def fprop(self, is_train):
+        if self.sel is not None:
+            x = self.inputs[0].data
+            self.outputs[0].data.copy_(x[:, self.sel, :].reshape(self.outputs[0].shape))
+
+    def bprop(self):
+        if self.sel is not None and self.inputs[0].grad is not None:
+            g = self.inputs[0].grad
+            g.zero_()
+            g[:, self.sel, :] = self.outputs[0].grad.view(g.shape[0], len(self.sel), g.shape[2])
+
+
+class ConcatLayer(Layer):
+    """concat_layer.cu / concat_3d_layer.cu: concatenate along ``axis`` (default 1)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        ax = cfg.axis if cfg.axis >= 0 else len(inputs[0].shape) + cfg.axis
+        self.axis = ax
+        shp = list(inputs[0].shape)
+        shp[ax] = sum(t.shape[ax] for t in inputs)
+        for t in inputs:
+            assert len(t.shape) == len(shp), "Concat rank mismatch"
+        self._out(0, shp, inputs[0].dtype)
+
+    def _views(self, which):
+        big = getattr(self.outputs[0], which)
+        outer = math.prod(self.outputs[0].shape[:self.axis])
+        big2 = big.reshape(outer, -1)
+        off = 0
+        res = []
+        for t in self.inputs:
+            w = math.prod(t.shape[self.axis:])
+            res.append((t, big2[:, off:off + w], outer, w))
+            off += w
+        return res
+
+    def fprop(self, is_train):
+        for t, dst, outer, w in self._views("data"):
+            D.copy2d(t.data.reshape(outer, w), dst)
+
+    def bprop(self):
+        for t, src, outer, w in self._views("grad"):
+            if t.grad is not None:
+                D.copy2d(src, t.grad.reshape(outer, w))
+
+
+class SliceLayer(Layer):
+    """slice_layer.cu: multiple [start,end) column ranges; also the fan-out copy layer inserted by
+    the graph builder (model_compile.cpp:624-684).  Backward sums overlapping ranges."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        x = inputs[0]
+        self.ranges = [tuple(r) for r in cfg.ranges]
+        assert len(self.ranges) == len(cfg.top_names), "Slice: one range per top"
+        for i, (a, b_) in enumerate(self.ranges):
+            assert 0 <= a < b_ <= x.shape[-1], "Slice range out of bound"
+            self._out(i, tuple(x.shape[:-1]) + (b_ - a,), x.dtype)
+        self.full_copy = all(r == (0, x.shape[-1]) for r in self.ranges)
+
+    def allocate(self):
+        x = self.inputs[0]
+        if self.full_copy:
+            # pure fan-out: forward aliases the input, backward accumulates
+            for o in self.outputs:
+                o.data = x.data
+                if self.ctx.is_train and o.dtype.is_floating_point and x.grad is not None:
+                    o.grad = torch.zeros(o.shape, dtype=o.dtype, device=self.ctx.device)
+                elif x.grad is None:
+                    o.needs_grad = False
+        else:
+            super().allocate()
+
+    def fprop(self, is_train):
+        if self.full_copy:
+            return
+        x2 = self.inputs[0].view2d()
+        for o, (a, b_) in zip(self.outputs, self.ranges):
+            D.copy2d(x2[:, a:b_], o.view2d())
+
+    def bprop(self):
+        g = self.inputs[0].grad
+        if g is None:
+            return
+        g2 = g.reshape(g.shape[0], -1) if g.dim() != 2 else g
+        if self.full_copy:
+            first = True
+            for o in self.outputs:
+                if o.grad is None:
+                    continue
+                if first:
+                    g.copy_(o.grad)
+                    first = False
+                else:
+                    g.add_(o.grad)
+            if first:
+                g.zero_()
+            return
+        g.zero_()
+        for o, (a, b_) in zip(self.outputs, self.ranges):
+            if o.grad is not None:
+                D.copy2d(o.view2d("grad"), g2[:, a:b_], accumulate=True)
+
+
+class SelectLayer(TorchLayer):
+    """select_layer.cu: index_select on ``dim``."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        shp = list(inputs[0].shape)
+        shp[cfg.dim] = len(cfg.index)
+        self._out(0, shp, inputs[0].dtype)
+
+    def forward(self, x):
+        idx = torch.tensor(self.cfg.index, device=x.device, dtype=torch.long)
+        return torch.index_select(x, self.cfg.dim, idx)
+
+
+class GatherLayer(TorchLayer):
+    """gather_layer.cu: gathers rows ``indices`` -> (num_indices, num_elems)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        x = inputs[0]
+        self._out(0, (len(cfg.indices),) + tuple(x.shape[1:]), x.dtype)
+
+    def forward(self, x):
+        idx = torch.tensor(self.cfg.indices, device=x.device, dtype=torch.long)
+        return torch.index_select(x, 0, idx)
+
+
+class ScaleLayer(TorchLayer):
+    """scale_layer.cu:32-78: axis 0 repeats every element ``factor`` times along the row, axis 1
+    repeats every row ``factor`` times."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b, n = inputs[0].shape
+        f = int(cfg.factor)
+        self._out(0, (b, n * f) if cfg.axis == 0 else (b * f, n), inputs[0].dtype)
+
+    def forward(self, x):
+        f = int(self.cfg.factor)
+        return x.repeat_interleave(f, dim=1) if self.cfg.axis == 0 else x.repeat_interleave(f, dim=0)
+
+
+class FusedReshapeConcatLayer(TorchLayer):
+    """fused_reshape_concat_layer.cu: inputs [b, F+1, e_i] -> item_his [b*F, sum e], item [b, sum e]."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b, f1 = inputs[0].shape[0], inputs[0].shape[1]
+        e = sum(t.shape[2] for t in inputs)
+        self._out(0, (b * (f1 - 1), e), inputs[0].dtype)
+        self._out(1, (b, e), inputs[0].dtype)
+
+    def forward(self, *xs):
+        x = torch.cat(xs, dim=2)
+        b, f1, e = x.shape
+        return x[:, :f1 - 1, :].reshape(b * (f1 - 1), e), x[:, f1 - 1, :]
+
+
+class FusedReshapeConcatGeneralLayer(TorchLayer):
+    """fused_reshape_concat_general_layer.cu: inputs [b, F, e_i] -> [b*F, sum e]."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b, f = inputs[0].shape[0], inputs[0].shape[1]
+        self._out(0, (b * f, sum(t.shape[2] for t in inputs)), inputs[0].dtype)
+
+    def forward(self, *xs):
+        x = torch.cat(xs, dim=2)
+        return x.reshape(-1, x.shape[2])
+
+
+# ------------------------------------------------------------------------- arithmetic / reductions
+class AddLayer(TorchLayer):
+    """add_layer.cu:28-77 (N inputs)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, *xs):
+        y = xs[0]
+        for x in xs[1:]:
+            y = y + x
+        return y
+
+
+class SubLayer(TorchLayer):
+    """sub_layer.cu"""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, x, y):
+        return x - y
+
+
+class ElementwiseMultiplyLayer(TorchLayer):
+    """elementwise_multiply_layer.cu (N inputs)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, *xs):
+        y = xs[0]
+        for x in xs[1:]:
+            y = y * x
+        return y
+
+
+class WeightMultiplyLayer(TorchLayer):
+    """weight_multiply_layer.cu:32-82: out[b, s*v + j] = in[b, s] * W[s, j]."""
+    trainable = True
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b, s = inputs[0].shape
+        ws, wv = cfg.weight_dims
+        assert ws == s, "WeightMultiply: weight_dims[0] must equal the slot dim"
+        self._param("W", (ws, wv), make_init(cfg.weight_init_type, ws, wv, "xavier"))
+        self._out(0, (b, ws * wv), inputs[0].dtype)
+
+    def forward(self, x):
+        w = self._ws[0].to(x.dtype)
+        return (x.unsqueeze(2) * w.unsqueeze(0)).reshape(x.shape[0], -1)
+
+
+class FmOrder2Layer(TorchLayer):
+    """fm_order2_layer.cu:24-91: 0.5 * ((sum_s v)^2 - sum_s v^2) per embedding element."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b, n = inputs[0].shape
+        assert cfg.out_dim > 0 and n % cfg.out_dim == 0
+        self._out(0, (b, cfg.out_dim), inputs[0].dtype)
+
+    def forward(self, x):
+        v = x.reshape(x.shape[0], -1, self.cfg.out_dim).float()
+        s = v.sum(1)
+        return (0.5 * (s * s - (v * v).sum(1))).to(x.dtype)
+
+
+class ReduceSumLayer(TorchLayer):
+    """reduce_sum_layer.cu: keepdim sum over ``axis``."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        shp = list(inputs[0].shape)
+        shp[cfg.axis] = 1
+        self._out(0, shp, inputs[0].dtype)
+
+    def forward(self, x):
+        return x.float().sum(self.cfg.axis, keepdim=True).to(x.dtype)
+
+
+class ReduceMeanLayer(TorchLayer):
+    """reduce_mean_layer.cu"""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        shp = list(inputs[0].shape)
+        shp[cfg.axis] = 1
+        self._out(0, shp, inputs[0].dtype)
+
+    def forward(self, x):
+        return x.float().mean(self.cfg.axis, keepdim=True).to(x.dtype)
+
+
+class MatrixMultiplyLayer(TorchLayer):
+    """matrix_multiply_layer.cu:135-180: 2Dx2D, 3Dx3D (batched), 2Dx3D -> 3D."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        a, b_ = inputs[0].shape, inputs[1].shape
+        if len(a) == 2 and len(b_) == 2:
+            out = (a[0], b_[1])
+        elif len(a) == 3 and len(b_) == 3:
+            out = (a[0], a[1], b_[2])
+        elif len(a) == 2 and len(b_) == 3:
+            out = (a[0], b_[1], b_[2])
+        else:
+            raise ValueError("MatrixMultiply: unsupported ranks")
+        self._out(0, out, inputs[0].dtype)
+
+    def forward(self, a, b_):
+        if a.dim() == 2 and b_.dim() == 3:
+            return (a @ b_.reshape(b_.shape[0], -1)).reshape(a.shape[0], b_.shape[1], b_.shape[2])
+        return torch.matmul(a, b_)
+
+
+# ------------------------------------------------------------------------- softmax / attention
+class SoftmaxLayer(TorchLayer):
+    """softmax_layer.cu:53-173 / masked_softmax_layer.cu:33-140 (mask==0 -> -10000 before softmax)."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, x, mask=None):
+        v = x.float()
+        if mask is not None:
+            v = v * getattr(self.cfg, "factor", 1.0) if False else v
+            v = torch.where(mask.float() > 0, v, torch.full_like(v, -10000.0))
+        return torch.softmax(v, dim=-1).to(x.dtype)
+
+
+class SequenceMaskLayer(Layer):
+    """sequence_mask_layer.cu:28-76: (len_from[b], len_to[b]) -> [b,1,Lf,Lt] 0/1 mask."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        b = inputs[0].shape[0]
+        self.lf, self.lt = int(cfg.max_sequence_len_from), int(cfg.max_sequence_len_to)
+        o = self._out(0, (b, 1, self.lf, self.lt), ctx.act_dtype)
+        o.needs_grad = False
+
+    def fprop(self, is_train):
+        lf = self.inputs[0].data.reshape(-1)[:self.outputs[0].shape[0]].float()
+        lt = self.inputs[1].data.reshape(-1)[:self.outputs[0].shape[0]].float()
+        dev = lf.device
+        mf = torch.arange(self.lf, device=dev).view(1, -1, 1) < lf.view(-1, 1, 1)
+        mt = torch.arange(self.lt, device=dev).view(1, 1, -1) < lt.view(-1, 1, 1)
+        self.outputs[0].data.copy_((mf & mt).unsqueeze(1).to(self.outputs[0].dtype))
+
+    def bprop(self):
+        pass
+
+
+class MultiHeadAttentionLayer(TorchLayer):
+    """multi_head_attention_layer.cu:33-519: O = softmax(QK^T/sqrt(dh) masked) V, heads split on
+    the hidden dim.  Projections are separate FC layers in the reference."""
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        q = inputs[0]
+        self.h = int(cfg.num_attention_heads)
+        assert q.shape[-1] % self.h == 0
+        self._out(0, q.shape, q.dtype)
+
+    def forward(self, q, k, v, mask=None):
+        b, sf, hd = q.shape
+        st = k.shape[1]
+        dh = hd // self.h
+        qh = q.reshape(b, sf, self.h, dh).transpose(1, 2).float()
+        kh = k.reshape(b, st, self.h, dh).transpose(1, 2).float()
+        vh = v.reshape(b, st, self.h, dh).transpose(1, 2).float()
+        s = torch.matmul(qh, kh.transpose(-1, -2)) / math.sqrt(dh)
+        if mask is not None:
+            s = torch.where(mask.float() > 0, s, torch.full_like(s, -10000.0))
+        p = torch.softmax(s, dim=-1)
+        o = torch.matmul(p, vh).transpose(1, 2).reshape(b, sf, hd)
+        return o.to(q.dtype)
+
+
+# ------------------------------------------------------------------------- normalisation / recurrent
+class BatchNormLayer(TorchLayer):
+    """batch_norm_layer.cu:155-185 (cuDNN in the reference): gamma, beta trainable; running
+    mean/var are non-trainable parameters saved to <dense>.ntp.json."""
+    trainable = True
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        n = inputs[0].shape[-1]
+        self._param("gamma", (1, n), make_init(cfg.gamma_init_type, n, n, "one"))
+        self._param("beta", (1, n), make_init(cfg.beta_init_type, n, n, "zero"))
+        self.momentum = float(cfg.factor)
+        self.eps = float(cfg.eps)
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+        key = "_bn_state_%s" % self.name
+        st = getattr(ctx.arena, key, None)
+        if st is None:
+            st = {"mean": torch.zeros(n), "var": torch.ones(n)}
+            setattr(ctx.arena, key, st)
+        self.state = st
+
+    def allocate(self):
+        super().allocate()
+        for k in ("mean", "var"):
+            self.state[k] = self.state[k].to(self.ctx.device)
+
+    def forward(self, x):
+        g, b_ = self._ws[0].reshape(-1), self._ws[1].reshape(-1)
+        xf = x.reshape(-1, x.shape[-1]).float()
+        if self.training:
+            mean = xf.mean(0)
+            var = xf.var(0, unbiased=False)
+            with torch.no_grad():
+                m = self.momentum
+                self.state["mean"].mul_(m).add_((1 - m) * mean.detach())
+                self.state["var"].mul_(m).add_((1 - m) * var.detach())
+        else:
+            mean, var = self.state["mean"], self.state["var"]
+        y = (xf - mean) / torch.sqrt(var + self.eps) * g + b_
+        return y.reshape(x.shape).to(x.dtype)
+
+
+class LayerNormLayer(TorchLayer):
+    """layer_norm_layer.cu:43-239"""
+    trainable = True
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        n = inputs[0].shape[-1]
+        self._param("gamma", (1, n), make_init(cfg.gamma_init_type, n, n, "one"))
+        self._param("beta", (1, n), make_init(cfg.beta_init_type, n, n, "zero"))
+        self._out(0, inputs[0].shape, inputs[0].dtype)
+
+    def forward(self, x):
+        n = x.shape[-1]
+        return F.layer_norm(x.float(), (n,), self._ws[0].reshape(-1), self._ws[1].reshape(-1),
+                            self.cfg.eps).to(x.dtype)
+
+
+class GRULayer(TorchLayer):
+    """gru_layer.cu:265 (cuDNN GRU in the reference): input (1, b*S*v) -> output (1, b*S*h)."""
+    trainable = True
+
+    def __init__(self, cfg, inputs, ctx):
+        super().__init__(cfg, inputs, ctx)
+        self.b, self.S, self.v, self.hid = cfg.batchsize, cfg.SeqLength, cfg.vector_size, cfg.num_output
+        h, v = self.hid, self.v
+        self._param("W_ih", (3 * h, v), make_init(cfg.weight_init_type, v, h, "xavier"))
+        self._param("W_hh", (3 * h, h), make_init(cfg.weight_init_type, h, h, "xavier"))
+        self._param("b_ih", (1, 3 * h), make_init(cfg.bias_init_type, h, h, "zero"))
+        self._param("b_hh", (1, 3 * h), make_init(cfg.bias_init_type, h, h, "zero"))
+        self._out(0, (1, self.b * self.S * h), inputs[0].dtype)
+
+    def forward(self, x):
+        wih, whh, bih, bhh = self._ws
+        xs = x.reshape(self.b, self.S, self.v).float()
+        h = torch.zeros(self.b, self.hid, device=x.device)
+        outs = []
+        for t in range(self.S):
+            gi = xs[:, t] @ wih.t() + bih.reshape(-1)
+            gh = h @ whh.t() + bhh.reshape(-1)
+            ir, iz, inn = gi.chunk(3, 1)
+            hr, hz, hn = gh.chunk(3, 1)
+            r = torch.sigmoid(ir + hr)
+            z = torch.sigmoid(iz + hz)
+            n = torch.tanh(inn + r * hn)
+            h = (1 - z) * n + z * h
+            outs.append(h)
+        return torch.stack(outs, 1).reshape(1, -1).to(x.dtype)

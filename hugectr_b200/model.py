@@ -1,0 +1,609 @@
+"""hugectr.Model: graph construction by tensor names, compile, fit/train/eval, checkpoints.
+
+Reference: HugeCTR/src/pybind/model.cpp (1508 lines), model_compile.cpp, model_pipeline.cpp,
+HugeCTR/include/pybind/model_wrapper.hpp:133-221.  Execution model here: one process per GPU; a
+training iteration = [H2D of the batch] + ONE statically scheduled step (embedding forward ->
+dense fprop -> dense bprop -> dense wgrad all-reduce -> fused dense optimizer -> fused embedding
+backward/update) that is captured into a CUDA graph on the first iterations (solver.use_cuda_graph).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time
+from typing import Dict, List, Optional
+
+import torch
+
+from . import metrics as M
+from .data.batch import HostBatch
+from .data.readers import SparseLayout, SyntheticReader
+from .embedding.collection import EmbeddingCollection, EmbeddingCollectionConfig
+from .enums import (DataReaderType_t, Embedding_t, Layer_t, MetricsRawType, MetricsType,
+                    Optimizer_t, Tensor_t, Update_t)
+from .layers import LOSS_LAYERS, BuildCtx, ParamArena, TensorBag
+from .lr_scheduler import LearningRateScheduler
+from .network import Network, insert_fanout_slices
+from .ops import dense as D
+from .parallel.comm import Comm
+from .solver import (DataReaderParams, DenseLayer, Input, OptParamsPy, Solver, SparseEmbedding)
+from .utils import logger
+
+DENSE_OPT_CODE = {Optimizer_t.SGD: D.D_SGD, Optimizer_t.AdaGrad: D.D_ADAGRAD,
+                  Optimizer_t.Adam: D.D_ADAM, Optimizer_t.Ftrl: D.D_FTRL,
+                  Optimizer_t.MomentumSGD: D.D_MOMENTUM, Optimizer_t.Nesterov: D.D_NESTEROV,
+                  Optimizer_t.RMSProp: D.D_RMSPROP}
+
+
+class TrainingCallback:
+    """Overridable hooks (training_callback_wrapper.hpp:62-86)."""
+
+    def on_training_start(self): pass
+    def on_training_end(self, current_iter: int): pass
+    def on_eval_start(self, current_iter: int): return False
+    def on_eval_end(self, current_iter: int, eval_results: dict): return False
+
+
+class Model:
+    def __init__(self, solver: Solver, reader_params: DataReaderParams,
+                 opt_params: Optional[OptParamsPy] = None, comm: Optional[Comm] = None):
+        self.solver = solver
+        self.reader_params = reader_params
+        self.opt_params = opt_params or OptParamsPy()
+        self.comm = comm or Comm.init_from_env()
+        self.device = self.comm.device
+        if solver.batchsize % max(1, solver.num_gpus) != 0:
+            raise ValueError("batchsize must be divisible by the total number of GPUs")  # model.cpp:357
+        if self.comm.world_size not in (1, solver.num_gpus):
+            logger.warning(f"vvgpu lists {solver.num_gpus} GPUs but the job runs {self.comm.world_size} ranks")
+        self.world = self.comm.world_size
+        self.input: Optional[Input] = None
+        self.sparse_embeddings: List[SparseEmbedding] = []
+        self.ebc_configs: List[EmbeddingCollectionConfig] = []
+        self.dense_layers: List[DenseLayer] = []
+        self.graph_order: List[object] = []
+        self.compiled = False
+        self.lr_sched = LearningRateScheduler(solver.lr, solver.warmup_steps, solver.decay_start,
+                                              solver.decay_steps, solver.decay_power, solver.end_lr)
+        self.callbacks = list(solver.training_callbacks)
+        self.embedding_frozen: Dict[str, bool] = {}
+        self.dense_frozen = False
+        self._graph = None
+        self._graph_warm = 0
+        self._iter = 0
+        self.mixed = bool(solver.use_mixed_precision)
+        self.act_dtype = torch.bfloat16 if self.mixed else torch.float32
+        self.key_dtype = torch.int64 if solver.i64_input_key else torch.int32
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ graph construction
+    def add(self, obj):
+        if self.compiled:
+            raise RuntimeError("model.add() after compile()")
+        if isinstance(obj, Input):
+            self.input = obj
+        elif isinstance(obj, SparseEmbedding):
+            self.sparse_embeddings.append(obj)
+        elif isinstance(obj, EmbeddingCollectionConfig):
+            self.ebc_configs.append(obj)
+        elif isinstance(obj, DenseLayer):
+            self.dense_layers.append(obj)
+        else:
+            raise TypeError(f"cannot add {type(obj)} to a Model")
+        self.graph_order.append(obj)
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, loss_names: Optional[List[str]] = None,
+                loss_weights: Optional[List[float]] = None):
+        assert self.input is not None, "model.add(Input) first"
+        s = self.solver
+        self.b_train = s.batchsize // self.world
+        self.b_eval = s.batchsize_eval // self.world
+        inp = self.input
+        self.layout = SparseLayout(inp.data_reader_sparse_param_array,
+                                   self.reader_params.slot_size_array)
+        self.arena = ParamArena()
+        self._build_embeddings()
+        self.net_train = self._build_network(True)
+        self.arena.begin_replay()
+        self.net_eval = self._build_network(False)
+        self.arena.end_replay()
+        self.arena.finalize(self.device, self.mixed, pad_to=max(1, 4 * self.world))
+        self.net_train.finalize()
+        self.net_eval.finalize()
+        self.arena.init_params(s.seed)
+        self._setup_losses(loss_names, loss_weights)
+        self._create_dense_optimizer()
+        self._create_metrics()
+        self._create_readers()
+        from .parallel.allreduce import ExchangeWgrad
+        self.exchange_wgrad = ExchangeWgrad(self.comm, self.arena.wgrad, s.all_reduce_algo)
+        self.compiled = True
+        if s.perf_logging:
+            logger.perf_log("init_stop")
+
+    def _src_tensors(self, b: int, is_train: bool):
+        inp = self.input
+        dev = self.device
+        t = {}
+        lab = TensorBag(inp.label_name, (b, inp.label_dim), torch.float32)
+        lab.data = torch.zeros(b, inp.label_dim, device=dev)
+        lab.needs_grad = False
+        t[inp.label_name] = lab
+        if len(inp.label_names) > 1:      # multi-label: per-label views (model_compile.cpp:88-95)
+            off = 0
+            for n, d in zip(inp.label_names, inp.label_dims):
+                lb = TensorBag(n, (b, d), torch.float32)
+                lb.data = lab.data[:, off:off + d]
+                lb.needs_grad = False
+                t[n] = lb
+                off += d
+        den = TensorBag(inp.dense_name, (b, inp.dense_dim), torch.float32)
+        den.data = torch.zeros(b, max(inp.dense_dim, 0), device=dev)
+        den.needs_grad = False
+        t[inp.dense_name] = den
+        return t
+
+    def _build_embeddings(self):
+        s = self.solver
+        hot = {p.top_name: max(p.nnz_per_slot) for p in self.input.data_reader_sparse_param_array}
+        self.ebcs_train, self.ebcs_eval = [], []
+        state_dtype = torch.float32
+        if os.environ.get("HCTR_EMB_STATE_BF16", "0") == "1":
+            state_dtype = torch.bfloat16
+        for cfg in self.ebc_configs:
+            for lk in cfg.lookups:
+                for bname in lk["bottoms"]:
+                    prm = [p for p in self.input.data_reader_sparse_param_array if p.top_name == bname]
+                    if not prm:
+                        raise KeyError(f"embedding_lookup bottom '{bname}' is not a sparse input")
+                    if prm[0].slot_num != 1:
+                        raise ValueError("EmbeddingCollection requires slot_num == 1 per sparse param")
+            e = EmbeddingCollection(cfg, self.b_train, hot, self.device, self.act_dtype, self.comm,
+                                    self.opt_params, self.key_dtype,
+                                    scaler=s.scaler if self.mixed else 1.0, state_dtype=state_dtype,
+                                    seed=s.seed,
+                                    fused=None if s.fused_embedding_comm else False)
+            self.ebcs_train.append(e)
+            self.ebcs_eval.append(e.eval_clone(self.b_eval))
+        self.legacy_train, self.legacy_eval = [], []
+        if self.sparse_embeddings:
+            from .embedding.sparse_embedding import SparseEmbeddingRuntime
+            for se in self.sparse_embeddings:
+                prm = [p for p in self.input.data_reader_sparse_param_array
+                       if p.top_name == se.bottom_name][0]
+                rt = SparseEmbeddingRuntime(se, prm, self.layout, self.b_train, self.device,
+                                            self.act_dtype, self.comm, se.optimizer or self.opt_params,
+                                            self.key_dtype, scaler=s.scaler if self.mixed else 1.0,
+                                            seed=s.seed)
+                self.legacy_train.append(rt)
+                self.legacy_eval.append(rt.eval_clone(self.b_eval))
+
+    def _build_network(self, is_train: bool) -> Network:
+        b = self.b_train if is_train else self.b_eval
+        ctx = BuildCtx(self.arena, self.device, self.act_dtype, b, is_train, self.solver, self.mixed)
+        src = self._src_tensors(b, is_train)
+        emb_tops = []
+        for e in (self.ebcs_train if is_train else self.ebcs_eval):
+            for name, shp in e.top_shapes().items():
+                tb = TensorBag(name, shp, self.act_dtype)
+                tb.data = e.top_data[name]
+                tb.grad = e.top_grad[name] if is_train else None
+                src[name] = tb
+                emb_tops.append(name)
+        for rt in (self.legacy_train if is_train else self.legacy_eval):
+            tb = TensorBag(rt.top_name, rt.top_shape, self.act_dtype)
+            tb.data = rt.top_data
+            tb.grad = rt.top_grad if is_train else None
+            src[rt.top_name] = tb
+            emb_tops.append(rt.top_name)
+        net = Network(ctx, src, emb_tops)
+        cfgs = insert_fanout_slices(self.dense_layers, list(src.keys()))
+        for c in cfgs:
+            net.add_layer(c)
+        if is_train:
+            self._resolved_layers = cfgs
+        return net
+
+    def _setup_losses(self, loss_names, loss_weights):
+        for net in (self.net_train, self.net_eval):
+            if not net.loss_layers:
+                raise RuntimeError("the model has no loss layer")
+            if loss_names:
+                wmap = dict(zip(loss_names, loss_weights))
+                for ll in net.loss_layers:
+                    ll.loss_weight = float(wmap.get(ll.cfg.top_names[0], 1.0))
+            elif len(self.input.label_names) > 1:
+                lw = dict(zip(self.input.label_names, self.input.label_weights))
+                for ll in net.loss_layers:
+                    ll.loss_weight = float(lw.get(ll.cfg.bottom_names[1], 1.0))
+
+    def _create_dense_optimizer(self):
+        o = self.opt_params
+        dev = self.device
+        n = self.arena.weights.numel()
+        ns = o.num_states
+        if o.optimizer_type == Optimizer_t.Adam:
+            ns = 2
+        self.opt_s0 = torch.zeros(n, device=dev) if ns >= 1 else None
+        self.opt_s1 = torch.zeros(n, device=dev) if ns >= 2 else None
+        if o.optimizer_type == Optimizer_t.AdaGrad and o.initial_accu_value != 0 and self.opt_s0 is not None:
+            self.opt_s0.fill_(o.initial_accu_value)
+        self.lr_t = torch.full((1,), float(self.solver.lr), device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dense_hp = {"scaler": self.solver.scaler if self.mixed else 1.0, "beta1": o.beta1,
+                         "beta2": o.beta2, "epsilon": o.epsilon, "lambda1": o.lambda1,
+                         "lambda2": o.lambda2, "ftrl_beta": o.beta, "momentum": o.momentum_factor}
+
+    def _create_metrics(self):
+        ncls = self.input.label_dim
+        self.metrics = [(k, thr, M.create_metric(k, self.comm, ncls))
+                        for k, thr in self.solver.metrics_spec.items()]
+
+    def _create_readers(self):
+        from .data import create_reader
+        self.reader_train = create_reader(self, True)
+        self.reader_eval = create_reader(self, False)
+
+    # ------------------------------------------------------------------ summary / json
+    def summary(self):
+        if self.comm.rank != 0:
+            return
+        line = "=" * 95
+        print(line)
+        print("%-28s%-32s%-35s" % ("Label", "Dense", "Sparse"))
+        inp = self.input
+        print("%-28s%-32s%-35s" % (inp.label_name, inp.dense_name,
+                                  ",".join(p.top_name for p in inp.data_reader_sparse_param_array)[:34]))
+        print("%-28s%-32s" % (f"(None, {inp.label_dim})", f"(None, {inp.dense_dim})"))
+        print("-" * 95)
+        print("%-36s%-30s%-30s%-20s" % ("Layer Type", "Input Name", "Output Name", "Output Shape"))
+        print("-" * 95)
+        for se in self.sparse_embeddings:
+            print("%-36s%-30s%-30s" % (se.embedding_type.name, se.bottom_name, se.sparse_embedding_name))
+        for e in getattr(self, "ebcs_train", []):
+            for tp in e.tops:
+                print("%-36s%-30s%-30s%-20s" % ("EmbeddingCollection", "", tp["name"],
+                                                f"(None, {tp['width']})"))
+        if self.compiled:
+            for (t, i, o, shp) in self.net_train.summary_rows():
+                print("%-36s%-30s%-30s%-20s" % (t, i[:29], o[:29], shp))
+        else:
+            for c in self.dense_layers:
+                print("%-36s%-30s%-30s" % (c.layer_type.name, ",".join(c.bottom_names)[:29],
+                                           ",".join(c.top_names)[:29]))
+        print(line)
+
+    def graph_to_json(self, graph_config_file: str):
+        from .graph_json import model_to_json
+        if self.comm.rank == 0:
+            with open(graph_config_file, "w") as f:
+                json.dump(model_to_json(self), f, indent=2)
+
+    def construct_from_json(self, graph_config_file: str, include_dense_network: bool = True):
+        from .graph_json import add_from_json
+        with open(graph_config_file) as f:
+            add_from_json(self, json.load(f), include_dense_network)
+
+    # ------------------------------------------------------------------ data
+    def _load_batch(self, hb: HostBatch, is_train: bool):
+        net = self.net_train if is_train else self.net_eval
+        inp = self.input
+        nb = True
+        net.tensors[inp.label_name].data.copy_(hb.label, non_blocking=nb)
+        if inp.dense_dim > 0:
+            net.tensors[inp.dense_name].data.copy_(hb.dense, non_blocking=nb)
+        ebcs = self.ebcs_train if is_train else self.ebcs_eval
+        legs = self.legacy_train if is_train else self.legacy_eval
+        if len(ebcs) == 1 and not legs:
+            ebcs[0].set_keys(hb.keys)
+        else:
+            b = self.b_train if is_train else self.b_eval
+            offs, _ = self.layout.key_block_offsets(b)
+            for e in ebcs:
+                for gl in e.glookups:
+                    o = offs[gl["bottom"]]
+                    e.key_views[gl["bottom"]].copy_(
+                        hb.keys[o:o + b * gl["hotness"]].view(b, gl["hotness"]), non_blocking=nb)
+            for rt in legs:
+                rt.set_keys(hb, offs, self.layout.nnz_block_offsets(b)[0])
+
+    def start_data_reading(self):
+        self.reader_train.start()
+        self.reader_eval.start()
+
+    def set_source(self, source=None, eval_source=None):
+        if source is not None:
+            self.reader_train.set_source(source)
+        if eval_source is not None:
+            self.reader_eval.set_source(eval_source)
+
+    def get_data_reader_train(self):
+        return self.reader_train
+
+    def get_data_reader_eval(self):
+        return self.reader_eval
+
+    def get_learning_rate_scheduler(self):
+        return self.lr_sched
+
+    # ------------------------------------------------------------------ one training step
+    def _step_body(self):
+        s = self.solver
+        D.lr_step(self.step_t, self.lr_t, s.lr, s.end_lr, s.decay_power, s.warmup_steps,
+                  s.decay_start, s.decay_steps)
+        net = self.net_train
+        for e in self.ebcs_train:
+            e.forward(True)
+        for rt in self.legacy_train:
+            rt.forward(True)
+        net.fprop(True)
+        net.bprop()
+        if not self.dense_frozen:
+            self.exchange_wgrad.allreduce()
+            D.dense_opt_step(DENSE_OPT_CODE[self.opt_params.optimizer_type], self.arena.weights,
+                             self.arena.wgrad, self.arena.weights16, self.opt_s0, self.opt_s1,
+                             self.lr_t, self.step_t, self.dense_hp, zero_grad=True)
+        else:
+            self.arena.wgrad.zero_()
+        for e in self.ebcs_train:
+            if not self.embedding_frozen.get("*", False):
+                e.backward(self.lr_t, self.step_t)
+        for rt in self.legacy_train:
+            if not self.embedding_frozen.get(rt.name, self.embedding_frozen.get("*", False)):
+                rt.backward(self.lr_t, self.step_t)
+
+    def _run_step(self):
+        use_graph = (self.solver.use_cuda_graph and self.device.type == "cuda"
+                     and os.environ.get("HCTR_DISABLE_CUDA_GRAPH", "0") == "0"
+                     and not self.legacy_train)
+        if not use_graph:
+            c0 = D.launch_count
+            self._step_body()
+            self.launches_per_step = D.launch_count - c0
+            return
+        if self._graph is None:
+            if self._graph_warm < 2:           # eager warm-up iterations (lazy inits, autotune)
+                c0 = D.launch_count
+                self._step_body()
+                self.launches_per_step = D.launch_count - c0
+                self._graph_warm += 1
+                return
+            torch.cuda.synchronize()
+            self.comm.barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_body()
+            self._graph = g
+            self.comm.barrier()                # pipeline.cpp:111-125 barrier after first capture
+            # capture does not execute: run the captured step now
+        self._graph.replay()
+
+    def train(self) -> bool:
+        """One iteration on the next batch (Model::train, model.cpp:1048-1138)."""
+        if not self.reader_train.is_started():
+            self.reader_train.start()
+        hb = self.reader_train.read_a_batch()
+        if hb is None:
+            return False
+        if self.reader_train.current_batch_incomplete() and self.solver.drop_incomplete_batch:
+            return True
+        self._load_batch(hb, True)
+        self._run_step()
+        self._iter += 1
+        self.lr_sched.step = self._iter
+        return True
+
+    def train_on_host_batch(self, hb: HostBatch):
+        self._load_batch(hb, True)
+        self._run_step()
+        self._iter += 1
+
+    def eval(self) -> bool:
+        if not self.reader_eval.is_started():
+            self.reader_eval.start()
+        hb = self.reader_eval.read_a_batch()
+        if hb is None:
+            return False
+        self._load_batch(hb, False)
+        for e in self.ebcs_eval:
+            e.forward(False)
+        for rt in self.legacy_eval:
+            rt.forward(False)
+        self.net_eval.fprop(False)
+        raw = self._raw_metrics()
+        for (_, _, m) in self.metrics:
+            m.set_current_batch_size(self.reader_eval.get_current_batchsize())
+            m.local_reduce(raw)
+        return True
+
+    def _raw_metrics(self):
+        net = self.net_eval
+        ll = net.loss_layers
+        if len(ll) == 1:
+            pred = ll[0].pred
+        else:
+            pred = torch.cat([l.pred.reshape(l.pred.shape[0], -1) for l in ll], 1)
+        label = net.tensors[self.input.label_name].data
+        nvalid = self.reader_eval.get_current_batchsize_per_device()
+        return {MetricsRawType.Loss: net.loss_value(), MetricsRawType.Pred: pred[:nvalid],
+                MetricsRawType.Label: label[:nvalid]}
+
+    def get_eval_metrics(self):
+        return [(k.name, m.finalize_metric()) for (k, _, m) in self.metrics]
+
+    def get_current_loss(self) -> float:
+        v = self.net_train.loss_value().detach().float().clone()
+        if self.world > 1:
+            self.comm.all_reduce(v)
+            v = v / self.world
+        return float(v.item())
+
+    def set_learning_rate(self, lr: float):
+        self.solver.lr = lr
+        self.lr_sched.base_lr = lr
+        self._graph = None
+
+    def reset_learning_rate_scheduler(self, base_lr, warmup_steps=1, decay_start=0, decay_steps=1,
+                                      decay_power=2.0, end_lr=0.0):
+        s = self.solver
+        s.lr, s.warmup_steps, s.decay_start = base_lr, warmup_steps, decay_start
+        s.decay_steps, s.decay_power, s.end_lr = decay_steps, decay_power, end_lr
+        self.lr_sched = LearningRateScheduler(base_lr, warmup_steps, decay_start, decay_steps,
+                                              decay_power, end_lr)
+        if self.compiled:
+            self.step_t.zero_()
+        self._graph = None
+
+    # ------------------------------------------------------------------ freeze
+    def freeze_embedding(self, name: Optional[str] = None):
+        self.embedding_frozen[name or "*"] = True
+        self._graph = None
+
+    def unfreeze_embedding(self, name: Optional[str] = None):
+        self.embedding_frozen[name or "*"] = False
+        self._graph = None
+
+    def freeze_dense(self):
+        self.dense_frozen = True
+        self._graph = None
+
+    def unfreeze_dense(self):
+        self.dense_frozen = False
+        self._graph = None
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, num_epochs: int = 0, max_iter: int = 2000, display: int = 200,
+            eval_interval: int = 1000, snapshot: int = 10000, snapshot_prefix: str = ""):
+        s = self.solver
+        if not self.compiled:
+            raise RuntimeError("call compile() before fit()")
+        rank0 = self.comm.rank == 0
+        if s.perf_logging:
+            logger.perf_log("run_start")
+        for cb in self.callbacks:
+            cb.on_training_start()
+        self.start_data_reading()
+        epoch_mode = num_epochs > 0
+        if epoch_mode:
+            self.reader_train.repeat = False
+            self.reader_eval.repeat = False
+            logger.info(f"Use epoch mode with number of epochs: {num_epochs}")
+        else:
+            logger.info(f"Use non-epoch mode with number of iterations: {max_iter}")
+        logger.info(f"Training batchsize: {s.batchsize}, evaluation batchsize: {s.batchsize_eval}")
+        logger.info(f"Evaluation interval: {eval_interval}, snapshot interval: {snapshot}")
+        logger.info(f"Dense network trainable: {not self.dense_frozen}")
+        logger.info(f"Use mixed precision: {self.mixed}, scaler: {s.scaler}, use cuda graph: {s.use_cuda_graph}")
+        logger.info(f"lr: {s.lr}, warmup_steps: {s.warmup_steps}, end_lr: {s.end_lr}")
+        logger.info(f"decay_start: {s.decay_start}, decay_steps: {s.decay_steps}, decay_power: {s.decay_power}")
+        t_start = time.time()
+        t_disp = time.time()
+        it = 0
+        epoch = 0
+        stop = False
+        total_iters = max_iter if not epoch_mode else 1 << 62
+        while it < total_iters and not stop:
+            ok = self.train()
+            if not ok:                                  # end of an epoch
+                epoch += 1
+                if not epoch_mode or epoch >= num_epochs:
+                    break
+                self.reader_train.set_source(None)
+                continue
+            it += 1
+            if display > 0 and it % display == 0:
+                loss = self.get_current_loss()
+                if math.isnan(loss):
+                    raise RuntimeError("Train Runtime error: Loss cannot converge")  # model.cpp:889
+                now = time.time()
+                logger.info("Iter: %d Time(%d iters): %.2fs Loss: %f lr:%f" %
+                            (it, display, now - t_disp, loss, float(self.lr_t.item())))
+                t_disp = now
+            if eval_interval > 0 and it % eval_interval == 0:
+                stop = self._evaluate(it, t_start) or stop
+            if snapshot > 0 and it % snapshot == 0 and it != max_iter:
+                self.save_params_to_files(snapshot_prefix, it)
+        for cb in self.callbacks:
+            cb.on_training_end(it)
+        if rank0:
+            logger.info("Finish %d iterations with batchsize: %d in %.2fs." %
+                        (it, s.batchsize, time.time() - t_start))
+        return it
+
+    def _evaluate(self, it: int, t_start: float) -> bool:
+        s = self.solver
+        for cb in self.callbacks:
+            cb.on_eval_start(it)
+        if s.perf_logging:
+            logger.perf_log("eval_start", it)
+        t0 = time.time()
+        self.reader_eval.set_source(None) if not self.reader_eval.repeat else None
+        for _ in range(s.max_eval_batches):
+            if not self.eval():
+                break
+        res = self.get_eval_metrics()
+        stop = False
+        results = {}
+        for (name, val), (kind, thr, _) in zip(res, self.metrics):
+            results[name] = val
+            logger.info("Evaluation, %s: %f" % (name, val))
+            if kind == MetricsType.AUC and thr < 1.0 and val >= thr:   # model.cpp:956-981
+                dt = time.time() - t_start
+                logger.info("Hit target accuracy AUC %f at %d / %d iterations with batchsize %d in %.2fs. "
+                            "Average speed %f records/s." % (val, it, it, s.batchsize, dt,
+                                                             it * s.batchsize / max(dt, 1e-9)))
+                stop = True
+        logger.info("Eval Time for %d iters: %.2fs" % (s.max_eval_batches, time.time() - t0))
+        if s.perf_logging:
+            logger.perf_log("eval_accuracy", results.get("AUC"), iter=it)
+            logger.perf_log("eval_stop", it)
+        for cb in self.callbacks:
+            if cb.on_eval_end(it, results):
+                stop = True
+        return stop
+
+    # ------------------------------------------------------------------ checkpoints
+    def save_params_to_files(self, prefix: str, iter: int = 0):
+        from .io.checkpoint import save_model
+        save_model(self, prefix, iter)
+
+    def download_params_to_files(self, prefix: str, iter: int = 0):
+        self.save_params_to_files(prefix, iter)
+
+    def load_dense_weights(self, path: str):
+        from .io.checkpoint import load_dense_weights
+        load_dense_weights(self, path)
+        self._graph = None
+
+    def load_dense_optimizer_states(self, path: str):
+        from .io.checkpoint import load_dense_opt_states
+        load_dense_opt_states(self, path)
+
+    def load_sparse_weights(self, paths):
+        from .io.checkpoint import load_sparse_weights
+        load_sparse_weights(self, paths)
+
+    def load_sparse_optimizer_states(self, paths):
+        from .io.checkpoint import load_sparse_opt_states
+        load_sparse_opt_states(self, paths)
+
+    def embedding_dump(self, path: str, table_names=None):
+        from .io.checkpoint import embedding_dump
+        embedding_dump(self, path, table_names)
+
+    def embedding_load(self, path: str, table_names=None):
+        from .io.checkpoint import embedding_load
+        embedding_load(self, path, table_names)
+
+    # ------------------------------------------------------------------ debugging
+    def check_out_tensor(self, name: str, which: Tensor_t = Tensor_t.Train):
+        net = self.net_train if which == Tensor_t.Train else self.net_eval
+        if name not in net.tensors:
+            raise KeyError(f"no tensor named {name}")
+        t = net.tensors[name].data.detach().float().cpu()
+        if self.world > 1:
+            parts = self.comm.all_gather_object(t)
+            t = torch.cat(parts, 0)
+        return t.numpy()
