@@ -1,0 +1,211 @@
+"""Parquet reader (C12): file list + _metadata.json schema, worker threads decode row groups with
+pyarrow into the common feature-major HostBatch; label/dense float32, categorical columns int64
+scalars (one-hot) or lists (multi-hot).  ``slot_size_array`` adds per-slot key offsets so one hash
+table can hold all slots (HugeCTR/src/pybind/add_input.cpp:314-318,
+docs/source/api/python_interface.md:397-473).  Reference pipeline: DataReader<T> +
+DataReaderWorkerGroupParquet (HugeCTR/src/data_readers/*.cpp) with cuDF decode; here decode is on
+CPU worker threads (no cuDF in this environment) and the batch lands in pinned memory.
+"""
+from __future__ import annotations
+
+import json
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from .batch import HostBatch
+from .readers import IDataReader
+
+
+def read_file_list(path: str):
+    with open(path) as f:
+        lines = [l.strip() for l in f if l.strip()]
+    n = int(lines[0])
+    files = lines[1:1 + n]
+    if len(files) != n:
+        raise RuntimeError(f"file list {path} announces {n} files but lists {len(files)}")
+    return files
+
+
+class ParquetReader(IDataReader):
+    def __init__(self, model, is_train: bool):
+        rp = model.reader_params
+        b = model.b_train if is_train else model.b_eval
+        super().__init__(b, model.comm.rank, model.world, repeat=model.solver.repeat_dataset)
+        self.file_list = rp.source[0] if is_train else rp.eval_source
+        self.inp = model.input
+        self.layout = model.layout
+        self.key_dtype = model.key_dtype
+        self.slot_offsets = None
+        n_slots = model.layout.total_slots
+        if rp.slot_size_array and len(rp.slot_size_array) >= n_slots and model.sparse_embeddings:
+            self.slot_offsets = np.concatenate([[0], np.cumsum(rp.slot_size_array[:n_slots])[:-1]]).astype("int64")
+        self.num_workers = max(1, min(rp.num_workers, 4))
+        self.q: "queue.Queue" = queue.Queue(maxsize=4)
+        self.thread = None
+        self._stop = threading.Event()
+        self.drop_incomplete = model.solver.drop_incomplete_batch
+
+    # -------------------------------------------------------------- producer
+    def _columns(self, files):
+        d = os.path.dirname(files[0])
+        meta_path = os.path.join(d, "_metadata.json")
+        inp = self.inp
+        nl, nd, ns = inp.label_dim, inp.dense_dim, self.layout.total_slots
+        if os.path.exists(meta_path):
+            m = json.load(open(meta_path))
+            lab = [c["index"] for c in m["labels"]][:nl]
+            con = [c["index"] for c in m["conts"]][:nd]
+            cat = [c["index"] for c in m["cats"]][:ns]
+        else:
+            lab, con, cat = list(range(nl)), list(range(nl, nl + nd)), list(range(nl + nd, nl + nd + ns))
+        return lab, con, cat
+
+    def _produce(self):
+        import pyarrow.parquet as pq
+        try:
+            files = read_file_list(self.file_list)
+            lab_i, con_i, cat_i = self._columns(files)
+            gb = self.b * self.world
+            carry = None
+            while not self._stop.is_set():
+                for fp in files:
+                    pf = pq.ParquetFile(fp)
+                    for rg in range(pf.num_row_groups):
+                        tbl = pf.read_row_group(rg)
+                        cols = [tbl.column(i) for i in range(tbl.num_columns)]
+                        n = tbl.num_rows
+                        lab = np.stack([cols[i].to_numpy().astype("float32") for i in lab_i], 1) \
+                            if lab_i else np.zeros((n, 0), "float32")
+                        den = np.stack([cols[i].to_numpy().astype("float32") for i in con_i], 1) \
+                            if con_i else np.zeros((n, 0), "float32")
+                        cats = []
+                        for i in cat_i:
+                            c = cols[i].combine_chunks()
+                            import pyarrow as pa
+                            if pa.types.is_list(c.type) or pa.types.is_large_list(c.type):
+                                offs = c.offsets.to_numpy()
+                                vals = c.values.to_numpy().astype("int64")
+                                cats.append((offs, vals))
+                            else:
+                                cats.append((None, c.to_numpy().astype("int64")))
+                        chunk = (lab, den, cats, n)
+                        carry = self._emit(chunk, carry, gb)
+                        if self._stop.is_set():
+                            return
+                if not self.repeat:
+                    break
+            if carry is not None and carry[3] > 0 and not self.drop_incomplete:
+                self._emit_batch(carry, carry[3])
+            self.q.put(None)
+        except Exception as e:  # surface errors to the consumer
+            self.q.put(e)
+
+    @staticmethod
+    def _slice_cat(cat, a, b):
+        offs, vals = cat
+        if offs is None:
+            return (None, vals[a:b])
+        o = offs[a:b + 1]
+        return (o - o[0], vals[o[0]:o[-1]])
+
+    @staticmethod
+    def _cat_concat(c1, c2):
+        if c1[0] is None:
+            return (None, np.concatenate([c1[1], c2[1]]))
+        o = np.concatenate([c1[0], c2[0][1:] + c1[0][-1]])
+        return (o, np.concatenate([c1[1], c2[1]]))
+
+    def _emit(self, chunk, carry, gb):
+        if carry is not None:
+            lab = np.concatenate([carry[0], chunk[0]])
+            den = np.concatenate([carry[1], chunk[1]])
+            cats = [self._cat_concat(a, b) for a, b in zip(carry[2], chunk[2])]
+            n = carry[3] + chunk[3]
+            chunk = (lab, den, cats, n)
+        lab, den, cats, n = chunk
+        pos = 0
+        while n - pos >= gb:
+            self._emit_batch((lab[pos:pos + gb], den[pos:pos + gb],
+                              [self._slice_cat(c, pos, pos + gb) for c in cats], gb), gb)
+            pos += gb
+        if pos == n:
+            return None
+        return (lab[pos:], den[pos:], [self._slice_cat(c, pos, n) for c in cats], n - pos)
+
+    def _emit_batch(self, chunk, nvalid_global):
+        lab, den, cats, n = chunk
+        b, r = self.b, self.rank
+        lo, hi = r * b, min((r + 1) * b, n)
+        nloc = max(0, hi - lo)
+        L = torch.zeros(b, self.inp.label_dim)
+        D = torch.zeros(b, self.inp.dense_dim)
+        if nloc > 0:
+            L[:nloc] = torch.from_numpy(lab[lo:hi])
+            D[:nloc] = torch.from_numpy(den[lo:hi])
+        blocks, nnzs = [], []
+        si = 0
+        for (name, S, H, fixed) in self.layout.blocks:
+            blk = np.full((b, S, H), -1, dtype="int64")
+            nz = np.zeros((S, b), dtype="int32")
+            for s in range(S):
+                offs, vals = self._slice_cat(cats[si], lo, hi) if nloc > 0 else (None, np.zeros(0, "int64"))
+                off_add = 0 if self.slot_offsets is None else self.slot_offsets[si]
+                if offs is None:
+                    blk[:nloc, s, 0] = vals[:nloc] + off_add
+                    nz[s, :nloc] = 1
+                else:
+                    cnt = np.minimum(np.diff(offs), H)
+                    for i in range(nloc):
+                        c = cnt[i]
+                        blk[i, s, :c] = vals[offs[i]:offs[i] + c] + off_add
+                    nz[s, :nloc] = cnt
+                si += 1
+            blocks.append(torch.from_numpy(blk.reshape(-1)))
+            nnzs.append(torch.from_numpy(nz.reshape(-1)))
+        keys = torch.cat(blocks).to(self.key_dtype) if blocks else torch.zeros(0, dtype=self.key_dtype)
+        nnz = torch.cat(nnzs) if nnzs else None
+        hb = HostBatch(L, D, keys, nnz, nloc).pin()
+        self.q.put((hb, nvalid_global))
+
+    # -------------------------------------------------------------- consumer
+    def start(self):
+        if self.thread is None:
+            self._stop.clear()
+            self.thread = threading.Thread(target=self._produce, daemon=True)
+            self.thread.start()
+        self.started = True
+
+    def set_source(self, source=None):
+        self.stop()
+        if source:
+            self.file_list = source if isinstance(source, str) else source[0]
+        self.q = queue.Queue(maxsize=4)
+        self.start()
+
+    def read_a_batch(self):
+        if self.thread is None:
+            self.start()
+        item = self.q.get()
+        if item is None:
+            self.thread = None
+            return None
+        if isinstance(item, Exception):
+            raise item
+        hb, nvalid = item
+        self.current_batchsize = nvalid
+        return hb
+
+    def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            try:
+                while True:
+                    self.q.get_nowait()
+            except queue.Empty:
+                pass
+            self.thread.join(timeout=2)
+            self.thread = None

@@ -167,6 +167,8 @@ class EmbeddingCollection:
         self.is_train = is_train
         self.hotness = dict(hotness)
         self.seed = seed
+        self._kb = 8 if key_dtype == torch.int64 else 4
+        self._abf = act_dtype == torch.bfloat16
         self._build_layout(hotness)
         self._build_storage(seed)
         self._alloc_buffers()
@@ -301,12 +303,19 @@ class EmbeddingCollection:
             if grp.s0 is not None and grp.opt.optimizer_type == Optimizer_t.AdaGrad \
                     and grp.opt.initial_accu_value != 0.0:
                 grp.s0.fill_(grp.opt.initial_accu_value)
+            R = self.world if grp.kind == "mp" else 1
+            po = 0
+            for l in grp.lookups:
+                l.pair_off = po
+                po += R * self.b * l.hotness
             grp.lookups_dev = E.lookups_to_device(grp.lookups, dev)
-            pairs = (self.world if grp.kind == "mp" else 1) * self.b * \
-                sum(l.hotness for l in grp.lookups)
+            pairs = po
             if self.is_train:
                 if grp.kind == "mp":
-                    grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev)
+                    import os
+                    grp.indexed = (dev.type == "cuda" and grp.pitch % 4 == 0
+                                   and os.environ.get("HCTR_EMB_BWD", "indexed") == "indexed")
+                    grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev, indexed=grp.indexed)
                 else:
                     grp.dense_wgrad = torch.zeros(n, dtype=torch.float32, device=dev)
                     grp.ws = None
@@ -387,7 +396,7 @@ class EmbeddingCollection:
             for grp in self.groups:
                 if grp.kind == "mp":
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
-                              self.peer_out, b, self.rank)
+                              self.peer_out, b, self.rank, key_bytes=self._kb, act_bf16=self._abf)
                 else:
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
                               [self.out_slab], b)
@@ -451,9 +460,15 @@ class EmbeddingCollection:
 
     def _accum_update(self, grp, key_bufs, grad_bufs, lr_t, step_t):
         o = grp.opt
-        if grp.kind == "mp":
+        if grp.kind == "mp" and getattr(grp, "indexed", False):
+            E.bwd_index(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, self.b, grp.ws,
+                        self.rank, key_bytes=self._kb)
+            E.bwd_reduce_update(o.optimizer_type, grp.lookups, grp.lookups_dev, grp.table, grp.s0,
+                                grp.s1, grp.pitch, key_bufs, grad_bufs, self.b, grp.ws, self._hp(o),
+                                lr_t, step_t, 1.0, self.rank, key_bytes=self._kb, act_bf16=self._abf)
+        elif grp.kind == "mp":
             E.backward_accum(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, grad_bufs,
-                             self.b, grp.ws, 1.0, self.rank)
+                             self.b, grp.ws, 1.0, self.rank, key_bytes=self._kb, act_bf16=self._abf)
             E.update(o.optimizer_type, grp.table, grp.s0, grp.s1, grp.pitch, grp.ws, self._hp(o),
                      lr_t, step_t)
         else:
@@ -478,6 +493,42 @@ class EmbeddingCollection:
                     .view(sl["rows"], grp.pitch)
                 keys = torch.arange(sl["rows"], dtype=torch.int64) * sl["k"] + sl["s"]
                 yield sl["table"], sl, keys, w, grp
+
+    def load_table_rows(self, name: str, keys: torch.Tensor, values: torch.Tensor, state=None):
+        """Scatter (key, row-vector) pairs of table ``name`` into the local shards (re-sharding on
+        load: only keys with key % num_shards == shard_id are kept, parameter_IO.cpp:262-350).
+        ``state``: optional list of per-state [n, ev] tensors (optimizer states)."""
+        keys = keys.to(torch.int64).cpu()
+        for grp in self.groups:
+            for sl in grp.table_slices:
+                if sl["table"] != name:
+                    continue
+                m = (keys % sl["k"] == sl["s"]) & (keys // sl["k"] < sl["rows"]) & (keys >= 0)
+                if not bool(m.any()):
+                    continue
+                rows = (sl["row_off"] + keys[m] // sl["k"]).to(grp.table.device)
+                c0, ev = sl["col0"], sl["ev"]
+                grp.table.view(-1, grp.pitch)[rows] = values[m][:, c0:c0 + ev].to(grp.table.device,
+                                                                                 torch.float32)
+                if state is not None:
+                    for st, dst in zip(state, (grp.s0, grp.s1)):
+                        if dst is not None and st is not None:
+                            dst.view(-1, grp.pitch)[rows] = st[m][:, c0:c0 + ev].to(dst.device, dst.dtype)
+
+    def dump_table_local(self, name: str):
+        """-> list of (keys int64 [n], values fp32 [n, ev_part], col0, states list) local shards."""
+        res = []
+        for grp in self.groups:
+            for sl in grp.table_slices:
+                if sl["table"] != name:
+                    continue
+                lo, hi = sl["row_off"], sl["row_off"] + sl["rows"]
+                w = grp.table.view(-1, grp.pitch)[lo:hi].detach().cpu()
+                keys = torch.arange(sl["rows"], dtype=torch.int64) * sl["k"] + sl["s"]
+                sts = [None if t is None else t.view(-1, grp.pitch)[lo:hi].detach().float().cpu()
+                       for t in (grp.s0, grp.s1)]
+                res.append((keys, w, sl["col0"], sts, grp.kind))
+        return res
 
     def memory_bytes(self) -> int:
         tot = 0

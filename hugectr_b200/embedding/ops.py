@@ -27,7 +27,8 @@ class CEmbLookup(C.Structure):
                 ("nnz_off", C.c_longlong), ("out_off", C.c_longlong), ("grad_off", C.c_longlong),
                 ("hotness", C.c_int), ("key_stride", C.c_int), ("num_shards", C.c_int),
                 ("shard_idx", C.c_int), ("out_stride", C.c_int), ("grad_stride", C.c_int),
-                ("combiner", C.c_int), ("ev_size", C.c_int), ("rows", C.c_int), ("pad_", C.c_int)]
+                ("combiner", C.c_int), ("ev_size", C.c_int), ("rows", C.c_int), ("pad_", C.c_int),
+                ("pair_off", C.c_longlong)]
 
 
 class CEmbParams(C.Structure):
@@ -42,6 +43,14 @@ class CUniqueTable(C.Structure):
     _fields_ = [("keys", C.c_void_p), ("vals", C.c_void_p), ("counter", C.c_void_p),
                 ("rows", C.c_void_p), ("slots", C.c_void_p), ("mask", C.c_uint),
                 ("max_unique", C.c_uint)]
+
+
+class CBwdIndex(C.Structure):
+    _fields_ = [("count", C.c_void_p), ("offsets", C.c_void_p), ("block_sums", C.c_void_p),
+                ("pair_uid", C.c_void_p), ("bucket_list", C.c_void_p), ("heavy_items", C.c_void_p),
+                ("heavy_count", C.c_void_p), ("heavy_scratch", C.c_void_p),
+                ("heavy_ticket", C.c_void_p), ("heavy_slot", C.c_void_p),
+                ("max_heavy_rows", C.c_uint), ("max_heavy_items", C.c_uint)]
 
 
 class COptHyper(C.Structure):
@@ -65,8 +74,13 @@ def lib():
         l.hctr_emb_update.argtypes = [vp, vp, vp, vp, C.POINTER(CUniqueTable), i, i, i,
                                       C.POINTER(COptHyper), vp, i, vp]
         l.hctr_emb_gather_rows.argtypes = [vp, vp, vp, ll, i, i, vp]
+        l.hctr_emb_bwd_index.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable),
+                                         C.POINTER(CBwdIndex), ll, i, vp]
+        l.hctr_emb_bwd_reduce_update.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable),
+                                                 C.POINTER(CBwdIndex), vp, vp, i, i,
+                                                 C.POINTER(COptHyper), f, i, vp, i, vp]
         for n in ("hctr_emb_forward", "hctr_emb_backward_accum", "hctr_emb_update",
-                  "hctr_emb_gather_rows"):
+                  "hctr_emb_gather_rows", "hctr_emb_bwd_index", "hctr_emb_bwd_reduce_update"):
             getattr(l, n).restype = i
         _lib = l
     return _lib
@@ -89,12 +103,13 @@ class LookupDesc:
     ev_size: int
     rows: int
     nnz_off: int = -1
+    pair_off: int = 0
 
     def to_c(self) -> CEmbLookup:
         return CEmbLookup(self.table_row_off, self.key_off, self.nnz_off, self.out_off,
                           self.grad_off, self.hotness, self.key_stride, self.num_shards,
                           self.shard_idx, self.out_stride, self.grad_stride, self.combiner,
-                          self.ev_size, self.rows, 0)
+                          self.ev_size, self.rows, 0, self.pair_off)
 
 
 def lookups_to_device(lookups: List[LookupDesc], device) -> torch.Tensor:
@@ -112,14 +127,14 @@ def _st(dev):
 
 # ----------------------------------------------------------------------------- forward
 def forward(lookups, lookups_dev, table, ev_pitch, key_bufs, out_bufs, batch, my_rank=0,
-            nnz_bufs=None):
+            nnz_bufs=None, key_bytes=4, act_bf16=True):
     """key_bufs / out_bufs: one entry per source rank (tensor, or int device pointer for peers)."""
     R = len(key_bufs)
     if table.is_cuda:
         p = CEmbParams()
         p.num_ranks, p.my_rank, p.batch, p.num_lookups = R, my_rank, batch, len(lookups)
-        kb = 4
-        out_bf16 = 1
+        kb = key_bytes
+        out_bf16 = int(act_bf16)
         for r in range(R):
             k, o = key_bufs[r], out_bufs[r]
             p.keys[r] = k if isinstance(k, int) else k.data_ptr()
@@ -158,8 +173,8 @@ def forward_reference(lookups, table, ev_pitch, key_bufs, out_bufs, batch, nnz_b
     for src in range(len(key_bufs)):
         kbuf, obuf = key_bufs[src].reshape(-1), out_bufs[src].reshape(-1)
         for lk in lookups:
-            keys = kbuf[lk.key_off:lk.key_off + batch * lk.key_stride].view(batch, lk.key_stride)
-            keys = keys[:, :lk.hotness]
+            keys = torch.as_strided(kbuf, (batch, lk.hotness), (lk.key_stride, 1),
+                                    kbuf.storage_offset() + lk.key_off)
             own, rows = _owned(lk, keys)
             nnz = torch.full((batch,), lk.hotness, device=keys.device)
             if lk.nnz_off >= 0 and nnz_bufs is not None:
@@ -169,7 +184,8 @@ def forward_reference(lookups, table, ev_pitch, key_bufs, out_bufs, batch, nnz_b
             pooled = v.sum(1)
             if lk.combiner == 1:
                 pooled = pooled / nnz.clamp(min=1).view(-1, 1).float()
-            o = torch.as_strided(obuf, (batch, lk.ev_size), (lk.out_stride, 1), lk.out_off)
+            o = torch.as_strided(obuf, (batch, lk.ev_size), (lk.out_stride, 1),
+                                 obuf.storage_offset() + lk.out_off)
             o.copy_(pooled.to(o.dtype))
 
 
@@ -177,7 +193,8 @@ def forward_reference(lookups, table, ev_pitch, key_bufs, out_bufs, batch, nnz_b
 class UniqueWorkspace:
     """Transient hash + fp32 per-unique-row gradient accumulator (device)."""
 
-    def __init__(self, max_pairs: int, ev_pitch: int, device, unique_ratio: float = 1.0):
+    def __init__(self, max_pairs: int, ev_pitch: int, device, unique_ratio: float = 1.0,
+                 indexed: bool = False):
         self.device = device
         self.ev = ev_pitch
         self.max_unique = max(16, int(max_pairs * unique_ratio))
@@ -191,24 +208,51 @@ class UniqueWorkspace:
             self.counter = torch.zeros(1, dtype=torch.int32, device=device)
             self.rows = torch.zeros(self.max_unique, dtype=torch.int64, device=device)
             self.slots = torch.zeros(self.max_unique, dtype=torch.int32, device=device)
-            self.wgrad = torch.zeros(self.max_unique, ev_pitch, dtype=torch.float32, device=device)
+            self.wgrad = None if indexed else torch.zeros(self.max_unique, ev_pitch,
+                                                          dtype=torch.float32, device=device)
             self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
             self.c = CUniqueTable(self.keys.data_ptr(), self.vals.data_ptr(),
                                   self.counter.data_ptr(), self.rows.data_ptr(),
                                   self.slots.data_ptr(), cap - 1, self.max_unique)
+            self.indexed = indexed
+            if indexed:
+                # counting-sort index (csrc/embedding_bwd.cu); the fp32 per-row accumulator is
+                # not needed on this path
+                self.wgrad = None
+                mu, mp = self.max_unique, max(int(max_pairs), 1)
+                i32 = dict(dtype=torch.int32, device=device)
+                self.count = torch.zeros(mu, **i32)
+                self.offsets = torch.zeros(mu + 1, **i32)
+                self.block_sums = torch.zeros((mu + 1023) // 1024 + 1, **i32)
+                self.pair_uid = torch.full((mp,), -1, **i32)
+                self.bucket_list = torch.zeros(mp, **i32)
+                self.max_heavy_rows = 8192
+                self.max_heavy_items = 65536
+                self.heavy_items = torch.zeros(2 * self.max_heavy_items, **i32)
+                self.heavy_count = torch.zeros(1, **i32)
+                self.heavy_slot = torch.zeros(1, **i32)
+                self.heavy_scratch = torch.zeros(self.max_heavy_rows, ev_pitch, dtype=torch.float32,
+                                                 device=device)
+                self.heavy_ticket = torch.zeros(self.max_heavy_rows, **i32)
+                self.ix = CBwdIndex(self.count.data_ptr(), self.offsets.data_ptr(),
+                                    self.block_sums.data_ptr(), self.pair_uid.data_ptr(),
+                                    self.bucket_list.data_ptr(), self.heavy_items.data_ptr(),
+                                    self.heavy_count.data_ptr(), self.heavy_scratch.data_ptr(),
+                                    self.heavy_ticket.data_ptr(), self.heavy_slot.data_ptr(),
+                                    self.max_heavy_rows, self.max_heavy_items)
         else:
             self.ref_rows = None
             self.ref_grads = None
 
 
 def backward_accum(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, batch, ws, grad_scale=1.0,
-                   my_rank=0, nnz_bufs=None, dense_wgrad=None):
+                   my_rank=0, nnz_bufs=None, dense_wgrad=None, key_bytes=4, act_bf16=True):
     """Accumulate bucket gradients per unique row (or into a dense wgrad for DP tables)."""
     R = len(key_bufs)
     if table.is_cuda:
         p = CEmbParams()
         p.num_ranks, p.my_rank, p.batch, p.num_lookups = R, my_rank, batch, len(lookups)
-        kb, gbf = 4, 1
+        kb, gbf = key_bytes, int(act_bf16)
         for r in range(R):
             k, g = key_bufs[r], grad_bufs[r]
             p.keys[r] = k if isinstance(k, int) else k.data_ptr()
@@ -239,14 +283,15 @@ def backward_accum(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, b
     for src in range(R):
         kbuf, gbuf = key_bufs[src].reshape(-1), grad_bufs[src].reshape(-1)
         for lk in lookups:
-            keys = kbuf[lk.key_off:lk.key_off + batch * lk.key_stride].view(batch, lk.key_stride)
-            keys = keys[:, :lk.hotness]
+            keys = torch.as_strided(kbuf, (batch, lk.hotness), (lk.key_stride, 1),
+                                    kbuf.storage_offset() + lk.key_off)
             own, rows = _owned(lk, keys)
             nnz = torch.full((batch,), lk.hotness, device=keys.device)
             if lk.nnz_off >= 0 and nnz_bufs is not None:
                 nnz = nnz_bufs[src].reshape(-1)[lk.nnz_off:lk.nnz_off + batch].long().clamp(max=lk.hotness)
                 own &= torch.arange(lk.hotness, device=keys.device).view(1, -1) < nnz.view(-1, 1)
-            g = torch.as_strided(gbuf, (batch, lk.ev_size), (lk.grad_stride, 1), lk.grad_off)
+            g = torch.as_strided(gbuf, (batch, lk.ev_size), (lk.grad_stride, 1),
+                                 gbuf.storage_offset() + lk.grad_off)
             g = g.float() * grad_scale
             if lk.combiner == 1:
                 g = g / nnz.clamp(min=1).view(-1, 1).float()
@@ -350,3 +395,62 @@ def gather_rows(table, ev_pitch, rows, out):
         return
     v = table.view(-1, ev_pitch)[rows.clamp(min=0)] * (rows >= 0).unsqueeze(-1)
     out.copy_(v.to(out.dtype))
+
+
+def _fill_params(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, batch, my_rank, nnz_bufs,
+                 key_bytes=4, act_bf16=True):
+    R = len(key_bufs)
+    p = CEmbParams()
+    p.num_ranks, p.my_rank, p.batch, p.num_lookups = R, my_rank, batch, len(lookups)
+    kb, gbf = key_bytes, int(act_bf16)
+    for r in range(R):
+        k = key_bufs[r]
+        p.keys[r] = k if isinstance(k, int) else k.data_ptr()
+        if not isinstance(k, int):
+            kb = k.element_size()
+        if grad_bufs is not None:
+            g = grad_bufs[r]
+            p.grad[r] = g if isinstance(g, int) else g.data_ptr()
+            if not isinstance(g, int):
+                gbf = int(g.dtype == torch.bfloat16)
+        if nnz_bufs is not None:
+            n = nnz_bufs[r]
+            p.nnz[r] = n if isinstance(n, int) else n.data_ptr()
+    p.lookups = lookups_dev.data_ptr()
+    p.table = table.data_ptr()
+    p.ev_size = ev_pitch
+    return p, kb, gbf
+
+
+def bwd_index(lookups, lookups_dev, table, ev_pitch, key_bufs, batch, ws, my_rank=0, nnz_bufs=None,
+              key_bytes=4):
+    """Gradient-independent part of the backward: unique rows + per-row bucket lists."""
+    p, kb, _ = _fill_params(lookups, lookups_dev, table, ev_pitch, key_bufs, None, batch, my_rank,
+                            nnz_bufs, key_bytes)
+    total_pairs = len(key_bufs) * batch * sum(l.hotness for l in lookups)
+    rc = lib().hctr_emb_bwd_index(C.byref(p), C.byref(ws.c), C.byref(ws.ix), total_pairs, kb,
+                                  _st(table.device))
+    if rc:
+        raise RuntimeError("hctr_emb_bwd_index failed")
+    D._count(5)
+
+
+def bwd_reduce_update(opt: Optimizer_t, lookups, lookups_dev, table, s0, s1, ev_pitch, key_bufs,
+                      grad_bufs, batch, ws, hp: dict, lr_t, step_t, grad_scale=1.0, my_rank=0,
+                      nnz_bufs=None, num_sms: int = 148, key_bytes=4, act_bf16=True):
+    """Fused gradient gather (local / peer loads) + duplicate reduction + optimizer."""
+    p, kb, gbf = _fill_params(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, batch,
+                              my_rank, nnz_bufs, key_bytes, act_bf16)
+    h = COptHyper(lr_t.data_ptr(), 1.0, hp.get("scaler", 1.0), hp.get("beta1", 0.9),
+                  hp.get("beta2", 0.999), hp.get("epsilon", 1e-7), hp.get("lambda1", 0.0),
+                  hp.get("lambda2", 0.0), hp.get("ftrl_beta", 0.0), hp.get("momentum", 0.0),
+                  hp.get("initial_accu_value", 0.0), step_t.data_ptr())
+    sbf = int(s0 is not None and s0.dtype == torch.bfloat16)
+    rc = lib().hctr_emb_bwd_reduce_update(C.byref(p), C.byref(ws.c), C.byref(ws.ix),
+                                          0 if s0 is None else s0.data_ptr(),
+                                          0 if s1 is None else s1.data_ptr(), OPT_CODE[opt], sbf,
+                                          C.byref(h), float(grad_scale), gbf, ws.overflow.data_ptr(),
+                                          num_sms, _st(table.device))
+    if rc:
+        raise RuntimeError(f"hctr_emb_bwd_reduce_update failed rc={rc}")
+    D._count(3)

@@ -1,0 +1,243 @@
+"""Legacy SparseEmbedding runtimes: DistributedSlotSparseEmbeddingHash and
+LocalizedSlotSparseEmbeddingHash (dynamic-vocabulary hash embeddings).
+
+Reference semantics:
+  Distributed  row-wise MP over all GPUs (owner = key % N), forward = hash get_insert -> pooled
+               partial sums for the whole global batch -> reduce-scatter; backward = all-gather of
+               top grads -> per-row update   (include/embeddings/distributed_slot_sparse_embedding_hash.hpp:41-440)
+  Localized    slot s lives on GPU s % N, forward = local pooled lookup -> all-to-all -> reorder
+               (include/embeddings/localized_slot_sparse_embedding_hash.hpp:217-345)
+  max_vocabulary_size_per_gpu = workspace_MB * 2^20 / ((1 + n_opt_states) * 4 * vec)  (model.cpp:186-196)
+  eval uses lookup-only (get_mark): unseen keys contribute zero vectors
+  check_overflow: "Runtime vocabulary size ... exceeds max_vocabulary_size_per_gpu"
+
+Implementation: keys are translated to dense rows by the GPU HashTable, then the SAME owner-side
+pool / accumulate / fused-update kernels as the EmbeddingCollection run on the row buffer; the
+exchange uses the collective back-end (all-gather of keys, all-to-all of pooled vectors).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List
+
+import numpy as np
+import torch
+
+from ..enums import Embedding_t, Optimizer_t, Update_t
+from ..utils import logger
+from . import ops as E
+from .hashtable import HashTable
+
+
+class SparseEmbeddingRuntime:
+    def __init__(self, cfg, param, layout, batch_per_gpu, device, act_dtype, comm, opt, key_dtype,
+                 scaler=1.0, seed=0, share_from=None):
+        self.cfg, self.param, self.layout = cfg, param, layout
+        self.name = cfg.sparse_embedding_name
+        self.top_name = cfg.sparse_embedding_name
+        self.b = batch_per_gpu
+        self.device, self.act_dtype, self.comm = device, act_dtype, comm
+        self.rank, self.world = comm.rank, comm.world_size
+        self.opt = opt
+        self.scaler = scaler
+        self.key_dtype = key_dtype
+        self.S = param.slot_num
+        self.H = max(param.nnz_per_slot)
+        self.vec = cfg.embedding_vec_size
+        self.localized = cfg.embedding_type != Embedding_t.DistributedSlotSparseEmbeddingHash
+        self.combiner = 1 if cfg.combiner == "mean" else 0
+        self.is_train = share_from is None
+        ns = opt.num_states
+        if share_from is None:
+            ws = cfg.workspace_size_per_gpu_in_mb
+            if cfg.max_vocabulary_size_per_gpu > 0:
+                self.max_rows = cfg.max_vocabulary_size_per_gpu
+            elif ws > 0:
+                self.max_rows = int(ws * 1024 * 1024 // ((1 + ns) * 4 * self.vec))
+            else:
+                self.max_rows = max(1024, sum(cfg.slot_size_array) // max(1, self.world) + 1024)
+            self.table = torch.zeros(self.max_rows * self.vec, dtype=torch.float32, device=device)
+            self._init_table(seed)
+            n = self.table.numel()
+            nst = 2 if opt.optimizer_type in (Optimizer_t.Adam, Optimizer_t.Ftrl) else (1 if ns >= 1 else 0)
+            self.s0 = torch.zeros(n, device=device) if nst >= 1 else None
+            self.s1 = torch.zeros(n, device=device) if nst >= 2 else None
+            if self.s0 is not None and opt.optimizer_type == Optimizer_t.AdaGrad:
+                self.s0.fill_(opt.initial_accu_value)
+            self.hash = HashTable(self.max_rows, device)
+            self.slot_of_row = torch.full((self.max_rows,), -1, dtype=torch.int64, device=device) \
+                if self.localized else None
+        else:
+            for k in ("max_rows", "table", "s0", "s1", "hash", "slot_of_row"):
+                setattr(self, k, getattr(share_from, k))
+        b, S, H, vec, W = self.b, self.S, self.H, self.vec, self.world
+        self.top_shape = (b, S, vec)
+        self.top_data = torch.zeros(b, S, vec, dtype=act_dtype, device=device)
+        self.top_grad = torch.zeros(b, S, vec, dtype=act_dtype, device=device) if self.is_train else None
+        self.keys_loc = torch.full((b * S * H,), -1, dtype=torch.int64, device=device)
+        self.keys_all = torch.full((W, b * S * H), -1, dtype=torch.int64, device=device)
+        self.rows_all = torch.full((W, b * S * H), -1, dtype=torch.int64, device=device)
+        self.partial = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device)
+        self.recv = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device)
+        self.grads_all = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device) if self.is_train else None
+        # one lookup per slot over the row buffer: keys [b, S, H] sample-major
+        self.lookups: List[E.LookupDesc] = []
+        for s in range(S):
+            self.lookups.append(E.LookupDesc(
+                table_row_off=0, key_off=s * H, out_off=s * vec, grad_off=s * vec, hotness=H,
+                key_stride=S * H, num_shards=1, shard_idx=0, out_stride=S * vec, grad_stride=S * vec,
+                combiner=0, ev_size=vec, rows=self.max_rows))
+        po = 0
+        for l in self.lookups:
+            l.pair_off = po
+            po += W * b * H
+        self.lookups_dev = E.lookups_to_device(self.lookups, device)
+        if self.is_train:
+            self.indexed = device.type == "cuda" and vec % 4 == 0 and \
+                os.environ.get("HCTR_EMB_BWD", "indexed") == "indexed"
+            self.ws = E.UniqueWorkspace(max(po, 1), vec, device, indexed=self.indexed)
+        self.slot_offsets = None
+        ssa = list(cfg.slot_size_array)
+        self._nnz_cnt = torch.ones(b, S, dtype=torch.float32, device=device)
+
+    def eval_clone(self, batch_per_gpu):
+        return SparseEmbeddingRuntime(self.cfg, self.param, self.layout, batch_per_gpu, self.device,
+                                      self.act_dtype, self.comm, self.opt, self.key_dtype, self.scaler,
+                                      0, share_from=self)
+
+    def _init_table(self, seed):
+        """U(+-sqrt(1/slot_size)) per slot when slot_size_array is given, else a global bound
+        (src/embeddings/init_embedding_functor.cu:34-55)."""
+        ssa = self.cfg.slot_size_array
+        vocab = max(1, sum(ssa) if ssa else self.max_rows * self.world)
+        bound = math.sqrt(1.0 / max(1.0, vocab / max(1, len(ssa) or 1)))
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed * 7919 + self.rank + 13)
+        self.table.uniform_(-bound, bound, generator=g)
+
+    # ------------------------------------------------------------------ data in
+    def set_keys(self, hb, key_offs, nnz_offs):
+        o = key_offs[self.param.top_name]
+        n = self.b * self.S * self.H
+        self.keys_loc.copy_(hb.keys[o:o + n].to(torch.int64), non_blocking=True)
+
+    def _owner_mask(self, keys_all):
+        """which keys of the gathered batch does this rank own"""
+        valid = keys_all >= 0
+        if self.localized:
+            slot = (torch.arange(keys_all.shape[1], device=keys_all.device) // self.H) % self.S
+            own = (slot % self.world) == self.rank
+            return valid & own.view(1, -1)
+        return valid & ((keys_all % self.world) == self.rank)
+
+    def check_overflow(self):
+        n = self.hash.size()
+        if n > self.max_rows:
+            raise RuntimeError(f"Runtime vocabulary size ({n}) exceeds max_vocabulary_size_per_gpu "
+                               f"({self.max_rows}) of {self.name}, new feature insertion failed.")
+
+    # ------------------------------------------------------------------ forward / backward
+    def forward(self, is_train: bool):
+        W, b, S, H, vec = self.world, self.b, self.S, self.H, self.vec
+        self.comm.all_gather(self.keys_all, self.keys_loc)
+        own = self._owner_mask(self.keys_all)
+        k = torch.where(own, self.keys_all, torch.full_like(self.keys_all, -1))
+        rows = self.hash.get_insert(k) if is_train else self.hash.get(k)
+        self.rows_all.copy_(rows)
+        if is_train and os.environ.get("HUGECTR_DISABLE_OVERFLOW_CHECK", "0") != "1":
+            self.check_overflow()
+        self.partial.zero_()
+        E.forward(self.lookups, self.lookups_dev, self.table, vec, list(self.rows_all.unbind(0)),
+                  list(self.partial.unbind(0)), b, self.rank)
+        self.comm.all_to_all(self.recv, self.partial)
+        out = self.recv.float().sum(0).view(b, S, vec)
+        if self.combiner == 1:
+            cnt = (self.keys_loc.view(b, S, H) >= 0).sum(-1).clamp(min=1).float()
+            self._nnz_cnt = cnt
+            out = out / cnt.unsqueeze(-1)
+        self.top_data.copy_(out.to(self.top_data.dtype))
+
+    def backward(self, lr_t, step_t):
+        W, b, S, H, vec = self.world, self.b, self.S, self.H, self.vec
+        g = self.top_grad
+        if self.combiner == 1:
+            g = (g.float() / self._nnz_cnt.unsqueeze(-1)).to(self.top_grad.dtype)
+        self.comm.all_gather(self.grads_all, g.reshape(-1))
+        kb = list(self.rows_all.unbind(0))
+        gb = list(self.grads_all.unbind(0))
+        hp = {"scaler": self.scaler, "beta1": self.opt.beta1, "beta2": self.opt.beta2,
+              "epsilon": self.opt.epsilon, "lambda1": self.opt.lambda1, "lambda2": self.opt.lambda2,
+              "ftrl_beta": self.opt.beta, "momentum": self.opt.momentum_factor}
+        if self.indexed:
+            E.bwd_index(self.lookups, self.lookups_dev, self.table, vec, kb, b, self.ws, self.rank)
+            E.bwd_reduce_update(self.opt.optimizer_type, self.lookups, self.lookups_dev, self.table,
+                                self.s0, self.s1, vec, kb, gb, b, self.ws, hp, lr_t, step_t, 1.0, self.rank)
+        else:
+            E.backward_accum(self.lookups, self.lookups_dev, self.table, vec, kb, gb, b, self.ws, 1.0,
+                             self.rank)
+            E.update(self.opt.optimizer_type, self.table, self.s0, self.s1, vec, self.ws, hp, lr_t, step_t)
+
+    # ------------------------------------------------------------------ checkpoint
+    def _gather_all(self):
+        keys, rows = self.hash.dump()
+        w = self.table.view(-1, self.vec)[rows.to(self.device)].cpu()
+        parts = self.comm.all_gather_object((keys, w))
+        return parts
+
+    def dump_parameters(self, path: str):
+        parts = self._gather_all()
+        if self.comm.rank == 0:
+            os.makedirs(path, exist_ok=True)
+            keys = torch.cat([p[0] for p in parts])
+            w = torch.cat([p[1] for p in parts])
+            keys.numpy().astype("<i8").tofile(os.path.join(path, "key"))
+            w.numpy().astype("<f4").tofile(os.path.join(path, "emb_vector"))
+            if self.localized:
+                slots = self._slot_ids(keys)
+                slots.numpy().astype("<u8").tofile(os.path.join(path, "slot_id"))
+        self.comm.barrier()
+
+    def _slot_ids(self, keys):
+        ssa = self.cfg.slot_size_array
+        if not ssa:
+            return torch.zeros_like(keys)
+        bounds = torch.tensor(np.cumsum([0] + list(ssa)), dtype=torch.int64)
+        return (torch.searchsorted(bounds, keys, right=True) - 1).clamp(0, len(ssa) - 1)
+
+    def load_parameters(self, path: str):
+        keys = torch.from_numpy(np.fromfile(os.path.join(path, "key"), dtype="<i8").astype("int64"))
+        w = torch.from_numpy(np.fromfile(os.path.join(path, "emb_vector"), dtype="<f4")).view(-1, self.vec)
+        if self.localized and os.path.exists(os.path.join(path, "slot_id")):
+            slot = torch.from_numpy(np.fromfile(os.path.join(path, "slot_id"), dtype="<u8").astype("int64"))
+            m = (slot % self.world) == self.rank
+        else:
+            m = (keys % self.world) == self.rank
+        k = keys[m]
+        rows = self.hash.get_insert(k.to(self.device))
+        self.check_overflow()
+        self.table.view(-1, self.vec)[rows] = w[m].to(self.device)
+
+    def dump_opt_states(self, path: str):
+        keys, rows = self.hash.dump()
+        st = [s.view(-1, self.vec)[rows.to(self.device)].cpu() for s in (self.s0, self.s1) if s is not None]
+        parts = self.comm.all_gather_object(st)
+        if self.comm.rank == 0:
+            with open(path, "wb") as f:
+                for i in range(len(st)):
+                    f.write(torch.cat([p[i] for p in parts]).numpy().astype("<f4").tobytes())
+        self.comm.barrier()
+
+    def load_opt_states(self, path: str):
+        raw = np.fromfile(path, dtype="<f4")
+        states = [s for s in (self.s0, self.s1) if s is not None]
+        if not states:
+            return
+        keys, rows = self.hash.dump()
+        parts = self.comm.all_gather_object(int(keys.numel()))
+        tot = sum(parts)
+        off = sum(parts[:self.rank])
+        per = tot * self.vec
+        for i, s in enumerate(states):
+            blk = torch.from_numpy(raw[i * per:(i + 1) * per].copy()).view(tot, self.vec)
+            s.view(-1, self.vec)[rows.to(self.device)] = blk[off:off + keys.numel()].to(self.device)

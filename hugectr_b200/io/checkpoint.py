@@ -1,0 +1,239 @@
+"""Checkpoint formats -- byte compatible with the reference:
+
+  dense   <prefix>_dense_<iter>.model        raw fp32 master weights, layer creation order, each layer in
+                                              set_weight order (MLP W0,b0,W1,b1..; MultiCross U,V,b per
+                                              layer; FC W,b), weights [in,out] row-major
+                                              (core23_network.cpp:113-141,301-314)
+          <prefix>_opt_dense_<iter>.model    raw optimizer state(s): state0 for all params, then state1
+          <prefix>_dense_<iter>.model.ntp.json   non-trainable params (BatchNorm running stats)
+  sparse  <prefix><i>_sparse_<iter>.model/   directory: key (int64 each), slot_id (uint64 each,
+          (legacy embeddings)                 Localized only), emb_vector (fp32 x vec)
+                                              (distributed_slot_sparse_embedding_hash.cu:802-955)
+          <prefix><i>_opt_sparse_<iter>.model concatenated raw per-state tensors
+  EBC     <path>/embedding_collection_<id>/meta_data   int[5]{ntables,key_type,emb_type,0,0},
+                                              int table_ids[], size_t key_nums[], int ev_lens[]
+          key<tid> / weight<tid> / opt<tid>   128-byte head int[32]{type(1 key,2 weight,3 opt), table_id}
+                                              then payload; load re-shards by key % num_shards
+                                              (parameter_IO.cpp:179-580, data_info.hpp:19-22)
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+
+import numpy as np
+import torch
+
+from ..utils import logger
+from .filesystem import FileSystemBuilder
+
+FILE_HEAD_NBYTES = 128
+META_HEAD_NBYTES = 20
+
+
+def _fs(path, model=None):
+    params = getattr(getattr(model, "reader_params", None), "data_source_params", None)
+    return FileSystemBuilder.build_by_path(path, params)
+
+
+# ------------------------------------------------------------------------------------ dense
+def dense_paths(prefix: str, it: int):
+    return (f"{prefix}_dense_{it}.model", f"{prefix}_opt_dense_{it}.model")
+
+
+def save_dense(model, prefix: str, it: int):
+    wpath, opath = dense_paths(prefix, it)
+    if model.comm.rank == 0:
+        fs = _fs(wpath, model)
+        fs.write(wpath, model.arena.dump_flat().numpy().astype("<f4").tobytes())
+        states = [model.arena.dump_state(s) for s in (model.opt_s0, model.opt_s1) if s is not None]
+        fs.write(opath, b"".join(s.numpy().astype("<f4").tobytes() for s in states))
+        ntp = {}
+        for k, v in vars(model.arena).items():
+            if k.startswith("_bn_state_"):
+                ntp[k[len("_bn_state_"):]] = {"mean": v["mean"].cpu().tolist(),
+                                              "var": v["var"].cpu().tolist()}
+        if ntp:
+            fs.write(wpath + ".ntp.json", json.dumps({"layers": ntp}).encode())
+    model.comm.barrier()
+
+
+def load_dense_weights(model, path: str):
+    raw = _fs(path, model).read(path)
+    flat = torch.from_numpy(np.frombuffer(raw, dtype="<f4").copy())
+    if flat.numel() != model.arena.num_params:
+        raise RuntimeError(f"dense model file has {flat.numel()} parameters, the network needs "
+                           f"{model.arena.num_params}")
+    model.arena.load_flat(flat)
+    ntp = path + ".ntp.json"
+    if os.path.exists(ntp):
+        d = json.loads(open(ntp).read())["layers"]
+        for k, v in d.items():
+            st = getattr(model.arena, "_bn_state_" + k, None)
+            if st is not None:
+                st["mean"].copy_(torch.tensor(v["mean"]))
+                st["var"].copy_(torch.tensor(v["var"]))
+
+
+def load_dense_opt_states(model, path: str):
+    raw = _fs(path, model).read(path)
+    flat = torch.from_numpy(np.frombuffer(raw, dtype="<f4").copy())
+    n = model.arena.num_params
+    states = [s for s in (model.opt_s0, model.opt_s1) if s is not None]
+    if flat.numel() != n * len(states):
+        raise RuntimeError("dense optimizer state file does not match the optimizer / network")
+    for i, s in enumerate(states):
+        model.arena.load_state(s, flat[i * n:(i + 1) * n])
+
+
+# ------------------------------------------------------------------------------------ legacy sparse
+def sparse_paths(prefix: str, i: int, it: int):
+    return (f"{prefix}{i}_sparse_{it}.model", f"{prefix}{i}_opt_sparse_{it}.model")
+
+
+def save_sparse(model, prefix: str, it: int):
+    for i, rt in enumerate(model.legacy_train):
+        d, o = sparse_paths(prefix, i, it)
+        rt.dump_parameters(d)
+        rt.dump_opt_states(o)
+
+
+def load_sparse_weights(model, paths):
+    if isinstance(paths, dict):
+        for name, p in paths.items():
+            rt = [r for r in model.legacy_train if r.name == name]
+            if not rt:
+                raise KeyError(f"no sparse embedding named {name}")
+            rt[0].load_parameters(p)
+    else:
+        for rt, p in zip(model.legacy_train, paths):
+            rt.load_parameters(p)
+
+
+def load_sparse_opt_states(model, paths):
+    if isinstance(paths, dict):
+        for name, p in paths.items():
+            [r for r in model.legacy_train if r.name == name][0].load_opt_states(p)
+    else:
+        for rt, p in zip(model.legacy_train, paths):
+            rt.load_opt_states(p)
+
+
+def save_model(model, prefix: str, it: int):
+    save_sparse(model, prefix, it)
+    save_dense(model, prefix, it)
+    if model.ebcs_train:
+        embedding_dump(model, f"{prefix}_ebc_{it}", None)
+    logger.info(f"Dumping dense weights / optimizer states / sparse models with prefix {prefix} iter {it}")
+
+
+# ------------------------------------------------------------------------------------ EBC
+def _file_head(ftype: int, table_id: int) -> bytes:
+    head = np.zeros(FILE_HEAD_NBYTES // 4, dtype="<i4")
+    head[0], head[1] = ftype, table_id
+    return head.tobytes()
+
+
+def _gather_table(model, ebc, name):
+    """rank 0 gets the whole table: (keys int64 [n], weights [n, ev], states)"""
+    parts = ebc.dump_table_local(name)
+    allp = model.comm.all_gather_object(parts) if model.world > 1 else [parts]
+    if model.comm.rank != 0:
+        return None
+    t = ebc.tmap[name]
+    ev = t.ev_size
+    seen = {}
+    for rank_parts in allp:
+        for (keys, w, c0, sts, kind) in rank_parts:
+            if kind == "dp" and seen.get(("dp", c0)):
+                continue                       # replicated: take one copy
+            seen[("dp", c0)] = kind == "dp"
+            seen.setdefault("chunks", []).append((keys, w, c0, sts))
+    chunks = seen.get("chunks", [])
+    allkeys = torch.unique(torch.cat([c[0] for c in chunks])) if chunks else torch.zeros(0, dtype=torch.int64)
+    n = allkeys.numel()
+    W = torch.zeros(n, ev)
+    S = [torch.zeros(n, ev), torch.zeros(n, ev)]
+    has_state = [False, False]
+    for (keys, w, c0, sts) in chunks:
+        pos = torch.searchsorted(allkeys, keys)
+        W[pos, c0:c0 + w.shape[1]] = w
+        for i, st in enumerate(sts):
+            if st is not None:
+                S[i][pos, c0:c0 + w.shape[1]] = st
+                has_state[i] = True
+    return allkeys, W, [S[i] if has_state[i] else None for i in range(2)]
+
+
+def embedding_dump(model, path: str, table_names=None):
+    fs = _fs(path, model)
+    for eid, ebc in enumerate(model.ebcs_train):
+        names = [t.name for t in ebc.tables]
+        sel = [n for n in names if table_names is None or n in table_names]
+        ids = sorted(names.index(n) for n in sel)
+        folder = f"{path}/embedding_collection_{eid}"
+        tabs = {}
+        for tid in ids:
+            tabs[tid] = _gather_table(model, ebc, names[tid])
+        if model.comm.rank == 0:
+            fs.create_dir(folder)
+            head = np.zeros(5, dtype="<i4")
+            head[0] = len(ids)
+            head[1] = 1 if model.key_dtype == torch.int64 else 0
+            head[2] = 0   # fp32 values
+            meta = head.tobytes() + np.asarray(ids, dtype="<i4").tobytes() + \
+                np.asarray([tabs[t][0].numel() for t in ids], dtype="<u8").tobytes() + \
+                np.asarray([ebc.tables[t].ev_size for t in ids], dtype="<i4").tobytes()
+            fs.write(f"{folder}/meta_data", meta)
+            kd = "<i8" if model.key_dtype == torch.int64 else "<u4"
+            for tid in ids:
+                keys, W, S = tabs[tid]
+                fs.write(f"{folder}/key{tid}", _file_head(1, tid) + keys.numpy().astype(kd).tobytes())
+                fs.write(f"{folder}/weight{tid}", _file_head(2, tid) + W.numpy().astype("<f4").tobytes())
+                st = [s for s in S if s is not None]
+                if st:
+                    fs.write(f"{folder}/opt{tid}", _file_head(3, tid) +
+                             b"".join(s.numpy().astype("<f4").tobytes() for s in st))
+        model.comm.barrier()
+
+
+def read_ebc_folder(folder: str, fs=None):
+    fs = fs or FileSystemBuilder.build_by_path(folder)
+    meta = fs.read(f"{folder}/meta_data")
+    head = np.frombuffer(meta[:META_HEAD_NBYTES], dtype="<i4")
+    n, key_type = int(head[0]), int(head[1])
+    off = META_HEAD_NBYTES
+    ids = np.frombuffer(meta[off:off + 4 * n], dtype="<i4"); off += 4 * n
+    knums = np.frombuffer(meta[off:off + 8 * n], dtype="<u8"); off += 8 * n
+    evs = np.frombuffer(meta[off:off + 4 * n], dtype="<i4")
+    kd = "<i8" if key_type == 1 else "<u4"
+    out = {}
+    for tid, kn, ev in zip(ids, knums, evs):
+        tid, kn, ev = int(tid), int(kn), int(ev)
+        kraw = fs.read(f"{folder}/key{tid}")[FILE_HEAD_NBYTES:]
+        wraw = fs.read(f"{folder}/weight{tid}")[FILE_HEAD_NBYTES:]
+        keys = torch.from_numpy(np.frombuffer(kraw, dtype=kd).astype("int64"))
+        W = torch.from_numpy(np.frombuffer(wraw, dtype="<f4").copy()).view(int(kn), int(ev))
+        S = None
+        if fs.exists(f"{folder}/opt{tid}"):
+            oraw = fs.read(f"{folder}/opt{tid}")[FILE_HEAD_NBYTES:]
+            o = torch.from_numpy(np.frombuffer(oraw, dtype="<f4").copy())
+            ns = o.numel() // max(1, int(kn) * int(ev))
+            S = [o[i * kn * ev:(i + 1) * kn * ev].view(int(kn), int(ev)) for i in range(int(ns))]
+        out[int(tid)] = (keys, W, S)
+    return out
+
+
+def embedding_load(model, path: str, table_names=None):
+    fs = _fs(path, model)
+    for eid, ebc in enumerate(model.ebcs_train):
+        folder = f"{path}/embedding_collection_{eid}"
+        tabs = read_ebc_folder(folder, fs)
+        names = [t.name for t in ebc.tables]
+        for tid, (keys, W, S) in tabs.items():
+            n = names[tid]
+            if table_names is not None and n not in table_names:
+                continue
+            ebc.load_table_rows(n, keys, W, S)
+    model.comm.barrier()

@@ -28,7 +28,10 @@ class MLPLayer(Layer):
                  default_init=("mlp", "mlp")):
         super().__init__(cfg, inputs, ctx)
         x = inputs[0]
-        assert len(x.shape) == 2, "MLP expects a 2-D bottom tensor"
+        self.lead = tuple(x.shape[:-1])
+        self.rows = 1
+        for d in self.lead:
+            self.rows *= d
         self.dims_out = list(num_outputs if num_outputs is not None else cfg.num_outputs)
         n = len(self.dims_out)
         acts = list(activations if activations is not None else cfg.activations)
@@ -42,7 +45,7 @@ class MLPLayer(Layer):
         self.async_wgrad = bool(getattr(cfg.compute_config, "async_wgrad", False))
         self.mixed = ctx.mixed
         self.W, self.B = [], []
-        k = x.shape[1]
+        k = x.shape[-1]
         self.k_in = k
         self.k_pad = _ceil8(k) if ctx.mixed else k
         kin = k
@@ -56,13 +59,13 @@ class MLPLayer(Layer):
             else:
                 self.B.append(None)
             kin = nout
-        self._out(0, (x.shape[0], self.dims_out[-1]))
+        self._out(0, self.lead + (self.dims_out[-1],))
         self._side = None
 
     # ------------------------------------------------------------------ buffers
     def allocate(self):
         super().allocate()
-        dev, dt, b = self.ctx.device, self.ctx.act_dtype, self.inputs[0].shape[0]
+        dev, dt, b = self.ctx.device, self.ctx.act_dtype, self.rows
         x = self.inputs[0]
         # input staging (cast / pad) only when needed
         self.x_stage = None
@@ -71,7 +74,7 @@ class MLPLayer(Layer):
         self.acts: List[torch.Tensor] = []
         for i, n in enumerate(self.dims_out):
             if i == len(self.dims_out) - 1:
-                self.acts.append(self.outputs[0].data)
+                self.acts.append(self.outputs[0].data.view(b, n))
             else:
                 self.acts.append(torch.zeros(b, n, dtype=dt, device=dev))
         if self.ctx.is_train:
@@ -83,7 +86,7 @@ class MLPLayer(Layer):
                     self.dacts.append(torch.zeros(b, n, dtype=dt, device=dev))
 
     def _x(self):
-        x = self.inputs[0].data
+        x = self.inputs[0].data.reshape(self.rows, self.k_in)
         if self.x_stage is None:
             return x
         if x.dtype == torch.float32 and self.x_stage.dtype == torch.bfloat16:
@@ -111,7 +114,7 @@ class MLPLayer(Layer):
     # ------------------------------------------------------------------ backward
     def bprop(self):
         n = len(self.dims_out)
-        dy = self.outputs[0].grad
+        dy = self.outputs[0].grad.view(self.rows, self.dims_out[-1])
         want_dx = self.inputs[0].grad is not None
         for i in range(n - 1, -1, -1):
             x_i = self._x_in if i == 0 else self.acts[i - 1]
@@ -147,15 +150,15 @@ class MLPLayer(Layer):
                 else:
                     G.gemm_bf16(dz, W.compute(self.mixed), self._dx_stage())
         if want_dx:
-            g = self.inputs[0].grad
+            g = self.inputs[0].grad.view(self.rows, self.k_in)
             st = self._dx_stage()
-            if st is not g:
+            if st.data_ptr() != g.data_ptr():
                 g.copy_(st[:, :self.k_in].to(g.dtype))
 
     def _dx_stage(self):
         g = self.inputs[0].grad
         if self.x_stage is None:
-            return g
+            return g.view(self.rows, self.k_in)
         if not hasattr(self, "_dxs"):
             self._dxs = torch.zeros_like(self.x_stage)
         return self._dxs

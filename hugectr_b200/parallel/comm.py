@@ -68,6 +68,13 @@ class Comm:
         self._heap = None
         self._p2p = None
 
+    @staticmethod
+    def single(device) -> "Comm":
+        """A world_size == 1 communicator even inside a multi-rank job (tests, oracles)."""
+        c = Comm.__new__(Comm)
+        c.device, c.group, c.rank, c.world_size, c._heap, c._p2p = device, None, 0, 1, None, False
+        return c
+
     # ---- bootstrap
     @staticmethod
     def init_from_env(device_type: Optional[str] = None) -> "Comm":

@@ -1,0 +1,118 @@
+"""Worker run under torch.distributed.run by the dist tests (gloo on CPU, nccl on GPU)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from hugectr_b200.embedding.collection import (EmbeddingCollection, EmbeddingCollectionConfig,  # noqa: E402
+                                               EmbeddingTableConfig)
+from hugectr_b200.enums import Optimizer_t  # noqa: E402
+from hugectr_b200.parallel.comm import Comm  # noqa: E402
+from hugectr_b200.solver import CreateOptimizer  # noqa: E402
+
+
+def make_cfg(world, plan):
+    sizes = [1000, 37, 5000, 64, 3000]
+    hot = {"d0": 3, "d1": 1, "d2": 12, "d3": 2, "d4": 4}
+    ev = 16
+    ts = [EmbeddingTableConfig(str(i), sizes[i], ev) for i in range(5)]
+    cfg = EmbeddingCollectionConfig()
+    cfg.embedding_lookup(ts, list(hot), "emb", ["sum", "mean", "sum", "sum", "mean"])
+    if plan == "mixed":
+        sm = [[0] * 5 for _ in range(world)]
+        for g in range(world):
+            sm[g][2] = 1            # table 2 row-sharded over all GPUs
+            sm[g][3] = 1            # table 3 data parallel
+        sm[0][0] = 1
+        sm[world - 1][1] = 1
+        sm[(world // 2)][4] = 1
+        cfg.shard(sm, [("mp", ["0", "1", "2", "4"]), ("dp", ["3"])])
+    elif plan == "column":
+        sm = [[1] * 5 for _ in range(world)]
+        cfg.shard(sm, [("mp", ["0", "1", ("2", world), "3", "4"])])
+    return cfg, sizes, hot, ev
+
+
+def run_ebc(plan, fused):
+    comm = Comm.init_from_env()
+    dev = comm.device
+    world, rank = comm.world_size, comm.rank
+    b = 32
+    cfg, sizes, hot, ev = make_cfg(world, plan)
+    opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.1, epsilon=1e-6)
+    act = torch.float32
+    e = EmbeddingCollection(cfg, b, hot, dev, act, comm, opt, seed=1, fused=fused)
+    cfg1, _, _, _ = make_cfg(1, "none")
+    ref = EmbeddingCollection(cfg1, b * world, hot, torch.device("cpu"), act,
+                              Comm.single(torch.device("cpu")), opt, seed=1)
+    gen = torch.Generator().manual_seed(5)
+    full = {str(i): torch.randn(sizes[i], ev, generator=gen) * 0.1 for i in range(5)}
+    for n, w in full.items():
+        k = torch.arange(w.shape[0])
+        e.load_table_rows(n, k, w)
+        ref.load_table_rows(n, k, w)
+    lr = torch.tensor([0.05])
+    st = torch.tensor([1], dtype=torch.int32)
+    lr_d, st_d = lr.to(dev), st.to(dev)
+    for it in range(3):
+        gk = [torch.randint(0, sizes[i], (b * world, h), generator=gen) for i, h in enumerate(hot.values())]
+        keys_ref = torch.cat([k.reshape(-1) for k in gk]).int()
+        keys_loc = torch.cat([k[rank * b:(rank + 1) * b].reshape(-1) for k in gk]).int()
+        grad = torch.randn(b * world, 5 * ev, generator=gen) * 0.1
+        e.set_keys(keys_loc.to(dev)); ref.set_keys(keys_ref)
+        e.forward(); ref.forward()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        out = e.top_data["emb"].float().cpu()
+        exp = ref.top_data["emb"][rank * b:(rank + 1) * b]
+        err = (out - exp).abs().max().item()
+        assert err < 1e-4, f"rank {rank} it {it} fwd err {err}"
+        e.top_grad["emb"].copy_(grad[rank * b:(rank + 1) * b].to(dev))
+        ref.top_grad["emb"].copy_(grad)
+        e.backward(lr_d, st_d); ref.backward(lr, st)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+    # compare every local shard with the reference table
+    for n in full:
+        rk, rw = ref.dump_table_local(n)[0][:2]
+        for (k, w, c0, sts, kind) in e.dump_table_local(n):
+            exp = rw[k][:, c0:c0 + w.shape[1]]
+            err = (w - exp).abs().max().item()
+            assert err < 2e-4, f"rank {rank} table {n} err {err}"
+    comm.barrier()
+    if rank == 0:
+        print(f"EBC_OK plan={plan} fused={fused} world={world}")
+
+
+def run_allreduce():
+    comm = Comm.init_from_env()
+    from hugectr_b200.parallel.p2p import P2PAllReduce
+    n = 4 * comm.world_size * 100003
+    buf = comm.symm_alloc(n, torch.float32)
+    ar = P2PAllReduce(comm, buf)
+    for it in range(5):
+        g = torch.Generator(device="cuda").manual_seed(it * 10 + comm.rank)
+        x = torch.randn(n, device="cuda", generator=g)
+        exp = x.clone()
+        dist.all_reduce(exp)
+        buf.copy_(x)
+        ar.run()
+        torch.cuda.synchronize()
+        err = (buf - exp).abs().max().item()
+        assert err < 1e-4, f"allreduce err {err}"
+    comm.barrier()
+    if comm.rank == 0:
+        print("ALLREDUCE_OK")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    if what == "ebc":
+        run_ebc(sys.argv[2], {"fused": True, "collective": False}[sys.argv[3]])
+    elif what == "allreduce":
+        run_allreduce()
+    if dist.is_initialized():
+        dist.destroy_process_group()

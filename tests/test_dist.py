@@ -1,0 +1,47 @@
+"""Multi-process tests: gloo/CPU (world 2) here, NCCL + P2P fused kernels on the GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(nproc, args, port, env=None, timeout=300):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(HERE, "dist_worker.py"), *args]
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("plan", ["mixed", "column"])
+def test_ebc_collective_gloo(plan):
+    out = _run(2, ["ebc", plan, "collective"], 29611, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "EBC_OK" in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["collective", "fused"])
+@pytest.mark.parametrize("plan", ["mixed", "column"])
+def test_ebc_multi_gpu(plan, mode):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = _run(min(n, 4), ["ebc", plan, mode], 29621)
+    assert "EBC_OK" in out
+
+
+@pytest.mark.gpu
+def test_p2p_allreduce():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = _run(min(n, 8), ["allreduce"], 29631)
+    assert "ALLREDUCE_OK" in out

