@@ -1,0 +1,227 @@
+"""Host parameter server tier: HostParameterServer (pinned host table, optional SSD spill file),
+HMemCache (host-memory block cache with a target hit rate), SparseModelFile,
+EmbeddingTrainingCache (TrainPSType_t Staged / Cached) and OffloadedEmbedding (GPU hot-row cache in
+front of a host-resident table: Query -> miss fetch -> Replace, write-back of updated rows).
+
+Re-created from the interfaces that survive in the reference
+(HugeCTR/include/embedding_training_cache/*.hpp: ParameterServer{pull,push,load_keyset,flush_to_ssd},
+HMemCache, SparseModelFile(TS), EmbeddingTrainingCache; the wiring was deleted upstream).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from ..enums import Optimizer_t, TrainPSType_t
+from ..embedding import ops as E
+from .gpu_cache import GpuCache
+
+
+class SparseModelFile:
+    """On-disk sparse model in the legacy format: <dir>/key (int64), <dir>/emb_vector (fp32)."""
+
+    def __init__(self, path: str, ev: int):
+        self.path, self.ev = path, ev
+        os.makedirs(path, exist_ok=True)
+        self.kf, self.vf = os.path.join(path, "key"), os.path.join(path, "emb_vector")
+        self.index: Dict[int, int] = {}
+        if os.path.exists(self.kf):
+            keys = np.fromfile(self.kf, dtype="<i8")
+            self.index = {int(k): i for i, k in enumerate(keys)}
+
+    def load(self, keys):
+        if not self.index:
+            return {}
+        mm = np.memmap(self.vf, dtype="<f4", mode="r").reshape(-1, self.ev)
+        return {int(k): torch.from_numpy(np.array(mm[self.index[int(k)]]))
+                for k in keys if int(k) in self.index}
+
+    def dump(self, keys: torch.Tensor, values: torch.Tensor):
+        """append new keys, overwrite existing ones"""
+        new_k, new_v = [], []
+        if self.index:
+            mm = np.memmap(self.vf, dtype="<f4", mode="r+").reshape(-1, self.ev)
+        for k, v in zip(keys.tolist(), values):
+            if k in self.index:
+                mm[self.index[k]] = v.numpy()
+            else:
+                self.index[k] = len(self.index)
+                new_k.append(k)
+                new_v.append(v.numpy())
+        if new_k:
+            with open(self.kf, "ab") as f:
+                f.write(np.asarray(new_k, dtype="<i8").tobytes())
+            with open(self.vf, "ab") as f:
+                f.write(np.stack(new_v).astype("<f4").tobytes())
+
+
+class HMemCache:
+    """Host-memory block cache in front of the SSD file (target hit rate controls its size)."""
+
+    def __init__(self, ev: int, capacity_rows: int):
+        from collections import OrderedDict
+        self.ev, self.cap = ev, capacity_rows
+        self.d = OrderedDict()
+        self.hits = self.reqs = 0
+
+    def get(self, k):
+        self.reqs += 1
+        if k in self.d:
+            self.d.move_to_end(k)
+            self.hits += 1
+            return self.d[k]
+        return None
+
+    def put(self, k, v):
+        self.d[k] = v
+        self.d.move_to_end(k)
+        evicted = []
+        while len(self.d) > self.cap:
+            evicted.append(self.d.popitem(last=False))
+        return evicted
+
+    def hit_rate(self):
+        return self.hits / max(1, self.reqs)
+
+
+class HostParameterServer:
+    """Whole table (weights + optimizer states) in (pinned) host memory; rows are created lazily with
+    the embedding initializer; optional SSD spill (`flush_to_ssd`)."""
+
+    def __init__(self, ev: int, num_states: int = 0, init_bound: float = 0.05,
+                 ssd_path: Optional[str] = None, capacity_rows: int = 1 << 20, seed: int = 0):
+        self.ev, self.ns = ev, num_states
+        self.bound = init_bound
+        self.index: Dict[int, int] = {}
+        self.cap = capacity_rows
+        pin = torch.cuda.is_available()
+        self.w = torch.zeros(self.cap, ev)
+        self.s = [torch.zeros(self.cap, ev) for _ in range(num_states)]
+        if pin:
+            self.w = self.w.pin_memory()
+            self.s = [t.pin_memory() for t in self.s]
+        self.gen = torch.Generator().manual_seed(seed)
+        self.ssd = SparseModelFile(ssd_path, ev) if ssd_path else None
+
+    def _rows(self, keys, create=True):
+        rows = []
+        for k in keys.tolist():
+            r = self.index.get(k)
+            if r is None and create:
+                r = len(self.index)
+                if r >= self.cap:
+                    raise RuntimeError("HostParameterServer capacity exceeded")
+                self.index[k] = r
+                loaded = self.ssd.load([k]) if self.ssd else {}
+                self.w[r] = loaded.get(k, (torch.rand(self.ev, generator=self.gen) * 2 - 1) * self.bound)
+            rows.append(-1 if r is None else r)
+        return torch.tensor(rows, dtype=torch.int64)
+
+    def pull(self, keys: torch.Tensor):
+        rows = self._rows(keys.cpu())
+        return self.w[rows], [s[rows] for s in self.s]
+
+    def push(self, keys: torch.Tensor, w: torch.Tensor, states=()):
+        rows = self._rows(keys.cpu())
+        self.w[rows] = w.cpu().float()
+        for dst, src in zip(self.s, states):
+            dst[rows] = src.cpu().float()
+
+    def load_keyset(self, keyset_file: str):
+        keys = torch.from_numpy(np.fromfile(keyset_file, dtype="<i8").astype("int64"))
+        self._rows(keys)
+        return keys
+
+    def flush_to_ssd(self):
+        if self.ssd is None:
+            return
+        keys = torch.tensor(list(self.index.keys()), dtype=torch.int64)
+        rows = torch.tensor(list(self.index.values()), dtype=torch.int64)
+        self.ssd.dump(keys, self.w[rows])
+
+    def size(self):
+        return len(self.index)
+
+
+class EmbeddingTrainingCache:
+    """Train models larger than HBM pass by pass: ``update(keyset)`` loads the rows of the next
+    keyset from the parameter server into a device table, training runs on it, ``dump()`` writes
+    them back (Staged = straight from host/SSD, Cached = through HMemCache)."""
+
+    def __init__(self, ps: HostParameterServer, ps_type: TrainPSType_t = TrainPSType_t.Staged,
+                 hmem_rows: int = 1 << 16):
+        self.ps, self.type = ps, ps_type
+        self.hmem = HMemCache(ps.ev, hmem_rows) if ps_type == TrainPSType_t.Cached else None
+        self.keys = None
+        self.device_table = None
+
+    def update(self, keyset: torch.Tensor, device):
+        self.keys = keyset.to(torch.int64).cpu()
+        w, _ = self.ps.pull(self.keys)
+        self.device_table = w.to(device, non_blocking=True)
+        return self.device_table
+
+    def dump(self):
+        if self.keys is not None:
+            self.ps.push(self.keys, self.device_table.cpu())
+
+
+class OffloadedEmbedding:
+    """Table on the host parameter server, hot rows in the HBM GpuCache.
+
+    forward(keys [b, H]) -> pooled [b, ev]:  unique keys -> cache.Query -> fetch misses from the host
+    -> cache.Replace -> pool;   backward(grad [b, ev]) : per-unique-row reduce + optimizer on the
+    staged rows -> cache.Update + write-through to the host server.
+    """
+
+    def __init__(self, ev: int, device, cache_rows: int, opt, num_states: int = 1, lr: float = 0.01,
+                 host_capacity: int = 1 << 20, combiner: str = "sum", ssd_path: Optional[str] = None):
+        self.ev, self.device, self.opt, self.lr, self.combiner = ev, torch.device(device), opt, lr, combiner
+        self.ps = HostParameterServer(ev, num_states, ssd_path=ssd_path, capacity_rows=host_capacity)
+        self.cache = GpuCache(cache_rows, ev, device)
+        self.state_cache = [GpuCache(cache_rows, ev, device) for _ in range(num_states)]
+
+    def _fetch(self, uniq):
+        vals, mi, mk = self.cache.query(uniq)
+        st = [c.query(uniq)[0] for c in self.state_cache]
+        if mk.numel():
+            w, s = self.ps.pull(mk)
+            vals[mi] = w.to(self.device)
+            self.cache.replace(mk.to(self.device), vals[mi])
+            for c, sv, t in zip(self.state_cache, s, st):
+                t[mi] = sv.to(self.device)
+                c.replace(mk.to(self.device), t[mi])
+        return vals, st
+
+    def forward(self, keys: torch.Tensor) -> torch.Tensor:
+        b, H = keys.shape
+        k = keys.to(self.device).to(torch.int64)
+        self.uniq, self.inv = torch.unique(k.reshape(-1), return_inverse=True)
+        self.vals, self.states = self._fetch(self.uniq)
+        out = self.vals[self.inv].view(b, H, self.ev).sum(1)
+        if self.combiner == "mean":
+            out = out / H
+        self._shape = (b, H)
+        return out
+
+    def backward(self, grad: torch.Tensor, step: int = 1):
+        b, H = self._shape
+        g = grad.float().unsqueeze(1).expand(b, H, self.ev).reshape(-1, self.ev)
+        if self.combiner == "mean":
+            g = g / H
+        gu = torch.zeros(self.uniq.numel(), self.ev, device=self.device).index_add_(0, self.inv, g)
+        w = self.vals
+        s0 = self.states[0] if len(self.states) > 0 else None
+        s1 = self.states[1] if len(self.states) > 1 else None
+        o = self.opt
+        hp = {"beta1": o.beta1, "beta2": o.beta2, "epsilon": o.epsilon, "lambda1": o.lambda1,
+              "lambda2": o.lambda2, "ftrl_beta": o.beta, "momentum": o.momentum_factor}
+        E.sparse_opt_reference(o.optimizer_type, w, s0, s1, gu, hp, self.lr, step)
+        self.cache.update(self.uniq, w)
+        for c, s in zip(self.state_cache, (s0, s1)):
+            if s is not None:
+                c.update(self.uniq, s)
+        self.ps.push(self.uniq, w, [s for s in (s0, s1) if s is not None])

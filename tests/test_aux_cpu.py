@@ -1,0 +1,160 @@
+"""CPU tests: hash table, gpu_cache (reference impl), HPS/offload, SOK, metrics, LR schedule,
+planner, logger, filesystem, DataGenerator/readers round trip."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hugectr_b200 as hugectr
+from hugectr_b200.parallel.comm import Comm, DeviceMap
+
+
+def test_hashtable_cpu():
+    from hugectr_b200.embedding.hashtable import HashTable
+    ht = HashTable(100, "cpu")
+    k = torch.tensor([5, 9, 5, -1, 1000000007])
+    r = ht.get_insert(k)
+    assert r.tolist() == [0, 1, 0, -1, 2] and ht.size() == 3
+    assert ht.get(torch.tensor([9, 77])).tolist() == [1, -1]
+    keys, rows = ht.dump()
+    assert keys.tolist() == [5, 9, 1000000007] and rows.tolist() == [0, 1, 2]
+
+
+def test_gpu_cache_reference_lru():
+    from hugectr_b200.cache import GpuCache
+    c = GpuCache(64, 4, "cpu", ways=32)
+    keys = torch.arange(10)
+    vals = torch.arange(40).float().view(10, 4)
+    out, mi, mk = c.query(keys)
+    assert mi.numel() == 10
+    c.replace(keys, vals)
+    out, mi, mk = c.query(torch.tensor([3, 99, 7]))
+    assert mi.tolist() == [1] and mk.tolist() == [99]
+    torch.testing.assert_close(out[0], vals[3])
+    c.update(torch.tensor([3, 1234]), torch.ones(2, 4))
+    torch.testing.assert_close(c.query(torch.tensor([3]))[0][0], torch.ones(4))
+    assert set(c.dump().tolist()) == set(range(10))
+
+
+def test_offloaded_embedding_matches_dense():
+    from hugectr_b200.cache import OffloadedEmbedding
+    opt = hugectr.CreateOptimizer(hugectr.Optimizer_t.AdaGrad, initial_accu_value=0.0, epsilon=1e-6)
+    e = OffloadedEmbedding(8, "cpu", cache_rows=64, opt=opt, num_states=1, lr=0.1)
+    keys = torch.randint(0, 500, (16, 3))
+    y = e.forward(keys)
+    w0, _ = e.ps.pull(e.uniq)
+    torch.testing.assert_close(y, w0[e.inv].view(16, 3, 8).sum(1))
+    e.backward(torch.ones(16, 8))
+    w1, s1 = e.ps.pull(e.uniq)
+    assert (w1 - w0).abs().max() > 0 and (s1[0] > 0).all()
+
+
+def test_sok_lookup_and_optimizer():
+    from hugectr_b200 import sok
+    sok.init(Comm.single(torch.device("cpu")))
+    v = sok.Variable(shape=(50, 4), name="v_test")
+    d = sok.DynamicVariable(4, name="d_test", init_capacity=8)
+    ids = torch.tensor([[1, 2, -1], [3, 3, 3]])
+    out = sok.lookup_sparse(v, ids, "mean")
+    exp = torch.stack([(v.weight[1] + v.weight[2]) / 2, v.weight[3]])
+    torch.testing.assert_close(out, exp)
+    big = torch.tensor([[10 ** 12, 5], [7, 10 ** 12]])
+    o2 = sok.lookup_sparse(d, big, "sum")
+    assert d.size == 3
+    (out.sum() + o2.sum()).backward()
+    opt = sok.OptimizerWrapper(hugectr.Optimizer_t.SGD, lr=0.5)
+    w_before = v.weight.clone()
+    opt.apply_gradients([v, d])
+    assert not torch.allclose(v.weight[3], w_before[3])
+    torch.testing.assert_close(v.weight[0], w_before[0])
+
+
+def test_sok_dump_load(tmp_path):
+    from hugectr_b200 import sok
+    sok.init(Comm.single(torch.device("cpu")))
+    v = sok.Variable(shape=(20, 4), name="v_dl")
+    sok.dump(str(tmp_path), [v])
+    w = v.weight.clone()
+    v.weight.zero_()
+    sok.load(str(tmp_path), [v])
+    torch.testing.assert_close(v.weight, w)
+
+
+def test_metrics_auc_matches_sklearn():
+    from sklearn.metrics import roc_auc_score
+    from hugectr_b200.metrics import auc_exact
+    g = torch.Generator().manual_seed(1)
+    p = torch.rand(5000, generator=g).round(decimals=2)   # many ties
+    y = (torch.rand(5000, generator=g) < p).float()
+    assert abs(auc_exact(p, y) - roc_auc_score(y.numpy(), p.numpy())) < 1e-6
+
+
+def test_lr_scheduler_and_device_map():
+    from hugectr_b200.lr_scheduler import LearningRateScheduler
+    s = LearningRateScheduler(1.0, warmup_steps=4, decay_start=6, decay_steps=4, decay_power=2.0, end_lr=0.1)
+    lrs = [s.get_next() for _ in range(12)]
+    assert lrs[:4] == [0.25, 0.5, 0.75, 1.0] and lrs[5] == 1.0
+    assert abs(lrs[7] - 0.25) < 1e-9 and lrs[-1] == 0.1
+    dm = DeviceMap([[0, 1], [0, 1]], "NodeFirst", my_node=1)
+    assert dm.get_global_id(0) == 1 and dm.get_global_id(1) == 3 and dm.size() == 4
+    dm2 = DeviceMap([[0, 1], [0, 1]], "LocalFirst", my_node=1)
+    assert dm2.get_global_id(0) == 2
+
+
+def test_planner_and_workspace():
+    from hugectr_b200.models.dlrm import CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES
+    from hugectr_b200.tools.planner import generate_plan
+    from hugectr_b200.tools.workspace_calculator import calculate
+    sm, st = generate_plan(CRITEO_TB_TABLE_SIZES, CRITEO_TB_MULTI_HOT, 8)
+    assert len(sm) == 8 and all(len(r) == 26 for r in sm)
+    kinds = dict((k, v) for k, v in st)
+    assert "mp" in kinds and "dp" in kinds
+    assert sum(sm[g][20] for g in range(8)) > 1          # hot table split row-wise
+    for t in range(26):
+        assert any(sm[g][t] for g in range(8))
+    assert calculate([1000] * 26, 16, hugectr.Optimizer_t.Adam) >= 1
+
+
+def test_solver_validation_and_json_optimizer():
+    with pytest.raises(RuntimeError):
+        hugectr.CreateSolver(use_mixed_precision=True, enable_tf32_compute=True)
+    o = hugectr.CreateOptimizer(hugectr.Optimizer_t.Ftrl, beta=0.1, lambda1=0.2, lambda2=0.3)
+    o2 = hugectr.OptParamsPy.from_json(o.to_json())
+    assert (o2.beta, o2.lambda1, o2.lambda2) == (0.1, 0.2, 0.3)
+
+
+def test_filesystem_and_logger(tmp_path, capsys):
+    from hugectr_b200.io import FileSystemBuilder
+    from hugectr_b200.utils import logger
+    fs = FileSystemBuilder.build_by_path(str(tmp_path / "a" / "b.bin"))
+    fs.write(str(tmp_path / "a" / "b.bin"), b"hello")
+    assert fs.read(str(tmp_path / "a" / "b.bin"), 1, 3) == b"ell"
+    assert fs.get_file_size(str(tmp_path / "a" / "b.bin")) == 5
+    logger.Logger.get().level = 2
+    logger.info("hi there")
+    assert "[HCTR]" in capsys.readouterr().out
+    with pytest.raises(logger.HctrError):
+        logger.check(False, hugectr.Error_t.WrongInput, "bad")
+
+
+def test_norm_checksum_detects_corruption(tmp_path):
+    from hugectr_b200.data.generator import DataGenerator, DataGeneratorParams
+    from hugectr_b200.data.norm_reader import DataCheckError
+    from hugectr_b200.models.legacy import build_dcn
+    slots = [50] * 4
+    p = DataGeneratorParams(hugectr.DataReaderType_t.Norm, 1, 13, 4, False,
+                            str(tmp_path / "l.txt"), str(tmp_path / "v.txt"), slots, num_files=1,
+                            eval_num_files=1, num_samples_per_file=64)
+    DataGenerator(p).generate()
+    f = str(tmp_path / "train" / "gen_0.data")
+    raw = bytearray(open(f, "rb").read())
+    raw[100] ^= 0xFF
+    open(f, "wb").write(raw)
+    m = build_dcn(batchsize=32, source=p.source, eval_source=p.eval_source, slot_sizes=slots,
+                  num_slots=4, fmt=hugectr.DataReaderType_t.Norm, workspace_mb=1,
+                  comm=Comm.single(torch.device("cpu")))
+    m.reader_params.check_type = hugectr.Check_t.Sum
+    m.compile()
+    with pytest.raises(DataCheckError):
+        m.train()
