@@ -170,23 +170,56 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------ column sum (bias grad)
-// out[n] += sum_m x[m, n]   (x bf16/fp32 row-major, ld) ; grid (ceil(N/64), splits)
+// out[n] += sum_m x[m, n]   (x bf16/fp32 row-major, ld).  Block = 32 column-groups (8 columns each,
+// one 16-byte load per row) x 8 row lanes; grid (ceil(N/256), row splits); fp32 atomics at the end.
 template <typename T>
 __global__ void __launch_bounds__(256)
     colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N, long long ld) {
-  __shared__ float sm[4][64];
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int rlane = threadIdx.x >> 6;  // 0..3
+  constexpr int VEC = 16 / sizeof(T);  // 8 bf16 or 4 fp32
+  __shared__ float sm[8][32 * VEC];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cg) * VEC;
   const int rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  float acc = 0.f;
-  if (col < N)
-    for (int r = r0 + rlane; r < r1; r += 4) acc += static_cast<float>(x[r * ld + col]);
-  sm[rlane][threadIdx.x & 63] = acc;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const bool vec_ok = (col + VEC <= N) && ((ld * sizeof(T)) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+  if (col < N) {
+    if (vec_ok) {
+      for (int r = r0 + rl; r < r1; r += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + col);
+        if constexpr (sizeof(T) == 2) {
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[2 * q] += bf16_lo(w[q]);
+            acc[2 * q + 1] += bf16_hi(w[q]);
+          }
+        } else {
+          acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+          acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+        }
+      }
+    } else {
+      for (int r = r0 + rl; r < r1; r += 8)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (col + j < N) acc[j] += static_cast<float>(x[r * ld + col + j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[rl][cg * VEC + j] = acc[j];
   __syncthreads();
-  if (rlane == 0 && col < N) {
-    const int c = threadIdx.x & 63;
-    atomicAdd(out + col, sm[0][c] + sm[1][c] + sm[2][c] + sm[3][c]);
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int gc = blockIdx.x * 32 * VEC + c;
+    if (gc < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += sm[r][c];
+      atomicAdd(out + gc, v);
+    }
   }
 }
 
@@ -425,7 +458,11 @@ extern "C" int hctr_bce_loss(const void* x, const float* y, void* dx, float* los
 
 extern "C" int hctr_colsum(const void* x, float* out, int M, int N, long long ld, int is_bf16,
                            void* stream) {
-  dim3 grid((N + 63) / 64, M >= 4096 ? 32 : (M >= 256 ? 8 : 1));
+  const int cols_per_block = is_bf16 ? 256 : 128;
+  const int gx = (N + cols_per_block - 1) / cols_per_block;
+  int gy = 1;
+  while (gx * gy < 296 && M / (gy * 2) >= 64) gy *= 2;   // ~2 waves of blocks
+  dim3 grid(gx, gy);
   if (is_bf16) colsum_kernel<bf16><<<grid, 256, 0, ST(stream)>>>((const bf16*)x, out, M, N, ld);
   else colsum_kernel<float><<<grid, 256, 0, ST(stream)>>>((const float*)x, out, M, N, ld);
   return OK();

@@ -27,24 +27,19 @@ namespace hctr {
 // One group of G lanes per (src rank, lookup, sample) bucket; each lane owns VEC consecutive
 // floats per 32*VEC-wide column chunk.  G*VEC >= ev for ev <= 128 (VEC=4), wider rows loop.
 template <typename KeyT, typename OutT, int VEC, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     emb_fwd_kernel(const EmbParams p, const int G, const long long total_items) {
+  // grid.y = (src rank, lookup): uniform per block, no per-thread integer division
   const int lane = threadIdx.x & 31;
   const int groups_per_warp = 32 / G;
   const int gl = lane % G;  // lane inside group
   const int gi = lane / G;  // group inside warp
-  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long item = warp_global * groups_per_warp + gi;
-  const bool active = item < total_items;
+  const int l = blockIdx.y % p.num_lookups;
+  const int src = blockIdx.y / p.num_lookups;
+  const int s = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * groups_per_warp + gi;
+  const bool active = s < p.batch;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (gi * G));
-
-  int s = 0, l = 0, src = 0;
-  if (active) {
-    s = static_cast<int>(item % p.batch);
-    const long long t = item / p.batch;
-    l = static_cast<int>(t % p.num_lookups);
-    src = static_cast<int>(t / p.num_lookups);
-  }
+  (void)total_items;
   const EmbLookup lk = p.lookups[l];
   const int ev = lk.ev_size;
   int nnz = lk.hotness;
@@ -73,8 +68,11 @@ __global__ void __launch_bounds__(256)
         const int j = j0 + u;
         const long long key = __shfl_sync(gmask, mykey, gi * G + (j < cnt ? j : 0));
         bool ok = (j < cnt) && key >= 0;
-        if (ok && lk.num_shards > 1) ok = (key % lk.num_shards) == lk.shard_idx;
-        const long long r = ok ? key / lk.num_shards : 0;
+        long long r = key;
+        if (lk.num_shards > 1) {   // block-uniform branch; table-wise shards skip the divisions
+          ok = ok && (key % lk.num_shards) == lk.shard_idx;
+          r = key / lk.num_shards;
+        }
         ok = ok && r < lk.rows;
         rp[u] = ok ? p.table + (lk.table_row_off + r) * static_cast<long long>(p.ev_size) : nullptr;
       }
@@ -307,11 +305,12 @@ extern "C" int hctr_emb_forward(const EmbParams* p, int max_ev, int key_bytes, i
   if (narrow) G = 8;
   const long long items = static_cast<long long>(p->num_ranks) * p->num_lookups * p->batch;
   if (items == 0) return 0;
-  const long long warps = (items + (32 / G) - 1) / (32 / G);
   const int threads = 256;
-  const long long blocks = (warps * 32 + threads - 1) / threads;
+  const int buckets_per_block = (threads / 32) * (32 / G);
+  const dim3 blocks((p->batch + buckets_per_block - 1) / buckets_per_block,
+                    p->num_ranks * p->num_lookups);
 #define LAUNCH(K, O, V, UU) \
-  emb_fwd_kernel<K, O, V, UU><<<(unsigned)blocks, threads, 0, st>>>(*p, G, items)
+  emb_fwd_kernel<K, O, V, UU><<<blocks, threads, 0, st>>>(*p, G, items)
 #define LAUNCH_U(K, O, V)            \
   if (narrow) { LAUNCH(K, O, V, 4); } \
   else { LAUNCH(K, O, V, 8); }

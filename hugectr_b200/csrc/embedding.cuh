@@ -106,7 +106,8 @@ HCTR_DEVICE unsigned int unique_get_insert(const UniqueTable& t, unsigned long l
         t.rows[uid] = row;
         t.slots[uid] = h;
       }
-      __threadfence();
+      // rows[]/slots[] are only consumed by later kernels (kernel boundary orders them); concurrent
+      // threads of this kernel need the uid alone, so no membar is required before publishing it
       atomicExch(&t.vals[h], uid);
       return uid;
     }

@@ -30,7 +30,9 @@ struct BwdIndex {
   unsigned int* offsets;      // [max_unique + 1]
   unsigned int* block_sums;   // [ceil(max_unique / 1024) + 1]
   int* pair_uid;              // [max_pairs]
-  unsigned int* bucket_list;  // [max_pairs] bucket ids grouped by uid
+  unsigned int* bucket_list;  // [max_pairs] gradient-row locators grouped by uid:
+                              //   (src rank << 28) | (element offset of the bucket's grad row >> 2)
+  float* bucket_scale;        // [max_pairs] per-entry scale (mean combiner) or null when all sums
   unsigned int* heavy_items;  // [max_heavy_items * 2] (uid, chunk)
   unsigned int* heavy_count;  // [1]
   float* heavy_scratch;       // [max_heavy_rows, ev]
@@ -60,12 +62,12 @@ HCTR_DEVICE PairInfo decode_pair(const EmbParams& p, const long long* s_pair_off
   }
   PairInfo r;
   r.l = lo;
-  const long long rem = pair - s_pair_off[lo];
-  const int H = __ldg(&p.lookups[lo].hotness);
-  const long long bucket = rem / H;
+  const unsigned int rem = static_cast<unsigned int>(pair - s_pair_off[lo]);
+  const unsigned int H = static_cast<unsigned int>(__ldg(&p.lookups[lo].hotness));
+  const unsigned int bucket = rem / H;
   r.h = static_cast<int>(rem - bucket * H);
-  r.src = static_cast<int>(bucket / p.batch);
-  r.s = static_cast<int>(bucket - static_cast<long long>(r.src) * p.batch);
+  r.src = static_cast<int>(bucket / static_cast<unsigned int>(p.batch));
+  r.s = static_cast<int>(bucket - static_cast<unsigned int>(r.src) * static_cast<unsigned int>(p.batch));
   return r;
 }
 
@@ -99,8 +101,12 @@ __global__ void __launch_bounds__(kIdxThreads)
                      static_cast<long long>(pi.s) * __ldg(&lk->key_stride) + pi.h;
     const long long key = static_cast<long long>(*kp);
     const int ns = __ldg(&lk->num_shards);
-    if (key < 0 || (ns > 1 && (key % ns) != __ldg(&lk->shard_idx))) continue;
-    const long long r = key / ns;
+    if (key < 0) continue;
+    long long r = key;
+    if (ns > 1) {
+      if ((key % ns) != __ldg(&lk->shard_idx)) continue;
+      r = key / ns;
+    }
     if (r >= __ldg(&lk->rows)) continue;
     const unsigned long long arow = static_cast<unsigned long long>(__ldg(&lk->table_row_off) + r);
     unsigned int hslot = hash64(arow) & (kSmemSlots - 1);
@@ -287,54 +293,27 @@ __global__ void __launch_bounds__(kIdxThreads)
     if (slot[q] < 0) continue;
     const long long pair = base + q * kIdxThreads + threadIdx.x;
     const PairInfo pi = decode_pair(p, s_pair_off, pair);
-    const unsigned int item =
-        static_cast<unsigned int>((static_cast<long long>(pi.src) * p.num_lookups + pi.l) * p.batch + pi.s);
-    ix.bucket_list[h_cnt[slot[q]] + rank_local[q]] = item;
+    const EmbLookup* lk = p.lookups + pi.l;
+    const long long goff = __ldg(&lk->grad_off) + static_cast<long long>(pi.s) * __ldg(&lk->grad_stride);
+    const unsigned int pos = h_cnt[slot[q]] + rank_local[q];
+    ix.bucket_list[pos] = (static_cast<unsigned int>(pi.src) << 28) | static_cast<unsigned int>(goff >> 2);
+    if (ix.bucket_scale != nullptr) {
+      float sc = 1.f;
+      if (__ldg(&lk->combiner) == 1) {
+        int nnz = __ldg(&lk->hotness);
+        const long long no = __ldg(&lk->nnz_off);
+        if (no >= 0) nnz = min(nnz, p.nnz[pi.src][no + pi.s]);
+        sc = 1.f / static_cast<float>(max(nnz, 1));
+      }
+      ix.bucket_scale[pos] = sc;
+    }
   }
 }
 
 // ---------------------------------------------------------------- D: reduce + optimizer
-struct LookupCache {
-  long long goff[256];
-  int gstride[256];
-  float scale[256];     // 1/H for fixed-hotness mean, 1 for sum, <0: variable nnz -> slow path
-};
-
 template <typename GradT>
-HCTR_DEVICE float4 load_bucket_grad(const EmbParams& p, const LookupCache* lc, bool cached,
-                                    unsigned int item, int col, float& scale) {
-  const int s = static_cast<int>(item % p.batch);
-  const unsigned int t = item / p.batch;
-  const int l = static_cast<int>(t % p.num_lookups);
-  const int src = static_cast<int>(t / p.num_lookups);
-  long long goff;
-  if (cached && lc->scale[l] >= 0.f) {
-    goff = lc->goff[l] + static_cast<long long>(s) * lc->gstride[l];
-    scale = lc->scale[l];
-  } else {
-    const EmbLookup* lk = p.lookups + l;
-    goff = __ldg(&lk->grad_off) + static_cast<long long>(s) * __ldg(&lk->grad_stride);
-    scale = 1.f;
-    if (__ldg(&lk->combiner) == 1) {
-      int nnz = __ldg(&lk->hotness);
-      const long long no = __ldg(&lk->nnz_off);
-      if (no >= 0) nnz = min(nnz, p.nnz[src][no + s]);
-      scale = 1.f / static_cast<float>(max(nnz, 1));
-    }
-  }
-  const GradT* gp = reinterpret_cast<const GradT*>(p.grad[src]) + goff + col;
-  return load_vec4<GradT>(gp);
-}
-
-HCTR_DEVICE void fill_lookup_cache(const EmbParams& p, LookupCache* lc) {
-  for (int i = threadIdx.x; i < p.num_lookups && i < 256; i += blockDim.x) {
-    const EmbLookup lk = p.lookups[i];
-    lc->goff[i] = lk.grad_off;
-    lc->gstride[i] = lk.grad_stride;
-    lc->scale[i] = (lk.combiner == 1) ? (lk.nnz_off >= 0 ? -1.f : 1.f / static_cast<float>(max(lk.hotness, 1)))
-                                      : 1.f;
-  }
-  __syncthreads();
+HCTR_DEVICE const GradT* locate_grad(const EmbParams& p, unsigned int e) {
+  return reinterpret_cast<const GradT*>(p.grad[e >> 28]) + (static_cast<long long>(e & 0x0FFFFFFFu) << 2);
 }
 
 // G lanes per unique row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the row),
@@ -344,9 +323,6 @@ __global__ void __launch_bounds__(256)
     emb_bwd_reduce_update_kernel(const EmbParams p, const UniqueTable ut, const BwdIndex ix,
                                  StateT* __restrict__ s0, StateT* __restrict__ s1, const OptHyper hp,
                                  const float grad_scale) {
-  __shared__ LookupCache lc;
-  const bool cached = p.num_lookups <= 256;
-  if (cached) fill_lookup_cache(p, &lc);
   const unsigned int n = min(*ut.counter, ut.max_unique);
   const float lr = (hp.lr_ptr ? *hp.lr_ptr : 1.f) * hp.lr_scale;
   float bc1 = 1.f, bc2 = 1.f;
@@ -386,21 +362,25 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (unsigned int j = o0; j < o1; j += 4) {
-      unsigned int items[4];
+      const GradT* gptr[4];
+      float sc[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) items[u] = (j + u < o1) ? ix.bucket_list[j + u] : 0xFFFFFFFFu;
+      for (int u = 0; u < 4; ++u) {
+        gptr[u] = nullptr;
+        sc[u] = 0.f;
+        if (j + u < o1) {
+          gptr[u] = locate_grad<GradT>(p, ix.bucket_list[j + u]);
+          sc[u] = ix.bucket_scale ? ix.bucket_scale[j + u] : 1.f;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int col = (c * G + gl) * 4;
         if (col < ev) {
-          float sc[4];
           float4 g[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            sc[u] = 0.f;
-            g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (items[u] != 0xFFFFFFFFu) g[u] = load_bucket_grad<GradT>(p, &lc, cached, items[u], col, sc[u]);
-          }
+          for (int u = 0; u < 4; ++u)
+            g[u] = gptr[u] ? load_vec4<GradT>(gptr[u] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             acc[c].x += g[u].x * sc[u]; acc[c].y += g[u].y * sc[u];
@@ -465,8 +445,10 @@ __global__ void __launch_bounds__(256)
           float sc[4];
           float4 g[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            g[u] = load_bucket_grad<GradT>(p, nullptr, false, ix.bucket_list[j + 8 * u], col, sc[u]);
+          for (int u = 0; u < 4; ++u) {
+            g[u] = load_vec4<GradT>(locate_grad<GradT>(p, ix.bucket_list[j + 8 * u]) + col);
+            sc[u] = ix.bucket_scale ? ix.bucket_scale[j + 8 * u] : 1.f;
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             acc.x += g[u].x * sc[u]; acc.y += g[u].y * sc[u];
@@ -474,8 +456,8 @@ __global__ void __launch_bounds__(256)
           }
         }
         for (; j < o1; j += 8) {
-          float sc;
-          const float4 g = load_bucket_grad<GradT>(p, nullptr, false, ix.bucket_list[j], col, sc);
+          const float sc = ix.bucket_scale ? ix.bucket_scale[j] : 1.f;
+          const float4 g = load_vec4<GradT>(locate_grad<GradT>(p, ix.bucket_list[j]) + col);
           acc.x += g.x * sc; acc.y += g.y * sc; acc.z += g.z * sc; acc.w += g.w * sc;
         }
         *reinterpret_cast<float4*>(sm + warp * ev + col) = acc;

@@ -39,7 +39,6 @@ __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restric
         return;
       }
       const unsigned long long row = atomicAdd(t.counter, 1ull);
-      __threadfence();
       atomicExch(reinterpret_cast<unsigned long long*>(&t.vals[h]), row);
       out[i] = (static_cast<long long>(row) < t.max_rows) ? static_cast<long long>(row) : -1;
       return;

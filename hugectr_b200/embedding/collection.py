@@ -315,7 +315,8 @@ class EmbeddingCollection:
                     import os
                     grp.indexed = (dev.type == "cuda" and grp.pitch % 4 == 0
                                    and os.environ.get("HCTR_EMB_BWD", "indexed") == "indexed")
-                    grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev, indexed=grp.indexed)
+                    grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev, indexed=grp.indexed,
+                                               need_scale=any(l.combiner == 1 for l in grp.lookups))
                 else:
                     grp.dense_wgrad = torch.zeros(n, dtype=torch.float32, device=dev)
                     grp.ws = None
@@ -386,35 +387,52 @@ class EmbeddingCollection:
         self.key_slab[:feature_major_keys.numel()].copy_(feature_major_keys.reshape(-1), non_blocking=True)
 
     def forward(self, is_train: bool = True):
+        self.forward_begin()
+        self.forward_compute()
+        self.forward_end()
+
+    def forward_begin(self):
+        """every rank's keys are in place (fused mode: device-side barrier; collective: all-gather)"""
+        if self.world > 1:
+            if self.fused:
+                self.comm.barrier_device()
+            else:
+                self.comm.all_gather(self.keys_all, self.key_slab)
+
+    def forward_compute(self):
         b = self.b
         if self.world == 1:
             for grp in self.groups:
                 E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
-                          [self.out_slab], b)
+                          [self.out_slab], b, key_bytes=self._kb, act_bf16=self._abf)
         elif self.fused:
-            self.comm.barrier_device()           # every rank's keys are in place
             for grp in self.groups:
                 if grp.kind == "mp":
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
                               self.peer_out, b, self.rank, key_bytes=self._kb, act_bf16=self._abf)
                 else:
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
-                              [self.out_slab], b)
-            self.comm.barrier_device()           # every owner finished writing my outputs
+                              [self.out_slab], b, key_bytes=self._kb, act_bf16=self._abf)
         else:
-            self.comm.all_gather(self.keys_all, self.key_slab)
             self.send_out.zero_()
             for grp in self.groups:
                 if grp.kind == "mp":
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch,
                               list(self.keys_all.unbind(0)), list(self.send_out.unbind(0)), b, self.rank)
-            self.comm.all_to_all(self.recv_out, self.send_out)
-            # each (rank, lookup) region of my slab is written by exactly one owner -> sum == place
-            self.out_slab.copy_(self.recv_out.sum(0))
-            for grp in self.groups:
-                if grp.kind == "dp":
-                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
-                              [self.out_slab], b)
+
+    def forward_end(self):
+        b = self.b
+        if self.world > 1:
+            if self.fused:
+                self.comm.barrier_device()       # every owner finished writing my outputs
+            else:
+                self.comm.all_to_all(self.recv_out, self.send_out)
+                # each (rank, lookup) region of my slab is written by exactly one owner
+                self.out_slab.copy_(self.recv_out.sum(0))
+                for grp in self.groups:
+                    if grp.kind == "dp":
+                        E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
+                                  [self.out_slab], b)
         self._reduce_partials()
 
     def _reduce_partials(self):
@@ -428,30 +446,38 @@ class EmbeddingCollection:
                 full = self.out_slab[tp["off"]:tp["off"] + b * tp["width"]].view(b, tp["width"])
                 full[:, gl["col"]:gl["col"] + w] = part.float().sum(1).to(full.dtype)
 
+    def _bwd_bufs(self, grp):
+        if self.world == 1 or grp.kind == "dp":
+            return [self.key_slab], [self.grad_slab]
+        if self.fused:
+            return self.peer_keys, self.peer_grad
+        return list(self.keys_all.unbind(0)), list(self.grads_all.unbind(0))
+
+    def backward_index(self):
+        """gradient-independent part of the backward (unique rows + bucket lists); may run on a
+        side stream concurrently with the dense network once the keys are in place."""
+        for grp in self.groups:
+            if grp.kind == "mp" and getattr(grp, "indexed", False):
+                kb, _ = self._bwd_bufs(grp)
+                E.bwd_index(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, kb, self.b, grp.ws,
+                            self.rank, key_bytes=self._kb)
+        self._index_done = True
+
     def backward(self, lr_t, step_t):
         """Consumes top grads (grad slab), updates local tables. grads are already / global batch."""
-        b = self.b
-        if self.world == 1:
-            kb, gb = [self.key_slab], [self.grad_slab]
-            for grp in self.groups:
-                self._accum_update(grp, kb, gb, lr_t, step_t)
-            return
-        if self.fused:
-            self.comm.barrier_device()           # all top-grads are final
-            for grp in self.groups:
-                if grp.kind == "mp":
-                    self._accum_update(grp, self.peer_keys, self.peer_grad, lr_t, step_t)
-                else:
-                    self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
-            self.comm.barrier_device()           # keys / grads may now be overwritten
-            return
-        self.comm.all_gather(self.grads_all, self.grad_slab)
-        for grp in self.groups:
-            if grp.kind == "mp":
-                self._accum_update(grp, list(self.keys_all.unbind(0)), list(self.grads_all.unbind(0)),
-                                   lr_t, step_t)
+        if not getattr(self, "_index_done", False):
+            self.backward_index()
+        self._index_done = False
+        if self.world > 1:
+            if self.fused:
+                self.comm.barrier_device()           # all top-grads are final
             else:
-                self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
+                self.comm.all_gather(self.grads_all, self.grad_slab)
+        for grp in self.groups:
+            kb, gb = self._bwd_bufs(grp)
+            self._accum_update(grp, kb, gb, lr_t, step_t)
+        if self.world > 1 and self.fused:
+            self.comm.barrier_device()               # keys / grads may now be overwritten
 
     def _hp(self, o: OptParamsPy):
         return {"scaler": self.scaler, "beta1": o.beta1, "beta2": o.beta2, "epsilon": o.epsilon,
@@ -461,8 +487,6 @@ class EmbeddingCollection:
     def _accum_update(self, grp, key_bufs, grad_bufs, lr_t, step_t):
         o = grp.opt
         if grp.kind == "mp" and getattr(grp, "indexed", False):
-            E.bwd_index(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, self.b, grp.ws,
-                        self.rank, key_bytes=self._kb)
             E.bwd_reduce_update(o.optimizer_type, grp.lookups, grp.lookups_dev, grp.table, grp.s0,
                                 grp.s1, grp.pitch, key_bufs, grad_bufs, self.b, grp.ws, self._hp(o),
                                 lr_t, step_t, 1.0, self.rank, key_bytes=self._kb, act_bf16=self._abf)

@@ -47,7 +47,8 @@ class CUniqueTable(C.Structure):
 
 class CBwdIndex(C.Structure):
     _fields_ = [("count", C.c_void_p), ("offsets", C.c_void_p), ("block_sums", C.c_void_p),
-                ("pair_uid", C.c_void_p), ("bucket_list", C.c_void_p), ("heavy_items", C.c_void_p),
+                ("pair_uid", C.c_void_p), ("bucket_list", C.c_void_p), ("bucket_scale", C.c_void_p),
+                ("heavy_items", C.c_void_p),
                 ("heavy_count", C.c_void_p), ("heavy_scratch", C.c_void_p),
                 ("heavy_ticket", C.c_void_p), ("heavy_slot", C.c_void_p),
                 ("max_heavy_rows", C.c_uint), ("max_heavy_items", C.c_uint)]
@@ -194,7 +195,7 @@ class UniqueWorkspace:
     """Transient hash + fp32 per-unique-row gradient accumulator (device)."""
 
     def __init__(self, max_pairs: int, ev_pitch: int, device, unique_ratio: float = 1.0,
-                 indexed: bool = False):
+                 indexed: bool = False, need_scale: bool = False):
         self.device = device
         self.ev = ev_pitch
         self.max_unique = max(16, int(max_pairs * unique_ratio))
@@ -226,6 +227,7 @@ class UniqueWorkspace:
                 self.block_sums = torch.zeros((mu + 1023) // 1024 + 1, **i32)
                 self.pair_uid = torch.full((mp,), -1, **i32)
                 self.bucket_list = torch.zeros(mp, **i32)
+                self.bucket_scale = torch.ones(mp, dtype=torch.float32, device=device) if need_scale else None
                 self.max_heavy_rows = 8192
                 self.max_heavy_items = 65536
                 self.heavy_items = torch.zeros(2 * self.max_heavy_items, **i32)
@@ -236,7 +238,9 @@ class UniqueWorkspace:
                 self.heavy_ticket = torch.zeros(self.max_heavy_rows, **i32)
                 self.ix = CBwdIndex(self.count.data_ptr(), self.offsets.data_ptr(),
                                     self.block_sums.data_ptr(), self.pair_uid.data_ptr(),
-                                    self.bucket_list.data_ptr(), self.heavy_items.data_ptr(),
+                                    self.bucket_list.data_ptr(),
+                                    0 if self.bucket_scale is None else self.bucket_scale.data_ptr(),
+                                    self.heavy_items.data_ptr(),
                                     self.heavy_count.data_ptr(), self.heavy_scratch.data_ptr(),
                                     self.heavy_ticket.data_ptr(), self.heavy_slot.data_ptr(),
                                     self.max_heavy_rows, self.max_heavy_items)

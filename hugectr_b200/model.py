@@ -334,12 +334,49 @@ class Model:
         D.lr_step(self.step_t, self.lr_t, s.lr, s.end_lr, s.decay_power, s.warmup_steps,
                   s.decay_start, s.decay_steps)
         net = self.net_train
-        for e in self.ebcs_train:
-            e.forward(True)
-        for rt in self.legacy_train:
-            rt.forward(True)
-        net.fprop(True)
-        net.bprop()
+        overlap = (self.device.type == "cuda" and not self.legacy_train and self.ebcs_train
+                   and os.environ.get("HCTR_DISABLE_OVERLAP", "0") == "0"
+                   and (s.train_intra_iteration_overlap or True))
+        frozen_emb = self.embedding_frozen.get("*", False)
+        if overlap:
+            # intra-iteration overlap (reference model_pipeline.cpp:299-345): embedding forward and
+            # the backward index build run on side streams next to the bottom MLP; the embedding
+            # reduce+update runs next to bottom-MLP bprop / all-reduce / dense optimizer.
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_s_emb"):
+                self._s_emb, self._s_idx = torch.cuda.Stream(), torch.cuda.Stream()
+            s_emb, s_idx = self._s_emb, self._s_idx
+            for e in self.ebcs_train:
+                e.forward_begin()
+            s_emb.wait_stream(main)
+            s_idx.wait_stream(main)
+            with torch.cuda.stream(s_emb):
+                for e in self.ebcs_train:
+                    e.forward_compute()
+            if not frozen_emb:
+                with torch.cuda.stream(s_idx):
+                    for e in self.ebcs_train:
+                        e.backward_index()
+            net.fprop(True, "bottom")
+            main.wait_stream(s_emb)
+            for e in self.ebcs_train:
+                e.forward_end()
+            net.fprop(True, "top")
+            net.bprop("top")
+            main.wait_stream(s_idx)
+            if not frozen_emb:
+                s_emb.wait_stream(main)
+                with torch.cuda.stream(s_emb):
+                    for e in self.ebcs_train:
+                        e.backward(self.lr_t, self.step_t)
+            net.bprop("bottom")
+        else:
+            for e in self.ebcs_train:
+                e.forward(True)
+            for rt in self.legacy_train:
+                rt.forward(True)
+            net.fprop(True)
+            net.bprop()
         if not self.dense_frozen:
             self.exchange_wgrad.allreduce()
             D.dense_opt_step(DENSE_OPT_CODE[self.opt_params.optimizer_type], self.arena.weights,
@@ -347,12 +384,15 @@ class Model:
                              self.lr_t, self.step_t, self.dense_hp, zero_grad=True)
         else:
             self.arena.wgrad.zero_()
-        for e in self.ebcs_train:
-            if not self.embedding_frozen.get("*", False):
-                e.backward(self.lr_t, self.step_t)
-        for rt in self.legacy_train:
-            if not self.embedding_frozen.get(rt.name, self.embedding_frozen.get("*", False)):
-                rt.backward(self.lr_t, self.step_t)
+        if overlap:
+            torch.cuda.current_stream().wait_stream(self._s_emb)
+        else:
+            for e in self.ebcs_train:
+                if not frozen_emb:
+                    e.backward(self.lr_t, self.step_t)
+            for rt in self.legacy_train:
+                if not self.embedding_frozen.get(rt.name, frozen_emb):
+                    rt.backward(self.lr_t, self.step_t)
 
     def _run_step(self):
         use_graph = (self.solver.use_cuda_graph and self.device.type == "cuda"
@@ -381,19 +421,74 @@ class Model:
         self._graph.replay()
 
     def train(self) -> bool:
-        """One iteration on the next batch (Model::train, model.cpp:1048-1138)."""
+        """One iteration on the next batch (Model::train, model.cpp:1048-1138).
+
+        With train_inter_iteration_overlap on a GPU the H2D copy of batch i+1 runs on a copy stream
+        while step i executes (double-buffered staging; reference model_pipeline.cpp:370-418)."""
         if not self.reader_train.is_started():
             self.reader_train.start()
-        hb = self.reader_train.read_a_batch()
-        if hb is None:
-            return False
-        if self.reader_train.current_batch_incomplete() and self.solver.drop_incomplete_batch:
-            return True
-        self._load_batch(hb, True)
+        prefetch = (self.device.type == "cuda" and self.solver.train_inter_iteration_overlap
+                    and len(self.ebcs_train) == 1 and not self.legacy_train
+                    and os.environ.get("HCTR_DISABLE_PREFETCH", "0") == "0")
+        if not prefetch:
+            hb = self.reader_train.read_a_batch()
+            if hb is None:
+                return False
+            if self.reader_train.current_batch_incomplete() and self.solver.drop_incomplete_batch:
+                return True
+            self._load_batch(hb, True)
+        else:
+            if getattr(self, "_staged", None) is None:
+                hb = self.reader_train.read_a_batch()
+                if hb is None:
+                    return False
+                self._stage_batch(hb)
+            if self._staged == "eof":
+                self._staged = None
+                return False
+            self._commit_staged()
         self._run_step()
         self._iter += 1
         self.lr_sched.step = self._iter
+        if prefetch:
+            nxt = self.reader_train.read_a_batch()
+            if nxt is None:
+                self._staged = "eof"
+            elif self.reader_train.current_batch_incomplete() and self.solver.drop_incomplete_batch:
+                self._staged = None
+            else:
+                self._stage_batch(nxt)
         return True
+
+    def _stage_batch(self, hb: HostBatch):
+        """H2D of a batch into staging buffers on the copy stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            dev = self.device
+            self._stg = {"label": torch.empty_like(self.net_train.tensors[self.input.label_name].data),
+                         "dense": torch.empty_like(self.net_train.tensors[self.input.dense_name].data),
+                         "keys": torch.empty_like(self.ebcs_train[0].key_slab)}
+            self._stg_free = torch.cuda.Event()
+            self._stg_free.record()
+        cs = self._copy_stream
+        cs.wait_event(self._stg_free)           # previous D2D commit has consumed the staging area
+        with torch.cuda.stream(cs):
+            self._stg["label"].copy_(hb.label, non_blocking=True)
+            if self.input.dense_dim > 0:
+                self._stg["dense"].copy_(hb.dense, non_blocking=True)
+            self._stg["keys"][:hb.keys.numel()].copy_(hb.keys, non_blocking=True)
+        self._staged = hb
+
+    def _commit_staged(self):
+        main = torch.cuda.current_stream()
+        main.wait_stream(self._copy_stream)
+        net = self.net_train
+        net.tensors[self.input.label_name].data.copy_(self._stg["label"], non_blocking=True)
+        if self.input.dense_dim > 0:
+            net.tensors[self.input.dense_name].data.copy_(self._stg["dense"], non_blocking=True)
+        self.ebcs_train[0].key_slab.copy_(self._stg["keys"], non_blocking=True)
+        self._stg_free.record(main)
+        self._staged = None
 
     def train_on_host_batch(self, hb: HostBatch):
         self._load_batch(hb, True)

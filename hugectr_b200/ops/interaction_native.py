@@ -33,7 +33,7 @@ def available(mlp, emb, out) -> bool:
         return False
     _lib()
     n = emb.shape[1] + 1
-    return bool(_ok) and n <= 32 and mlp.shape[1] % 8 == 0 and mlp.shape[1] <= 128
+    return bool(_ok) and n <= 32 and mlp.shape[1] % 16 == 0 and mlp.shape[1] <= 128
 
 
 def fwd(mlp, emb, out):
