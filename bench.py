@@ -184,11 +184,18 @@ def main():
             "gpu_launches": int(launches_per_step * K),
             "gpu_launches_per_step": int(launches_per_step),
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    # orderly teardown: drop the captured graph (it references NCCL kernels and peer mappings) before
+    # the process group goes away, then leave without running interpreter finalizers that can block
+    # on IPC-mapped memory of ranks that are already gone
+    model._graph = None
+    torch.cuda.synchronize()
     if n > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
-    return 0
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

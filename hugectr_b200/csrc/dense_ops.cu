@@ -345,12 +345,23 @@ __global__ void ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* _
 // DCNv2 backward elementwise fusion for one cross layer (bf16, vectorised x8):
 //   dt  = dy * x0                       (input of the V^T dgrad GEMM)
 //   dx0 = (first ? 0 : dx0) + dy * t    (accumulated over layers)
+//   db += column sums of dt             (bias gradient, fused: no separate reduction pass)
+// grid = (column blocks of 256 threads x 8 columns, row splits); a thread owns 8 fixed columns and
+// walks its rows, so the bias partial sums stay in registers until one atomicAdd per column.
 __global__ void __launch_bounds__(256)
     cross_bwd_ew_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
                         const bf16* __restrict__ t, bf16* __restrict__ dt, float* __restrict__ dx0,
-                        long long n8, int first) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+                        float* __restrict__ db, int rows, int cols, int first) {
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;        // 8-column group
+  const int ngroups = cols >> 3;
+  if (c8 >= ngroups) return;
+  const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const long long i = static_cast<long long>(r) * ngroups + c8;
     const uint4 a = reinterpret_cast<const uint4*>(dy)[i];
     const uint4 b = reinterpret_cast<const uint4*>(x0)[i];
     const uint4 c = reinterpret_cast<const uint4*>(t)[i];
@@ -370,13 +381,21 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float d0 = bf16_lo(aw[q]), d1 = bf16_hi(aw[q]);
-      ow[q] = pack_bf16x2(d0 * bf16_lo(bw[q]), d1 * bf16_hi(bw[q]));
+      const float e0 = d0 * bf16_lo(bw[q]), e1 = d1 * bf16_hi(bw[q]);
+      ow[q] = pack_bf16x2(e0, e1);
+      // bias grad sums the bf16-rounded dt (what the GEMMs consume)
+      bsum[2 * q] += bf16_lo(ow[q]);
+      bsum[2 * q + 1] += bf16_hi(ow[q]);
       acc[2 * q] += d0 * bf16_lo(cw[q]);
       acc[2 * q + 1] += d1 * bf16_hi(cw[q]);
     }
     reinterpret_cast<uint4*>(dt)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     reinterpret_cast<float4*>(dx0)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     reinterpret_cast<float4*>(dx0)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  if (db != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(db + c8 * 8 + j, bsum[j]);
   }
 }
 // out(bf16) = a(bf16) + b(bf16) [+ c(fp32)]   (vectorised x8) : dxl = dy + dxl_gemm (+ dx0 on last)
@@ -523,10 +542,15 @@ extern "C" int hctr_elementwise(const void* a, const void* b, void* o, long long
 }
 
 extern "C" int hctr_cross_bwd_ew(const void* dy, const void* x0, const void* t, void* dt,
-                                 float* dx0, long long n, int first, void* stream) {
-  if (n % 8) return -2;
-  cross_bwd_ew_kernel<<<grid_for(n / 8, 256), 256, 0, ST(stream)>>>(
-      (const bf16*)dy, (const bf16*)x0, (const bf16*)t, (bf16*)dt, dx0, n / 8, first);
+                                 float* dx0, float* db, int rows, int cols, int first,
+                                 void* stream) {
+  if (cols % 8) return -2;
+  const int gx = (cols / 8 + 255) / 256;
+  int gy = (148 * 8) / gx;
+  if (gy > rows) gy = rows;
+  if (gy < 1) gy = 1;
+  cross_bwd_ew_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(
+      (const bf16*)dy, (const bf16*)x0, (const bf16*)t, (bf16*)dt, dx0, db, rows, cols, first);
   return OK();
 }
 

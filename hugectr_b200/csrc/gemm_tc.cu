@@ -56,7 +56,10 @@ struct SmemLayout {
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 align slack
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// MC == 2: thread-block cluster of two CTAs stacked along M that share the B tile -- each CTA loads
+// half of it and TMA-multicasts it into both shared memories (halves the L2->SM operand traffic of
+// B; the kernel is L2-bandwidth bound at CTR shapes, see profiles/).
+template <int BN, bool A_MN, bool B_MN, int MC>
 __global__ void __launch_bounds__(kNumThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmParams p) {
@@ -75,7 +78,13 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp_idx = threadIdx.x >> 5;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // work items are (m-group of MC tiles, n tile, k split); the CTAs of a cluster take the MC
+  // consecutive m tiles of one item
+  const int m_groups = (p.m_tiles + MC - 1) / MC;
+  const int total_tiles = m_groups * p.n_tiles * p.splits;
+  const int cta_rank = (MC > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = (MC > 1) ? (blockIdx.x / MC) : blockIdx.x;
+  const int num_clusters = (MC > 1) ? (gridDim.x / MC) : gridDim.x;
 
   if (warp_idx == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -84,7 +93,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   if (warp_idx == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MC);   // every CTA of the cluster must have drained the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -98,6 +107,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -106,10 +116,10 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const int n_blk = t % p.n_tiles;
-        const int m_blk = (t / p.n_tiles) % p.m_tiles;
-        const int split = t / (p.n_tiles * p.m_tiles);
+        const int m_blk = ((t / p.n_tiles) % m_groups) * MC + cta_rank;
+        const int split = t / (p.n_tiles * m_groups);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BN;
@@ -126,12 +136,29 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);
           }
-          if constexpr (B_MN) {
+          if constexpr (MC == 1) {
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(sb + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + c * 64, k0);
+            } else {
+              tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            }
           } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+            // this CTA fetches its 1/MC share of the B tile and multicasts it to the whole cluster
+            constexpr uint16_t kMask = (1u << MC) - 1;
+            if constexpr (B_MN) {
+              constexpr int kChunks = BN / 64 / MC;
+#pragma unroll
+              for (int c = 0; c < kChunks; ++c) {
+                const int cc = cta_rank * kChunks + c;
+                tma_load_2d_mc(sb + cc * (BLOCK_K * 128), &tmB, &full_bar[stage], n0 + cc * 64, k0, kMask);
+              }
+            } else {
+              constexpr int kRowsPer = BN / MC;
+              tma_load_2d_mc(sb + cta_rank * (kRowsPer * 128), &tmB, &full_bar[stage], k0,
+                             n0 + cta_rank * kRowsPer, kMask);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -148,8 +175,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int split = t / (p.n_tiles * p.m_tiles);
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      const int split = t / (p.n_tiles * m_groups);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -175,7 +202,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
                      b_desc + static_cast<uint64_t>(k * b_step), idesc,
                      (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                   // frees the smem slot
+          if constexpr (MC == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot
+          else umma_commit_mc(&empty_bar[stage], (1u << MC) - 1);  // ... in every CTA of the cluster
           if (kb == kb1 - 1) umma_commit(&tmem_full[as]);   // accumulator ready
         }
         __syncwarp();
@@ -196,9 +224,9 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     int as = 0;
     uint32_t aphase = 0;
     const int flags = p.flags;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int n_blk = t % p.n_tiles;
-      const int m_blk = (t / p.n_tiles) % p.m_tiles;
+      const int m_blk = ((t / p.n_tiles) % m_groups) * MC + cta_rank;
       const int m = m_blk * BLOCK_M + ew * 32 + lane;
       const bool row_ok = m < p.M;
       mbar_wait(&tmem_full[as], aphase);
@@ -342,6 +370,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -385,21 +414,35 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t inner, uint6
 
 static int g_num_sms = 0;
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MC>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                   cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MC>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) !=
         cudaSuccess)
       return -3;
     attr_set = true;
   }
-  const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  const int m_groups = (p.m_tiles + MC - 1) / MC;
+  const int total = m_groups * p.n_tiles * p.splits;       // cluster work items
+  int clusters = g_num_sms / MC;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * MC);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return -4;
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -423,6 +466,8 @@ extern "C" int hctr_gemm_bf16(const void* A, const void* B, void* out, int M, in
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int mc = (block_n >= 1000) ? 2 : 1;   // block_n = 1000 + BN selects the 2-CTA multicast kernel
+  if (block_n >= 1000) block_n -= 1000;
   const int BN = (block_n == 256 || block_n == 64) ? block_n : 128;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -446,19 +491,23 @@ extern "C" int hctr_gemm_bf16(const void* A, const void* B, void* out, int M, in
   else      rc = make_tmap_bf16(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
   if (rc) return rc;
   if (b_mn) rc = make_tmap_bf16(&tb, B, N, K, ldb, 64, BLOCK_K);
-  else      rc = make_tmap_bf16(&tb, B, K, N, ldb, BLOCK_K, BN);
+  else      rc = make_tmap_bf16(&tb, B, K, N, ldb, BLOCK_K, BN / mc);
   if (rc) return rc - 10;
 
-#define HCTR_DISPATCH(BNV)                                                        \
+#define HCTR_DISPATCH(BNV, MCV)                                                   \
   if (a_mn) {                                                                     \
-    if (b_mn) return launch<BNV, true, true>(ta, tb, p, stream);                  \
-    return launch<BNV, true, false>(ta, tb, p, stream);                           \
+    if (b_mn) return launch<BNV, true, true, MCV>(ta, tb, p, stream);             \
+    return launch<BNV, true, false, MCV>(ta, tb, p, stream);                      \
   } else {                                                                        \
-    if (b_mn) return launch<BNV, false, true>(ta, tb, p, stream);                 \
-    return launch<BNV, false, false>(ta, tb, p, stream);                          \
+    if (b_mn) return launch<BNV, false, true, MCV>(ta, tb, p, stream);            \
+    return launch<BNV, false, false, MCV>(ta, tb, p, stream);                     \
   }
-  if (BN == 256) { HCTR_DISPATCH(256) }
-  if (BN == 64) { HCTR_DISPATCH(64) }
-  HCTR_DISPATCH(128)
+  if (mc == 2) {
+    if (BN == 256) { HCTR_DISPATCH(256, 2) }
+    HCTR_DISPATCH(128, 2)
+  }
+  if (BN == 256) { HCTR_DISPATCH(256, 1) }
+  if (BN == 64) { HCTR_DISPATCH(64, 1) }
+  HCTR_DISPATCH(128, 1)
 #undef HCTR_DISPATCH
 }

@@ -109,8 +109,7 @@ class MultiCrossLayer(Layer):
         for l in range(L - 1, -1, -1):
             xl = self._xl(l)
             first = (l == L - 1)
-            D.cross_bwd_ew(dy, x0, self.T[l], self.dT, self.dx0, first)
-            D.colsum_accum(self.dT, self.Bv[l].g.reshape(-1))
+            D.cross_bwd_ew(dy, x0, self.T[l], self.dT, self.dx0, first, self.Bv[l].g.reshape(-1))
             # dV += H^T dT
             G.gemm_bf16(self.H[l], self.dT, self.V[l].g, a_mn=True, b_mn=True,
                         flags=G.EPI_ATOMIC, splits=2)

@@ -81,6 +81,31 @@ def gemm_reference(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, 
     return out
 
 
+_bn_override = {}
+
+
+def _pick_block_n(M, N, K, splits):
+    """Tile / cluster choice.  1000 + BN selects the 2-CTA cluster kernel that multicasts the B tile
+    (halves the L2->SM traffic of B; the GEMM is L2-bandwidth bound at these shapes)."""
+    import os
+    ov = os.environ.get("HCTR_GEMM_BN")
+    if ov:
+        return int(ov)
+    if N <= 64:
+        return 64
+    m_t = (M + 127) // 128
+    # Measured on B200 (profiles/gemm_microbench.md): the single-CTA kernel is bound by shared-memory
+    # bandwidth (UMMA operand reads + TMA writes), so BN=256 (1.33x fewer smem bytes per MAC) wins
+    # whenever it does not lose a wave to quantisation; the cluster-multicast variant (1000+BN)
+    # relieves L2 only and is not selected automatically.
+    def waves(bn):
+        items = m_t * ((N + bn - 1) // bn) * max(1, splits)
+        return (items + 147) // 148
+    if N >= 256 and waves(256) * 2 * 0.75 < waves(128):
+        return 256
+    return 128
+
+
 def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
               aux=None, alpha=1.0, flags=0, splits=1, block_n=0):
     """out[M,N] = epilogue(alpha * op(a) @ op(b)).
@@ -98,9 +123,7 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
     if splits > 1:
         flags |= EPI_ATOMIC
     if block_n == 0:
-        block_n = 256 if (N % 256 == 0 and (M // 128) * (N // 256) >= 120) else 128
-        if N <= 64:
-            block_n = 64
+        block_n = _pick_block_n(M, N, K, splits)
     stream = torch.cuda.current_stream(a.device).cuda_stream
     rc = _lib().hctr_gemm_bf16(
         a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),

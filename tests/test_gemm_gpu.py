@@ -24,7 +24,7 @@ def test_gemm_majors(a_mn, b_mn, M, N, K):
     assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256, 1128, 1256])
 def test_gemm_bias_relu(bn):
     torch.manual_seed(1)
     M, N, K = 1024, 512, 256
@@ -69,3 +69,17 @@ def test_gemm_cross_epilogue():
                            flags=G.EPI_CROSS | G.EPI_OUT_F32)
     assert (aux.float() - aux_ref).abs().max().item() <= 2e-2 * aux_ref.abs().max().item() + 1e-2
     assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 2e-2
+
+
+@pytest.mark.parametrize("bn", [1128, 1256])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(6912, 1024, 512), (1000, 328, 136), (384, 512, 3456)])
+def test_gemm_cluster_multicast(bn, a_mn, b_mn, M, N, K):
+    torch.manual_seed(0)
+    a = _mk((K, M) if a_mn else (M, K), 0.5)
+    b = _mk((K, N) if b_mn else (N, K), 0.5)
+    out = G.gemm_bf16(a, b, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+    ref = G.gemm_reference(a, b, a_mn, b_mn, flags=G.EPI_OUT_F32)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
