@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny tables (debug only; not a valid number)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--plan", default="auto")
+    ap.add_argument("--profile", default="", help="dump a torch.profiler kernel table (rank 0) here")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -117,6 +118,18 @@ def main():
     sync_all()
     launches_per_step = model.launches_per_step
 
+    if args.profile:
+        # kernel-level breakdown with CUPTI (never used for reported numbers)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(5):
+                model._run_step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            os.makedirs(os.path.dirname(args.profile) or ".", exist_ok=True)
+            with open(args.profile, "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60,
+                                                  max_name_column_width=90))
     # ---------------- device-timed steps: inputs pre-staged on device, exactly K steps
     K = args.steps
     stop_evt, samples = threading.Event(), []

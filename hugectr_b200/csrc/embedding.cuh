@@ -42,6 +42,10 @@ struct EmbParams {
   int ev_size;                   // row pitch of the arena (all tables of a group share it)
 };
 
+struct PeerStage {
+  void* dst[kMaxRanks];
+};
+
 struct UniqueTable {
   unsigned long long* keys;  // [capacity] hash keys (arena row index)
   unsigned int* vals;        // [capacity] compact unique id

@@ -355,6 +355,11 @@ class EmbeddingCollection:
             self.peer_keys = self.comm.peer_ptrs(self.key_slab)
             self.peer_out = self.comm.peer_ptrs(self.out_slab)
             self.peer_grad = self.comm.peer_ptrs(self.grad_slab) if self.is_train else None
+            if self.is_train:
+                # local staging slabs (same layout as a peer's grad slab); own slot aliases my slab
+                self.grad_stage = [self.grad_slab if r == self.rank else
+                                   torch.zeros(max(self.top_slab_elems, 1), dtype=self.act_dtype, device=dev)
+                                   for r in range(self.world)]
         elif self.world > 1:
             self.keys_all = torch.zeros(self.world, max(self.key_slab_elems, 1),
                                         dtype=self.key_dtype, device=dev)
@@ -450,8 +455,13 @@ class EmbeddingCollection:
         if self.world == 1 or grp.kind == "dp":
             return [self.key_slab], [self.grad_slab]
         if self.fused:
-            return self.peer_keys, self.peer_grad
+            return self.peer_keys, (self.grad_stage if self._stage_ok(grp) else self.peer_grad)
         return list(self.keys_all.unbind(0)), list(self.grads_all.unbind(0))
+
+    def _stage_ok(self, grp) -> bool:
+        esz = 2 if self._abf else 4
+        return (grp.pitch * esz) % 16 == 0 and all((l.grad_off * esz) % 16 == 0 and
+                                                   (l.grad_stride * esz) % 16 == 0 for l in grp.lookups)
 
     def backward_index(self):
         """gradient-independent part of the backward (unique rows + bucket lists); may run on a
@@ -471,6 +481,11 @@ class EmbeddingCollection:
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()           # all top-grads are final
+                for grp in self.groups:              # backward "all-to-all": bulk peer loads
+                    if grp.kind == "mp" and grp.lookups and self._stage_ok(grp):
+                        E.pull_grads(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
+                                     self.peer_grad, self.grad_stage, self.b, self.rank,
+                                     key_bytes=self._kb, act_bf16=self._abf)
             else:
                 self.comm.all_gather(self.grads_all, self.grad_slab)
         for grp in self.groups:

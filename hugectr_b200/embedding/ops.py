@@ -80,6 +80,8 @@ def lib():
         l.hctr_emb_bwd_reduce_update.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable),
                                                  C.POINTER(CBwdIndex), vp, vp, i, i,
                                                  C.POINTER(COptHyper), f, i, vp, i, vp]
+        l.hctr_emb_pull_grads.argtypes = [C.POINTER(CEmbParams), C.POINTER(vp), i, vp]
+        l.hctr_emb_pull_grads.restype = i
         for n in ("hctr_emb_forward", "hctr_emb_backward_accum", "hctr_emb_update",
                   "hctr_emb_gather_rows", "hctr_emb_bwd_index", "hctr_emb_bwd_reduce_update"):
             getattr(l, n).restype = i
@@ -458,3 +460,16 @@ def bwd_reduce_update(opt: Optimizer_t, lookups, lookups_dev, table, s0, s1, ev_
     if rc:
         raise RuntimeError(f"hctr_emb_bwd_reduce_update failed rc={rc}")
     D._count(3)
+
+
+def pull_grads(lookups, lookups_dev, table, ev_pitch, key_bufs, peer_grad_ptrs, stage_tensors, batch,
+               my_rank, key_bytes=4, act_bf16=True):
+    """Copy the gradient rows of this rank's lookups from every peer's grad slab into local staging
+    slabs (same layout) with coalesced peer loads."""
+    p, _, gbf = _fill_params(lookups, lookups_dev, table, ev_pitch, key_bufs, peer_grad_ptrs, batch,
+                             my_rank, None, key_bytes, act_bf16)
+    arr = (C.c_void_p * len(stage_tensors))(*[t.data_ptr() for t in stage_tensors])
+    rc = lib().hctr_emb_pull_grads(C.byref(p), arr, gbf, _st(table.device))
+    if rc:
+        raise RuntimeError("hctr_emb_pull_grads failed")
+    D._count()

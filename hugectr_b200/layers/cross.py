@@ -118,15 +118,16 @@ class MultiCrossLayer(Layer):
             # dU += x_l^T dH
             G.gemm_bf16(xl, self.dH, self.U[l].g, a_mn=True, b_mn=True, flags=G.EPI_ATOMIC,
                         splits=2)
-            # dx_l (through U) = dH U^T  (B operand [N=w, K=p] K-major == U row-major)
-            G.gemm_bf16(self.dH, self.U[l].compute(self.mixed), self.dXg)
+            # dx_l = dH U^T + dy (+ dx0 on the first layer): the residual adds ride in the GEMM
+            # epilogue (B operand [N=w, K=p] K-major == U row-major)
             if l == 0:
                 out = self.inputs[0].grad
                 if out is not None:
-                    D.add3(dy, self.dXg, self.dx0, out)
+                    G.gemm_bf16(self.dH, self.U[l].compute(self.mixed), out, xl=dy, addf=self.dx0,
+                                flags=G.EPI_ADD)
             else:
                 out = self.dX[l & 1]
-                D.add3(dy, self.dXg, None, out)
+                G.gemm_bf16(self.dH, self.U[l].compute(self.mixed), out, xl=dy, flags=G.EPI_ADD)
                 dy = out
 
     def _bprop_v1(self):

@@ -20,6 +20,7 @@ EPI_ACCUM = 8
 EPI_CROSS = 16
 EPI_MASK = 32
 EPI_SIGMOID = 64
+EPI_ADD = 128
 
 _c = ctypes
 _sig_set = False
@@ -34,7 +35,10 @@ def _lib():
             _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
             _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_int,
             _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_void_p, _c.c_longlong,
-            _c.c_void_p, _c.c_longlong, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]
+            _c.c_void_p, _c.c_longlong, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+            _c.c_longlong, _c.c_void_p]
+        lib.hctr_gemm_bf16_2sm.restype = _c.c_int
+        lib.hctr_gemm_bf16_2sm.argtypes = lib.hctr_gemm_bf16.argtypes
         _sig_set = True
     return lib
 
@@ -54,7 +58,7 @@ def tc_eligible(a: torch.Tensor, b: torch.Tensor, a_mn: bool, b_mn: bool) -> boo
 
 
 def gemm_reference(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
-                   alpha=1.0, flags=0, out=None, aux=None):
+                   alpha=1.0, flags=0, out=None, aux=None, addf=None):
     """fp32 PyTorch oracle with the same epilogue semantics as the kernel."""
     A = a.float().t() if a_mn else a.float()          # [M, K]
     B = b.float() if b_mn else b.float().t()          # [K, N]
@@ -65,6 +69,10 @@ def gemm_reference(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, 
         if aux is not None:
             aux.copy_(v.to(aux.dtype))
         v = x0.float() * v + xl.float()
+    if flags & EPI_ADD:
+        v = v + xl.float()
+        if addf is not None:
+            v = v + addf.float()
     if flags & EPI_MASK:
         v = v * (mask.float() > 0)
     if flags & EPI_RELU:
@@ -101,13 +109,13 @@ def _pick_block_n(M, N, K, splits):
     def waves(bn):
         items = m_t * ((N + bn - 1) // bn) * max(1, splits)
         return (items + 147) // 148
-    if N >= 256 and waves(256) * 2 * 0.75 < waves(128):
+    if N >= 256 and waves(256) * 2 * 0.85 < waves(128):
         return 256
     return 128
 
 
 def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
-              aux=None, alpha=1.0, flags=0, splits=1, block_n=0):
+              aux=None, alpha=1.0, flags=0, splits=1, block_n=0, addf=None):
     """out[M,N] = epilogue(alpha * op(a) @ op(b)).
 
     a: ``[M,K]`` (K-major) or ``[K,M]`` when ``a_mn``;  b: ``[N,K]`` or ``[K,N]`` when ``b_mn``.
@@ -119,18 +127,23 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else a.dtype)
     if not tc_eligible(a, b, a_mn, b_mn) or out.stride(1) != 1:
-        return gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux)
+        return gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux, addf)
     if splits > 1:
         flags |= EPI_ATOMIC
     if block_n == 0:
         block_n = _pick_block_n(M, N, K, splits)
     stream = torch.cuda.current_stream(a.device).cuda_stream
-    rc = _lib().hctr_gemm_bf16(
+    fn = _lib().hctr_gemm_bf16
+    if block_n >= 2000:           # 2000 + BN : cta_group::2 kernel (CTA pair, 256 x BN tile)
+        fn = _lib().hctr_gemm_bf16_2sm
+        block_n -= 2000
+    rc = fn(
         a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
         out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(mask),
         0 if mask is None else mask.stride(0), _ptr(x0), _ptr(xl),
-        0 if x0 is None else x0.stride(0), _ptr(aux), 0 if aux is None else aux.stride(0),
-        float(alpha), int(flags), int(splits), int(block_n), stream)
+        0 if xl is None else xl.stride(0), _ptr(aux), 0 if aux is None else aux.stride(0),
+        float(alpha), int(flags), int(splits), int(block_n), _ptr(addf),
+        0 if addf is None else addf.stride(0), stream)
     if rc != 0:
         raise RuntimeError(f"hctr_gemm_bf16 failed rc={rc} M={M} N={N} K={K}")
     return out

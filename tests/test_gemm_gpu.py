@@ -24,7 +24,7 @@ def test_gemm_majors(a_mn, b_mn, M, N, K):
     assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256, 1128, 1256])
+@pytest.mark.parametrize("bn", [64, 128, 256, 1128, 1256, 2128, 2256])
 def test_gemm_bias_relu(bn):
     torch.manual_seed(1)
     M, N, K = 1024, 512, 256
@@ -71,8 +71,8 @@ def test_gemm_cross_epilogue():
     assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 2e-2
 
 
-@pytest.mark.parametrize("bn", [1128, 1256])
-@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("bn", [1128, 1256, 2128, 2256])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(6912, 1024, 512), (1000, 328, 136), (384, 512, 3456)])
 def test_gemm_cluster_multicast(bn, a_mn, b_mn, M, N, K):
     torch.manual_seed(0)

@@ -23,7 +23,7 @@ for (M, N, K, tag) in [(b,1024,3456,"top0"),(b,1024,1024,"top1"),(b,512,1024,"to
                        (8192,8192,8192,"sq8k")]:
     a = torch.randn(M, K, device="cuda").bfloat16(); w = torch.randn(K, N, device="cuda").bfloat16() * 0.05
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    for bn in (128, 256, 1128, 1256):
+    for bn in (128, 256, 2128, 2256):
         t = timeit(lambda: G.gemm_bf16(a, w, out, b_mn=True, block_n=bn))
         res.append(dict(tag=tag, M=M, N=N, K=K, bn=bn, ms=t, tflops=2*M*N*K/t/1e9))
     t = timeit(lambda: torch.matmul(a, w, out=out))
@@ -32,7 +32,7 @@ for (M, N, K, tag) in [(b,1024,3456,"top0"),(b,1024,1024,"top1"),(b,512,1024,"to
     dy = torch.randn(M, N, device="cuda").bfloat16()
     dw = torch.zeros(K, N, device="cuda")
     for sp in (1, 2, 4):
-        for bn in (128, 1128, 1256):
+        for bn in (128, 2128, 2256):
             t = timeit(lambda: G.gemm_bf16(a, dy, dw, a_mn=True, b_mn=True, flags=G.EPI_ATOMIC, splits=sp, block_n=bn))
             res.append(dict(tag=tag+"_wgrad", M=K, N=N, K=M, bn=f"split{sp}_bn{bn}", ms=t, tflops=2*M*N*K/t/1e9))
     t = timeit(lambda: torch.matmul(a.t(), dy))
