@@ -360,38 +360,54 @@ __global__ void __launch_bounds__(256)
   float bsum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const long long i = static_cast<long long>(r) * ngroups + c8;
-    const uint4 a = reinterpret_cast<const uint4*>(dy)[i];
-    const uint4 b = reinterpret_cast<const uint4*>(x0)[i];
-    const uint4 c = reinterpret_cast<const uint4*>(t)[i];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w},
-                   cw[4] = {c.x, c.y, c.z, c.w};
-    uint32_t ow[4];
-    float acc[8];
-    if (!first) {
-      const float4 p0 = reinterpret_cast<const float4*>(dx0)[2 * i];
-      const float4 p1 = reinterpret_cast<const float4*>(dx0)[2 * i + 1];
-      acc[0] = p0.x; acc[1] = p0.y; acc[2] = p0.z; acc[3] = p0.w;
-      acc[4] = p1.x; acc[5] = p1.y; acc[6] = p1.z; acc[7] = p1.w;
-    } else {
+  constexpr int NR = 4;   // rows in flight per thread: 4 x (3 x 16 B + 2 x 16 B) loads issued together
+  for (int rb = r0; rb < r1; rb += NR) {
+    uint4 a[NR], b[NR], c[NR];
+    float4 p0[NR], p1[NR];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int u = 0; u < NR; ++u) {
+      const int r = rb + u;
+      if (r < r1) {
+        const long long i = static_cast<long long>(r) * ngroups + c8;
+        a[u] = reinterpret_cast<const uint4*>(dy)[i];
+        b[u] = reinterpret_cast<const uint4*>(x0)[i];
+        c[u] = reinterpret_cast<const uint4*>(t)[i];
+        if (!first) {
+          p0[u] = reinterpret_cast<const float4*>(dx0)[2 * i];
+          p1[u] = reinterpret_cast<const float4*>(dx0)[2 * i + 1];
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float d0 = bf16_lo(aw[q]), d1 = bf16_hi(aw[q]);
-      const float e0 = d0 * bf16_lo(bw[q]), e1 = d1 * bf16_hi(bw[q]);
-      ow[q] = pack_bf16x2(e0, e1);
-      // bias grad sums the bf16-rounded dt (what the GEMMs consume)
-      bsum[2 * q] += bf16_lo(ow[q]);
-      bsum[2 * q + 1] += bf16_hi(ow[q]);
-      acc[2 * q] += d0 * bf16_lo(cw[q]);
-      acc[2 * q + 1] += d1 * bf16_hi(cw[q]);
+    for (int u = 0; u < NR; ++u) {
+      const int r = rb + u;
+      if (r >= r1) continue;
+      const long long i = static_cast<long long>(r) * ngroups + c8;
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bw[4] = {b[u].x, b[u].y, b[u].z, b[u].w},
+                     cw[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+      uint32_t ow[4];
+      float acc[8];
+      if (!first) {
+        acc[0] = p0[u].x; acc[1] = p0[u].y; acc[2] = p0[u].z; acc[3] = p0[u].w;
+        acc[4] = p1[u].x; acc[5] = p1[u].y; acc[6] = p1[u].z; acc[7] = p1[u].w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float d0 = bf16_lo(aw[q]), d1 = bf16_hi(aw[q]);
+        const float e0 = d0 * bf16_lo(bw[q]), e1 = d1 * bf16_hi(bw[q]);
+        ow[q] = pack_bf16x2(e0, e1);
+        bsum[2 * q] += bf16_lo(ow[q]);       // bias grad sums the bf16-rounded dt (what the GEMMs consume)
+        bsum[2 * q + 1] += bf16_hi(ow[q]);
+        acc[2 * q] += d0 * bf16_lo(cw[q]);
+        acc[2 * q + 1] += d1 * bf16_hi(cw[q]);
+      }
+      reinterpret_cast<uint4*>(dt)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      reinterpret_cast<float4*>(dx0)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      reinterpret_cast<float4*>(dx0)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
-    reinterpret_cast<uint4*>(dt)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    reinterpret_cast<float4*>(dx0)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    reinterpret_cast<float4*>(dx0)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   if (db != nullptr) {
 #pragma unroll

@@ -241,10 +241,7 @@ __global__ void __launch_bounds__(256)
         float4 g = *reinterpret_cast<float4*>(gsrc + col);
         *reinterpret_cast<float4*>(gsrc + col) = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 w = *reinterpret_cast<float4*>(table + base + col);
-        apply_opt<OPT, StateT>(w.x, g.x * inv_scaler, s0, s1, base + col, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.y, g.y * inv_scaler, s0, s1, base + col + 1, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.z, g.z * inv_scaler, s0, s1, base + col + 2, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.w, g.w * inv_scaler, s0, s1, base + col + 3, hp, lr, bc1, bc2);
+        apply_opt4<OPT, StateT>(w, make_float4(g.x * inv_scaler, g.y * inv_scaler, g.z * inv_scaler, g.w * inv_scaler), s0, s1, base + col, hp, lr, bc1, bc2);
         *reinterpret_cast<float4*>(table + base + col) = w;
       }
     } else {

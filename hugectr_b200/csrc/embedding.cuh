@@ -184,4 +184,35 @@ HCTR_DEVICE void apply_opt(float& w, float g, StateT* s0, StateT* s1, long long 
   }
 }
 
+
+// 4-wide variant: optimizer state is loaded / stored as one vector (16 B fp32, 8 B bf16) instead of
+// four scalar accesses per lane.
+template <int OPT, typename StateT>
+HCTR_DEVICE void apply_opt4(float4& w, const float4 g, StateT* s0, StateT* s1, long long idx,
+                            const OptHyper& hp, float lr, float bc1, float bc2) {
+  constexpr bool kHasS0 = (OPT != OPT_SGD);
+  constexpr bool kHasS1 = (OPT == OPT_ADAM || OPT == OPT_FTRL);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if constexpr (kHasS0) {
+    const float4 v = load_vec4<StateT>(s0 + idx);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+  }
+  if constexpr (kHasS1) {
+    const float4 v = load_vec4<StateT>(s1 + idx);
+    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+  }
+  float ww[4] = {w.x, w.y, w.z, w.w};
+  const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    // run the scalar rule on local copies of the state
+    float sa = a[j], sb = b[j];
+    apply_opt<OPT, float>(ww[j], gg[j], &sa, &sb, 0, hp, lr, bc1, bc2);
+    a[j] = sa; b[j] = sb;
+  }
+  w = make_float4(ww[0], ww[1], ww[2], ww[3]);
+  if constexpr (kHasS0) store_vec4<StateT>(s0 + idx, a[0], a[1], a[2], a[3]);
+  if constexpr (kHasS1) store_vec4<StateT>(s1 + idx, b[0], b[1], b[2], b[3]);
+}
+
 }  // namespace hctr

@@ -394,10 +394,7 @@ __global__ void __launch_bounds__(256)
       const int col = (c * G + gl) * 4;
       if (col < ev) {
         float4 w = *reinterpret_cast<float4*>(p.table + base + col);
-        apply_opt<OPT, StateT>(w.x, acc[c].x * inv_scaler, s0, s1, base + col, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.y, acc[c].y * inv_scaler, s0, s1, base + col + 1, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.z, acc[c].z * inv_scaler, s0, s1, base + col + 2, hp, lr, bc1, bc2);
-        apply_opt<OPT, StateT>(w.w, acc[c].w * inv_scaler, s0, s1, base + col + 3, hp, lr, bc1, bc2);
+        apply_opt4<OPT, StateT>(w, make_float4(acc[c].x * inv_scaler, acc[c].y * inv_scaler, acc[c].z * inv_scaler, acc[c].w * inv_scaler), s0, s1, base + col, hp, lr, bc1, bc2);
         *reinterpret_cast<float4*>(p.table + base + col) = w;
       }
     }

@@ -102,16 +102,17 @@ def _pick_block_n(M, N, K, splits):
     if N <= 64:
         return 64
     m_t = (M + 127) // 128
-    # Measured on B200 (profiles/gemm_microbench.md): the single-CTA kernel is bound by shared-memory
-    # bandwidth (UMMA operand reads + TMA writes), so BN=256 (1.33x fewer smem bytes per MAC) wins
-    # whenever it does not lose a wave to quantisation; the cluster-multicast variant (1000+BN)
-    # relieves L2 only and is not selected automatically.
+    if m_t < 2:
+        return 128
+    # Measured on B200 (profiles/gemm_microbench_*.jsonl): the cta_group::2 kernel (2000 + BN, one
+    # 256 x BN UMMA per CTA pair) beats the 1-SM kernel on every DLRM shape; the 256-wide pair tile
+    # is ~12 % more efficient per MAC but loses when it costs an extra wave.
     def waves(bn):
-        items = m_t * ((N + bn - 1) // bn) * max(1, splits)
-        return (items + 147) // 148
-    if N >= 256 and waves(256) * 2 * 0.85 < waves(128):
-        return 256
-    return 128
+        items = ((m_t + 1) // 2) * ((N + bn - 1) // bn) * max(1, splits)
+        return (items + 73) // 74
+    if N >= 256 and waves(256) * 2 * 0.88 <= waves(128):
+        return 2256
+    return 2128
 
 
 def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
