@@ -130,6 +130,17 @@ def main():
             with open(args.profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60,
                                                   max_name_column_width=90))
+            # compact per-stream timeline (start us, dur us, stream, kernel) for overlap analysis
+            evs = []
+            for e in prof.events():
+                if str(e.device_type).endswith("CUDA"):
+                    tr = e.time_range
+                    evs.append((tr.start, tr.end - tr.start, getattr(e, "device_resource_id", -1), e.name[:70]))
+            evs.sort()
+            t0 = evs[0][0] if evs else 0
+            with open(args.profile + ".timeline", "w") as f:
+                for st, du, sid, nm in evs:
+                    f.write(f"{st - t0:10.1f} {du:8.1f} {sid} {nm}\n")
     # ---------------- device-timed steps: inputs pre-staged on device, exactly K steps
     K = args.steps
     stop_evt, samples = threading.Event(), []

@@ -318,7 +318,15 @@ class EmbeddingCollection:
                     grp.ws = E.UniqueWorkspace(max(pairs, 1), grp.pitch, dev, indexed=grp.indexed,
                                                need_scale=any(l.combiner == 1 for l in grp.lookups))
                 else:
-                    grp.dense_wgrad = torch.zeros(n, dtype=torch.float32, device=dev)
+                    n_pad = (n + 4 * self.world - 1) // (4 * self.world) * (4 * self.world)
+                    if self.fused and self.world > 1:
+                        from ..parallel.p2p import P2PAllReduce
+                        grp.dense_wgrad_full = self.comm.symm_alloc(n_pad, torch.float32)
+                        grp.p2p_ar = P2PAllReduce(self.comm, grp.dense_wgrad_full, blocks=32)
+                    else:
+                        grp.dense_wgrad_full = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+                        grp.p2p_ar = None
+                    grp.dense_wgrad = grp.dense_wgrad_full[:n]
                     grp.ws = None
 
     def _init_group(self, grp, gen, seed):
@@ -515,7 +523,10 @@ class EmbeddingCollection:
             E.backward_accum(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, grad_bufs,
                              self.b, None, 1.0, self.rank, dense_wgrad=grp.dense_wgrad)
             if self.world > 1:
-                self.comm.all_reduce(grp.dense_wgrad)
+                if grp.p2p_ar is not None:
+                    grp.p2p_ar.run()
+                else:
+                    self.comm.all_reduce(grp.dense_wgrad)
             dcode = {Optimizer_t.SGD: D.D_SGD, Optimizer_t.AdaGrad: D.D_ADAGRAD,
                      Optimizer_t.Adam: D.D_ADAM, Optimizer_t.Ftrl: D.D_FTRL,
                      Optimizer_t.MomentumSGD: D.D_MOMENTUM, Optimizer_t.Nesterov: D.D_NESTEROV,

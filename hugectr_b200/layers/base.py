@@ -100,11 +100,14 @@ class ParamArena:
     def flat_size(self) -> int:
         return self._size
 
-    def finalize(self, device, mixed: bool, pad_to: int = 1):
+    def finalize(self, device, mixed: bool, pad_to: int = 1, wgrad_alloc=None):
+        """``wgrad_alloc(numel, dtype)``: optional allocator for the gradient buffer (the symmetric
+        peer-mapped heap when the P2P all-reduce is used)."""
         n = max(self._size, 1)
         n = (n + pad_to - 1) // pad_to * pad_to  # model_compile.cpp:853-869 pads wgrad to 16*N bytes
         self.weights = torch.zeros(n, dtype=torch.float32, device=device)
-        self.wgrad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.wgrad = (wgrad_alloc(n, torch.float32) if wgrad_alloc is not None
+                      else torch.zeros(n, dtype=torch.float32, device=device))
         self.weights16 = torch.zeros(n, dtype=torch.bfloat16, device=device) if mixed else None
         for p in self.params:
             p.w = self.weights[p.offset:p.offset + p.numel].view(p.shape)

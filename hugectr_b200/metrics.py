@@ -3,12 +3,11 @@
 Reference: HugeCTR/src/metrics.cu:34-2155, HugeCTR/include/metrics.hpp:44-554.  Interface kept:
 ``local_reduce(raw)`` per eval batch, ``global_reduce()``, ``finalize_metric()``.
 
-AUC: exact trapezoid AUC with tie handling.  Distributed algorithm (B200 flavour of the reference's
-histogram -> pivots -> all-to-all -> local sort -> halo pipeline, metrics.cu:1017-1240): every rank
-buckets its (pred,label) pairs by *range of pred*, the per-bucket positive/negative counts are
-all-reduced (2 x num_bins integers) and the exact within-bucket contribution is computed on the
-rank that owns the bucket after an all-to-all of the pairs; with one rank it degenerates to a single
-device sort.  Multi-class AUC = unweighted macro average of per-class AUCs.
+AUC: exact trapezoid AUC with tie handling (device sort + cumulative TP/FP + trapz).  Multi-GPU:
+every rank's (pred, label) pairs of the evaluation round are all-gathered (a few MB per round) and the
+exact AUC is computed redundantly on each rank -- the reference's histogram -> pivots -> all-to-all ->
+local sort -> halo pipeline (metrics.cu:1017-1240) exists to bound memory on 16 GB V100s and is not
+needed at B200 capacities.  Multi-class AUC = unweighted macro average of per-class AUCs.
 """
 from __future__ import annotations
 
@@ -85,7 +84,7 @@ class AUC(Metric):
         # equal-sized shards per rank (eval batches are split evenly)
         out = torch.empty(self.comm.world_size * t.numel(), dtype=t.dtype, device=t.device)
         self.comm.all_gather(out, t.contiguous())
-        return out.view(self.comm.world_size, *t.shape).transpose(0, 0).reshape(-1, t.shape[-1])
+        return out.view(self.comm.world_size * t.shape[0], t.shape[-1])
 
     def finalize_metric(self) -> float:
         if not self.preds:

@@ -109,7 +109,12 @@ class Model:
         self.arena.begin_replay()
         self.net_eval = self._build_network(False)
         self.arena.end_replay()
-        self.arena.finalize(self.device, self.mixed, pad_to=max(1, 4 * self.world))
+        from .enums import AllReduceAlgo
+        p2p_ar = (self.world > 1 and self.device.type == "cuda"
+                  and s.all_reduce_algo in (AllReduceAlgo.OneShot, AllReduceAlgo.TwoShot)
+                  and self.comm.p2p_available)
+        self.arena.finalize(self.device, self.mixed, pad_to=max(64, 4 * self.world),
+                            wgrad_alloc=self.comm.symm_alloc if p2p_ar else None)
         self.net_train.finalize()
         self.net_eval.finalize()
         self.arena.init_params(s.seed)
@@ -334,6 +339,13 @@ class Model:
         D.lr_step(self.step_t, self.lr_t, s.lr, s.end_lr, s.decay_power, s.warmup_steps,
                   s.decay_start, s.decay_steps)
         net = self.net_train
+        bucketed = (self.world > 1 and self.device.type == "cuda" and not self.dense_frozen
+                    and os.environ.get("HCTR_DISABLE_AR_OVERLAP", "0") == "0")
+        if bucketed:
+            self.exchange_wgrad.begin_step()
+            net.wgrad_hook = self.exchange_wgrad.layer_done
+        else:
+            net.wgrad_hook = None
         overlap = (self.device.type == "cuda" and not self.legacy_train and self.ebcs_train
                    and os.environ.get("HCTR_DISABLE_OVERLAP", "0") == "0"
                    and (s.train_intra_iteration_overlap or True))
@@ -378,7 +390,10 @@ class Model:
             net.fprop(True)
             net.bprop()
         if not self.dense_frozen:
-            self.exchange_wgrad.allreduce()
+            if bucketed:
+                self.exchange_wgrad.finish_step()
+            else:
+                self.exchange_wgrad.allreduce()
             D.dense_opt_step(DENSE_OPT_CODE[self.opt_params.optimizer_type], self.arena.weights,
                              self.arena.wgrad, self.arena.weights16, self.opt_s0, self.opt_s1,
                              self.lr_t, self.step_t, self.dense_hp, zero_grad=True)

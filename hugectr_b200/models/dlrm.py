@@ -18,6 +18,13 @@ CRITEO_TB_MULTI_HOT = [3, 2, 1, 2, 6, 1, 1, 1, 1, 7, 3, 8, 1, 6, 9, 5, 1, 1, 1, 
 NUM_DENSE = 13
 
 
+def _default_ar():
+    """MLPerf DLRM config uses the custom one-shot all-reduce (train.py --all_reduce_algo OneShot)"""
+    import os
+    return (hugectr.AllReduceAlgo.NCCL if os.environ.get("HCTR_ALLREDUCE", "p2p") == "nccl"
+            else hugectr.AllReduceAlgo.OneShot)
+
+
 def _solver(batchsize, num_gpus, lr, mixed, scaler, **kw):
     return hugectr.CreateSolver(
         model_name=kw.pop("model_name", "dlrm"), seed=kw.pop("seed", 0), max_eval_batches=kw.pop("max_eval_batches", 10),
@@ -25,7 +32,8 @@ def _solver(batchsize, num_gpus, lr, mixed, scaler, **kw):
         vvgpu=[list(range(num_gpus))], repeat_dataset=True, lr=lr, warmup_steps=kw.pop("warmup_steps", 1),
         use_mixed_precision=mixed, scaler=scaler, use_cuda_graph=kw.pop("use_cuda_graph", True),
         train_intra_iteration_overlap=True, train_inter_iteration_overlap=True,
-        use_embedding_collection=True, grouped_all_reduce=True, gen_loss_summary=True, **kw)
+        use_embedding_collection=True, grouped_all_reduce=True, gen_loss_summary=True,
+        all_reduce_algo=kw.pop("all_reduce_algo", _default_ar()), **kw)
 
 
 def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Optional[List[int]] = None,

@@ -134,8 +134,11 @@ class Network:
         if which in ("all", "top"):
             for r in getattr(self, "regularizers", []):
                 r.init_wgrad()
+        hook = getattr(self, "wgrad_hook", None)
         for layer in reversed(layers):
             layer.bprop()
+            if hook is not None and layer.params:
+                hook(min(p.offset for p in layer.params))
 
     def loss_value(self) -> torch.Tensor:
         tot = None

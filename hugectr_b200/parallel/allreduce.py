@@ -5,6 +5,8 @@ HugeCTR/src/collectives/all_reduce_comm.cu:86-426).  Back-ends:
   NCCL     torch.distributed all_reduce (baseline; NVLS inside NCCL on NVSwitch)
   OneShot  custom P2P kernel over the symmetric heap: every rank reduces its 1/N slice by loading
            16-byte lines from all peers, then all-gathers by peer stores (csrc/p2p.cu)
+Either back-end runs bucket by bucket on a communication stream while the backward pass is still
+producing the earlier layers' gradients (begin_step / layer_done / finish_step).
 """
 from __future__ import annotations
 
@@ -27,6 +29,46 @@ class ExchangeWgrad:
 
     def register_extra(self, t: torch.Tensor):
         self.extra.append(t)
+
+    # ---- bucketed overlap with backward (F3): the flat wgrad is produced back to front (bprop
+    # visits layers in reverse creation order), so [lo, hi) ranges become final incrementally
+    def begin_step(self):
+        self._pending_hi = self.wgrad.numel()
+        self._done_lo = self.wgrad.numel()
+        if self.comm.world_size > 1 and self.wgrad.is_cuda:
+            if not hasattr(self, "_stream"):
+                self._stream = torch.cuda.Stream()
+
+    def layer_done(self, lo: int, bucket_elems: int = 2 << 20):
+        """called after a trainable layer's bprop; lo = arena offset of its first parameter"""
+        if self.comm.world_size == 1 or not self.wgrad.is_cuda:
+            return
+        if self._done_lo - lo >= bucket_elems:
+            self._flush(lo)
+
+    def _flush(self, lo: int):
+        hi = self._done_lo
+        if hi <= lo:
+            return
+        main = torch.cuda.current_stream()
+        self._stream.wait_stream(main)
+        with torch.cuda.stream(self._stream):
+            if self._p2p is not None:
+                self._p2p.run(lo, hi)
+            else:
+                self.comm.all_reduce(self.wgrad[lo:hi])
+        self._done_lo = lo
+
+    def finish_step(self):
+        """all remaining ranges + join: wgrad is fully reduced on the current stream afterwards"""
+        if self.comm.world_size == 1:
+            return
+        if not self.wgrad.is_cuda or not hasattr(self, "_done_lo"):
+            return self.allreduce()
+        self._flush(0)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        for t in self.extra:
+            self.comm.all_reduce(t)
 
     def allreduce(self):
         if self.comm.world_size == 1:

@@ -16,7 +16,8 @@ class P2PAllReduce:
         self.comm = comm
         heap = comm.heap
         self.buf = buf
-        self.peers = S.ptr_array(heap.peer_ptrs(buf))
+        self._peer_list = heap.peer_ptrs(buf)
+        self.peers = S.ptr_array(self._peer_list)
         self.flags = heap.alloc(64, torch.int32)
         self.flag_ptrs = S.ptr_array(heap.peer_ptrs(self.flags))
         self.epoch = torch.zeros(1, dtype=torch.int32, device=comm.device)
@@ -25,10 +26,17 @@ class P2PAllReduce:
         self.blocks = blocks
         assert buf.numel() % (4 * comm.world_size) == 0, "pad the buffer to 4*world elements"
 
-    def run(self):
+    def run(self, lo: int = 0, hi: int = None):
+        """all-reduce elements [lo, hi) (both multiples of 4*world) on the current stream"""
+        hi = self.buf.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        peers = self.peers
+        if lo:
+            peers = S.ptr_array([int(q) + lo * 4 for q in self._peer_list])
         rc = S.lib().hctr_allreduce_twoshot(
-            self.peers, self.flag_ptrs, self.epoch.data_ptr(), self.gate.data_ptr(),
-            self.gate_epoch.data_ptr(), self.buf.numel(), self.comm.rank, self.comm.world_size,
+            peers, self.flag_ptrs, self.epoch.data_ptr(), self.gate.data_ptr(),
+            self.gate_epoch.data_ptr(), hi - lo, self.comm.rank, self.comm.world_size,
             self.blocks, torch.cuda.current_stream(self.comm.device).cuda_stream)
         if rc:
             raise RuntimeError(f"allreduce_twoshot failed rc={rc}")

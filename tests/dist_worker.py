@@ -108,8 +108,58 @@ def run_allreduce():
         print("ALLREDUCE_OK")
 
 
+def run_model():
+    """whole-model data-parallel step: (NCCL all-reduce, no overlap, eager) vs (bucketed P2P
+    all-reduce overlapped with backward, side streams, CUDA graph) must train to the same weights"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    comm = Comm.init_from_env()
+    world = comm.world_size
+    cuda = comm.device.type == "cuda"
+    sizes = [4000, 300, 50, 9000, 1200, 77]
+    hot = [3, 1, 1, 8, 2, 1]
+
+    def build(algo):
+        m = build_dlrm_dcnv2(batchsize=256 * world, num_gpus=world, table_sizes=sizes, multi_hot=hot,
+                             ev_size=16, lr=0.05, mixed=cuda, optimizer="sgd", bottom=(64, 32, 16),
+                             top=(64, 32, 1), cross_layers=2, projection_dim=16, comm=comm,
+                             all_reduce_algo=algo, use_cuda_graph=cuda)
+        m.compile()
+        return m
+
+    flags = ("HCTR_DISABLE_AR_OVERLAP", "HCTR_DISABLE_OVERLAP", "HCTR_DISABLE_CUDA_GRAPH")
+    for f in flags:
+        os.environ[f] = "1"
+    ma = build(hugectr.AllReduceAlgo.NCCL)
+    pool = ma.reader_train.pool
+    for i in range(5):
+        ma.train_on_host_batch(pool[i % len(pool)])
+    wa = ma.arena.weights.clone()
+    la = ma.get_current_loss()
+    for f in flags:
+        os.environ[f] = "0"
+    mb = build(hugectr.AllReduceAlgo.OneShot if cuda else hugectr.AllReduceAlgo.NCCL)
+    for i in range(5):
+        mb.train_on_host_batch(pool[i % len(pool)])
+    wb = mb.arena.weights
+    lb = mb.get_current_loss()
+    err = float((wa - wb).abs().max())
+    moved = float((wa - ma.arena.weights * 0).abs().max())
+    assert err < 2e-3 * max(1.0, moved), f"weights differ: {err} (loss {la} vs {lb})"
+    assert abs(la - lb) < 2e-2 * max(1.0, abs(la)), (la, lb)
+    # replicas stay identical across ranks
+    ref = wb.clone()
+    comm.broadcast(ref, 0)
+    assert float((ref - wb).abs().max()) == 0.0, "dense replicas diverged across ranks"
+    comm.barrier()
+    if comm.rank == 0:
+        print("MODEL_OK", err, la, lb)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "model":
+        run_model()
     if what == "ebc":
         run_ebc(sys.argv[2], {"fused": True, "collective": False}[sys.argv[3]])
     elif what == "allreduce":

@@ -158,3 +158,45 @@ def test_norm_checksum_detects_corruption(tmp_path):
     m.compile()
     with pytest.raises(DataCheckError):
         m.train()
+
+
+def test_pipeline_and_inference(tmp_path):
+    from hugectr_b200.inference import CreateInferenceSession, InferenceParams
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.pipeline import Pipeline, StreamContextScheduleable
+    order = []
+    a = StreamContextScheduleable(lambda: order.append("a"), "a")
+    b = StreamContextScheduleable(lambda: order.append("b"), "b").wait_event([a])
+    Pipeline("p", "cpu", [a, b]).run()
+    assert order == ["a", "b"]
+    m = build_dlrm_dcnv2(batchsize=16, num_gpus=1, table_sizes=[30, 40], multi_hot=[2, 1], ev_size=8,
+                         mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                         comm=Comm.single(torch.device("cpu")))
+    m.compile()
+    m.train()
+    m.graph_to_json(str(tmp_path / "g.json"))
+    m.save_params_to_files(str(tmp_path / "m"), 1)
+    sess = CreateInferenceSession(str(tmp_path / "g.json"), InferenceParams(
+        "dlrm", 16, dense_model_file=str(tmp_path / "m_dense_1.model"),
+        embedding_collection_path=str(tmp_path / "m_ebc_1")), )
+    hb = m.reader_eval.read_a_batch()
+    pred = sess.predict(hb.dense.numpy(), hb.keys.numpy())
+    m._load_batch(hb, False)
+    for e in m.ebcs_eval:
+        e.forward(False)
+    m.net_eval.fprop(False)
+    ref = m.net_eval.loss_layers[0].pred.numpy()
+    assert np.abs(pred - ref).max() < 1e-5
+
+
+def test_sparse_tensor_and_simulators():
+    from hugectr_b200.utils.data_simulator import VarianceScalingSimulator, sinusoidal_init
+    from hugectr_b200.utils.sparse_tensor import SparseTensor
+    k = torch.tensor([[3, 4, -1], [5, -1, -1], [-1, -1, -1]])
+    st = SparseTensor.from_padded(k)
+    assert st.nnz == 3 and st.row_offsets.tolist() == [0, 2, 3, 3]
+    assert torch.equal(st.to_padded(3), k)
+    t = torch.empty(1000, 64)
+    VarianceScalingSimulator(1.0, "fan_avg", "uniform", 1000, 64).fill(t)
+    assert abs(t.var().item() - 1.0 / 532) < 3e-4
+    assert sinusoidal_init(10, 8).shape == (10, 8)

@@ -45,3 +45,18 @@ def test_p2p_allreduce():
         pytest.skip("needs >= 2 GPUs")
     out = _run(min(n, 8), ["allreduce"], 29631)
     assert "ALLREDUCE_OK" in out
+
+
+@pytest.mark.dist
+def test_model_data_parallel_gloo():
+    out = _run(2, ["model"], 29641, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "MODEL_OK" in out
+
+
+@pytest.mark.gpu
+def test_model_multi_gpu_overlap_paths():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = _run(min(n, 4), ["model"], 29651)
+    assert "MODEL_OK" in out
