@@ -343,75 +343,114 @@ __global__ void ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* _
 }
 
 // DCNv2 backward elementwise fusion for one cross layer (bf16, vectorised x8):
-//   dt  = dy * x0                       (input of the V^T dgrad GEMM)
-//   dx0 = (first ? 0 : dx0) + dy * t    (accumulated over layers)
-//   db += column sums of dt             (bias gradient, fused: no separate reduction pass)
-// grid = (column blocks of 256 threads x 8 columns, row splits); a thread owns 8 fixed columns and
-// walks its rows, so the bias partial sums stay in registers until one atomicAdd per column.
+//   dt  = dy * x0                                   (input of the V^T dgrad GEMM)
+//   dx0 = (first ? 0 : dx0) + dy * t (+ dy if last) (accumulated over layers; on the last layer the
+//         residual dy is folded in so the final dgrad GEMM epilogue adds ONE bf16 tensor)
+//   db += column sums of dt                         (bias gradient, fused: no separate reduction)
+// block = 16 column groups (128 columns) x 16 row lanes; a thread owns 8 fixed columns and walks
+// rows ry, ry+16, ... of its row split with 4 rows of 16-byte loads in flight; bias partials stay in
+// registers, are combined through shared memory and leave as one atomicAdd per column per block.
+template <typename AccT>
 __global__ void __launch_bounds__(256)
     cross_bwd_ew_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
-                        const bf16* __restrict__ t, bf16* __restrict__ dt, float* __restrict__ dx0,
-                        float* __restrict__ db, int rows, int cols, int first) {
-  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;        // 8-column group
+                        const bf16* __restrict__ t, bf16* __restrict__ dt, AccT* __restrict__ dx0,
+                        float* __restrict__ db, int rows, int cols, int mode) {
+  constexpr bool kAccBf16 = sizeof(AccT) == 2;
+  __shared__ float red[16][16][9];
+  const int cx = threadIdx.x & 15, ry = threadIdx.x >> 4;
   const int ngroups = cols >> 3;
-  if (c8 >= ngroups) return;
+  const int c8 = blockIdx.x * 16 + cx;
+  const bool col_ok = c8 < ngroups;
   const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  const bool first = mode & 1, last = mode & 2;
   float bsum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
-  constexpr int NR = 4;   // rows in flight per thread: 4 x (3 x 16 B + 2 x 16 B) loads issued together
-  for (int rb = r0; rb < r1; rb += NR) {
-    uint4 a[NR], b[NR], c[NR];
-    float4 p0[NR], p1[NR];
+  constexpr int NR = 4;
+  if (col_ok) {
+    for (int rb = r0 + ry; rb < r1; rb += 16 * NR) {
+      uint4 a[NR], b[NR], c[NR], pb[NR];
+      float4 p0[NR], p1[NR];
 #pragma unroll
-    for (int u = 0; u < NR; ++u) {
-      const int r = rb + u;
-      if (r < r1) {
-        const long long i = static_cast<long long>(r) * ngroups + c8;
-        a[u] = reinterpret_cast<const uint4*>(dy)[i];
-        b[u] = reinterpret_cast<const uint4*>(x0)[i];
-        c[u] = reinterpret_cast<const uint4*>(t)[i];
-        if (!first) {
-          p0[u] = reinterpret_cast<const float4*>(dx0)[2 * i];
-          p1[u] = reinterpret_cast<const float4*>(dx0)[2 * i + 1];
+      for (int u = 0; u < NR; ++u) {
+        const int r = rb + 16 * u;
+        if (r < r1) {
+          const long long i = static_cast<long long>(r) * ngroups + c8;
+          a[u] = reinterpret_cast<const uint4*>(dy)[i];
+          b[u] = reinterpret_cast<const uint4*>(x0)[i];
+          c[u] = reinterpret_cast<const uint4*>(t)[i];
+          if (!first) {
+            if constexpr (kAccBf16) {
+              pb[u] = reinterpret_cast<const uint4*>(dx0)[i];
+            } else {
+              p0[u] = reinterpret_cast<const float4*>(dx0)[2 * i];
+              p1[u] = reinterpret_cast<const float4*>(dx0)[2 * i + 1];
+            }
+          }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < NR; ++u) {
-      const int r = rb + u;
-      if (r >= r1) continue;
-      const long long i = static_cast<long long>(r) * ngroups + c8;
-      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bw[4] = {b[u].x, b[u].y, b[u].z, b[u].w},
-                     cw[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
-      uint32_t ow[4];
-      float acc[8];
-      if (!first) {
-        acc[0] = p0[u].x; acc[1] = p0[u].y; acc[2] = p0[u].z; acc[3] = p0[u].w;
-        acc[4] = p1[u].x; acc[5] = p1[u].y; acc[6] = p1[u].z; acc[7] = p1[u].w;
-      } else {
+      for (int u = 0; u < NR; ++u) {
+        const int r = rb + 16 * u;
+        if (r >= r1) continue;
+        const long long i = static_cast<long long>(r) * ngroups + c8;
+        const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bw[4] = {b[u].x, b[u].y, b[u].z, b[u].w},
+                       cw[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+        uint32_t ow[4];
+        float acc[8];
+        if (!first) {
+          if constexpr (kAccBf16) {
+            const uint32_t pw[4] = {pb[u].x, pb[u].y, pb[u].z, pb[u].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int q = 0; q < 4; ++q) {
+              acc[2 * q] = bf16_lo(pw[q]);
+              acc[2 * q + 1] = bf16_hi(pw[q]);
+            }
+          } else {
+            acc[0] = p0[u].x; acc[1] = p0[u].y; acc[2] = p0[u].z; acc[3] = p0[u].w;
+            acc[4] = p1[u].x; acc[5] = p1[u].y; acc[6] = p1[u].z; acc[7] = p1[u].w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float d0 = bf16_lo(aw[q]), d1 = bf16_hi(aw[q]);
+          const float e0 = d0 * bf16_lo(bw[q]), e1 = d1 * bf16_hi(bw[q]);
+          ow[q] = pack_bf16x2(e0, e1);
+          bsum[2 * q] += bf16_lo(ow[q]);       // bias grad sums the bf16-rounded dt (what the GEMMs consume)
+          bsum[2 * q + 1] += bf16_hi(ow[q]);
+          acc[2 * q] += d0 * bf16_lo(cw[q]) + (last ? d0 : 0.f);
+          acc[2 * q + 1] += d1 * bf16_hi(cw[q]) + (last ? d1 : 0.f);
+        }
+        reinterpret_cast<uint4*>(dt)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if constexpr (kAccBf16) {
+          reinterpret_cast<uint4*>(dx0)[i] =
+              make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+        } else {
+          reinterpret_cast<float4*>(dx0)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          reinterpret_cast<float4*>(dx0)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float d0 = bf16_lo(aw[q]), d1 = bf16_hi(aw[q]);
-        const float e0 = d0 * bf16_lo(bw[q]), e1 = d1 * bf16_hi(bw[q]);
-        ow[q] = pack_bf16x2(e0, e1);
-        bsum[2 * q] += bf16_lo(ow[q]);       // bias grad sums the bf16-rounded dt (what the GEMMs consume)
-        bsum[2 * q + 1] += bf16_hi(ow[q]);
-        acc[2 * q] += d0 * bf16_lo(cw[q]);
-        acc[2 * q + 1] += d1 * bf16_hi(cw[q]);
-      }
-      reinterpret_cast<uint4*>(dt)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      reinterpret_cast<float4*>(dx0)[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      reinterpret_cast<float4*>(dx0)[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
   }
   if (db != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(db + c8 * 8 + j, bsum[j]);
+    for (int j = 0; j < 8; ++j) red[ry][cx][j] = bsum[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int gx_ = threadIdx.x >> 3, j = threadIdx.x & 7;
+      const int col = (blockIdx.x * 16 + gx_) * 8 + j;
+      if (col < cols) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int y = 0; y < 16; ++y) sacc += red[y][gx_][j];
+        atomicAdd(db + col, sacc);
+      }
+    }
   }
 }
 // out(bf16) = a(bf16) + b(bf16) [+ c(fp32)]   (vectorised x8) : dxl = dy + dxl_gemm (+ dx0 on last)
@@ -558,15 +597,19 @@ extern "C" int hctr_elementwise(const void* a, const void* b, void* o, long long
 }
 
 extern "C" int hctr_cross_bwd_ew(const void* dy, const void* x0, const void* t, void* dt,
-                                 float* dx0, float* db, int rows, int cols, int first,
-                                 void* stream) {
+                                 void* dx0, float* db, int rows, int cols, int mode,
+                                 int dx0_bf16, int row_splits, void* stream) {
   if (cols % 8) return -2;
-  const int gx = (cols / 8 + 255) / 256;
-  int gy = (148 * 8) / gx;
-  if (gy > rows) gy = rows;
+  const int gx = (cols / 8 + 15) / 16;
+  int gy = row_splits > 0 ? row_splits : (148 * 4 + gx - 1) / gx;
+  if (gy * 16 > rows) gy = (rows + 15) / 16;
   if (gy < 1) gy = 1;
-  cross_bwd_ew_kernel<<<dim3(gx, gy), 256, 0, ST(stream)>>>(
-      (const bf16*)dy, (const bf16*)x0, (const bf16*)t, (bf16*)dt, dx0, db, rows, cols, first);
+  if (dx0_bf16)
+    cross_bwd_ew_kernel<bf16><<<dim3(gx, gy), 256, 0, ST(stream)>>>(
+        (const bf16*)dy, (const bf16*)x0, (const bf16*)t, (bf16*)dt, (bf16*)dx0, db, rows, cols, mode);
+  else
+    cross_bwd_ew_kernel<float><<<dim3(gx, gy), 256, 0, ST(stream)>>>(
+        (const bf16*)dy, (const bf16*)x0, (const bf16*)t, (bf16*)dt, (float*)dx0, db, rows, cols, mode);
   return OK();
 }
 

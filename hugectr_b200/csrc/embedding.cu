@@ -214,6 +214,67 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Data-parallel tables (small, replicated): dense wgrad [rows, pitch] += scattered bag gradients of
+// the LOCAL batch.  Hot rows of tiny tables would serialise global reductions on a handful of L2
+// lines, so a block (one lookup x one chunk of samples) first accumulates into a shared-memory copy
+// of the table when it fits and flushes it with one vector reduction per non-zero 16-byte group.
+template <typename KeyT, typename GradT>
+__global__ void __launch_bounds__(256)
+    emb_dp_wgrad_kernel(const EmbParams p, float* __restrict__ wgrad, const float grad_scale,
+                        const int smem_floats) {
+  extern __shared__ float dp_acc[];
+  const EmbLookup lk = p.lookups[blockIdx.y];
+  const int ev = lk.ev_size, pitch = p.ev_size;
+  const long long tbl_floats = static_cast<long long>(lk.rows) * ev;
+  const bool priv = tbl_floats <= smem_floats;
+  const int per = (p.batch + gridDim.x - 1) / gridDim.x;
+  const int s0 = blockIdx.x * per, s1 = min(p.batch, s0 + per);
+  if (priv) {
+    for (int i = threadIdx.x; i < tbl_floats; i += blockDim.x) dp_acc[i] = 0.f;
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const KeyT* keys = reinterpret_cast<const KeyT*>(p.keys[0]) + lk.key_off;
+  const GradT* grads = reinterpret_cast<const GradT*>(p.grad[0]) + lk.grad_off;
+  for (int s = s0 + warp; s < s1; s += 8) {
+    int nnz = lk.hotness;
+    if (lk.nnz_off >= 0) nnz = min(lk.hotness, p.nnz[0][lk.nnz_off + s]);
+    if (nnz <= 0) continue;
+    float scale = grad_scale;
+    if (lk.combiner == 1) scale /= static_cast<float>(nnz);
+    const KeyT* kb = keys + static_cast<long long>(s) * lk.key_stride;
+    const GradT* gp = grads + static_cast<long long>(s) * lk.grad_stride;
+    for (int col = lane * 4; col < ev; col += 128) {
+      float4 v = load_vec4<GradT>(gp + col);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      for (int h = 0; h < nnz; ++h) {
+        const long long key = static_cast<long long>(kb[h]);
+        if (key < 0 || key >= lk.rows) continue;
+        if (priv) {
+          float* d = dp_acc + key * ev + col;
+          atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
+        } else {
+          float* d = wgrad + (lk.table_row_off + key) * pitch + col;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y),
+                       "f"(v.z), "f"(v.w) : "memory");
+        }
+      }
+    }
+  }
+  if (priv) {
+    __syncthreads();
+    for (long long i = threadIdx.x * 4ll; i < tbl_floats; i += blockDim.x * 4ll) {
+      const float4 v = *reinterpret_cast<const float4*>(dp_acc + i);
+      if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+      const long long r = i / ev;
+      const int c = static_cast<int>(i - r * ev);
+      float* d = wgrad + (lk.table_row_off + r) * pitch + c;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w) : "memory");
+    }
+  }
+}
+
 // One warp per unique row: reads the accumulated fp32 gradient (and zeroes it for the next step),
 // updates weight + optimizer state in place and releases the row's hash slot.
 template <int OPT, typename StateT>
@@ -361,12 +422,36 @@ extern "C" int hctr_emb_forward(const EmbParams* p, int max_ev, int key_bytes, i
 
 extern "C" int hctr_emb_backward_accum(const EmbParams* p, const UniqueTable* ut,
                                        float* wgrad_unique, float grad_scale, int max_ev,
-                                       int key_bytes, int grad_bf16, void* stream_) {
+                                       int key_bytes, int grad_bf16, int dp_ev4, void* stream_) {
+  // dp_ev4: every lookup's ev_size is a multiple of 4 and its gradient rows are 16-byte aligned
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int vec = (max_ev % 4 == 0) ? 4 : 1;
   const int G = pick_group(max_ev, vec);
   const long long items = static_cast<long long>(p->num_ranks) * p->num_lookups * p->batch;
   if (items == 0) return 0;
+  if (ut->keys == nullptr && p->num_ranks == 1 && dp_ev4 && p->ev_size % 4 == 0) {
+    // dense wgrad of replicated tables: privatised block-level accumulation
+    constexpr int kSmem = 96 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(emb_dp_wgrad_kernel<int, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      cudaFuncSetAttribute(emb_dp_wgrad_kernel<int, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      cudaFuncSetAttribute(emb_dp_wgrad_kernel<long long, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      cudaFuncSetAttribute(emb_dp_wgrad_kernel<long long, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      attr_set = true;
+    }
+    int chunks = (2 * 148 + p->num_lookups - 1) / p->num_lookups;
+    if (chunks > 64) chunks = 64;
+    if (chunks * 8 > p->batch) chunks = (p->batch + 7) / 8;
+    if (chunks < 1) chunks = 1;
+    const dim3 grid(chunks, p->num_lookups);
+#define LAUNCH_DP(K, O) \
+  emb_dp_wgrad_kernel<K, O><<<grid, 256, kSmem, st>>>(*p, wgrad_unique, grad_scale, kSmem / 4)
+    if (key_bytes == 8) { if (grad_bf16) LAUNCH_DP(long long, __nv_bfloat16); else LAUNCH_DP(long long, float); }
+    else { if (grad_bf16) LAUNCH_DP(int, __nv_bfloat16); else LAUNCH_DP(int, float); }
+#undef LAUNCH_DP
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   const long long warps = (items + (32 / G) - 1) / (32 / G);
   const int threads = 256;
   const long long blocks = (warps * 32 + threads - 1) / threads;

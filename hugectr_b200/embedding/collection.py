@@ -481,24 +481,42 @@ class EmbeddingCollection:
                             self.rank, key_bytes=self._kb)
         self._index_done = True
 
-    def backward(self, lr_t, step_t):
-        """Consumes top grads (grad slab), updates local tables. grads are already / global batch."""
+    def backward(self, lr_t, step_t, dp_stream=None):
+        """Consumes top grads (grad slab), updates local tables. grads are already / global batch.
+
+        Data-parallel groups only need the local gradients: their accumulate -> all-reduce ->
+        optimizer chain runs on ``dp_stream`` (when given) next to the model-parallel chain, and in the
+        same position on every rank (the all-reduce is a rendezvous)."""
         if not getattr(self, "_index_done", False):
             self.backward_index()
         self._index_done = False
+        dp_groups = [g for g in self.groups if g.kind == "dp"]
+        mp_groups = [g for g in self.groups if g.kind != "dp"]
+        side = dp_stream is not None and self.device.type == "cuda" and bool(dp_groups)
+        if side:
+            cur = torch.cuda.current_stream()
+            dp_stream.wait_stream(cur)
+            with torch.cuda.stream(dp_stream):
+                for grp in dp_groups:
+                    self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()           # all top-grads are final
-                for grp in self.groups:              # backward "all-to-all": bulk peer loads
-                    if grp.kind == "mp" and grp.lookups and self._stage_ok(grp):
+                for grp in mp_groups:                # backward "all-to-all": bulk peer loads
+                    if grp.lookups and self._stage_ok(grp):
                         E.pull_grads(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
                                      self.peer_grad, self.grad_stage, self.b, self.rank,
                                      key_bytes=self._kb, act_bf16=self._abf)
             else:
                 self.comm.all_gather(self.grads_all, self.grad_slab)
-        for grp in self.groups:
+        for grp in mp_groups:
             kb, gb = self._bwd_bufs(grp)
             self._accum_update(grp, kb, gb, lr_t, step_t)
+        if side:
+            torch.cuda.current_stream().wait_stream(dp_stream)
+        else:
+            for grp in dp_groups:
+                self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
         if self.world > 1 and self.fused:
             self.comm.barrier_device()               # keys / grads may now be overwritten
 

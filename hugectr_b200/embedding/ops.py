@@ -71,7 +71,7 @@ def lib():
         vp, i, f, ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
         l.hctr_emb_forward.argtypes = [C.POINTER(CEmbParams), i, i, i, vp]
         l.hctr_emb_backward_accum.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable), vp, f,
-                                              i, i, i, vp]
+                                              i, i, i, i, vp]
         l.hctr_emb_update.argtypes = [vp, vp, vp, vp, C.POINTER(CUniqueTable), i, i, i,
                                       C.POINTER(COptHyper), vp, i, vp]
         l.hctr_emb_gather_rows.argtypes = [vp, vp, vp, ll, i, i, vp]
@@ -279,8 +279,11 @@ def backward_accum(lookups, lookups_dev, table, ev_pitch, key_bufs, grad_bufs, b
             dst = dense_wgrad.data_ptr()
         else:
             ut, dst = ws.c, ws.wgrad.data_ptr()
+        esz = 2 if gbf else 4
+        ev4 = int(all(l.ev_size % 4 == 0 and (l.grad_off * esz) % 16 == 0 and
+                      (l.grad_stride * esz) % 16 == 0 for l in lookups))
         rc = lib().hctr_emb_backward_accum(C.byref(p), C.byref(ut), dst, float(grad_scale), max_ev,
-                                           kb, gbf, _st(table.device))
+                                           kb, gbf, ev4, _st(table.device))
         if rc:
             raise RuntimeError("hctr_emb_backward_accum failed")
         D._count()

@@ -61,7 +61,9 @@ class MultiCrossLayer(Layer):
                 self.dH = torch.zeros(b, self.p, dtype=dt, device=dev)
                 self.dXg = torch.zeros(b, self.w, dtype=dt, device=dev)
                 self.dX = [torch.zeros(b, self.w, dtype=dt, device=dev) for _ in range(2)]
-                self.dx0 = torch.zeros(b, self.w, dtype=torch.float32, device=dev)
+                # running sum of dy_l * T_l in the activation dtype (fp32 math in registers); the
+                # last layer folds the residual dy in, so the final dgrad epilogue adds one tensor
+                self.dx0 = torch.zeros(b, self.w, dtype=dt, device=dev)
         else:
             if self.ctx.is_train:
                 self.dots = [torch.zeros(b, 1, dtype=torch.float32, device=dev) for _ in range(L)]
@@ -109,7 +111,8 @@ class MultiCrossLayer(Layer):
         for l in range(L - 1, -1, -1):
             xl = self._xl(l)
             first = (l == L - 1)
-            D.cross_bwd_ew(dy, x0, self.T[l], self.dT, self.dx0, first, self.Bv[l].g.reshape(-1))
+            D.cross_bwd_ew(dy, x0, self.T[l], self.dT, self.dx0, first, self.Bv[l].g.reshape(-1),
+                           last=(l == 0))
             # dV += H^T dT
             G.gemm_bf16(self.H[l], self.dT, self.V[l].g, a_mn=True, b_mn=True,
                         flags=G.EPI_ATOMIC, splits=2)
@@ -123,7 +126,7 @@ class MultiCrossLayer(Layer):
             if l == 0:
                 out = self.inputs[0].grad
                 if out is not None:
-                    G.gemm_bf16(self.dH, self.U[l].compute(self.mixed), out, xl=dy, addf=self.dx0,
+                    G.gemm_bf16(self.dH, self.U[l].compute(self.mixed), out, xl=self.dx0,
                                 flags=G.EPI_ADD)
             else:
                 out = self.dX[l & 1]

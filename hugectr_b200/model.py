@@ -356,7 +356,11 @@ class Model:
             # reduce+update runs next to bottom-MLP bprop / all-reduce / dense optimizer.
             main = torch.cuda.current_stream()
             if not hasattr(self, "_s_emb"):
-                self._s_emb, self._s_idx = torch.cuda.Stream(), torch.cuda.Stream()
+                # the embedding forward gates the top MLP: high priority.  The backward index build
+                # is only needed at the end of the step: same (lowest) priority as everything else,
+                # so forward CTAs are scheduled ahead of its still-pending blocks.
+                self._s_emb = torch.cuda.Stream(priority=int(os.environ.get("HCTR_PRIO_EMB", "-1")))
+                self._s_idx = torch.cuda.Stream(priority=int(os.environ.get("HCTR_PRIO_IDX", "0")))
             s_emb, s_idx = self._s_emb, self._s_idx
             for e in self.ebcs_train:
                 e.forward_begin()
@@ -380,7 +384,7 @@ class Model:
                 s_emb.wait_stream(main)
                 with torch.cuda.stream(s_emb):
                     for e in self.ebcs_train:
-                        e.backward(self.lr_t, self.step_t)
+                        e.backward(self.lr_t, self.step_t, dp_stream=s_idx)
             net.bprop("bottom")
         else:
             for e in self.ebcs_train:
@@ -428,7 +432,9 @@ class Model:
             torch.cuda.synchronize()
             self.comm.barrier()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            prio = int(os.environ.get("HCTR_PRIO_MAIN", "0"))
+            cap_stream = torch.cuda.Stream(priority=prio) if prio != 0 else None
+            with torch.cuda.graph(g, stream=cap_stream):
                 self._step_body()
             self._graph = g
             self.comm.barrier()                # pipeline.cpp:111-125 barrier after first capture

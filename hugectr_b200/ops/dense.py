@@ -46,7 +46,7 @@ def lib():
         l.hctr_copy2d.argtypes = [vp, vp, ll, i, ll, ll, i, i, vp]
         l.hctr_cast_pad.argtypes = [vp, vp, ll, i, i, ll, vp]
         l.hctr_elementwise.argtypes = [vp, vp, vp, ll, i, f, i, vp]
-        l.hctr_cross_bwd_ew.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
+        l.hctr_cross_bwd_ew.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
         l.hctr_add3.argtypes = [vp, vp, vp, vp, ll, vp]
         for n in ("hctr_dense_opt", "hctr_lr_step", "hctr_bce_loss", "hctr_colsum", "hctr_fc1_fwd",
                   "hctr_fc1_bwd", "hctr_copy2d", "hctr_cast_pad", "hctr_elementwise",
@@ -194,24 +194,28 @@ def elementwise(op, a, b, out, alpha=0.0):
     out.copy_(r.to(out.dtype))
 
 
-def cross_bwd_ew(dy, x0, t, dt, dx0, first, db=None):
-    """dt = dy*x0 ; dx0 = (0 if first else dx0) + dy*t ; db (fp32 [cols]) += colsum(dt)."""
+def cross_bwd_ew(dy, x0, t, dt, dx0, first, db=None, last=False, row_splits=0):
+    """dt = dy*x0 ; dx0 = (0 if first else dx0) + dy*t (+ dy if last) ; db (fp32 [cols]) += colsum(dt).
+    dx0 is fp32 or bf16 (accumulated in fp32 registers either way)."""
     if _native_ok(dy, x0, t, dt) and dy.dtype == torch.bfloat16 and dy.is_contiguous() \
             and x0.is_contiguous() and t.is_contiguous() and dy.shape[-1] % 8 == 0:
         rows, cols = dy.shape[0], dy.shape[1]
         _chk(lib().hctr_cross_bwd_ew(dy.data_ptr(), x0.data_ptr(), t.data_ptr(), dt.data_ptr(),
                                      dx0.data_ptr(), 0 if db is None else db.data_ptr(), rows, cols,
-                                     int(first), _st(dy)), "cross_bwd_ew")
+                                     int(bool(first)) | (2 if last else 0),
+                                     int(dx0.dtype == torch.bfloat16), int(row_splits), _st(dy)),
+             "cross_bwd_ew")
         return
     d = dy.float()
     dtv = (d * x0.float()).to(dt.dtype)
     dt.copy_(dtv)
     if db is not None:
         db.add_(dtv.float().sum(0))
+    acc = d * t.float() + (d if last else 0.0)
     if first:
-        dx0.copy_(d * t.float())
+        dx0.copy_(acc.to(dx0.dtype))
     else:
-        dx0.add_(d * t.float())
+        dx0.copy_((dx0.float() + acc).to(dx0.dtype))
 
 
 def add3(a, b, c, out):
