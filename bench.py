@@ -63,6 +63,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny tables (debug only; not a valid number)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--plan", default="auto")
+    ap.add_argument("--cap-rows", type=int, default=0,
+                    help="cap every table at this many rows (profiling under ncu only; INVALID as a bench number)")
     ap.add_argument("--profile", default="", help="dump a torch.profiler kernel table (rank 0) here")
     args = ap.parse_args()
 
@@ -91,10 +93,12 @@ def main():
     n = args.gpus
     b = args.per_gpu_batch
     tables = CRITEO_TB_TABLE_SIZES if not args.small else [min(t, 100000) for t in CRITEO_TB_TABLE_SIZES]
+    if args.cap_rows > 0:
+        tables = [min(t, args.cap_rows) for t in tables]
     # 104 GB of fp32 tables + 104 GB of fp32 AdaGrad state do not fit one 180 GB GPU: at N == 1 the
     # AdaGrad accumulators are stored in bf16 (weights stay fp32, math fp32); N >= 2 keeps fp32 state
     state = "fp32"
-    if n == 1 and not args.small:
+    if n == 1 and not args.small and not args.cap_rows:
         os.environ["HCTR_EMB_STATE_BF16"] = "1"
         state = "bf16"
     os.environ.setdefault("HCTR_SYNTH_POOL", "8")
@@ -200,7 +204,7 @@ def main():
                        "parallelism": f"dp{n} dense + model-parallel embeddings (plan={args.plan})",
                        "embedding_weights": "fp32", "embedding_opt_state": state,
                        "l2_hygiene": "inputs_exceed_L2 (>=100 GB tables random access, ~1 GB activations/step)",
-                       "cuda_graph": not args.no_graph, "small_tables_debug": bool(args.small),
+                       "cuda_graph": not args.no_graph, "small_tables_debug": bool(args.small or args.cap_rows),
                        "final_loss": loss},
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": max(ms_e2e, wall_ms) / K,

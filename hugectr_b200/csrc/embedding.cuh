@@ -215,4 +215,29 @@ HCTR_DEVICE void apply_opt4(float4& w, const float4 g, StateT* s0, StateT* s1, l
   if constexpr (kHasS1) store_vec4<StateT>(s1 + idx, b[0], b[1], b[2], b[3]);
 }
 
+// variant with the weight / first state vector already in registers (loaded early by the caller so
+// their latency overlaps the gradient gather); the caller stores w, this stores the states.
+template <int OPT, typename StateT>
+HCTR_DEVICE void apply_opt4_pre(float4& w, const float4 g, const float4 s0v, StateT* s0, StateT* s1,
+                                long long idx, const OptHyper& hp, float lr, float bc1, float bc2) {
+  constexpr bool kHasS0 = (OPT != OPT_SGD);
+  constexpr bool kHasS1 = (OPT == OPT_ADAM || OPT == OPT_FTRL);
+  float a[4] = {s0v.x, s0v.y, s0v.z, s0v.w}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if constexpr (kHasS1) {
+    const float4 v = load_vec4<StateT>(s1 + idx);
+    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+  }
+  float ww[4] = {w.x, w.y, w.z, w.w};
+  const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float sa = a[j], sb = b[j];
+    apply_opt<OPT, float>(ww[j], gg[j], &sa, &sb, 0, hp, lr, bc1, bc2);
+    a[j] = sa; b[j] = sb;
+  }
+  w = make_float4(ww[0], ww[1], ww[2], ww[3]);
+  if constexpr (kHasS0) store_vec4<StateT>(s0 + idx, a[0], a[1], a[2], a[3]);
+  if constexpr (kHasS1) store_vec4<StateT>(s1 + idx, b[0], b[1], b[2], b[3]);
+}
+
 }  // namespace hctr

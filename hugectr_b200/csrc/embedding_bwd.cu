@@ -119,17 +119,88 @@ __global__ void __launch_bounds__(kIdxThreads)
     slot[q] = static_cast<int>(hslot);
   }
   __syncthreads();
-  // one global get_insert + count update per distinct row of the block
-  for (int i = threadIdx.x; i < kSmemSlots; i += blockDim.x) {
-    const unsigned long long k = h_keys[i];
-    if (k != kEmptyKey) {
-      const unsigned int u = unique_get_insert(ut, k);
-      if (u < ut.max_unique) {
-        atomicAdd(&ix.count[u], h_cnt[i]);
-        h_cnt[i] = u;
-      } else {
-        h_cnt[i] = kInvalidVal;
+  // One global insert per distinct row of the block.  Unique ids are handed out with ONE atomicAdd
+  // on the global counter per block (a per-key atomicAdd on that single address serialises in L2
+  // and was the whole kernel's critical path): (1) claim / find the global hash slot of every
+  // distinct row without waiting, (2) block-scan the number of newly claimed rows, reserve the id
+  // range, publish the ids, (3) only then wait for ids owned by other blocks -- every block
+  // publishes before it waits, so the waits cannot form a cycle.
+  constexpr int kSlotIters = kSmemSlots / kIdxThreads;
+  unsigned int gslot[kSlotIters];
+  unsigned int newmask = 0, nnew = 0;
+#pragma unroll
+  for (int k = 0; k < kSlotIters; ++k) {
+    const unsigned long long key = h_keys[threadIdx.x + k * kIdxThreads];
+    gslot[k] = kInvalidVal;
+    if (key != kEmptyKey) {
+      unsigned int h = hash64(key) & ut.mask;
+      while (true) {
+        const unsigned long long prev = atomicCAS(&ut.keys[h], kEmptyKey, key);
+        if (prev == kEmptyKey) {
+          newmask |= 1u << k;
+          ++nnew;
+          break;
+        }
+        if (prev == key) break;
+        h = (h + 1) & ut.mask;
       }
+      gslot[k] = h;
+    }
+  }
+  __shared__ unsigned int s_warp_sum[kIdxThreads / 32];
+  __shared__ unsigned int s_base;
+  unsigned int incl = nnew;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += v;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp_sum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tot = 0;
+#pragma unroll
+    for (int w = 0; w < kIdxThreads / 32; ++w) {
+      const unsigned int v = s_warp_sum[w];
+      s_warp_sum[w] = tot;
+      tot += v;
+    }
+    s_base = tot ? atomicAdd(ut.counter, tot) : 0u;
+  }
+  __syncthreads();
+  unsigned int next_uid = s_base + s_warp_sum[threadIdx.x >> 5] + incl - nnew;
+#pragma unroll
+  for (int k = 0; k < kSlotIters; ++k) {
+    if (newmask & (1u << k)) {
+      const unsigned int uid = next_uid++;
+      const unsigned int h = gslot[k];
+      if (uid < ut.max_unique) {
+        ut.rows[uid] = h_keys[threadIdx.x + k * kIdxThreads];
+        ut.slots[uid] = h;
+      }
+      // rows[]/slots[] are consumed by later kernels only; concurrent blocks need the id alone
+      atomicExch(&ut.vals[h], uid);
+      gslot[k] = uid | 0x80000000u;  // resolved (ids are < 2^31)
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kSlotIters; ++k) {
+    const int i = threadIdx.x + k * kIdxThreads;
+    if (h_keys[i] == kEmptyKey) continue;
+    unsigned int u;
+    if (gslot[k] & 0x80000000u) {
+      u = gslot[k] & 0x7FFFFFFFu;
+    } else {
+      const volatile unsigned int* vp = reinterpret_cast<volatile unsigned int*>(&ut.vals[gslot[k]]);
+      do {
+        u = *vp;
+      } while (u == kInvalidVal);
+    }
+    if (u < ut.max_unique) {
+      atomicAdd(&ix.count[u], h_cnt[i]);
+      h_cnt[i] = u;
+    } else {
+      h_cnt[i] = kInvalidVal;
     }
   }
   __syncthreads();
@@ -316,13 +387,18 @@ HCTR_DEVICE const GradT* locate_grad(const EmbParams& p, unsigned int e) {
   return reinterpret_cast<const GradT*>(p.grad[e >> 28]) + (static_cast<long long>(e & 0x0FFFFFFFu) << 2);
 }
 
-// G lanes per unique row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the row),
-// 4 buckets unrolled -> up to 16 independent 8/16-byte gradient loads in flight per lane.
+// G lanes per unique row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the row).
+// The per-row dependency chain  offsets/rows[uid] -> bucket_list[] -> gradient rows -> weight/state
+// is software-pipelined over the rows a lane group visits: while row i is reduced, the bucket
+// entries of row i+1 and the offsets of row i+2 are already in flight, and the weight / state
+// vectors of row i are requested BEFORE its gradients, so one DRAM latency is exposed per row
+// instead of four.
 template <int OPT, typename StateT, typename GradT, int G>
 __global__ void __launch_bounds__(256)
     emb_bwd_reduce_update_kernel(const EmbParams p, const UniqueTable ut, const BwdIndex ix,
                                  StateT* __restrict__ s0, StateT* __restrict__ s1, const OptHyper hp,
                                  const float grad_scale) {
+  constexpr bool kHasS0 = (OPT != OPT_SGD);
   const unsigned int n = min(*ut.counter, ut.max_unique);
   const float lr = (hp.lr_ptr ? *hp.lr_ptr : 1.f) * hp.lr_scale;
   float bc1 = 1.f, bc2 = 1.f;
@@ -338,9 +414,44 @@ __global__ void __launch_bounds__(256)
   const int ev = p.ev_size;
   constexpr int NC = (G == 8) ? 4 : 8;             // chunks per lane
   const unsigned int groups = ((gridDim.x * blockDim.x) >> 5) * GPW;
-  for (unsigned int uid = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + gi; uid < n;
-       uid += groups) {
-    const unsigned int o0 = ix.offsets[uid], o1 = ix.offsets[uid + 1];
+  const unsigned int first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + gi;
+  const bool has_scale = ix.bucket_scale != nullptr;
+
+  // stage A: offsets + arena row of a unique id
+  unsigned int a_o0[3], a_o1[3];
+  unsigned long long a_row[3];
+  // stage B: first four bucket entries (+ scales) of a row
+  unsigned int b_e[2][4];
+  float b_s[2][4];
+  auto load_a = [&](unsigned int u, int k) {
+    a_o0[k] = a_o1[k] = 0u;
+    a_row[k] = 0ull;
+    if (u < n) {
+      a_o0[k] = ix.offsets[u];
+      a_o1[k] = ix.offsets[u + 1];
+      a_row[k] = ut.rows[u];
+    }
+  };
+  auto load_b = [&](int ka, int kb) {
+    const unsigned int o0 = a_o0[ka], o1 = a_o1[ka];
+    const bool light = (o1 - o0) <= kHeavy;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      b_e[kb][u] = 0xFFFFFFFFu;
+      b_s[kb][u] = 1.f;
+      if (light && o0 + u < o1) {
+        b_e[kb][u] = ix.bucket_list[o0 + u];
+        if (has_scale) b_s[kb][u] = ix.bucket_scale[o0 + u];
+      }
+    }
+  };
+  load_a(first, 0);
+  load_a(first + groups, 1);
+  load_b(0, 0);
+  for (unsigned int uid = first; uid < n; uid += groups) {
+    load_a(uid + 2 * groups, 2);
+    load_b(1, 1);
+    const unsigned int o0 = a_o0[0], o1 = a_o1[0];
     const unsigned int cnt = o1 - o0;
     if (cnt > kHeavy) {
       if (gl == 0) {
@@ -354,54 +465,76 @@ __global__ void __launch_bounds__(256)
           }
         }
       }
-      continue;
-    }
-    const unsigned long long row = ut.rows[uid];
-    const long long base = static_cast<long long>(row) * ev;
-    float4 acc[NC];
+    } else {
+      const long long base = static_cast<long long>(a_row[0]) * ev;
+      // weight / state first: independent of the gradients
+      float4 wv[NC], sv[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (unsigned int j = o0; j < o1; j += 4) {
-      const GradT* gptr[4];
-      float sc[4];
+      for (int c = 0; c < NC; ++c) {
+        const int col = (c * G + gl) * 4;
+        wv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < ev) {
+          wv[c] = *reinterpret_cast<const float4*>(p.table + base + col);
+          if constexpr (kHasS0) sv[c] = load_vec4<StateT>(s0 + base + col);
+        }
+      }
+      float4 acc[NC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        gptr[u] = nullptr;
-        sc[u] = 0.f;
-        if (j + u < o1) {
-          gptr[u] = locate_grad<GradT>(p, ix.bucket_list[j + u]);
-          sc[u] = ix.bucket_scale ? ix.bucket_scale[j + u] : 1.f;
+      for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (unsigned int j = o0; j < o1; j += 4) {
+        const GradT* gptr[4];
+        float sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          gptr[u] = nullptr;
+          sc[u] = 0.f;
+          if (j + u < o1) {
+            const unsigned int e = (j == o0) ? b_e[0][u] : ix.bucket_list[j + u];
+            gptr[u] = locate_grad<GradT>(p, e);
+            sc[u] = (j == o0) ? b_s[0][u] : (has_scale ? ix.bucket_scale[j + u] : 1.f);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int col = (c * G + gl) * 4;
+          if (col < ev) {
+            float4 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              g[u] = gptr[u] ? load_vec4<GradT>(gptr[u] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[c].x += g[u].x * sc[u]; acc[c].y += g[u].y * sc[u];
+              acc[c].z += g[u].z * sc[u]; acc[c].w += g[u].w * sc[u];
+            }
+          }
         }
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int col = (c * G + gl) * 4;
         if (col < ev) {
-          float4 g[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            g[u] = gptr[u] ? load_vec4<GradT>(gptr[u] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc[c].x += g[u].x * sc[u]; acc[c].y += g[u].y * sc[u];
-            acc[c].z += g[u].z * sc[u]; acc[c].w += g[u].w * sc[u];
-          }
+          float4 w = wv[c];
+          apply_opt4_pre<OPT, StateT>(w, make_float4(acc[c].x * inv_scaler, acc[c].y * inv_scaler,
+                                                     acc[c].z * inv_scaler, acc[c].w * inv_scaler),
+                                      sv[c], s0, s1, base + col, hp, lr, bc1, bc2);
+          *reinterpret_cast<float4*>(p.table + base + col) = w;
         }
       }
-    }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = (c * G + gl) * 4;
-      if (col < ev) {
-        float4 w = *reinterpret_cast<float4*>(p.table + base + col);
-        apply_opt4<OPT, StateT>(w, make_float4(acc[c].x * inv_scaler, acc[c].y * inv_scaler, acc[c].z * inv_scaler, acc[c].w * inv_scaler), s0, s1, base + col, hp, lr, bc1, bc2);
-        *reinterpret_cast<float4*>(p.table + base + col) = w;
+      if (gl == 0) {
+        const unsigned int slot = ut.slots[uid];
+        ut.keys[slot] = kEmptyKey;
+        ut.vals[slot] = kInvalidVal;
       }
     }
-    if (gl == 0) {
-      const unsigned int slot = ut.slots[uid];
-      ut.keys[slot] = kEmptyKey;
-      ut.vals[slot] = kInvalidVal;
+    // rotate the pipeline registers
+    a_o0[0] = a_o0[1]; a_o1[0] = a_o1[1]; a_row[0] = a_row[1];
+    a_o0[1] = a_o0[2]; a_o1[1] = a_o1[2]; a_row[1] = a_row[2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      b_e[0][u] = b_e[1][u];
+      b_s[0][u] = b_s[1][u];
     }
   }
 }
