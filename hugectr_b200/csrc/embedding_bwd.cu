@@ -387,6 +387,28 @@ HCTR_DEVICE const GradT* locate_grad(const EmbParams& p, unsigned int e) {
   return reinterpret_cast<const GradT*>(p.grad[e >> 28]) + (static_cast<long long>(e & 0x0FFFFFFFu) << 2);
 }
 
+// Heavy rows (more than kHeavy occurrences) are listed as (uid, chunk) work items right after the
+// offsets are known, i.e. during the index build, so the heavy kernel can run NEXT TO the light-row
+// kernel instead of after it.
+__global__ void __launch_bounds__(256)
+    emb_bwd_heavy_list_kernel(const UniqueTable ut, const BwdIndex ix) {
+  const unsigned int n = min(*ut.counter, ut.max_unique);
+  for (unsigned int uid = blockIdx.x * blockDim.x + threadIdx.x; uid < n;
+       uid += gridDim.x * blockDim.x) {
+    const unsigned int cnt = ix.offsets[uid + 1] - ix.offsets[uid];
+    if (cnt <= kHeavy) continue;
+    const unsigned int nch = (cnt + kChunk - 1) / kChunk;
+    const unsigned int slot = atomicAdd(ix.heavy_slot, 1u);
+    const unsigned int base = atomicAdd(ix.heavy_count, nch);
+    for (unsigned int c = 0; c < nch; ++c) {
+      if (base + c < ix.max_heavy_items && slot < ix.max_heavy_rows) {
+        ix.heavy_items[2 * (base + c)] = uid;
+        ix.heavy_items[2 * (base + c) + 1] = (slot << 12) | c;   // <= 4096 chunks per row
+      }
+    }
+  }
+}
+
 // G lanes per unique row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the row).
 // The per-row dependency chain  offsets/rows[uid] -> bucket_list[] -> gradient rows -> weight/state
 // is software-pipelined over the rows a lane group visits: while row i is reduced, the bucket
@@ -454,17 +476,7 @@ __global__ void __launch_bounds__(256)
     const unsigned int o0 = a_o0[0], o1 = a_o1[0];
     const unsigned int cnt = o1 - o0;
     if (cnt > kHeavy) {
-      if (gl == 0) {
-        const unsigned int nch = (cnt + kChunk - 1) / kChunk;
-        const unsigned int slot = atomicAdd(ix.heavy_slot, 1u);
-        const unsigned int base = atomicAdd(ix.heavy_count, nch);
-        for (unsigned int c = 0; c < nch; ++c) {
-          if (base + c < ix.max_heavy_items && slot < ix.max_heavy_rows) {
-            ix.heavy_items[2 * (base + c)] = uid;
-            ix.heavy_items[2 * (base + c) + 1] = (slot << 12) | c;   // <= 4096 chunks per row
-          }
-        }
-      }
+      // handled by emb_bwd_heavy_kernel (listed by emb_bwd_heavy_list_kernel)
     } else {
       const long long base = static_cast<long long>(a_row[0]) * ev;
       // weight / state first: independent of the gradients
@@ -654,9 +666,25 @@ extern "C" int hctr_emb_bwd_index(const EmbParams* p, const UniqueTable* ut, con
                                        ix->heavy_slot);
   scan_apply_kernel<<<nb, 1024, 0, st>>>(ix->count, ix->block_sums, ix->offsets, ut->counter,
                                          ut->max_unique);
+  emb_bwd_heavy_list_kernel<<<148 * 4, 256, 0, st>>>(*ut, *ix);
   emb_bwd_fill_kernel<<<blocks, kIdxThreads, 0, st>>>(*p, *ix, total_pairs);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
+// fork/join helper: the heavy-row kernel runs on an internal side stream next to the light-row
+// kernel (event dependencies are captured into CUDA graphs like any other cross-stream edge)
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok() {
+    if (s) return true;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+    return true;
+  }
+};
+static SideStream g_heavy_side;
 
 template <int OPT, typename StateT>
 static int launch_reduce(const EmbParams* p, const UniqueTable* ut, const BwdIndex* ix, void* s0,
@@ -665,6 +693,21 @@ static int launch_reduce(const EmbParams* p, const UniqueTable* ut, const BwdInd
   const int blocks = num_sms * 8;
   const size_t smem = 8 * static_cast<size_t>(p->ev_size) * sizeof(float);
   const bool g8 = p->ev_size <= 128;
+  // heavy rows first, on the side stream: its (small, latency-bound) blocks become resident before
+  // the bandwidth-bound light-row kernel fills the rest of every SM
+  const bool fork = g_heavy_side.ok();
+  cudaStream_t hs = fork ? g_heavy_side.s : st;
+  if (fork) {
+    cudaEventRecord(g_heavy_side.fork, st);
+    cudaStreamWaitEvent(hs, g_heavy_side.fork, 0);
+  }
+  if (grad_bf16)
+    emb_bwd_heavy_kernel<OPT, StateT, __nv_bfloat16><<<num_sms * 4, 256, smem, hs>>>(
+        *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
+  else
+    emb_bwd_heavy_kernel<OPT, StateT, float><<<num_sms * 4, 256, smem, hs>>>(
+        *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
+  if (fork) cudaEventRecord(g_heavy_side.join, hs);
   if (grad_bf16) {
     if (g8)
       emb_bwd_reduce_update_kernel<OPT, StateT, __nv_bfloat16, 8><<<blocks, 256, 0, st>>>(
@@ -672,8 +715,6 @@ static int launch_reduce(const EmbParams* p, const UniqueTable* ut, const BwdInd
     else
       emb_bwd_reduce_update_kernel<OPT, StateT, __nv_bfloat16, 32><<<blocks, 256, 0, st>>>(
           *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
-    emb_bwd_heavy_kernel<OPT, StateT, __nv_bfloat16><<<num_sms * 4, 256, smem, st>>>(
-        *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
   } else {
     if (g8)
       emb_bwd_reduce_update_kernel<OPT, StateT, float, 8><<<blocks, 256, 0, st>>>(
@@ -681,9 +722,8 @@ static int launch_reduce(const EmbParams* p, const UniqueTable* ut, const BwdInd
     else
       emb_bwd_reduce_update_kernel<OPT, StateT, float, 32><<<blocks, 256, 0, st>>>(
           *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
-    emb_bwd_heavy_kernel<OPT, StateT, float><<<num_sms * 4, 256, smem, st>>>(
-        *p, *ut, *ix, (StateT*)s0, (StateT*)s1, *hp, grad_scale);
   }
+  if (fork) cudaStreamWaitEvent(st, g_heavy_side.join, 0);
   return 0;
 }
 

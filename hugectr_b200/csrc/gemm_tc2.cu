@@ -10,6 +10,7 @@
 //   * both CTAs run the fused epilogue on their own 128 TMEM lanes and release the accumulator stage
 //     with a remote mbarrier arrive on the leader
 #include <cstdio>
+#include <cstdlib>
 
 #include "gemm_epilogue.cuh"
 
@@ -64,20 +65,32 @@ HCTR_DEVICE void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
                : "memory");
 }
 
-template <int BN>
+constexpr int kSlabBytes = 32 * 128;          // [32 rows x 64 bf16], 128-byte swizzled rows
+constexpr int kSmemLimit = 232448;            // 227 KB opt-in limit of sm_100
+
+template <int BN, int KIND>
 struct Smem2 {
   static constexpr int kABytes = T2_BLOCK_M * T2_BLOCK_K * 2;      // this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * T2_BLOCK_K * 2;        // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024;
+  // epilogue slabs per warp: 2 output buffers (+2 aux-output for CROSS) + 2 x (operand slabs)
+  static constexpr int kLdTensors = KIND == EK_CROSS ? 2 : (KIND == EK_GENERIC ? 0 : 1);
+  static constexpr int kStSlabs = KIND == EK_CROSS ? 4 : 2;
+  static constexpr int kWarpEpiBytes = (kStSlabs + 2 * kLdTensors) * kSlabBytes;
+  static constexpr int kEpiBytes = 4 * kWarpEpiBytes;
+  static constexpr int kMaxStages = (BN == 256) ? 6 : 8;
+  static constexpr int kFit = (kSmemLimit - 2048 - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 + 1024 + kEpiBytes;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(T2_THREADS, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
-  using L = Smem2<BN>;
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+                    const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmXl,
+                    const GemmParams p, const int tma_epi) {
+  using L = Smem2<BN, KIND>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -90,6 +103,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
   uint64_t* tmem_full = bars + 2 * kStages;     // per CTA: accumulator ready (leader commit, multicast)
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // leader only: 8 epilogue warps of the pair
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_bar = bars + 2 * kStages + 6;   // 2 operand-slab barriers per epilogue warp
+  uint8_t* epi_smem = smem + kStages * L::kStageBytes + 1024;
 
   const int warp_idx = threadIdx.x >> 5;
   const int cta_rank = static_cast<int>(cluster_ctarank());
@@ -112,6 +127,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) tmem_alloc_2sm(tmem_ptr, 2 * BN);
@@ -215,28 +231,114 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
     int as = 0;
     uint32_t aphase = 0;
     const int flags = p.flags;
-    for (int t = pair_id; t < total_items; t += num_pairs) {
-      const int n_blk = t % p.n_tiles;
-      const int m_blk = ((t / p.n_tiles) % m_pairs) * 2 + cta_rank;
-      const int m = m_blk * T2_BLOCK_M + ew * 32 + lane;
-      const bool row_ok = m < p.M;
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
+    if (!tma_epi) {
+      // ---- direct epilogue (fp32 / atomic outputs, unaligned operands): one thread per row
+      for (int t = pair_id; t < total_items; t += num_pairs) {
+        const int n_blk = t % p.n_tiles;
+        const int m_blk = ((t / p.n_tiles) % m_pairs) * 2 + cta_rank;
+        const int m = m_blk * T2_BLOCK_M + ew * 32 + lane;
+        const bool row_ok = m < p.M;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + as * BN + c * 32 + (static_cast<uint32_t>(ew * 32) << 16), r);
-        tmem_ld_wait();
-        epilogue_chunk(p, flags, m, row_ok, n0, r);
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + as * BN + c * 32 + (static_cast<uint32_t>(ew * 32) << 16), r);
+          tmem_ld_wait();
+          epilogue_chunk(p, flags, m, row_ok, n0, r);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);   // 8 arrivals (4 warps x 2 CTAs)
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);   // 8 arrivals (4 warps x 2 CTAs)
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
+    } else {
+      // ---- TMA-staged epilogue: per-warp [32 x 64] slabs, bulk tensor stores, operand slabs
+      // requested two 64-column groups (>= one 128-column tile) ahead
+      constexpr int kG = BN / 64;
+      constexpr int kLd = L::kLdTensors;
+      const uint32_t wbase = smem_u32(epi_smem + ew * L::kWarpEpiBytes);
+      const uint32_t ld_base = wbase + L::kStSlabs * kSlabBytes;
+      uint64_t* lbar = epi_bar + ew * 2;
+      const bool has_aux = (KIND == EK_CROSS) && p.aux != nullptr;
+      // issue cursor of the operand loads (runs two groups ahead of the consume cursor)
+      int it = pair_id, ig = 0;
+      uint32_t qi = 0;
+      auto issue_next = [&]() {
+        if constexpr (kLd > 0) {
+          if (it < total_items) {
+            if (lane == 0) {
+              const int n0 = (it % p.n_tiles) * BN + ig * 64;
+              const int m0 = (((it / p.n_tiles) % m_pairs) * 2 + cta_rank) * T2_BLOCK_M + ew * 32;
+              const uint32_t b = qi & 1u;
+              uint8_t* dst = epi_smem + ew * L::kWarpEpiBytes + L::kStSlabs * kSlabBytes +
+                             b * (kLd * kSlabBytes);
+              mbar_arrive_expect_tx(&lbar[b], kLd * kSlabBytes);
+              tma_load_2d(dst, &tmX0, &lbar[b], n0, m0);
+              if constexpr (kLd == 2) tma_load_2d(dst + kSlabBytes, &tmXl, &lbar[b], n0, m0);
+            }
+            ++qi;
+            if (++ig == kG) {
+              ig = 0;
+              it += num_pairs;
+            }
+          }
+        }
+      };
+      issue_next();
+      issue_next();
+      uint32_t q = 0;
+      for (int t = pair_id; t < total_items; t += num_pairs) {
+        const int n_blk = t % p.n_tiles;
+        const int m0 = (((t / p.n_tiles) % m_pairs) * 2 + cta_rank) * T2_BLOCK_M + ew * 32;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < kG; ++g, ++q) {
+          const uint32_t b = q & 1u;
+          const uint32_t st_out = wbase + b * kSlabBytes;
+          const uint32_t st_aux = has_aux ? wbase + (2 + b) * kSlabBytes : 0u;
+          const uint32_t ld_a = ld_base + b * (kLd * kSlabBytes);
+          const uint32_t ld_b = (KIND == EK_CROSS) ? ld_a + kSlabBytes : ld_a;
+          // the slab pair `b` was handed to the TMA store engine two groups ago
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          if constexpr (kLd > 0) mbar_wait(&lbar[b], (q >> 1) & 1u);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c = g * 2 + half;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + as * BN + c * 32 + (static_cast<uint32_t>(ew * 32) << 16), r);
+            tmem_ld_wait();
+            epilogue_chunk_tma<KIND>(p, flags, lane, n_blk * BN + c * 32, half, r, st_out, st_aux, ld_a,
+                                     ld_b);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int n0 = n_blk * BN + g * 64;
+            if (n0 < p.N) {
+              tma_store_2d(&tmOut, epi_smem + ew * L::kWarpEpiBytes + b * kSlabBytes, n0, m0);
+              if (has_aux)
+                tma_store_2d(&tmAux, epi_smem + ew * L::kWarpEpiBytes + (2 + b) * kSlabBytes, n0, m0);
+            }
+            tma_store_commit();
+          }
+          issue_next();   // operand slab `b` has been fully consumed (ordered by the __syncwarp above)
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
+      if (lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -281,12 +383,17 @@ static int make_tmap2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
 
 static int g2_num_sms = 0;
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                   cudaStream_t stream) {
-  using L = Smem2<BN>;
+struct EpiMaps {
+  CUtensorMap out, aux, x0, xl;
+  int enabled;
+};
+
+template <int BN, bool A_MN, bool B_MN, int KIND>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
+                   const GemmParams& p, cudaStream_t stream) {
+  using L = Smem2<BN, KIND>;
   static bool attr_set = false;
-  auto kern = gemm_tc2_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc2_kernel<BN, A_MN, B_MN, KIND>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess)
       return -3;
@@ -308,7 +415,8 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return -4;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.aux, em.x0, em.xl, p, em.enabled) != cudaSuccess)
+    return -4;
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -354,15 +462,49 @@ extern "C" int hctr_gemm_bf16_2sm(const void* A, const void* B, void* out, int M
   if (b_mn) rc = make_tmap2(&tb, B, N, K, ldb, 64, T2_BLOCK_K);
   else      rc = make_tmap2(&tb, B, K, N, ldb, T2_BLOCK_K, BN / 2);
   if (rc) return rc - 10;
-#define HCTR_DISPATCH2(BNV)                                                  \
+  // TMA epilogue: bf16 output, 16-byte aligned operands with 16-byte multiple row pitches
+  int kind = epi_kind_of(flags, addf);
+  EpiMaps em;
+  em.enabled = 0;
+  auto tma_ok = [](const void* ptr, long long ld) {
+    return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0;
+  };
+  static const bool tma_epi_off = getenv("HCTR_GEMM_DIRECT_EPI") != nullptr;
+  if (kind >= 0 && !tma_epi_off && tma_ok(out, ldo)) {
+    bool ok = make_tmap2(&em.out, out, N, M, ldo, 64, 32) == 0;
+    em.aux = em.x0 = em.xl = em.out;
+    if (ok && kind == EK_CROSS) {
+      ok = tma_ok(x0, ldx) && tma_ok(xl, ldx) && (aux == nullptr || tma_ok(aux, ldaux)) &&
+           make_tmap2(&em.x0, x0, N, M, ldx, 64, 32) == 0 && make_tmap2(&em.xl, xl, N, M, ldx, 64, 32) == 0 &&
+           (aux == nullptr || make_tmap2(&em.aux, aux, N, M, ldaux, 64, 32) == 0);
+    } else if (ok && kind == EK_ADD) {
+      ok = tma_ok(xl, ldx) && make_tmap2(&em.x0, xl, N, M, ldx, 64, 32) == 0;
+    } else if (ok && kind == EK_MASK) {
+      ok = tma_ok(mask, ldmask) && make_tmap2(&em.x0, mask, N, M, ldmask, 64, 32) == 0;
+    }
+    em.enabled = ok ? 1 : 0;
+  }
+  if (!em.enabled) {
+    kind = EK_GENERIC;
+    em.out = em.aux = em.x0 = em.xl = ta;   // unused
+  }
+#define HCTR_DISPATCH2K(BNV, KV)                                             \
   if (a_mn) {                                                                \
-    if (b_mn) return launch2<BNV, true, true>(ta, tb, p, stream);            \
-    return launch2<BNV, true, false>(ta, tb, p, stream);                     \
+    if (b_mn) return launch2<BNV, true, true, KV>(ta, tb, em, p, stream);        \
+    return launch2<BNV, true, false, KV>(ta, tb, em, p, stream);                 \
   } else {                                                                   \
-    if (b_mn) return launch2<BNV, false, true>(ta, tb, p, stream);           \
-    return launch2<BNV, false, false>(ta, tb, p, stream);                    \
+    if (b_mn) return launch2<BNV, false, true, KV>(ta, tb, em, p, stream);       \
+    return launch2<BNV, false, false, KV>(ta, tb, em, p, stream);                \
+  }
+#define HCTR_DISPATCH2(BNV)                                                  \
+  switch (kind) {                                                            \
+    case EK_CROSS: HCTR_DISPATCH2K(BNV, EK_CROSS)                            \
+    case EK_ADD: HCTR_DISPATCH2K(BNV, EK_ADD)                                \
+    case EK_MASK: HCTR_DISPATCH2K(BNV, EK_MASK)                              \
+    default: HCTR_DISPATCH2K(BNV, EK_GENERIC)                                \
   }
   if (BN == 256) { HCTR_DISPATCH2(256) }
   HCTR_DISPATCH2(128)
+#undef HCTR_DISPATCH2K
 #undef HCTR_DISPATCH2
 }

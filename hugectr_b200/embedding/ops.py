@@ -441,7 +441,7 @@ def bwd_index(lookups, lookups_dev, table, ev_pitch, key_bufs, batch, ws, my_ran
                                   _st(table.device))
     if rc:
         raise RuntimeError("hctr_emb_bwd_index failed")
-    D._count(5)
+    D._count(6)
 
 
 def bwd_reduce_update(opt: Optimizer_t, lookups, lookups_dev, table, s0, s1, ev_pitch, key_bufs,
