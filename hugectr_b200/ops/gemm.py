@@ -132,7 +132,13 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
     if splits > 1:
         flags |= EPI_ATOMIC
     if block_n == 0:
-        block_n = _pick_block_n(M, N, K, splits)
+        block_n = _tuned_block_n(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags,
+                                 splits, addf)
+    _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, block_n, addf)
+    return out
+
+
+def _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, block_n, addf):
     stream = torch.cuda.current_stream(a.device).cuda_stream
     fn = _lib().hctr_gemm_bf16
     if block_n >= 2000:           # 2000 + BN : cta_group::2 kernel (CTA pair, 256 x BN tile)
@@ -147,4 +153,49 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
         0 if addf is None else addf.stride(0), stream)
     if rc != 0:
         raise RuntimeError(f"hctr_gemm_bf16 failed rc={rc} M={M} N={N} K={K}")
-    return out
+
+
+# ----------------------------------------------------------------------------- tile autotuner
+# The analogue of the reference's cublasLt algorithm search (GemmFunctor::search_algorithm,
+# HugeCTR/src/layers/functors/fused_fc_layer_functors.cu: 16 heuristics x 100 repetitions at
+# initialisation): the first time a (shape, layout, epilogue) is seen outside graph capture, the
+# candidate tile configurations are timed on scratch outputs and the fastest is cached.
+_TUNE_CACHE = {}
+
+
+def _tuned_block_n(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, addf):
+    import os
+    heur = _pick_block_n(M, N, K, splits)
+    if heur < 2000 or os.environ.get("HCTR_GEMM_AUTOTUNE", "1") == "0" or os.environ.get("HCTR_GEMM_BN"):
+        return heur
+    key = (M, N, K, bool(a_mn), bool(b_mn), int(flags), int(splits), out.dtype, out.stride(0),
+           aux is not None, bias is not None)
+    hit = _TUNE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if torch.cuda.is_current_stream_capturing():
+        return heur
+    cands = [2128, 2256] if N >= 256 else [2128]
+    if len(cands) == 1:
+        _TUNE_CACHE[key] = cands[0]
+        return cands[0]
+    so = torch.empty_strided(out.size(), out.stride(), dtype=out.dtype, device=out.device)
+    if flags & (EPI_ATOMIC | EPI_ACCUM):
+        so.zero_()
+    sa = (torch.empty_strided(aux.size(), aux.stride(), dtype=aux.dtype, device=aux.device)
+          if aux is not None else None)
+    best, best_t = heur, float("inf")
+    for bn in cands:
+        for _ in range(2):
+            _launch(a, b, so, M, N, K, a_mn, b_mn, bias, mask, x0, xl, sa, alpha, flags, splits, bn, addf)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            _launch(a, b, so, M, N, K, a_mn, b_mn, bias, mask, x0, xl, sa, alpha, flags, splits, bn, addf)
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        if t < best_t:
+            best, best_t = bn, t
+    _TUNE_CACHE[key] = best
+    return best
