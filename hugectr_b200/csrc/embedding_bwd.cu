@@ -39,6 +39,9 @@ struct BwdIndex {
   unsigned int* heavy_ticket; // [max_heavy_rows]
   unsigned int* heavy_slot;   // [1] allocator of scratch rows
   unsigned int max_heavy_rows, max_heavy_items;
+  uint2* light_list;          // [max_unique] (uid, offset | (count-1) << 30) of rows with <= 4 entries
+  uint2* medium_list;         // [max_unique] (uid, offset) of rows with 5..kHeavy entries
+  unsigned int* class_count;  // [2] light / medium list lengths
 };
 
 // ---------------------------------------------------------------- A: unique ids + counts
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(1024)
 }
 __global__ void __launch_bounds__(1024)
     scan_sums_kernel(unsigned int* sums, const unsigned int* n_ptr, unsigned int max_n,
-                     unsigned int* heavy_count, unsigned int* heavy_slot) {
+                     unsigned int* heavy_count, unsigned int* heavy_slot, unsigned int* class_count) {
   // single block: exclusive scan of the block sums in place
   const unsigned int n = min(*n_ptr, max_n);
   const unsigned int nb = (n + 1023) / 1024;
@@ -249,6 +252,8 @@ __global__ void __launch_bounds__(1024)
     carry_s = 0;
     *heavy_count = 0;
     *heavy_slot = 0;
+    class_count[0] = 0;
+    class_count[1] = 0;
   }
   __syncthreads();
   for (unsigned int base = 0; base < nb; base += 1024) {
@@ -387,41 +392,83 @@ HCTR_DEVICE const GradT* locate_grad(const EmbParams& p, unsigned int e) {
   return reinterpret_cast<const GradT*>(p.grad[e >> 28]) + (static_cast<long long>(e & 0x0FFFFFFFu) << 2);
 }
 
-// Heavy rows (more than kHeavy occurrences) are listed as (uid, chunk) work items right after the
-// offsets are known, i.e. during the index build, so the heavy kernel can run NEXT TO the light-row
-// kernel instead of after it.
-__global__ void __launch_bounds__(256)
-    emb_bwd_heavy_list_kernel(const UniqueTable ut, const BwdIndex ix) {
+// Unique rows are classified by their number of occurrences right after the offsets are known (during
+// the index build, off the critical path):
+//   light  (<= 4 entries, ~94 % of the rows): compact list of (uid, offset | (count-1) << 30)
+//   medium (5..kHeavy):                       compact list of (uid, offset)
+//   heavy  (> kHeavy):                        (uid, chunk) work items of the block-per-chunk kernel
+// so that the update kernels run UNIFORM work per lane group: with the power-law tail, four rows
+// sharing a warp would otherwise wait for the longest of them (2.6x measured slowdown).
+// List positions are reserved with one atomicAdd per block and class.
+constexpr unsigned int kLightMax = 4;
+__global__ void __launch_bounds__(1024)
+    emb_bwd_classify_kernel(const UniqueTable ut, const BwdIndex ix) {
+  __shared__ unsigned int s_cnt[2][32];
+  __shared__ unsigned int s_base[2];
   const unsigned int n = min(*ut.counter, ut.max_unique);
-  for (unsigned int uid = blockIdx.x * blockDim.x + threadIdx.x; uid < n;
-       uid += gridDim.x * blockDim.x) {
-    const unsigned int cnt = ix.offsets[uid + 1] - ix.offsets[uid];
-    if (cnt <= kHeavy) continue;
-    const unsigned int nch = (cnt + kChunk - 1) / kChunk;
-    const unsigned int slot = atomicAdd(ix.heavy_slot, 1u);
-    const unsigned int base = atomicAdd(ix.heavy_count, nch);
-    for (unsigned int c = 0; c < nch; ++c) {
-      if (base + c < ix.max_heavy_items && slot < ix.max_heavy_rows) {
-        ix.heavy_items[2 * (base + c)] = uid;
-        ix.heavy_items[2 * (base + c) + 1] = (slot << 12) | c;   // <= 4096 chunks per row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned int uid = base + threadIdx.x;
+    unsigned int cnt = 0, o0 = 0;
+    if (uid < n) {
+      o0 = ix.offsets[uid];
+      cnt = ix.offsets[uid + 1] - o0;
+    }
+    const bool is_light = cnt >= 1 && cnt <= kLightMax;
+    const bool is_medium = cnt > kLightMax && cnt <= kHeavy;
+    const unsigned int bl = __ballot_sync(0xffffffffu, is_light);
+    const unsigned int bm = __ballot_sync(0xffffffffu, is_medium);
+    if (lane == 0) {
+      s_cnt[0][warp] = __popc(bl);
+      s_cnt[1][warp] = __popc(bm);
+    }
+    __syncthreads();
+    if (warp < 2) {   // warp 0 scans the light counts, warp 1 the medium counts
+      unsigned int v = s_cnt[warp][lane], x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      s_cnt[warp][lane] = x - v;
+      if (lane == 31) s_base[warp] = x ? atomicAdd(&ix.class_count[warp], x) : 0u;
+    }
+    __syncthreads();
+    const unsigned int below = (1u << lane) - 1u;
+    if (is_light) {
+      const unsigned int pos = s_base[0] + s_cnt[0][warp] + __popc(bl & below);
+      ix.light_list[pos] = make_uint2(uid, o0 | ((cnt - 1u) << 30));
+    } else if (is_medium) {
+      const unsigned int pos = s_base[1] + s_cnt[1][warp] + __popc(bm & below);
+      ix.medium_list[pos] = make_uint2(uid, o0);
+    } else if (cnt > kHeavy) {
+      const unsigned int nch = (cnt + kChunk - 1) / kChunk;
+      const unsigned int slot = atomicAdd(ix.heavy_slot, 1u);
+      const unsigned int hb = atomicAdd(ix.heavy_count, nch);
+      for (unsigned int c = 0; c < nch; ++c) {
+        if (hb + c < ix.max_heavy_items && slot < ix.max_heavy_rows) {
+          ix.heavy_items[2 * (hb + c)] = uid;
+          ix.heavy_items[2 * (hb + c) + 1] = (slot << 12) | c;   // <= 4096 chunks per row
+        }
       }
     }
+    __syncthreads();
   }
 }
 
-// G lanes per unique row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the row).
-// The per-row dependency chain  offsets/rows[uid] -> bucket_list[] -> gradient rows -> weight/state
-// is software-pipelined over the rows a lane group visits: while row i is reduced, the bucket
-// entries of row i+1 and the offsets of row i+2 are already in flight, and the weight / state
-// vectors of row i are requested BEFORE its gradients, so one DRAM latency is exposed per row
-// instead of four.
+// Light + medium rows: fused gradient reduction and optimizer step.
+// Light part: G lanes per row (G = 8: four rows per warp, every lane owns 4 float4 chunks of the
+// row), exactly one gather round per row.  The chain  record -> (arena row, bucket entries) ->
+// (weight, state, gradient rows)  is software-pipelined over the rows a lane group visits: record i+2
+// and the row id / entries of i+1 are in flight while row i is reduced, and the weight / state
+// vectors are requested together with the gradients, so ONE DRAM latency is exposed per row.
+// Medium part: one warp per row, 8 gradient rows in flight per round.
 template <int OPT, typename StateT, typename GradT, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (G == 8) ? 3 : 2)
     emb_bwd_reduce_update_kernel(const EmbParams p, const UniqueTable ut, const BwdIndex ix,
                                  StateT* __restrict__ s0, StateT* __restrict__ s1, const OptHyper hp,
                                  const float grad_scale) {
   constexpr bool kHasS0 = (OPT != OPT_SGD);
-  const unsigned int n = min(*ut.counter, ut.max_unique);
   const float lr = (hp.lr_ptr ? *hp.lr_ptr : 1.f) * hp.lr_scale;
   float bc1 = 1.f, bc2 = 1.f;
   if constexpr (OPT == OPT_ADAM) {
@@ -431,95 +478,78 @@ __global__ void __launch_bounds__(256)
   }
   const float inv_scaler = grad_scale / hp.scaler;
   const int lane = threadIdx.x & 31;
-  const int gl = lane % G, gi = lane / G;
-  constexpr int GPW = 32 / G;
   const int ev = p.ev_size;
-  constexpr int NC = (G == 8) ? 4 : 8;             // chunks per lane
-  const unsigned int groups = ((gridDim.x * blockDim.x) >> 5) * GPW;
-  const unsigned int first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + gi;
   const bool has_scale = ix.bucket_scale != nullptr;
+  const unsigned int n_light = min(ix.class_count[0], ut.max_unique);
+  const unsigned int n_medium = min(ix.class_count[1], ut.max_unique);
+  const unsigned int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int num_warps = (gridDim.x * blockDim.x) >> 5;
 
-  // stage A: offsets + arena row of a unique id
-  unsigned int a_o0[3], a_o1[3];
-  unsigned long long a_row[3];
-  // stage B: first four bucket entries (+ scales) of a row
-  unsigned int b_e[2][4];
-  float b_s[2][4];
-  auto load_a = [&](unsigned int u, int k) {
-    a_o0[k] = a_o1[k] = 0u;
-    a_row[k] = 0ull;
-    if (u < n) {
-      a_o0[k] = ix.offsets[u];
-      a_o1[k] = ix.offsets[u + 1];
-      a_row[k] = ut.rows[u];
-    }
-  };
-  auto load_b = [&](int ka, int kb) {
-    const unsigned int o0 = a_o0[ka], o1 = a_o1[ka];
-    const bool light = (o1 - o0) <= kHeavy;
+  // ------------------------------------------------------------------ light rows
+  {
+    const int gl = lane % G, gi = lane / G;
+    constexpr int GPW = 32 / G;
+    constexpr int NC = (G == 8) ? 4 : 8;             // chunks per lane
+    const unsigned int groups = num_warps * GPW;
+    const unsigned int first = warp_global * GPW + gi;
+    uint2 rec[3];                 // stage R: list records of rows i, i+1, i+2
+    unsigned long long row[2];    // stage A: arena row of rows i, i+1
+    unsigned int ent[2][4];       //          and their bucket entries / scales
+    float esc[2][4];
+    auto load_r = [&](unsigned int i, int k) {
+      rec[k] = make_uint2(0u, 0u);
+      if (i < n_light) rec[k] = ix.light_list[i];
+    };
+    auto load_a = [&](unsigned int i, int kr, int ka) {
+      row[ka] = 0ull;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      b_e[kb][u] = 0xFFFFFFFFu;
-      b_s[kb][u] = 1.f;
-      if (light && o0 + u < o1) {
-        b_e[kb][u] = ix.bucket_list[o0 + u];
-        if (has_scale) b_s[kb][u] = ix.bucket_scale[o0 + u];
+      for (int u = 0; u < 4; ++u) {
+        ent[ka][u] = 0xFFFFFFFFu;
+        esc[ka][u] = 1.f;
       }
-    }
-  };
-  load_a(first, 0);
-  load_a(first + groups, 1);
-  load_b(0, 0);
-  for (unsigned int uid = first; uid < n; uid += groups) {
-    load_a(uid + 2 * groups, 2);
-    load_b(1, 1);
-    const unsigned int o0 = a_o0[0], o1 = a_o1[0];
-    const unsigned int cnt = o1 - o0;
-    if (cnt > kHeavy) {
-      // handled by emb_bwd_heavy_kernel (listed by emb_bwd_heavy_list_kernel)
-    } else {
-      const long long base = static_cast<long long>(a_row[0]) * ev;
-      // weight / state first: independent of the gradients
-      float4 wv[NC], sv[NC];
+      if (i < n_light) {
+        const unsigned int o0 = rec[kr].y & 0x3FFFFFFFu, cnt = (rec[kr].y >> 30) + 1u;
+        row[ka] = ut.rows[rec[kr].x];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u < cnt) {
+            ent[ka][u] = ix.bucket_list[o0 + u];
+            if (has_scale) esc[ka][u] = ix.bucket_scale[o0 + u];
+          }
+        }
+      }
+    };
+    load_r(first, 0);
+    load_r(first + groups, 1);
+    load_a(first, 0, 0);
+    for (unsigned int i = first; i < n_light; i += groups) {
+      load_r(i + 2 * groups, 2);
+      load_a(i + groups, 1, 1);
+      const unsigned int uid = rec[0].x;
+      const long long base = static_cast<long long>(row[0]) * ev;
+      float4 wv[NC], sv[NC], acc[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const int col = (c * G + gl) * 4;
-        wv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        sv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[c] = sv[c] = acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col < ev) {
           wv[c] = *reinterpret_cast<const float4*>(p.table + base + col);
           if constexpr (kHasS0) sv[c] = load_vec4<StateT>(s0 + base + col);
         }
       }
-      float4 acc[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (unsigned int j = o0; j < o1; j += 4) {
-        const GradT* gptr[4];
-        float sc[4];
+      for (int c = 0; c < NC; ++c) {
+        const int col = (c * G + gl) * 4;
+        if (col < ev) {
+          float4 g[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          gptr[u] = nullptr;
-          sc[u] = 0.f;
-          if (j + u < o1) {
-            const unsigned int e = (j == o0) ? b_e[0][u] : ix.bucket_list[j + u];
-            gptr[u] = locate_grad<GradT>(p, e);
-            sc[u] = (j == o0) ? b_s[0][u] : (has_scale ? ix.bucket_scale[j + u] : 1.f);
-          }
-        }
+          for (int u = 0; u < 4; ++u)
+            g[u] = ent[0][u] != 0xFFFFFFFFu ? load_vec4<GradT>(locate_grad<GradT>(p, ent[0][u]) + col)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int col = (c * G + gl) * 4;
-          if (col < ev) {
-            float4 g[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              g[u] = gptr[u] ? load_vec4<GradT>(gptr[u] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              acc[c].x += g[u].x * sc[u]; acc[c].y += g[u].y * sc[u];
-              acc[c].z += g[u].z * sc[u]; acc[c].w += g[u].w * sc[u];
-            }
+          for (int u = 0; u < 4; ++u) {
+            acc[c].x += g[u].x * esc[0][u]; acc[c].y += g[u].y * esc[0][u];
+            acc[c].z += g[u].z * esc[0][u]; acc[c].w += g[u].w * esc[0][u];
           }
         }
       }
@@ -539,14 +569,55 @@ __global__ void __launch_bounds__(256)
         ut.keys[slot] = kEmptyKey;
         ut.vals[slot] = kInvalidVal;
       }
-    }
-    // rotate the pipeline registers
-    a_o0[0] = a_o0[1]; a_o1[0] = a_o1[1]; a_row[0] = a_row[1];
-    a_o0[1] = a_o0[2]; a_o1[1] = a_o1[2]; a_row[1] = a_row[2];
+      rec[0] = rec[1];
+      rec[1] = rec[2];
+      row[0] = row[1];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      b_e[0][u] = b_e[1][u];
-      b_s[0][u] = b_s[1][u];
+      for (int u = 0; u < 4; ++u) {
+        ent[0][u] = ent[1][u];
+        esc[0][u] = esc[1][u];
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ medium rows: warp per row
+  for (unsigned int i = warp_global; i < n_medium; i += num_warps) {
+    const uint2 r = ix.medium_list[i];
+    const unsigned int uid = r.x, o0 = r.y;
+    const unsigned int o1 = ix.offsets[uid + 1];
+    const long long base = static_cast<long long>(ut.rows[uid]) * ev;
+    for (int col = lane * 4; col < ev; col += 128) {
+      float4 w = *reinterpret_cast<const float4*>(p.table + base + col);
+      float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (kHasS0) sv = load_vec4<StateT>(s0 + base + col);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (unsigned int j = o0; j < o1; j += 8) {
+        float4 g[8];
+        float sc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sc[u] = 0.f;
+          if (j + u < o1) {
+            g[u] = load_vec4<GradT>(locate_grad<GradT>(p, ix.bucket_list[j + u]) + col);
+            sc[u] = has_scale ? ix.bucket_scale[j + u] : 1.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc.x += g[u].x * sc[u]; acc.y += g[u].y * sc[u];
+          acc.z += g[u].z * sc[u]; acc.w += g[u].w * sc[u];
+        }
+      }
+      apply_opt4_pre<OPT, StateT>(w, make_float4(acc.x * inv_scaler, acc.y * inv_scaler,
+                                                 acc.z * inv_scaler, acc.w * inv_scaler),
+                                  sv, s0, s1, base + col, hp, lr, bc1, bc2);
+      *reinterpret_cast<float4*>(p.table + base + col) = w;
+    }
+    if (lane == 0) {
+      const unsigned int slot = ut.slots[uid];
+      ut.keys[slot] = kEmptyKey;
+      ut.vals[slot] = kInvalidVal;
     }
   }
 }
@@ -663,10 +734,10 @@ extern "C" int hctr_emb_bwd_index(const EmbParams* p, const UniqueTable* ut, con
   const unsigned int nb = (ut->max_unique + 1023) / 1024;
   scan_block_sums_kernel<<<nb, 1024, 0, st>>>(ix->count, ix->block_sums, ut->counter, ut->max_unique);
   scan_sums_kernel<<<1, 1024, 0, st>>>(ix->block_sums, ut->counter, ut->max_unique, ix->heavy_count,
-                                       ix->heavy_slot);
+                                       ix->heavy_slot, ix->class_count);
   scan_apply_kernel<<<nb, 1024, 0, st>>>(ix->count, ix->block_sums, ix->offsets, ut->counter,
                                          ut->max_unique);
-  emb_bwd_heavy_list_kernel<<<148 * 4, 256, 0, st>>>(*ut, *ix);
+  emb_bwd_classify_kernel<<<148, 1024, 0, st>>>(*ut, *ix);
   emb_bwd_fill_kernel<<<blocks, kIdxThreads, 0, st>>>(*p, *ix, total_pairs);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -678,7 +749,11 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool ok() {
     if (s) return true;
-    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
+    // highest priority: the (small) heavy-row blocks must become resident before the light-row
+    // kernel occupies every SM, whatever order the graph scheduler releases the two nodes in
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
     cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
     return true;
@@ -690,9 +765,9 @@ template <int OPT, typename StateT>
 static int launch_reduce(const EmbParams* p, const UniqueTable* ut, const BwdIndex* ix, void* s0,
                          void* s1, const OptHyper* hp, float grad_scale, int grad_bf16, int num_sms,
                          cudaStream_t st) {
-  const int blocks = num_sms * 8;
   const size_t smem = 8 * static_cast<size_t>(p->ev_size) * sizeof(float);
   const bool g8 = p->ev_size <= 128;
+  const int blocks = num_sms * (g8 ? 3 : 2);   // one resident wave of grid-stride blocks
   // heavy rows first, on the side stream: its (small, latency-bound) blocks become resident before
   // the bandwidth-bound light-row kernel fills the rest of every SM
   const bool fork = g_heavy_side.ok();

@@ -51,7 +51,8 @@ class CBwdIndex(C.Structure):
                 ("heavy_items", C.c_void_p),
                 ("heavy_count", C.c_void_p), ("heavy_scratch", C.c_void_p),
                 ("heavy_ticket", C.c_void_p), ("heavy_slot", C.c_void_p),
-                ("max_heavy_rows", C.c_uint), ("max_heavy_items", C.c_uint)]
+                ("max_heavy_rows", C.c_uint), ("max_heavy_items", C.c_uint),
+                ("light_list", C.c_void_p), ("medium_list", C.c_void_p), ("class_count", C.c_void_p)]
 
 
 class COptHyper(C.Structure):
@@ -238,6 +239,9 @@ class UniqueWorkspace:
                 self.heavy_scratch = torch.zeros(self.max_heavy_rows, ev_pitch, dtype=torch.float32,
                                                  device=device)
                 self.heavy_ticket = torch.zeros(self.max_heavy_rows, **i32)
+                self.light_list = torch.zeros(2 * mu, **i32)
+                self.medium_list = torch.zeros(2 * mu, **i32)
+                self.class_count = torch.zeros(2, **i32)
                 self.ix = CBwdIndex(self.count.data_ptr(), self.offsets.data_ptr(),
                                     self.block_sums.data_ptr(), self.pair_uid.data_ptr(),
                                     self.bucket_list.data_ptr(),
@@ -245,7 +249,9 @@ class UniqueWorkspace:
                                     self.heavy_items.data_ptr(),
                                     self.heavy_count.data_ptr(), self.heavy_scratch.data_ptr(),
                                     self.heavy_ticket.data_ptr(), self.heavy_slot.data_ptr(),
-                                    self.max_heavy_rows, self.max_heavy_items)
+                                    self.max_heavy_rows, self.max_heavy_items,
+                                    self.light_list.data_ptr(), self.medium_list.data_ptr(),
+                                    self.class_count.data_ptr())
         else:
             self.ref_rows = None
             self.ref_grads = None

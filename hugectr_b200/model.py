@@ -339,10 +339,10 @@ class Model:
         D.lr_step(self.step_t, self.lr_t, s.lr, s.end_lr, s.decay_power, s.warmup_steps,
                   s.decay_start, s.decay_steps)
         net = self.net_train
-        bucketed = (self.world > 1 and self.device.type == "cuda" and not self.dense_frozen
+        bucketed = (self.device.type == "cuda" and not self.dense_frozen
                     and os.environ.get("HCTR_DISABLE_AR_OVERLAP", "0") == "0")
         if bucketed:
-            self.exchange_wgrad.begin_step()
+            self.exchange_wgrad.begin_step(after_bucket=self._dense_opt_range)
             net.wgrad_hook = self.exchange_wgrad.layer_done
         else:
             net.wgrad_hook = None
@@ -395,12 +395,10 @@ class Model:
             net.bprop()
         if not self.dense_frozen:
             if bucketed:
-                self.exchange_wgrad.finish_step()
+                self.exchange_wgrad.finish_step()      # all-reduce + optimizer, bucket by bucket
             else:
                 self.exchange_wgrad.allreduce()
-            D.dense_opt_step(DENSE_OPT_CODE[self.opt_params.optimizer_type], self.arena.weights,
-                             self.arena.wgrad, self.arena.weights16, self.opt_s0, self.opt_s1,
-                             self.lr_t, self.step_t, self.dense_hp, zero_grad=True)
+                self._dense_opt_range(0, self.arena.weights.numel())
         else:
             self.arena.wgrad.zero_()
         if overlap:
@@ -412,6 +410,14 @@ class Model:
             for rt in self.legacy_train:
                 if not self.embedding_frozen.get(rt.name, frozen_emb):
                     rt.backward(self.lr_t, self.step_t)
+
+    def _dense_opt_range(self, lo: int, hi: int):
+        """fused dense optimizer over arena elements [lo, hi) (also zeroes that wgrad range)"""
+        a = self.arena
+        sl = lambda t: None if t is None else t[lo:hi]
+        D.dense_opt_step(DENSE_OPT_CODE[self.opt_params.optimizer_type], a.weights[lo:hi],
+                         a.wgrad[lo:hi], sl(a.weights16), sl(self.opt_s0), sl(self.opt_s1),
+                         self.lr_t, self.step_t, self.dense_hp, zero_grad=True)
 
     def _run_step(self):
         use_graph = (self.solver.use_cuda_graph and self.device.type == "cuda"

@@ -32,16 +32,18 @@ class ExchangeWgrad:
 
     # ---- bucketed overlap with backward (F3): the flat wgrad is produced back to front (bprop
     # visits layers in reverse creation order), so [lo, hi) ranges become final incrementally
-    def begin_step(self):
-        self._pending_hi = self.wgrad.numel()
+    def begin_step(self, after_bucket=None):
+        """``after_bucket(lo, hi)``: optional callback run on the communication stream right after
+        the bucket's all-reduce (the fused dense optimizer of that parameter range), so neither the
+        reduction nor the update of the big upper layers sits at the tail of the step."""
         self._done_lo = self.wgrad.numel()
-        if self.comm.world_size > 1 and self.wgrad.is_cuda:
-            if not hasattr(self, "_stream"):
-                self._stream = torch.cuda.Stream()
+        self._after = after_bucket
+        if self.wgrad.is_cuda and not hasattr(self, "_stream"):
+            self._stream = torch.cuda.Stream()
 
     def layer_done(self, lo: int, bucket_elems: int = 2 << 20):
         """called after a trainable layer's bprop; lo = arena offset of its first parameter"""
-        if self.comm.world_size == 1 or not self.wgrad.is_cuda:
+        if not self.wgrad.is_cuda:
             return
         if self._done_lo - lo >= bucket_elems:
             self._flush(lo)
@@ -53,18 +55,23 @@ class ExchangeWgrad:
         main = torch.cuda.current_stream()
         self._stream.wait_stream(main)
         with torch.cuda.stream(self._stream):
-            if self._p2p is not None:
-                self._p2p.run(lo, hi)
-            else:
-                self.comm.all_reduce(self.wgrad[lo:hi])
+            if self.comm.world_size > 1:
+                if self._p2p is not None:
+                    self._p2p.run(lo, hi)
+                else:
+                    self.comm.all_reduce(self.wgrad[lo:hi])
+            if self._after is not None:
+                self._after(lo, hi)
         self._done_lo = lo
 
     def finish_step(self):
-        """all remaining ranges + join: wgrad is fully reduced on the current stream afterwards"""
-        if self.comm.world_size == 1:
-            return
+        """all remaining ranges + join: wgrad is fully reduced (and, with ``after_bucket``, applied)
+        on the current stream afterwards"""
         if not self.wgrad.is_cuda or not hasattr(self, "_done_lo"):
-            return self.allreduce()
+            self.allreduce()
+            if getattr(self, "_after", None) is not None:
+                self._after(0, self.wgrad.numel())
+            return
         self._flush(0)
         torch.cuda.current_stream().wait_stream(self._stream)
         for t in self.extra:
