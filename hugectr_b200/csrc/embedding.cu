@@ -56,50 +56,104 @@ __global__ void __launch_bounds__(256, 3)
     for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
   const int nchunk = (ev + G * VEC - 1) / (G * VEC);
 
-  for (int h0 = 0; h0 < nnz; h0 += G) {
-    // lanes of the group fetch up to G keys at once (coalesced peer/local read)
-    long long mykey = -1;
-    if (h0 + gl < nnz) mykey = static_cast<long long>(kbase[h0 + gl]);
-    const int cnt = min(G, nnz - h0);
-    for (int j0 = 0; j0 < cnt; j0 += U) {
-      const float* rp[U];
+  // gathers U rows (rp[u] == nullptr: skip) into the accumulators
+  auto gather = [&](const float* const (&rp)[U]) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u;
-        const long long key = __shfl_sync(gmask, mykey, gi * G + (j < cnt ? j : 0));
-        bool ok = (j < cnt) && key >= 0;
-        long long r = key;
-        if (lk.num_shards > 1) {   // block-uniform branch; table-wise shards skip the divisions
-          ok = ok && (key % lk.num_shards) == lk.shard_idx;
-          r = key / lk.num_shards;
-        }
-        ok = ok && r < lk.rows;
-        rp[u] = ok ? p.table + (lk.table_row_off + r) * static_cast<long long>(p.ev_size) : nullptr;
-      }
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < nchunk) {
+        const int col = (c * G + gl) * VEC;
+        if (col < ev) {
+          if constexpr (VEC == 4) {
+            float4 v[U];
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < nchunk) {
-          const int col = (c * G + gl) * VEC;
-          if (col < ev) {
-            if constexpr (VEC == 4) {
-              float4 v[U];
+            for (int u = 0; u < U; ++u)
+              v[u] = rp[u] ? __ldg(reinterpret_cast<const float4*>(rp[u] + col))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int u = 0; u < U; ++u)
-                v[u] = rp[u] ? __ldg(reinterpret_cast<const float4*>(rp[u] + col))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int u = 0; u < U; ++u) {
-                acc[c][0] += v[u].x; acc[c][1] += v[u].y; acc[c][2] += v[u].z; acc[c][3] += v[u].w;
-              }
-            } else {
-              float v[U];
-#pragma unroll
-              for (int u = 0; u < U; ++u) v[u] = rp[u] ? __ldg(rp[u] + col) : 0.f;
-#pragma unroll
-              for (int u = 0; u < U; ++u) acc[c][0] += v[u];
+            for (int u = 0; u < U; ++u) {
+              acc[c][0] += v[u].x; acc[c][1] += v[u].y; acc[c][2] += v[u].z; acc[c][3] += v[u].w;
             }
+          } else {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = rp[u] ? __ldg(rp[u] + col) : 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc[c][0] += v[u];
           }
         }
+      }
+    }
+  };
+
+  if (lk.num_shards > 1) {
+    // Row-sharded table (block-uniform branch): this shard owns ~1/num_shards of the bag, so the
+    // owned keys are compacted first -- every lane fetches up to 4 keys, a group ballot marks the
+    // owned ones, and rows are gathered U at a time from the compacted set.  (Gathering in key order
+    // would issue one row per round for an 8-way shard: a chain of dependent DRAM latencies.)
+    const int KPL = (G >= 32) ? 1 : ((G >= 16) ? 2 : 4);   // keys per lane and round; KPL * G <= 32
+    const unsigned int ns = static_cast<unsigned int>(lk.num_shards);
+    for (int h0 = 0; h0 < nnz; h0 += KPL * G) {
+      unsigned int rowv[4] = {0u, 0u, 0u, 0u};
+      unsigned int m = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < KPL) {
+          const int h = h0 + i * G + gl;
+          bool ok = false;
+          if (h < nnz) {
+            const long long key = static_cast<long long>(kbase[h]);
+            if (key >= 0) {
+              const unsigned long long uk = static_cast<unsigned long long>(key);
+              unsigned long long q;
+              unsigned int rem;
+              if (uk <= 0xFFFFFFFFull) {        // 32-bit fast path (no 64-bit division)
+                const unsigned int k32 = static_cast<unsigned int>(uk);
+                q = k32 / ns;
+                rem = k32 - static_cast<unsigned int>(q) * ns;
+              } else {
+                q = uk / ns;
+                rem = static_cast<unsigned int>(uk - q * ns);
+              }
+              ok = rem == static_cast<unsigned int>(lk.shard_idx) && q < static_cast<unsigned long long>(lk.rows);
+              rowv[i] = static_cast<unsigned int>(q);
+            }
+          }
+          const unsigned int bal = (__ballot_sync(gmask, ok) >> (gi * G)) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+          m |= bal << (i * G);
+        }
+      }
+      while (m) {               // group-uniform
+        const float* rp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          rp[u] = nullptr;
+          const bool take = m != 0u;
+          const int b = take ? (__ffs(m) - 1) : 0;
+          if (take) m &= m - 1u;
+          const int i = b / G, sl = b - i * G;
+          const unsigned int cand = i == 0 ? rowv[0] : (i == 1 ? rowv[1] : (i == 2 ? rowv[2] : rowv[3]));
+          const unsigned int r = __shfl_sync(gmask, cand, gi * G + sl);
+          if (take) rp[u] = p.table + (lk.table_row_off + r) * static_cast<long long>(p.ev_size);
+        }
+        gather(rp);
+      }
+    }
+  } else {
+    for (int h0 = 0; h0 < nnz; h0 += G) {
+      // lanes of the group fetch up to G keys at once (coalesced peer/local read)
+      long long mykey = -1;
+      if (h0 + gl < nnz) mykey = static_cast<long long>(kbase[h0 + gl]);
+      const int cnt = min(G, nnz - h0);
+      for (int j0 = 0; j0 < cnt; j0 += U) {
+        const float* rp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          const long long key = __shfl_sync(gmask, mykey, gi * G + (j < cnt ? j : 0));
+          const bool ok = (j < cnt) && key >= 0 && key < lk.rows;
+          rp[u] = ok ? p.table + (lk.table_row_off + key) * static_cast<long long>(p.ev_size) : nullptr;
+        }
+        gather(rp);
       }
     }
   }

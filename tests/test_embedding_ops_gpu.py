@@ -66,3 +66,40 @@ def test_cross_bwd_elementwise(acc):
     tol = 0.05 if acc == torch.bfloat16 else 1e-4
     assert (dx0.float().cpu() - ref_dx0).abs().max().item() < tol * max(1.0, ref_dx0.abs().max().item())
     assert (db.cpu() - ref_db).abs().max().item() < 1e-2 * max(1.0, ref_db.abs().max().item())
+
+
+@pytest.mark.parametrize("ev,shards", [(128, 8), (64, 3), (16, 2), (256, 4)])
+def test_forward_row_sharded_compacted_gather(ev, shards):
+    """row-sharded lookups take the compacted-gather path of emb_fwd_kernel (ballot over up to 4 keys
+    per lane); compare one shard's partial pooling with the PyTorch reference"""
+    torch.manual_seed(5)
+    b = 333
+    specs = [(5000, 100, 0), (900, 7, 1), (77, 1, 0), (4000, 27, 1)]   # (vocab, hotness, combiner)
+    shard = shards - 1
+    lookups, koff, ooff, roff = [], 0, 0, 0
+    for vocab, h, c in specs:
+        rows = (vocab - shard + shards - 1) // shards
+        lookups.append(E.LookupDesc(table_row_off=roff, key_off=koff, out_off=ooff, grad_off=ooff,
+                                    hotness=h, key_stride=h, num_shards=shards, shard_idx=shard,
+                                    out_stride=ev, grad_stride=ev, combiner=c, ev_size=ev, rows=rows))
+        koff += b * h
+        ooff += b * ev
+        roff += rows
+    # one unsharded lookup in the same launch (regular path)
+    lookups.append(E.LookupDesc(table_row_off=roff, key_off=koff, out_off=ooff, grad_off=ooff, hotness=5,
+                                key_stride=5, num_shards=1, shard_idx=0, out_stride=ev, grad_stride=ev,
+                                combiner=0, ev_size=ev, rows=600))
+    keys = torch.cat([torch.randint(0, v, (b * h,), dtype=torch.int32) for v, h, _ in specs] +
+                     [torch.randint(0, 600, (b * 5,), dtype=torch.int32)])
+    ooff += b * ev
+    roff += 600
+    table = torch.randn(roff * ev)
+    ref = torch.zeros(ooff)
+    E.forward(lookups, None, table, ev, [keys], [ref], b)
+    dev = torch.device("cuda")
+    out = torch.zeros(ooff, device=dev)
+    E.forward(lookups, E.lookups_to_device(lookups, dev), table.to(dev), ev, [keys.to(dev)], [out], b,
+              key_bytes=4, act_bf16=False)
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), err
