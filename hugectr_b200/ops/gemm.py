@@ -153,6 +153,8 @@ def _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flag
         0 if addf is None else addf.stride(0), stream)
     if rc != 0:
         raise RuntimeError(f"hctr_gemm_bf16 failed rc={rc} M={M} N={N} K={K}")
+    from . import dense as _D
+    _D._count()
 
 
 # ----------------------------------------------------------------------------- tile autotuner
