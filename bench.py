@@ -121,6 +121,7 @@ def main():
         model.train()
     sync_all()
     launches_per_step = model.launches_per_step
+    loss_trace = [model.get_current_loss()]
 
     if args.profile:
         # kernel-level breakdown with CUPTI (never used for reported numbers)
@@ -150,16 +151,30 @@ def main():
     stop_evt, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop_evt, samples, dev.index or 0), daemon=True)
     th.start()
-    hb_cycle = [pool[i % len(pool)] for i in range(K)]
+    # device-resident copies of the batch pool: every timed step trains a different batch (a D2D
+    # refresh of label / dense / keys, ~6 MB, is part of the timed region)
+    inp = model.input
+    t_label = model.net_train.tensors[inp.label_name].data
+    t_dense = model.net_train.tensors[inp.dense_name].data
+    ebc0 = model.ebcs_train[0]
+    dev_pool = [(hb.label.to(dev).view_as(t_label), hb.dense.to(dev).view_as(t_dense).to(t_dense.dtype),
+                 hb.keys.to(dev)) for hb in pool[:8]]
+
+    def load_resident(i):
+        lab, den, keys = dev_pool[i % len(dev_pool)]
+        t_label.copy_(lab, non_blocking=True)
+        t_dense.copy_(den, non_blocking=True)
+        ebc0.key_slab[:keys.numel()].copy_(keys, non_blocking=True)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        # the batch of this step is already resident (loaded by the previous _load_batch)
+        load_resident(i)
         model._run_step()
     e1.record()
     sync_all()
     ms_dev = e0.elapsed_time(e1)
+    loss_trace.append(model.get_current_loss())
     t_ms = torch.tensor([ms_dev], device=dev)
     if n > 1:
         torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
@@ -205,7 +220,8 @@ def main():
                        "embedding_weights": "fp32", "embedding_opt_state": state,
                        "l2_hygiene": "inputs_exceed_L2 (>=100 GB tables random access, ~1 GB activations/step)",
                        "cuda_graph": not args.no_graph, "small_tables_debug": bool(args.small or args.cap_rows),
-                       "final_loss": loss},
+                       "final_loss": loss,
+                       "loss_after_warmup_timed_e2e": [round(x, 5) for x in loss_trace + [loss]]},
             "clocks": summarize_clocks(samples),
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": max(ms_e2e, wall_ms) / K,
                     "h2d_bytes_per_step": hb.h2d_bytes() * 1, "d2h_bytes_per_step": 4},

@@ -613,6 +613,37 @@ extern "C" int hctr_cross_bwd_ew(const void* dy, const void* x0, const void* t, 
   return OK();
 }
 
+// out[s, col0 + j] = sum_i part[s, i, j]   (partial pooled vectors of a row-sharded table, k shards)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    partial_sum_kernel(const T* __restrict__ part, T* __restrict__ out, int rows, int k, int w,
+                       long long out_stride, int col0) {
+  const long long total = static_cast<long long>(rows) * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long s = i / w;
+    const int j = static_cast<int>(i - s * w);
+    const T* p = part + s * k * w + j;
+    float acc = 0.f;
+    for (int q = 0; q < k; ++q) acc += static_cast<float>(p[static_cast<long long>(q) * w]);
+    out[s * out_stride + col0 + j] = static_cast<T>(acc);
+  }
+}
+
+extern "C" int hctr_partial_sum(const void* part, void* out, int rows, int k, int w,
+                                long long out_stride, int col0, int is_bf16, void* stream) {
+  const long long total = static_cast<long long>(rows) * w;
+  if (total == 0) return 0;
+  const int blocks = grid_for(total, 256);
+  if (is_bf16)
+    partial_sum_kernel<bf16><<<blocks, 256, 0, ST(stream)>>>((const bf16*)part, (bf16*)out, rows, k, w,
+                                                             out_stride, col0);
+  else
+    partial_sum_kernel<float><<<blocks, 256, 0, ST(stream)>>>((const float*)part, (float*)out, rows, k,
+                                                              w, out_stride, col0);
+  return OK();
+}
+
 extern "C" int hctr_add3(const void* a, const void* b, const float* c, void* o, long long n,
                          void* stream) {
   if (n % 8) return -2;

@@ -457,7 +457,8 @@ class EmbeddingCollection:
                     .view(b, gl["k"], w)
                 tp = self.tops[gl["top"]]
                 full = self.out_slab[tp["off"]:tp["off"] + b * tp["width"]].view(b, tp["width"])
-                full[:, gl["col"]:gl["col"] + w] = part.float().sum(1).to(full.dtype)
+                from ..ops import dense as D
+                D.partial_sum(part, full, gl["col"], gl["k"], w)
 
     def _bwd_bufs(self, grp):
         if self.world == 1 or grp.kind == "dp":

@@ -218,6 +218,23 @@ def cross_bwd_ew(dy, x0, t, dt, dx0, first, db=None, last=False, row_splits=0):
         dx0.copy_((dx0.float() + acc).to(dx0.dtype))
 
 
+def partial_sum(part, out2d, col0, k, w):
+    """out2d[:, col0:col0+w] = part.view(rows, k, w).sum(1)  (partials of a row-sharded table)"""
+    rows = out2d.shape[0]
+    if _native_ok(part, out2d) and part.dtype == out2d.dtype and part.is_contiguous() \
+            and part.dtype in (torch.bfloat16, torch.float32) and out2d.stride(1) == 1:
+        l = lib()
+        if not hasattr(l, "_ps_ready"):
+            l.hctr_partial_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_longlong, C.c_int, C.c_int, C.c_void_p]
+            l.hctr_partial_sum.restype = C.c_int
+            l._ps_ready = True
+        _chk(l.hctr_partial_sum(part.data_ptr(), out2d.data_ptr(), rows, k, w, out2d.stride(0), col0,
+                                int(part.dtype == torch.bfloat16), _st(part)), "partial_sum")
+        return
+    out2d[:, col0:col0 + w] = part.reshape(rows, k, w).float().sum(1).to(out2d.dtype)
+
+
 def add3(a, b, c, out):
     """out = a + b (+ c fp32)."""
     if _native_ok(a, b, out) and a.dtype == torch.bfloat16 and a.is_contiguous() and \

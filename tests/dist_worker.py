@@ -156,8 +156,79 @@ def run_model():
         print("MODEL_OK", err, la, lb)
 
 
+def run_equiv():
+    """N-rank training (data-parallel dense, model-parallel / data-parallel embeddings) must equal
+    single-process training on the concatenation of the ranks' batches."""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.batch import HostBatch
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    comm = Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+    cuda = comm.device.type == "cuda"
+    sizes = [4000, 300, 50, 9000, 1200, 77]
+    hot = [3, 1, 1, 8, 2, 1]
+    b = 128
+    kw = dict(table_sizes=sizes, multi_hot=hot, ev_size=16, lr=0.05, mixed=False, optimizer="sgd",
+              bottom=(64, 32, 16), top=(64, 32, 1), cross_layers=2, projection_dim=16,
+              use_cuda_graph=False)
+    # table 0 row-sharded over every rank, table 3 on the last rank, the small tables data-parallel
+    sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]
+    sm[world - 1][3] = 1
+    plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+    m = build_dlrm_dcnv2(batchsize=b * world, num_gpus=world, comm=comm, shard_plan=plan, **kw)
+    m.compile()
+    single = Comm.single(comm.device)
+    ref = build_dlrm_dcnv2(batchsize=b * world, num_gpus=1, comm=single, **kw)
+    ref.compile()
+    # identical initial embedding tables: copy the reference's rows into the sharded model
+    for e_ref, e in zip(ref.ebcs_train, m.ebcs_train):
+        for name in list(e_ref.tmap.keys()):
+            ev = e_ref.tmap[name].ev_size
+            for keys, vals, col0, _, _ in e_ref.dump_table_local(name):
+                e.load_table_rows(name, keys, vals[:, :ev].cpu())
+    m.arena.weights.copy_(ref.arena.weights)
+    m.arena.sync_shadow()
+    pool = m.reader_train.pool
+    blocks = m.layout.blocks
+    for step in range(3):
+        hb = pool[step % len(pool)]
+        allb = comm.all_gather_object((hb.label.clone(), hb.dense.clone(), hb.keys.clone()))
+        labels = torch.cat([x[0] for x in allb])
+        dense = torch.cat([x[1] for x in allb])
+        keys, off = [], 0
+        for (_, S, H, _) in blocks:
+            n = b * S * H
+            keys.append(torch.cat([x[2][off:off + n] for x in allb]))
+            off += n
+        big = HostBatch(labels, dense, torch.cat(keys), None, b * world)
+        m.train_on_host_batch(hb)
+        ref.train_on_host_batch(big)
+        l_m, l_r = m.get_current_loss(), ref.get_current_loss()
+        assert abs(l_m - l_r) < 2e-3 * max(1.0, abs(l_r)), (step, l_m, l_r)
+    err = float((m.arena.weights - ref.arena.weights).abs().max())
+    assert err < 2e-3, f"dense weights differ from the single-process run: {err}"
+    # embedding rows: gather every local shard and compare with the reference table
+    for e_ref, e in zip(ref.ebcs_train, m.ebcs_train):
+        for name in list(e_ref.tmap.keys()):
+            ev = e_ref.tmap[name].ev_size
+            rk, rv = None, None
+            for keys, vals, col0, _, _ in e_ref.dump_table_local(name):
+                rk, rv = keys.cpu(), vals[:, :ev].cpu()
+            for keys, vals, col0, _, _ in e.dump_table_local(name):
+                if len(keys) == 0:
+                    continue
+                idx = torch.searchsorted(rk, keys.cpu())
+                d = (rv[idx] - vals[:, :ev].cpu()).abs().max().item()
+                assert d < 2e-3, f"table {name} differs: {d}"
+    comm.barrier()
+    if rank == 0:
+        print("EQUIV_OK", err)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "equiv":
+        run_equiv()
     if what == "model":
         run_model()
     if what == "ebc":

@@ -60,3 +60,18 @@ def test_model_multi_gpu_overlap_paths():
         pytest.skip("needs >= 2 GPUs")
     out = _run(min(n, 4), ["model"], 29651)
     assert "MODEL_OK" in out
+
+
+@pytest.mark.dist
+def test_multi_rank_equals_single_process_gloo():
+    out = _run(2, ["equiv"], 29661, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "EQUIV_OK" in out
+
+
+@pytest.mark.gpu
+def test_multi_gpu_equals_single_gpu():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = _run(min(n, 8), ["equiv"], 29671)
+    assert "EQUIV_OK" in out
