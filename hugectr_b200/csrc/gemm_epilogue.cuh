@@ -32,6 +32,8 @@ struct GemmParams {
   int flags;
   const float* addf;
   long long ldaddf;
+  float* colsum;   // optional fp32 [N]: += column sums of the (bf16-rounded) output -- the bias gradient
+                   // of the layer that consumes this GEMM's output as its dY (TMA epilogue only)
 };
 
 

@@ -339,6 +339,7 @@ extern "C" int hctr_gemm_bf16(const void* A, const void* B, void* out, int M, in
   p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0);
   p.xl = reinterpret_cast<const __nv_bfloat16*>(xl); p.ldx = ldx;
   p.alpha = alpha; p.flags = flags; p.addf = addf; p.ldaddf = ldaddf;
+  p.colsum = nullptr;
 
   CUtensorMap ta, tb;
   int rc;

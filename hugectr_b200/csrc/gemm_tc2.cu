@@ -319,6 +319,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
           }
           fence_proxy_async();
           __syncwarp();
+          if (p.colsum != nullptr) {
+            // fused bias gradient of the consumer layer: column sums of this warp's finished slab
+            // (lane owns 2 columns; a slab row is read conflict-free: all lanes hit the same 128 bytes)
+            const int rows_valid = min(32, p.M - m0);
+            float cs0 = 0.f, cs1 = 0.f;
+            for (int r = 0; r < rows_valid; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                           : "r"(st_out + slab_off(r, lane >> 2) + ((lane & 3) << 2)));
+              cs0 += bf16_lo(w);
+              cs1 += bf16_hi(w);
+            }
+            const int col = n_blk * BN + g * 64 + 2 * lane;
+            if (rows_valid > 0) {
+              if (col < p.N) atomicAdd(p.colsum + col, cs0);
+              if (col + 1 < p.N) atomicAdd(p.colsum + col + 1, cs1);
+            }
+          }
           if (lane == 0) {
             const int n0 = n_blk * BN + g * 64;
             if (n0 < p.N) {
@@ -430,7 +448,7 @@ extern "C" int hctr_gemm_bf16_2sm(const void* A, const void* B, void* out, int M
                                   const float* bias, const void* mask, long long ldmask,
                                   const void* x0, const void* xl, long long ldx, void* aux,
                                   long long ldaux, float alpha, int flags, int splits, int block_n,
-                                  const float* addf, long long ldaddf, void* stream_) {
+                                  const float* addf, long long ldaddf, float* colsum, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (g2_num_sms == 0) {
     int dev = 0;
@@ -454,6 +472,7 @@ extern "C" int hctr_gemm_bf16_2sm(const void* A, const void* B, void* out, int M
   p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0);
   p.xl = reinterpret_cast<const __nv_bfloat16*>(xl); p.ldx = ldx;
   p.alpha = alpha; p.flags = flags; p.addf = addf; p.ldaddf = ldaddf;
+  p.colsum = nullptr;
   CUtensorMap ta, tb;
   int rc;
   if (a_mn) rc = make_tmap2(&ta, A, M, K, lda, 64, T2_BLOCK_K);
@@ -484,17 +503,25 @@ extern "C" int hctr_gemm_bf16_2sm(const void* A, const void* B, void* out, int M
     }
     em.enabled = ok ? 1 : 0;
   }
+  // the fused column sums need the staged slabs; rows >= M must be zero in the slab, which holds for
+  // the bias-free mask / plain epilogues (zero-filled operands)
+  bool colsum_fused = false;
+  if (em.enabled && colsum != nullptr && bias == nullptr && (kind == EK_MASK || (kind == EK_GENERIC && !(flags & EPI_SIGMOID)))) {
+    p.colsum = colsum;
+    colsum_fused = true;
+  }
   if (!em.enabled) {
     kind = EK_GENERIC;
     em.out = em.aux = em.x0 = em.xl = ta;   // unused
   }
+#define HCTR_RET2(X) { const int rc_ = (X); return (rc_ == 0 && colsum_fused) ? 100 : rc_; }
 #define HCTR_DISPATCH2K(BNV, KV)                                             \
   if (a_mn) {                                                                \
-    if (b_mn) return launch2<BNV, true, true, KV>(ta, tb, em, p, stream);        \
-    return launch2<BNV, true, false, KV>(ta, tb, em, p, stream);                 \
+    if (b_mn) HCTR_RET2((launch2<BNV, true, true, KV>(ta, tb, em, p, stream)))        \
+    HCTR_RET2((launch2<BNV, true, false, KV>(ta, tb, em, p, stream)))                 \
   } else {                                                                   \
-    if (b_mn) return launch2<BNV, false, true, KV>(ta, tb, em, p, stream);       \
-    return launch2<BNV, false, false, KV>(ta, tb, em, p, stream);                \
+    if (b_mn) HCTR_RET2((launch2<BNV, false, true, KV>(ta, tb, em, p, stream)))       \
+    HCTR_RET2((launch2<BNV, false, false, KV>(ta, tb, em, p, stream)))                \
   }
 #define HCTR_DISPATCH2(BNV)                                                  \
   switch (kind) {                                                            \

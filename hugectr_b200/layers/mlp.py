@@ -116,6 +116,7 @@ class MLPLayer(Layer):
         n = len(self.dims_out)
         dy = self.outputs[0].grad.view(self.rows, self.dims_out[-1])
         want_dx = self.inputs[0].grad is not None
+        bgrad_done = set()   # layers whose bias gradient came out of the upstream dgrad epilogue
         for i in range(n - 1, -1, -1):
             x_i = self._x_in if i == 0 else self.acts[i - 1]
             if i == n - 1:
@@ -138,15 +139,22 @@ class MLPLayer(Layer):
                           None if self.B[i] is None else self.B[i].g.reshape(-1),
                           mask_relu=(i > 0 and self.relu[i - 1]))
                 continue
-            if self.B[i] is not None:
+            if self.B[i] is not None and i not in bgrad_done:
                 D.colsum_accum(dz, self.B[i].g.reshape(-1))
             # wgrad: dW[k, n] += x^T dz   (both operands MN-major, fp32 atomic split-K, beta = 1)
             self._wgrad(x_i, dz, W)
             if need_dx:
                 if i > 0:
+                    # the dgrad epilogue also accumulates the bias gradient of layer i-1 (column sums
+                    # of its dY) when it can; gemm_bf16 falls back to a separate reduction otherwise
+                    bg = None
+                    if self.B[i - 1] is not None and not (self.dims_out[i - 1] == 1 and self.W[i - 1].shape[0] >= 8):
+                        bg = self.B[i - 1].g.reshape(-1)
                     G.gemm_bf16(dz, W.compute(self.mixed)[:W.shape[0]], self.dacts[i - 1],
                                 mask=self.acts[i - 1] if self.relu[i - 1] else None,
-                                flags=G.EPI_MASK if self.relu[i - 1] else 0)
+                                flags=G.EPI_MASK if self.relu[i - 1] else 0, colsum=bg)
+                    if bg is not None:
+                        bgrad_done.add(i - 1)
                 else:
                     G.gemm_bf16(dz, W.compute(self.mixed), self._dx_stage())
         if want_dx:

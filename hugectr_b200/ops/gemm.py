@@ -38,7 +38,7 @@ def _lib():
             _c.c_void_p, _c.c_longlong, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
             _c.c_longlong, _c.c_void_p]
         lib.hctr_gemm_bf16_2sm.restype = _c.c_int
-        lib.hctr_gemm_bf16_2sm.argtypes = lib.hctr_gemm_bf16.argtypes
+        lib.hctr_gemm_bf16_2sm.argtypes = lib.hctr_gemm_bf16.argtypes[:-1] + [_c.c_void_p, _c.c_void_p]
         _sig_set = True
     return lib
 
@@ -116,8 +116,12 @@ def _pick_block_n(M, N, K, splits):
 
 
 def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
-              aux=None, alpha=1.0, flags=0, splits=1, block_n=0, addf=None):
+              aux=None, alpha=1.0, flags=0, splits=1, block_n=0, addf=None, colsum=None):
     """out[M,N] = epilogue(alpha * op(a) @ op(b)).
+
+    ``colsum`` (fp32 [N], optional): += column sums of the bf16 output, i.e. the bias gradient of the
+    layer that consumes ``out`` as its dY.  Fused into the TMA epilogue when possible, otherwise one
+    extra reduction kernel; either way ``colsum`` is up to date on return.
 
     a: ``[M,K]`` (K-major) or ``[K,M]`` when ``a_mn``;  b: ``[N,K]`` or ``[K,N]`` when ``b_mn``.
     """
@@ -128,33 +132,44 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else a.dtype)
     if not tc_eligible(a, b, a_mn, b_mn) or out.stride(1) != 1:
-        return gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux, addf)
+        r = gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux, addf)
+        if colsum is not None:
+            colsum.add_(out.float().sum(0))
+        return r
     if splits > 1:
         flags |= EPI_ATOMIC
     if block_n == 0:
         block_n = _tuned_block_n(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags,
                                  splits, addf)
-    _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, block_n, addf)
+    fused = _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits,
+                    block_n, addf, colsum)
+    if colsum is not None and not fused:
+        from . import dense as _D
+        _D.colsum_accum(out, colsum)
     return out
 
 
-def _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, block_n, addf):
+def _launch(a, b, out, M, N, K, a_mn, b_mn, bias, mask, x0, xl, aux, alpha, flags, splits, block_n, addf,
+            colsum=None):
+    """-> True when the kernel also accumulated the column sums into ``colsum``"""
     stream = torch.cuda.current_stream(a.device).cuda_stream
-    fn = _lib().hctr_gemm_bf16
+    args = [a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+            out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(mask),
+            0 if mask is None else mask.stride(0), _ptr(x0), _ptr(xl),
+            0 if xl is None else xl.stride(0), _ptr(aux), 0 if aux is None else aux.stride(0),
+            float(alpha), int(flags), int(splits), 0, _ptr(addf),
+            0 if addf is None else addf.stride(0)]
     if block_n >= 2000:           # 2000 + BN : cta_group::2 kernel (CTA pair, 256 x BN tile)
-        fn = _lib().hctr_gemm_bf16_2sm
-        block_n -= 2000
-    rc = fn(
-        a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
-        out.stride(0), int(a_mn), int(b_mn), _ptr(bias), _ptr(mask),
-        0 if mask is None else mask.stride(0), _ptr(x0), _ptr(xl),
-        0 if xl is None else xl.stride(0), _ptr(aux), 0 if aux is None else aux.stride(0),
-        float(alpha), int(flags), int(splits), int(block_n), _ptr(addf),
-        0 if addf is None else addf.stride(0), stream)
-    if rc != 0:
+        args[22] = int(block_n - 2000)
+        rc = _lib().hctr_gemm_bf16_2sm(*args, _ptr(colsum), stream)
+    else:
+        args[22] = int(block_n)
+        rc = _lib().hctr_gemm_bf16(*args, stream)
+    if rc not in (0, 100):
         raise RuntimeError(f"hctr_gemm_bf16 failed rc={rc} M={M} N={N} K={K}")
     from . import dense as _D
     _D._count()
+    return rc == 100
 
 
 # ----------------------------------------------------------------------------- tile autotuner

@@ -83,3 +83,18 @@ def test_gemm_cluster_multicast(bn, a_mn, b_mn, M, N, K):
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
+
+
+@pytest.mark.parametrize("bn", [0, 2128, 2256, 128])
+@pytest.mark.parametrize("M,N,K,masked", [(6912, 512, 1024, True), (300, 200, 136, True), (1000, 328, 512, False)])
+def test_gemm_fused_bias_gradient(bn, M, N, K, masked):
+    """colsum= accumulates the column sums of the (bf16) output: fused in the TMA epilogue of the 2-SM
+    kernel, separate reduction otherwise; ragged M / N edges must not contribute"""
+    torch.manual_seed(7)
+    dy, w = _mk((M, K), 0.5), _mk((N, K), 0.5)
+    mask = (torch.randn(M, N, device="cuda") > 0).to(torch.bfloat16) if masked else None
+    cs = torch.full((N,), 1.5, device="cuda")
+    out = G.gemm_bf16(dy, w, mask=mask, flags=G.EPI_MASK if masked else 0, block_n=bn, colsum=cs)
+    torch.cuda.synchronize()
+    ref = out.float().sum(0) + 1.5
+    assert (cs - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-2
