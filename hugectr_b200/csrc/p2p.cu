@@ -49,7 +49,8 @@ __device__ __forceinline__ void grid_peer_barrier(const PeerPtrs& flags, uint32_
   if (threadIdx.x == 0) {
     __threadfence_system();
     const uint32_t prev = atomicAdd(&local_gate[0], 1u);
-    if (prev == gridDim.x * (epoch + 1) - 1) {
+    if (prev == gridDim.x - 1) {
+      local_gate[0] = 0;   // re-armed before anyone is released (grid sizes may differ per launch)
       const uint32_t e = *epoch_ctr + 1;
       *epoch_ctr = e;
       for (int t = 0; t < n; ++t)

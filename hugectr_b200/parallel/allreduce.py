@@ -39,7 +39,8 @@ class ExchangeWgrad:
         self._done_lo = self.wgrad.numel()
         self._after = after_bucket
         if self.wgrad.is_cuda and not hasattr(self, "_stream"):
-            self._stream = torch.cuda.Stream()
+            self._stream = torch.cuda.Stream()       # all-reduces, back to back
+            self._opt_stream = torch.cuda.Stream()   # per-bucket optimizer slices, behind their bucket
 
     def layer_done(self, lo: int, bucket_elems: int = 2 << 20):
         """called after a trainable layer's bprop; lo = arena offset of its first parameter"""
@@ -60,7 +61,10 @@ class ExchangeWgrad:
                     self._p2p.run(lo, hi)
                 else:
                     self.comm.all_reduce(self.wgrad[lo:hi])
-            if self._after is not None:
+        if self._after is not None:
+            # the update of this bucket must not delay the next bucket's all-reduce
+            self._opt_stream.wait_stream(self._stream)
+            with torch.cuda.stream(self._opt_stream):
                 self._after(lo, hi)
         self._done_lo = lo
 
@@ -74,6 +78,7 @@ class ExchangeWgrad:
             return
         self._flush(0)
         torch.cuda.current_stream().wait_stream(self._stream)
+        torch.cuda.current_stream().wait_stream(self._opt_stream)
         for t in self.extra:
             self.comm.all_reduce(t)
 

@@ -34,10 +34,14 @@ class P2PAllReduce:
         peers = self.peers
         if lo:
             peers = S.ptr_array([int(q) + lo * 4 for q in self._peer_list])
+        # small ranges: fewer blocks (the kernel holds an in-kernel grid barrier, so every block must
+        # become resident next to whatever else is running before any data moves)
+        per_rank_vec4 = (hi - lo) // (4 * self.comm.world_size)
+        blocks = max(4, min(self.blocks, (per_rank_vec4 + 1023) // 1024))
         rc = S.lib().hctr_allreduce_twoshot(
             peers, self.flag_ptrs, self.epoch.data_ptr(), self.gate.data_ptr(),
             self.gate_epoch.data_ptr(), hi - lo, self.comm.rank, self.comm.world_size,
-            self.blocks, torch.cuda.current_stream(self.comm.device).cuda_stream)
+            blocks, torch.cuda.current_stream(self.comm.device).cuda_stream)
         if rc:
             raise RuntimeError(f"allreduce_twoshot failed rc={rc}")
         D._count()
