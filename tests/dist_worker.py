@@ -225,8 +225,37 @@ def run_equiv():
         print("EQUIV_OK", err)
 
 
+def run_legacy():
+    """legacy embeddings (Distributed = row-sharded over all ranks, Localized = slot s on rank s % N)
+    trained data-parallel: replicas stay identical and the loss is finite"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models import build_dcn, build_deepfm
+    comm = Comm.init_from_env()
+    world = comm.world_size
+    slots = [120] * 26
+    for build, kw in ((build_dcn, {}),
+                      (build_deepfm, {"embedding_type": hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash})):
+        m = build(batchsize=64 * world, vvgpu=[list(range(world))], slot_sizes=slots, workspace_mb=2,
+                  comm=comm, max_eval_batches=1, **kw)
+        m.compile()
+        for _ in range(4):
+            assert m.train()
+        loss = m.get_current_loss()
+        assert loss == loss and abs(loss) < 1e4, loss
+        w = m.arena.weights.clone()
+        comm.broadcast(w, 0)
+        assert float((w - m.arena.weights).abs().max()) < 1e-6, "dense replicas diverged"
+        m.eval()
+        m.get_eval_metrics()
+    comm.barrier()
+    if comm.rank == 0:
+        print("LEGACY_OK")
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "legacy":
+        run_legacy()
     if what == "equiv":
         run_equiv()
     if what == "model":

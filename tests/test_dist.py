@@ -75,3 +75,18 @@ def test_multi_gpu_equals_single_gpu():
         pytest.skip("needs >= 2 GPUs")
     out = _run(min(n, 8), ["equiv"], 29671)
     assert "EQUIV_OK" in out
+
+
+@pytest.mark.dist
+def test_legacy_embeddings_gloo():
+    out = _run(2, ["legacy"], 29681, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "LEGACY_OK" in out
+
+
+@pytest.mark.gpu
+def test_legacy_embeddings_multi_gpu():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = _run(min(n, 4), ["legacy"], 29691)
+    assert "LEGACY_OK" in out
