@@ -24,6 +24,37 @@ BASELINE_SAMPLES_PER_S = 14.7e6   # implied HugeCTR MLPerf v3.1 rat
 
 
 def clocks_sampler(stop_evt, out, gpu_index):
+    """SM clock + throttle reasons during the timed region: NVML (a few microseconds per query, 2 ms
+    period) when available, else nvidia-smi polling.  Rows: [idx, sm_mhz, sm_max_mhz, power,
+    reasons_mask, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES remaps indices: resolve the physical device through its UUID/PCI id
+        import torch
+        props = torch.cuda.get_device_properties(gpu_index)
+        h = None
+        try:
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        R_HW = getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)
+        R_HWT = getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)
+        R_SWT = getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)
+        R_PWR = getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)
+        act = lambda m, b: "Active" if (m & b) else "Not Active"
+        while not stop_evt.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            m = int(get_reasons(h))
+            out.append([str(gpu_index), str(sm), str(mx), "0", hex(m), act(m, R_HW), act(m, R_HWT),
+                        act(m, R_SWT), act(m, R_PWR)])
+            stop_evt.wait(0.002)
+        return
+    except Exception:
+        pass
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
