@@ -156,7 +156,7 @@ def run_model():
         print("MODEL_OK", err, la, lb)
 
 
-def run_equiv():
+def run_equiv(optimizer="sgd"):
     """N-rank training (data-parallel dense, model-parallel / data-parallel embeddings) must equal
     single-process training on the concatenation of the ranks' batches."""
     import hugectr_b200 as hugectr
@@ -168,7 +168,8 @@ def run_equiv():
     sizes = [4000, 300, 50, 9000, 1200, 77]
     hot = [3, 1, 1, 8, 2, 1]
     b = 128
-    kw = dict(table_sizes=sizes, multi_hot=hot, ev_size=16, lr=0.05, mixed=False, optimizer="sgd",
+    kw = dict(table_sizes=sizes, multi_hot=hot, ev_size=16, lr=0.05 if optimizer == "sgd" else 0.01,
+              mixed=False, optimizer=optimizer,
               bottom=(64, 32, 16), top=(64, 32, 1), cross_layers=2, projection_dim=16,
               use_cuda_graph=False)
     # table 0 row-sharded over every rank, table 3 on the last rank, the small tables data-parallel
@@ -257,7 +258,7 @@ if __name__ == "__main__":
     if what == "legacy":
         run_legacy()
     if what == "equiv":
-        run_equiv()
+        run_equiv(sys.argv[2] if len(sys.argv) > 2 else "sgd")
     if what == "model":
         run_model()
     if what == "ebc":

@@ -63,8 +63,9 @@ def test_model_multi_gpu_overlap_paths():
 
 
 @pytest.mark.dist
-def test_multi_rank_equals_single_process_gloo():
-    out = _run(2, ["equiv"], 29661, env={"CUDA_VISIBLE_DEVICES": ""})
+@pytest.mark.parametrize("opt", ["sgd", "adagrad"])
+def test_multi_rank_equals_single_process_gloo(opt):
+    out = _run(2, ["equiv", opt], 29661, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "EQUIV_OK" in out
 
 
@@ -73,7 +74,9 @@ def test_multi_gpu_equals_single_gpu():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    out = _run(min(n, 8), ["equiv"], 29671)
+    out = _run(min(n, 8), ["equiv", "sgd"], 29671)
+    assert "EQUIV_OK" in out
+    out = _run(min(n, 8), ["equiv", "adagrad"], 29673)
     assert "EQUIV_OK" in out
 
 
