@@ -164,6 +164,11 @@ class EmbeddingCollection:
         self.placement = resolve_placement(cfg, self.world)
         self.native = device.type == "cuda"
         self.fused = (self.native and self.world > 1 and comm.p2p_available) if fused is None else fused
+        # node-aware two-stage exchange (collective path only; inside one NVSwitch box the fused
+        # peer-memory kernels are used instead)
+        self.hier = (not self.fused and self.world > 1
+                     and cfg.comm_strategy == CommunicationStrategy.Hierarchical
+                     and getattr(comm, "num_nodes", 1) > 1)
         self.is_train = is_train
         self.hotness = dict(hotness)
         self.seed = seed
@@ -409,6 +414,8 @@ class EmbeddingCollection:
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()
+            elif self.hier:
+                self.comm.hier_all_gather(self.keys_all, self.key_slab)
             else:
                 self.comm.all_gather(self.keys_all, self.key_slab)
 
@@ -439,9 +446,12 @@ class EmbeddingCollection:
             if self.fused:
                 self.comm.barrier_device()       # every owner finished writing my outputs
             else:
-                self.comm.all_to_all(self.recv_out, self.send_out)
-                # each (rank, lookup) region of my slab is written by exactly one owner
-                self.out_slab.copy_(self.recv_out.sum(0))
+                if self.hier:
+                    self.out_slab.copy_(self.comm.hier_all_to_all_sum(self.send_out))
+                else:
+                    self.comm.all_to_all(self.recv_out, self.send_out)
+                    # each (rank, lookup) region of my slab is written by exactly one owner
+                    self.out_slab.copy_(self.recv_out.sum(0))
                 for grp in self.groups:
                     if grp.kind == "dp":
                         E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
@@ -508,6 +518,8 @@ class EmbeddingCollection:
                         E.pull_grads(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
                                      self.peer_grad, self.grad_stage, self.b, self.rank,
                                      key_bytes=self._kb, act_bf16=self._abf)
+            elif self.hier:
+                self.comm.hier_all_gather(self.grads_all, self.grad_slab)
             else:
                 self.comm.all_gather(self.grads_all, self.grad_slab)
         for grp in mp_groups:

@@ -58,6 +58,8 @@ class Model:
         if self.comm.world_size not in (1, solver.num_gpus):
             logger.warning(f"vvgpu lists {solver.num_gpus} GPUs but the job runs {self.comm.world_size} ranks")
         self.world = self.comm.world_size
+        if self.world > 1 and len(solver.vvgpu) > 1 and hasattr(self.comm, "set_topology"):
+            self.comm.set_topology(len(solver.vvgpu[0]))       # several nodes: vvgpu = one list per node
         self.input: Optional[Input] = None
         self.sparse_embeddings: List[SparseEmbedding] = []
         self.ebc_configs: List[EmbeddingCollectionConfig] = []

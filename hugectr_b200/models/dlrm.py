@@ -26,10 +26,13 @@ def _default_ar():
 
 
 def _solver(batchsize, num_gpus, lr, mixed, scaler, **kw):
+    gpn = kw.pop("gpus_per_node", 0)      # > 0: several nodes -> one vvgpu list per node
+    vvgpu = [list(range(num_gpus))] if not gpn or gpn >= num_gpus else \
+        [list(range(gpn)) for _ in range(num_gpus // gpn)]
     return hugectr.CreateSolver(
         model_name=kw.pop("model_name", "dlrm"), seed=kw.pop("seed", 0), max_eval_batches=kw.pop("max_eval_batches", 10),
         batchsize_eval=kw.pop("batchsize_eval", batchsize), batchsize=batchsize,
-        vvgpu=[list(range(num_gpus))], repeat_dataset=True, lr=lr, warmup_steps=kw.pop("warmup_steps", 1),
+        vvgpu=vvgpu, repeat_dataset=True, lr=lr, warmup_steps=kw.pop("warmup_steps", 1),
         use_mixed_precision=mixed, scaler=scaler, use_cuda_graph=kw.pop("use_cuda_graph", True),
         train_intra_iteration_overlap=True, train_inter_iteration_overlap=True,
         use_embedding_collection=True, grouped_all_reduce=True, gen_loss_summary=True,
@@ -41,7 +44,7 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
                      mixed: bool = True, scaler: float = 1.0, source=None, shard_plan=None,
                      optimizer: str = "adagrad", bottom=(512, 256, 128),
                      top=(1024, 1024, 512, 256, 1), cross_layers: int = 3, projection_dim: int = 512,
-                     comm=None, **solver_kw) -> "hugectr.Model":
+                     comm=None, comm_strategy=None, **solver_kw) -> "hugectr.Model":
     table_sizes = list(table_sizes or CRITEO_TB_TABLE_SIZES)
     multi_hot = list(multi_hot or CRITEO_TB_MULTI_HOT)
     n = len(table_sizes)
@@ -65,7 +68,8 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
             hugectr.DataReaderSparseParam(f"data{i}", multi_hot[i], True, 1) for i in range(n)]))
     tables = [hugectr.EmbeddingTableConfig(name=str(i), max_vocabulary_size=table_sizes[i],
                                            ev_size=ev_size) for i in range(n)]
-    ebc = hugectr.EmbeddingCollectionConfig(use_exclusive_keys=True)
+    ebc = hugectr.EmbeddingCollectionConfig(
+        use_exclusive_keys=True, comm_strategy=comm_strategy or hugectr.CommunicationStrategy.Uniform)
     ebc.embedding_lookup(table_config=tables, bottom_name=[f"data{i}" for i in range(n)],
                          top_name="sparse_embedding", combiner=["sum"] * n)
     if shard_plan is None:

@@ -156,6 +156,60 @@ class Comm:
             self.all_to_all(o.view(self.world_size, 1), t.view(self.world_size, 1))
             self.all_reduce(t)
 
+    # ---- node topology (hierarchical collectives)
+    def set_topology(self, gpus_per_node: int):
+        """Declare the node structure (global rank = node * gpus_per_node + local id, the LocalFirst
+        layout of torchrun).  Builds one intra-node group per node and one inter-node group per local
+        id; collective over ALL ranks (every rank creates every group in the same order)."""
+        if getattr(self, "_topo", None) == gpus_per_node:
+            return
+        L = int(gpus_per_node)
+        if self.world_size == 1 or L <= 0 or L >= self.world_size or self.world_size % L:
+            self._topo, self.num_nodes, self.local_size = gpus_per_node, 1, self.world_size
+            self.node, self.local_id, self.intra, self.inter = 0, self.rank, self, None
+            return
+        nodes = self.world_size // L
+        self.num_nodes, self.local_size = nodes, L
+        self.node, self.local_id = self.rank // L, self.rank % L
+        intra = inter = None
+        for n in range(nodes):
+            g = dist.new_group([n * L + l for l in range(L)])
+            if n == self.node:
+                intra = g
+        for l in range(L):
+            g = dist.new_group([n * L + l for n in range(nodes)])
+            if l == self.local_id:
+                inter = g
+        self.intra, self.inter = Comm(self.device, intra), Comm(self.device, inter)
+        self._topo = gpus_per_node
+
+    def hier_all_to_all_sum(self, send: torch.Tensor) -> torch.Tensor:
+        """send[d] = my partial contribution to rank d ([world, n]); returns sum over all ranks of
+        their contribution to me ([n]).  Two stages like the reference's hierarchical model-parallel
+        embedding (hier_model_parallel_embedding.cpp:183-230): partial sums that leave the node for
+        the same destination are reduced inside the node first (reduce-scatter onto the local rank
+        with the destination's local id), then ONE exchange per node pair between same-local-id
+        ranks."""
+        nodes, L = self.num_nodes, self.local_size
+        n = send.shape[-1]
+        by_local = send.view(nodes, L, n).transpose(0, 1).contiguous()      # [L, nodes, n]
+        red = torch.empty(nodes, n, dtype=send.dtype, device=send.device)
+        self.intra.reduce_scatter(red, by_local)                            # sum over my node
+        recv = torch.empty_like(red)
+        self.inter.all_to_all(recv, red)                                    # chunk m <-> node m
+        return recv.float().sum(0).to(send.dtype)
+
+    def hier_all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        """out [world, n] <- every rank's inp [n], gathered across nodes first (same local id), then
+        inside the node"""
+        nodes, L = self.num_nodes, self.local_size
+        n = inp.numel()
+        stage1 = torch.empty(nodes, n, dtype=inp.dtype, device=inp.device)
+        self.inter.all_gather(stage1, inp)
+        stage2 = torch.empty(L, nodes, n, dtype=inp.dtype, device=inp.device)
+        self.intra.all_gather(stage2, stage1)
+        out.view(nodes, L, n).copy_(stage2.transpose(0, 1))
+
     # ---- symmetric heap / P2P
     @property
     def p2p_available(self) -> bool:

@@ -156,7 +156,7 @@ def run_model():
         print("MODEL_OK", err, la, lb)
 
 
-def run_equiv(optimizer="sgd"):
+def run_equiv(optimizer="sgd", gpus_per_node=0):
     """N-rank training (data-parallel dense, model-parallel / data-parallel embeddings) must equal
     single-process training on the concatenation of the ranks' batches."""
     import hugectr_b200 as hugectr
@@ -176,8 +176,15 @@ def run_equiv(optimizer="sgd"):
     sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]
     sm[world - 1][3] = 1
     plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
-    m = build_dlrm_dcnv2(batchsize=b * world, num_gpus=world, comm=comm, shard_plan=plan, **kw)
+    hkw = {}
+    if gpus_per_node:
+        # logical nodes: hierarchical two-stage exchange (intra-node reduce, inter-node same-local-id)
+        hkw = dict(gpus_per_node=gpus_per_node, comm_strategy=hugectr.CommunicationStrategy.Hierarchical,
+                   fused_embedding_comm=False)
+    m = build_dlrm_dcnv2(batchsize=b * world, num_gpus=world, comm=comm, shard_plan=plan, **kw, **hkw)
     m.compile()
+    if gpus_per_node:
+        assert m.ebcs_train[0].hier and comm.num_nodes == world // gpus_per_node
     single = Comm.single(comm.device)
     ref = build_dlrm_dcnv2(batchsize=b * world, num_gpus=1, comm=single, **kw)
     ref.compile()
@@ -258,7 +265,7 @@ if __name__ == "__main__":
     if what == "legacy":
         run_legacy()
     if what == "equiv":
-        run_equiv(sys.argv[2] if len(sys.argv) > 2 else "sgd")
+        run_equiv(sys.argv[2] if len(sys.argv) > 2 else "sgd", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     if what == "model":
         run_model()
     if what == "ebc":

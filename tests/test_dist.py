@@ -93,3 +93,10 @@ def test_legacy_embeddings_multi_gpu():
         pytest.skip("needs >= 2 GPUs")
     out = _run(min(n, 4), ["legacy"], 29691)
     assert "LEGACY_OK" in out
+
+
+@pytest.mark.dist
+def test_hierarchical_exchange_gloo():
+    """2 logical nodes x 2 ranks: node-aware two-stage embedding exchange == single process"""
+    out = _run(4, ["equiv", "sgd", "2"], 29701, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "EQUIV_OK" in out
