@@ -14,7 +14,10 @@ from typing import List, Sequence, Tuple
 def generate_plan(table_sizes: Sequence[int], multi_hot: Sequence[int], num_gpus: int,
                   ev_size: int = 128, plan: str = "auto", dp_threshold_rows: int = 4096,
                   mem_comm_bw_ratio: float = 6.5e12 / 770e9, mem_cap_gb: float = 150.0,
-                  bytes_per_elem: int = 8) -> Tuple[List[List[int]], list]:
+                  bytes_per_elem: int = 8, num_nodes: int = 1) -> Tuple[List[List[int]], list]:
+    """``num_nodes`` > 1 (hier-auto of the reference planner): the shards of a row-split table are
+    kept inside ONE node (the least loaded) so that the hierarchical exchange reduces their partial
+    sums before anything crosses the node boundary."""
     n = len(table_sizes)
     names = [str(i) for i in range(n)]
     if num_gpus == 1:
@@ -41,9 +44,15 @@ def generate_plan(table_sizes: Sequence[int], multi_hot: Sequence[int], num_gpus
     load = [0.0] * num_gpus
     mem = [0.0] * num_gpus
     sm = [[0] * n for _ in range(num_gpus)]
+    gpn = num_gpus // max(1, num_nodes)
     for t in sorted(mp, key=lambda t: -cost(t, shards[t]) * shards[t]):
         k = shards[t]
-        order = sorted(range(num_gpus), key=lambda g: (load[g], mem[g]))
+        cand = range(num_gpus)
+        if num_nodes > 1 and 1 < k <= gpn:
+            node_load = [sum(load[nd * gpn:(nd + 1) * gpn]) for nd in range(num_nodes)]
+            nd = min(range(num_nodes), key=lambda i: node_load[i])
+            cand = range(nd * gpn, (nd + 1) * gpn)
+        order = sorted(cand, key=lambda g: (load[g], mem[g]))
         for g in order[:k]:
             sm[g][t] = 1
             load[g] += cost(t, k)
@@ -57,3 +66,60 @@ def generate_plan(table_sizes: Sequence[int], multi_hot: Sequence[int], num_gpus
     if dp:
         strategy.append(("dp", [names[t] for t in dp]))
     return sm, strategy
+
+
+def plan_report(table_sizes: Sequence[int], multi_hot: Sequence[int], shard_matrix, ev_size: int = 128,
+                bytes_per_elem: int = 8) -> dict:
+    """per-GPU lookup load (rows gathered per sample) and table memory (GB) of a plan"""
+    g = len(shard_matrix)
+    n = len(table_sizes)
+    k = [sum(shard_matrix[r][t] for r in range(g)) for t in range(n)]
+    load = [sum(multi_hot[t] / k[t] for t in range(n) if shard_matrix[r][t]) for r in range(g)]
+    mem = [sum(table_sizes[t] * ev_size * bytes_per_elem / 1e9 / k[t] for t in range(n)
+               if shard_matrix[r][t]) for r in range(g)]
+    return {"shards_per_table": k, "lookups_per_sample": load, "memory_gb": mem,
+            "imbalance": max(load) / (sum(load) / g) if sum(load) else 1.0}
+
+
+def save_plan(path: str, shard_matrix, shard_strategy, column_wise=None):
+    import json
+    with open(path, "w") as f:
+        json.dump({"shard_matrix": shard_matrix, "shard_strategy": [[k, list(v)] for k, v in shard_strategy],
+                   "shard_column_wise": column_wise or []}, f, indent=1)
+
+
+def load_plan(path: str):
+    import json
+    with open(path) as f:
+        d = json.load(f)
+    return d["shard_matrix"], [(k, v) for k, v in d["shard_strategy"]], d.get("shard_column_wise", [])
+
+
+def main(argv=None):
+    """python -m hugectr_b200.tools.planner --num-gpus 8 [--num-nodes 1] [--plan auto] --out plan.json
+    (Criteo-TB DLRM-DCNv2 tables by default; --slot-sizes / --multi-hot override)"""
+    import argparse
+    from ..models.dlrm import CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--num-gpus", type=int, required=True)
+    ap.add_argument("--num-nodes", type=int, default=1)
+    ap.add_argument("--plan", default="auto", choices=["auto", "round_robin", "uniform"])
+    ap.add_argument("--slot-sizes", default="")
+    ap.add_argument("--multi-hot", default="")
+    ap.add_argument("--ev-size", type=int, default=128)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args(argv)
+    sizes = [int(x) for x in a.slot_sizes.split(",")] if a.slot_sizes else CRITEO_TB_TABLE_SIZES
+    hot = [int(x) for x in a.multi_hot.split(",")] if a.multi_hot else CRITEO_TB_MULTI_HOT
+    sm, st = generate_plan(sizes, hot, a.num_gpus, ev_size=a.ev_size, plan=a.plan, num_nodes=a.num_nodes)
+    rep = plan_report(sizes, hot, sm, a.ev_size)
+    print("lookups/sample per GPU:", [round(x, 1) for x in rep["lookups_per_sample"]])
+    print("table memory per GPU (GB):", [round(x, 1) for x in rep["memory_gb"]])
+    print("imbalance (max/mean): %.3f" % rep["imbalance"])
+    if a.out:
+        save_plan(a.out, sm, st)
+    return sm, st
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,18 @@ def test_planner_and_workspace():
     for t in range(26):
         assert any(sm[g][t] for g in range(8))
     assert calculate([1000] * 26, 16, hugectr.Optimizer_t.Adam) >= 1
+    from hugectr_b200.tools import planner
+    rep = planner.plan_report(CRITEO_TB_TABLE_SIZES, CRITEO_TB_MULTI_HOT, sm)
+    assert rep["imbalance"] < 1.6 and max(rep["memory_gb"]) < 150
+    # node-aware plan: all shards of the split hot table live on one node
+    sm2, _ = generate_plan(CRITEO_TB_TABLE_SIZES, CRITEO_TB_MULTI_HOT, 16, num_nodes=2)
+    owners = [g for g in range(16) if sm2[g][20]]
+    assert len(owners) > 1 and len({g // 8 for g in owners}) == 1
+    import os, tempfile
+    pth = os.path.join(tempfile.mkdtemp(), "plan.json")
+    planner.main(["--num-gpus", "8", "--out", pth])
+    sm3, st3, _ = planner.load_plan(pth)
+    assert sm3 == sm and [k for k, _ in st3] == [k for k, _ in st]
 
 
 def test_solver_validation_and_json_optimizer():
