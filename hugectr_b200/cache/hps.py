@@ -95,7 +95,6 @@ class HostParameterServer:
                  ssd_path: Optional[str] = None, capacity_rows: int = 1 << 20, seed: int = 0):
         self.ev, self.ns = ev, num_states
         self.bound = init_bound
-        self.index: Dict[int, int] = {}
         self.cap = capacity_rows
         pin = torch.cuda.is_available()
         self.w = torch.zeros(self.cap, ev)
@@ -105,8 +104,58 @@ class HostParameterServer:
             self.s = [t.pin_memory() for t in self.s]
         self.gen = torch.Generator().manual_seed(seed)
         self.ssd = SparseModelFile(ssd_path, ev) if ssd_path else None
+        # key -> row index: native sharded hash maps + OpenMP row movers (csrc/host/param_server.cpp);
+        # a Python dict when the host library cannot be built
+        self._h = None
+        self.index: Dict[int, int] = {}
+        try:
+            import ctypes as C
+            from .. import _native
+            lib = _native.host_lib()
+            vp, ll = C.c_void_p, C.c_longlong
+            lib.hctr_ps_create.restype = vp
+            lib.hctr_ps_destroy.argtypes = [vp]
+            lib.hctr_ps_size.argtypes = [vp]
+            lib.hctr_ps_size.restype = ll
+            lib.hctr_ps_lookup.argtypes = [vp, vp, ll, vp, vp, C.c_int, ll]
+            lib.hctr_ps_lookup.restype = ll
+            lib.hctr_ps_dump.argtypes = [vp, vp, vp]
+            lib.hctr_ps_dump.restype = ll
+            lib.hctr_ps_gather.argtypes = [vp, vp, ll, ll, vp]
+            lib.hctr_ps_scatter.argtypes = [vp, vp, ll, ll, vp]
+            self._lib = lib
+            self._h = lib.hctr_ps_create()
+        except Exception:  # pragma: no cover - no compiler available
+            self._h = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                self._lib.hctr_ps_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
 
     def _rows(self, keys, create=True):
+        keys = keys.reshape(-1).to(torch.int64).contiguous()
+        if self._h is not None:
+            n = keys.numel()
+            rows = torch.empty(n, dtype=torch.int64)
+            is_new = torch.zeros(n, dtype=torch.uint8)
+            created = self._lib.hctr_ps_lookup(self._h, keys.data_ptr(), n, rows.data_ptr(),
+                                               is_new.data_ptr(), int(create), self.cap)
+            if created < 0:
+                raise RuntimeError("HostParameterServer capacity exceeded")
+            if created > 0:
+                nr = rows[is_new.bool()]
+                init = (torch.rand(nr.numel(), self.ev, generator=self.gen) * 2 - 1) * self.bound
+                if self.ssd:
+                    loaded = self.ssd.load(keys[is_new.bool()].tolist())
+                    for j, k in enumerate(keys[is_new.bool()].tolist()):
+                        if k in loaded:
+                            init[j] = loaded[k]
+                self.w[nr] = init
+            return rows
         rows = []
         for k in keys.tolist():
             r = self.index.get(k)
@@ -120,15 +169,39 @@ class HostParameterServer:
             rows.append(-1 if r is None else r)
         return torch.tensor(rows, dtype=torch.int64)
 
+    def _gather(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+        if self._h is None:
+            return table[rows]
+        out = torch.empty(rows.numel(), self.ev)
+        self._lib.hctr_ps_gather(table.data_ptr(), rows.data_ptr(), rows.numel(), self.ev * 4, out.data_ptr())
+        return out
+
+    def _scatter(self, table: torch.Tensor, rows: torch.Tensor, src: torch.Tensor):
+        src = src.detach().cpu().float().contiguous()
+        if self._h is None:
+            table[rows] = src
+            return
+        self._lib.hctr_ps_scatter(table.data_ptr(), rows.data_ptr(), rows.numel(), self.ev * 4, src.data_ptr())
+
     def pull(self, keys: torch.Tensor):
         rows = self._rows(keys.cpu())
-        return self.w[rows], [s[rows] for s in self.s]
+        return self._gather(self.w, rows), [self._gather(s, rows) for s in self.s]
 
     def push(self, keys: torch.Tensor, w: torch.Tensor, states=()):
         rows = self._rows(keys.cpu())
-        self.w[rows] = w.cpu().float()
+        self._scatter(self.w, rows, w)
         for dst, src in zip(self.s, states):
-            dst[rows] = src.cpu().float()
+            self._scatter(dst, rows, src)
+
+    def items(self):
+        """-> (keys int64 [n], rows int64 [n]) of every stored row"""
+        if self._h is not None:
+            n = int(self._lib.hctr_ps_size(self._h))
+            k, r = torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.int64)
+            c = self._lib.hctr_ps_dump(self._h, k.data_ptr(), r.data_ptr()) if n else 0
+            return k[:c], r[:c]
+        return (torch.tensor(list(self.index.keys()), dtype=torch.int64),
+                torch.tensor(list(self.index.values()), dtype=torch.int64))
 
     def load_keyset(self, keyset_file: str):
         keys = torch.from_numpy(np.fromfile(keyset_file, dtype="<i8").astype("int64"))
@@ -138,11 +211,12 @@ class HostParameterServer:
     def flush_to_ssd(self):
         if self.ssd is None:
             return
-        keys = torch.tensor(list(self.index.keys()), dtype=torch.int64)
-        rows = torch.tensor(list(self.index.values()), dtype=torch.int64)
+        keys, rows = self.items()
         self.ssd.dump(keys, self.w[rows])
 
     def size(self):
+        if self._h is not None:
+            return int(self._lib.hctr_ps_size(self._h))
         return len(self.index)
 
 

@@ -212,3 +212,31 @@ def test_sparse_tensor_and_simulators():
     VarianceScalingSimulator(1.0, "fan_avg", "uniform", 1000, 64).fill(t)
     assert abs(t.var().item() - 1.0 / 532) < 3e-4
     assert sinusoidal_init(10, 8).shape == (10, 8)
+
+
+def test_native_parameter_server_index(tmp_path):
+    """csrc/host/param_server.cpp: deterministic row assignment, duplicates, capacity roll-back, SSD
+    spill round trip"""
+    from hugectr_b200.cache.hps import HostParameterServer
+    ps = HostParameterServer(4, num_states=1, init_bound=0.1, capacity_rows=8, ssd_path=str(tmp_path / "ssd"))
+    assert ps._h is not None, "native host library was not built"
+    k = torch.tensor([7, 3, 7, 1 << 40, 3])
+    w, (s0,) = ps.pull(k)
+    assert ps.size() == 3 and w.shape == (5, 4)
+    torch.testing.assert_close(w[0], w[2])
+    torch.testing.assert_close(w[1], w[4])
+    assert (w.abs() <= 0.1).all() and (s0 == 0).all()
+    ps.push(torch.tensor([3, 1 << 40]), torch.ones(2, 4), [torch.full((2, 4), 2.0)])
+    w2, (s2,) = ps.pull(torch.tensor([1 << 40, 3, 7]))
+    torch.testing.assert_close(w2[:2], torch.ones(2, 4))
+    torch.testing.assert_close(s2[:2], torch.full((2, 4), 2.0))
+    torch.testing.assert_close(w2[2], w[0])
+    keys, rows = ps.items()
+    assert dict(zip(keys.tolist(), rows.tolist())) == {7: 0, 3: 1, 1 << 40: 2}
+    with pytest.raises(RuntimeError):
+        ps.pull(torch.arange(100, 110))            # 3 + 10 > capacity 8: nothing is inserted
+    assert ps.size() == 3
+    ps.flush_to_ssd()
+    ps2 = HostParameterServer(4, num_states=1, capacity_rows=8, ssd_path=str(tmp_path / "ssd"))
+    w3, _ = ps2.pull(torch.tensor([3]))
+    torch.testing.assert_close(w3[0], torch.ones(4))
