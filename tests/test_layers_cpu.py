@@ -174,3 +174,160 @@ def test_bce_loss_semantics():
     torch.testing.assert_close(x.grad, (torch.sigmoid(x.data) - y.data) / 8, atol=1e-6, rtol=1e-5)
     layer.fprop(False)
     torch.testing.assert_close(layer.pred, torch.sigmoid(x.data))
+
+
+# ---------------------------------------------------------------------------- remaining layer types
+def test_batchnorm_train_and_eval():
+    layer, ins, _ = build(L.BatchNorm, [(16, 6)], factor=0.9, eps=1e-5)
+    bn = torch.nn.BatchNorm1d(6, eps=1e-5, momentum=0.1)
+    bn.train()
+
+    def ref(x, g, b):
+        return torch.nn.functional.batch_norm(x, None, None, g.reshape(-1), b.reshape(-1), True, 0.1, 1e-5)
+    check(layer, ins, ref)
+    # running statistics (momentum = factor) then inference with them
+    x = ins[0].data
+    m = x.mean(0) * 0.1
+    v = 0.9 + 0.1 * x.var(0, unbiased=False)
+    torch.testing.assert_close(layer.state["mean"], m, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(layer.state["var"], v, atol=1e-5, rtol=1e-4)
+    layer.fprop(False)
+    g, b = layer.params[0].w.reshape(-1), layer.params[1].w.reshape(-1)
+    torch.testing.assert_close(layer.outputs[0].data, (x - m) / torch.sqrt(v + 1e-5) * g + b,
+                               atol=1e-4, rtol=1e-3)
+
+
+def test_prelu_dice_and_dropout_and_cast():
+    layer, ins, _ = build(L.PReLU_Dice, [(32, 5)], elu_alpha=0.2, eps=1e-8)
+
+    def dice(x):
+        ex = x.mean(0, keepdim=True)
+        var = (x * x).mean(0, keepdim=True) - ex * ex
+        p = torch.sigmoid((x - ex) / torch.sqrt(var + 1e-8))
+        return p * x + (1 - p) * 0.2 * x
+    check(layer, ins, dice)
+    # dropout: inverted scaling, mask reused by bprop, identity in eval
+    layer, ins, _ = build(L.Dropout, [(64, 50)], dropout_rate=0.25)
+    layer.fprop(True)
+    y, x = layer.outputs[0].data, ins[0].data
+    kept = y != 0
+    torch.testing.assert_close(y[kept], x[kept] / 0.75)
+    assert 0.6 < kept.float().mean().item() < 0.9
+    layer.outputs[0].grad.fill_(1.0)
+    layer.bprop()
+    torch.testing.assert_close(ins[0].grad, kept.float() / 0.75)
+    layer.fprop(False)
+    torch.testing.assert_close(layer.outputs[0].data, x)
+    # cast: value preserving round trip through the compute dtype
+    layer, ins, _ = build(L.Cast, [(4, 6)])
+    layer.fprop(True)
+    torch.testing.assert_close(layer.outputs[0].data.float(), ins[0].data, atol=1e-2, rtol=1e-2)
+
+
+def test_concat3d_dotproduct_reluhalf_general_reshape_concat():
+    layer, ins, _ = build(L.Concat3D, [(4, 2, 5), (4, 3, 5)], axis=1)
+    check(layer, ins, lambda a, b: torch.cat([a, b], 1))
+    layer, ins, _ = build(L.Concat3D, [(4, 3, 2), (4, 3, 6)], axis=2)
+    check(layer, ins, lambda a, b: torch.cat([a, b], 2))
+    layer, ins, _ = build(L.DotProduct, [(4, 7), (4, 7)])
+    check(layer, ins, lambda a, b: a * b)
+    layer, ins, _ = build(L.ReLUHalf, [(4, 7)])
+    check(layer, ins, torch.relu)
+    layer, ins, _ = build(L.FusedReshapeConcatGeneral, [(3, 4, 2), (3, 4, 5)], tops=("o",))
+    check(layer, ins, lambda a, b: torch.cat([a, b], 2).reshape(12, 7))
+
+
+def test_masked_softmax_and_sequence_mask():
+    arena = ParamArena()
+    ctx = BuildCtx(arena, torch.device("cpu"), torch.float32, 4, True, CreateSolver(), False)
+    lf = TensorBag("lf", (4, 1), torch.float32)
+    lt = TensorBag("lt", (4, 1), torch.float32)
+    lf.data = torch.tensor([[1.], [3.], [2.], [0.]])
+    lt.data = torch.tensor([[2.], [1.], [3.], [3.]])
+    lf.needs_grad = lt.needs_grad = False
+    sm = LAYER_REGISTRY[L.SequenceMask](DenseLayer(L.SequenceMask, ["lf", "lt"], ["mask"],
+                                                   max_sequence_len_from=3, max_sequence_len_to=3),
+                                        [lf, lt], ctx)
+    sm.allocate()
+    sm.fprop(True)
+    m = sm.outputs[0].data
+    assert m.shape == (4, 1, 3, 3)
+    exp1 = torch.zeros(3, 3)
+    exp1[:3, :1] = 1            # sample 1: from-length 3, to-length 1
+    torch.testing.assert_close(m[1, 0], exp1)
+    assert m[3].sum() == 0      # from-length 0
+    # masked softmax: masked positions get (numerically) zero probability, rows still sum to one
+    x = TensorBag("x", (4, 1, 3, 3), torch.float32)
+    x.data = torch.randn(4, 1, 3, 3)
+    x.grad = torch.zeros(4, 1, 3, 3)
+    ms = LAYER_REGISTRY[L.MaskedSoftmax](DenseLayer(L.MaskedSoftmax, ["x", "mask"], ["p"]),
+                                         [x, sm.outputs[0]], ctx)
+    ms.allocate()
+    ms.fprop(True)
+    p = ms.outputs[0].data
+    ref = torch.softmax(torch.where(m > 0, x.data, torch.full_like(x.data, -10000.0)), -1)
+    torch.testing.assert_close(p, ref, atol=1e-6, rtol=1e-5)
+    assert (p[0, 0, 0, 2:] < 1e-6).all()
+
+
+def test_gru_matches_torch():
+    b, S, v, h = 3, 4, 5, 6
+    layer, ins, _ = build(L.GRU, [(1, b * S * v)], batchsize=b, SeqLength=S, vector_size=v, num_output=h)
+    layer.fprop(True)
+    gru = torch.nn.GRU(v, h, batch_first=True)
+    with torch.no_grad():
+        gru.weight_ih_l0.copy_(layer.params[0].w)
+        gru.weight_hh_l0.copy_(layer.params[1].w)
+        gru.bias_ih_l0.copy_(layer.params[2].w.reshape(-1))
+        gru.bias_hh_l0.copy_(layer.params[3].w.reshape(-1))
+    x = ins[0].data.reshape(b, S, v).clone().requires_grad_(True)
+    y, _ = gru(x)
+    torch.testing.assert_close(layer.outputs[0].data.reshape(b, S, h), y.detach(), atol=1e-5, rtol=1e-4)
+    g = torch.randn_like(y)
+    layer.outputs[0].grad.copy_(g.reshape(1, -1))
+    for p in layer.params:
+        p.g.zero_()
+    layer.bprop()
+    y.backward(g)
+    torch.testing.assert_close(ins[0].grad.reshape(b, S, v), x.grad, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(layer.params[0].g, gru.weight_ih_l0.grad, atol=1e-5, rtol=1e-4)
+
+
+def _loss_layer(lt, logits, labels, **kw):
+    arena = ParamArena()
+    ctx = BuildCtx(arena, torch.device("cpu"), torch.float32, logits.shape[0], True, CreateSolver(), False)
+    x = TensorBag("logit", tuple(logits.shape), torch.float32)
+    x.data = logits.clone()
+    x.grad = torch.zeros_like(logits)
+    y = TensorBag("label", tuple(labels.shape), torch.float32)
+    y.data = labels.clone()
+    y.needs_grad = False
+    layer = LAYER_REGISTRY[lt](DenseLayer(lt, ["logit", "label"], ["loss"], **kw), [x, y], ctx)
+    layer.allocate()
+    layer.fprop(True)
+    return layer, x
+
+
+def test_cross_entropy_and_multi_cross_entropy_losses():
+    torch.manual_seed(1)
+    z = torch.randn(8, 2)
+    lab = (torch.rand(8, 1) > 0.5).float()
+    layer, x = _loss_layer(L.CrossEntropyLoss, z, lab)
+    zz = z.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(zz, lab.reshape(-1).long())
+    ref.backward()
+    torch.testing.assert_close(layer.outputs[0].data[0], ref.detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(x.grad, zz.grad, atol=1e-6, rtol=1e-5)
+    # multi-label weighted BCE with a missing label (-1)
+    z = torch.randn(6, 3)
+    lab = (torch.rand(6, 3) > 0.5).float()
+    lab[2, 1] = -1.0
+    tw = [0.2, 0.5, 0.3]
+    layer, x = _loss_layer(L.MultiCrossEntropyLoss, z, lab, target_weight_vec=tw)
+    zz = z.clone().requires_grad_(True)
+    valid = (lab > -0.5).float()
+    per = torch.nn.functional.binary_cross_entropy_with_logits(zz, lab.clamp(min=0), reduction="none")
+    ref = (per * valid * torch.tensor(tw)).sum() / (6 * 3)     # loss.cu:313,327: / (batch * labels)
+    ref.backward()
+    torch.testing.assert_close(layer.outputs[0].data[0], ref.detach(), atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(x.grad, zz.grad, atol=1e-6, rtol=1e-4)
