@@ -23,10 +23,11 @@ class Regularizer:
     def rterm(self) -> torch.Tensor:
         tot = None
         for p in self.params:
+            # l1_regularizer.cu:47 (lambda / batch), l2_regularizer.cu:45 (lambda / (2 * batch))
             if self.kind == Regularizer_t.L1:
-                v = p.w.abs().sum() * self.lam
+                v = p.w.abs().sum() * (self.lam / self.batch)
             else:
-                v = (p.w * p.w).sum() * (self.lam * 0.5)
+                v = (p.w * p.w).sum() * (self.lam * 0.5 / self.batch)
             tot = v if tot is None else tot + v
         return tot
 
