@@ -177,6 +177,47 @@ class SparseEmbeddingRuntime:
             E.backward_accum(self.lookups, self.lookups_dev, self.table, vec, kb, gb, b, self.ws, 1.0,
                              self.rank)
             E.update(self.opt.optimizer_type, self.table, self.s0, self.s1, vec, self.ws, hp, lr_t, step_t)
+        if self.opt.update_type in (Update_t.Global, Update_t.LazyGlobal) and \
+                self.opt.optimizer_type in (Optimizer_t.Adam, Optimizer_t.MomentumSGD, Optimizer_t.Nesterov):
+            self._global_sweep(lr_t, step_t)
+
+    def _global_sweep(self, lr_t, step_t):
+        """Update_t.Global (sparse_optimizer.cu:241-292): the touched rows were updated by the fused
+        kernel above; every OTHER allocated row gets the dense-optimizer step with a zero gradient
+        (moments decay, the weight keeps moving along the decayed momentum), which makes the sparse
+        update mathematically identical to the dense optimizer.  LazyGlobal (the reference's cheaper
+        approximation of the same thing) takes this exact path too."""
+        vec = self.vec
+        n = min(int(self.hash.size()), self.max_rows)
+        if n == 0:
+            return
+        touched = torch.zeros(self.max_rows, dtype=torch.bool, device=self.device)
+        r = self.rows_all.reshape(-1)
+        touched[r[r >= 0]] = True
+        unt = (~touched[:n]).unsqueeze(1)
+        w = self.table.view(-1, vec)[:n]
+        s0 = self.s0.view(-1, vec)[:n]
+        lr = lr_t.reshape(()).float()
+        o = self.opt
+        zero = torch.zeros((), device=self.device)
+        if o.optimizer_type == Optimizer_t.Adam:
+            t = step_t.reshape(()).float()
+            alpha = lr * torch.sqrt(1.0 - o.beta2 ** t) / (1.0 - o.beta1 ** t)
+            s1 = self.s1.view(-1, vec)[:n]
+            m = torch.where(unt, s0 * o.beta1, s0)
+            v = torch.where(unt, s1 * o.beta2, s1)
+            w.sub_(torch.where(unt, alpha * m / (v.sqrt() + o.epsilon), zero))
+            s0.copy_(m)
+            s1.copy_(v)
+        elif o.optimizer_type == Optimizer_t.MomentumSGD:
+            m = torch.where(unt, s0 * o.momentum_factor, s0)
+            w.add_(torch.where(unt, m, zero))
+            s0.copy_(m)
+        else:  # Nesterov: a' = mu a ; w += -mu a + (1 + mu) a'
+            mu = o.momentum_factor
+            an = s0 * mu
+            w.add_(torch.where(unt, -mu * s0 + (1.0 + mu) * an, zero))
+            s0.copy_(torch.where(unt, an, s0))
 
     # ------------------------------------------------------------------ checkpoint (SURVEY 3.6)
     def _gather_all(self):

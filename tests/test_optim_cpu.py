@@ -152,3 +152,52 @@ def test_ranking_metrics_against_closed_forms():
     auc.local_reduce({R.Pred: p3, R.Label: y3})
     exp = np.mean([roc_auc_score(y3[:, c].numpy(), p3[:, c].numpy()) for c in range(3)])
     assert abs(auc.finalize_metric() - exp) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["adam", "momentum", "nesterov"])
+def test_legacy_embedding_global_update_equals_dense_optimizer(kind):
+    """Update_t.Global on the legacy hashed embedding == the dense torch optimizer over the whole
+    table (untouched rows keep decaying / moving), sparse_optimizer.cu:241-292"""
+    from hugectr_b200.data.batch import HostBatch
+    from hugectr_b200.embedding.sparse_embedding import SparseEmbeddingRuntime
+    from hugectr_b200.parallel.comm import Comm
+    torch.manual_seed(0)
+    b, S, H, vec, vocab = 8, 2, 2, 4, 40
+    opt = {"adam": hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.Global, epsilon=1e-7),
+           "momentum": hugectr.CreateOptimizer(hugectr.Optimizer_t.MomentumSGD, hugectr.Update_t.Global,
+                                               momentum_factor=0.9),
+           "nesterov": hugectr.CreateOptimizer(hugectr.Optimizer_t.Nesterov, hugectr.Update_t.Global,
+                                               momentum_factor=0.9)}[kind]
+    cfg = hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash, 0, vec, "sum",
+                                  "emb", "data", slot_size_array=[vocab // 2] * 2, optimizer=opt)
+    cfg.max_vocabulary_size_per_gpu = 64
+    prm = hugectr.DataReaderSparseParam("data", H, True, S)
+    dev = torch.device("cpu")
+    rt = SparseEmbeddingRuntime(cfg, prm, None, b, dev, torch.float32, Comm.single(dev), opt, torch.int64)
+    W = torch.nn.Parameter(rt.table.view(-1, vec).clone())
+    lr = 0.05
+    # Adam: the framework's own dense rule (epsilon outside the bias-corrected root, Appendix A.2) --
+    # checked against torch.optim.Adam above; torch's epsilon placement differs for near-zero moments
+    m_d, v_d = torch.zeros_like(W), torch.zeros_like(W)
+    topt = {"adam": lambda: None,
+            "momentum": lambda: torch.optim.SGD([W], lr=lr, momentum=0.9),
+            "nesterov": lambda: torch.optim.SGD([W], lr=lr, momentum=0.9, nesterov=True)}[kind]()
+    for step in range(1, 6):
+        keys = torch.randint(0, vocab, (b * S * H,))
+        hb = HostBatch(torch.zeros(b, 1), torch.zeros(b, 0), keys, None, b)
+        rt.set_keys(hb, {"data": 0}, {})
+        rt.forward(True)
+        g = torch.randn(b, S, vec)
+        rt.top_grad.copy_(g)
+        rows = rt.rows_all.view(b, S, H).clone()
+        rt.backward(torch.tensor([lr]), torch.tensor([step], dtype=torch.int32))
+        dense = torch.zeros_like(W)
+        dense.index_add_(0, rows.reshape(-1), g.unsqueeze(2).expand(b, S, H, vec).reshape(-1, vec))
+        if kind == "adam":
+            D.dense_opt_reference(D.D_ADAM, W.data, dense, None, m_d, v_d, lr, step,
+                                  {"beta1": 0.9, "beta2": 0.999, "epsilon": 1e-7})
+        else:
+            W.grad = dense
+            topt.step()
+    n = rt.hash.size()
+    torch.testing.assert_close(rt.table.view(-1, vec)[:n], W.detach()[:n], atol=2e-5, rtol=1e-4)
