@@ -164,6 +164,9 @@ class EmbeddingCollection:
         self.placement = resolve_placement(cfg, self.world)
         self.native = device.type == "cuda"
         self.fused = (self.native and self.world > 1 and comm.p2p_available) if fused is None else fused
+        # requester-side split of row-sharded bags (see _build_layout); experimental, off by default
+        import os as _os
+        self.shard_split = _os.environ.get("HCTR_SHARD_SPLIT", "0") == "1" and self.world > 1
         # node-aware two-stage exchange (collective path only; inside one NVSwitch box the fused
         # peer-memory kernels are used instead)
         self.hier = (not self.fused and self.world > 1
@@ -216,7 +219,9 @@ class EmbeddingCollection:
             self.tops.append({"name": lk["top"], "width": width, "batch_major": lk["batch_major"],
                               "lookups": ids, "off": ooff})
             ooff += b * width
+        self.user_key_elems = koff
         self.key_slab_elems = koff
+        self.nnz_slab_elems = 0
         self.top_slab_elems = ooff
         # partial blocks for row-sharded lookups (k > 1 on the mp side)
         poff = ooff
@@ -224,6 +229,16 @@ class EmbeddingCollection:
             pl = self.placement[gl["table"]]
             k = len(pl.shard_gpus) // pl.col_factor if pl.kind == "mp" else 1
             gl["k"] = k
+            if getattr(self, "shard_split", False) and pl.kind == "mp" and k > 1 and pl.col_factor == 1 \
+                    and gl["combiner"] == "sum":
+                # Requester-side split: every rank rewrites its bag of a row-sharded table into k
+                # compacted per-shard lists of LOCAL ROW INDICES (key // k) plus their lengths, stored
+                # behind the user keys in the (symmetric) key slab.  A shard owner then reads only
+                # its 1/k of the bag instead of scanning all of it and filtering `key % k`.
+                gl["split_off"] = self.key_slab_elems
+                gl["split_nnz_off"] = self.nnz_slab_elems
+                self.key_slab_elems += k * b * gl["hotness"]
+                self.nnz_slab_elems += k * b
             if pl.kind == "mp" and k > 1:
                 gl["partial_off"] = poff
                 gl["partial_w"] = k * gl["ev"] * (gl["hotness"] if gl["combiner"] == "concat" else 1)
@@ -278,13 +293,17 @@ class EmbeddingCollection:
                             base = gl["out_off"]
                             ostride = gl["out_stride"]
                             ocol = sub * gl["ev"] + sl["col0"]
+                        split = "split_off" in gl and pl.kind == "mp" and sl["k"] > 1
                         grp.lookups.append(E.LookupDesc(
-                            table_row_off=sl["row_off"], key_off=gl["key_off"] + sub,
+                            table_row_off=sl["row_off"],
+                            key_off=(gl["split_off"] + sl["s"] * b * H) if split else gl["key_off"] + sub,
                             out_off=base + ocol, grad_off=gl["out_off"] + sub * gl["ev"] + sl["col0"],
-                            hotness=1 if concat else H, key_stride=H, num_shards=sl["k"],
-                            shard_idx=sl["s"], out_stride=ostride, grad_stride=gl["out_stride"],
+                            hotness=1 if concat else H, key_stride=H,
+                            num_shards=1 if split else sl["k"], shard_idx=0 if split else sl["s"],
+                            out_stride=ostride, grad_stride=gl["out_stride"],
                             combiner=1 if gl["combiner"] in ("mean", "average") else 0,
-                            ev_size=sl["ev"], rows=sl["rows"]))
+                            ev_size=sl["ev"], rows=sl["rows"],
+                            nnz_off=(gl["split_nnz_off"] + sl["s"] * b) if split else -1))
         self.groups = list(groups.values())
         dev = self.device
         gen = torch.Generator(device="cpu")
@@ -362,10 +381,15 @@ class EmbeddingCollection:
         alloc = self.comm.symm_alloc if self.fused else \
             (lambda n, dt: torch.zeros(n, dtype=dt, device=dev))
         self.key_slab = alloc(max(self.key_slab_elems, 1), self.key_dtype)
+        self.nnz_slab = alloc(max(self.nnz_slab_elems, 1), torch.int32) if self.nnz_slab_elems else None
+        self.peer_nnz = None
+        self.nnz_all = None
         self.out_slab = alloc(max(self.out_slab_elems, 1), self.act_dtype)
         self.grad_slab = alloc(max(self.top_slab_elems, 1), self.act_dtype) if self.is_train else None
         if self.fused:
             self.peer_keys = self.comm.peer_ptrs(self.key_slab)
+            if self.nnz_slab is not None:
+                self.peer_nnz = self.comm.peer_ptrs(self.nnz_slab)
             self.peer_out = self.comm.peer_ptrs(self.out_slab)
             self.peer_grad = self.comm.peer_ptrs(self.grad_slab) if self.is_train else None
             if self.is_train:
@@ -376,6 +400,8 @@ class EmbeddingCollection:
         elif self.world > 1:
             self.keys_all = torch.zeros(self.world, max(self.key_slab_elems, 1),
                                         dtype=self.key_dtype, device=dev)
+            if self.nnz_slab is not None:
+                self.nnz_all = torch.zeros(self.world, self.nnz_slab_elems, dtype=torch.int32, device=dev)
             self.send_out = torch.zeros(self.world, max(self.out_slab_elems, 1),
                                         dtype=self.act_dtype, device=dev)
             self.recv_out = torch.zeros_like(self.send_out)
@@ -409,15 +435,32 @@ class EmbeddingCollection:
         self.forward_compute()
         self.forward_end()
 
+    def _nnz_bufs(self, grp):
+        """per-source-rank bag-length buffers of the split lists (None when the split is off)"""
+        if self.nnz_slab is None or grp.kind != "mp":
+            return None
+        if self.fused:
+            return self.peer_nnz
+        return list(self.nnz_all.unbind(0))
+
     def forward_begin(self):
         """every rank's keys are in place (fused mode: device-side barrier; collective: all-gather)"""
+        if self.nnz_slab is not None:
+            for gl in self.glookups:
+                if "split_off" in gl:
+                    E.shard_split(self.key_slab, gl["key_off"], self.b, gl["hotness"], gl["k"],
+                                  gl["split_off"], self.nnz_slab, gl["split_nnz_off"])
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()
             elif self.hier:
                 self.comm.hier_all_gather(self.keys_all, self.key_slab)
+                if self.nnz_all is not None:
+                    self.comm.hier_all_gather(self.nnz_all, self.nnz_slab)
             else:
                 self.comm.all_gather(self.keys_all, self.key_slab)
+                if self.nnz_all is not None:
+                    self.comm.all_gather(self.nnz_all, self.nnz_slab)
 
     def forward_compute(self):
         b = self.b
@@ -429,7 +472,8 @@ class EmbeddingCollection:
             for grp in self.groups:
                 if grp.kind == "mp":
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
-                              self.peer_out, b, self.rank, key_bytes=self._kb, act_bf16=self._abf)
+                              self.peer_out, b, self.rank, nnz_bufs=self._nnz_bufs(grp),
+                              key_bytes=self._kb, act_bf16=self._abf)
                 else:
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
                               [self.out_slab], b, key_bytes=self._kb, act_bf16=self._abf)
@@ -438,7 +482,8 @@ class EmbeddingCollection:
             for grp in self.groups:
                 if grp.kind == "mp":
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch,
-                              list(self.keys_all.unbind(0)), list(self.send_out.unbind(0)), b, self.rank)
+                              list(self.keys_all.unbind(0)), list(self.send_out.unbind(0)), b, self.rank,
+                              nnz_bufs=self._nnz_bufs(grp))
 
     def forward_end(self):
         b = self.b
@@ -489,7 +534,7 @@ class EmbeddingCollection:
             if grp.kind == "mp" and getattr(grp, "indexed", False):
                 kb, _ = self._bwd_bufs(grp)
                 E.bwd_index(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, kb, self.b, grp.ws,
-                            self.rank, key_bytes=self._kb)
+                            self.rank, nnz_bufs=self._nnz_bufs(grp), key_bytes=self._kb)
         self._index_done = True
 
     def backward(self, lr_t, step_t, dp_stream=None):
@@ -543,10 +588,12 @@ class EmbeddingCollection:
         if grp.kind == "mp" and getattr(grp, "indexed", False):
             E.bwd_reduce_update(o.optimizer_type, grp.lookups, grp.lookups_dev, grp.table, grp.s0,
                                 grp.s1, grp.pitch, key_bufs, grad_bufs, self.b, grp.ws, self._hp(o),
-                                lr_t, step_t, 1.0, self.rank, key_bytes=self._kb, act_bf16=self._abf)
+                                lr_t, step_t, 1.0, self.rank, nnz_bufs=self._nnz_bufs(grp),
+                                key_bytes=self._kb, act_bf16=self._abf)
         elif grp.kind == "mp":
             E.backward_accum(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, key_bufs, grad_bufs,
-                             self.b, grp.ws, 1.0, self.rank, key_bytes=self._kb, act_bf16=self._abf)
+                             self.b, grp.ws, 1.0, self.rank, nnz_bufs=self._nnz_bufs(grp),
+                             key_bytes=self._kb, act_bf16=self._abf)
             E.update(o.optimizer_type, grp.table, grp.s0, grp.s1, grp.pitch, grp.ws, self._hp(o),
                      lr_t, step_t)
         else:

@@ -129,6 +129,41 @@ def _st(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+# ----------------------------------------------------------------------------- shard split
+def shard_split(key_slab, key_off, batch, hotness, k, split_off, nnz_slab, nnz_off):
+    """Rewrite the bag ``key_slab[key_off : key_off + batch*hotness]`` ([batch, hotness], -1 = empty) of
+    a table that is row-sharded k ways into k compacted lists of local row indices (key // k for the
+    keys with key % k == j, original order, -1 padded) at ``split_off + j*batch*hotness`` and their
+    lengths at ``nnz_slab[nnz_off + j*batch : ...]``."""
+    if key_slab.is_cuda:
+        l = lib()
+        if not hasattr(l, "_split_ready"):
+            l.hctr_emb_shard_split.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_void_p]
+            l.hctr_emb_shard_split.restype = C.c_int
+            l._split_ready = True
+        esz = key_slab.element_size()
+        rc = l.hctr_emb_shard_split(key_slab.data_ptr() + key_off * esz,
+                                    key_slab.data_ptr() + split_off * esz,
+                                    nnz_slab.data_ptr() + nnz_off * 4, batch, hotness, k, esz,
+                                    _st(key_slab.device))
+        if rc:
+            raise RuntimeError("hctr_emb_shard_split failed")
+        D._count()
+        return
+    keys = key_slab[key_off:key_off + batch * hotness].view(batch, hotness).long()
+    out = key_slab[split_off:split_off + k * batch * hotness].view(k, batch, hotness)
+    cnts = nnz_slab[nnz_off:nnz_off + k * batch].view(k, batch)
+    pos = torch.arange(hotness).view(1, -1)
+    for j in range(k):
+        m = (keys >= 0) & (keys % k == j)
+        order = torch.argsort((~m).to(torch.int8), dim=1, stable=True)
+        rows = torch.div(keys, k, rounding_mode="floor").gather(1, order)
+        cnt = m.sum(1)
+        out[j].copy_(torch.where(pos < cnt.view(-1, 1), rows, torch.full_like(rows, -1)).to(out.dtype))
+        cnts[j].copy_(cnt.to(torch.int32))
+
+
 # ----------------------------------------------------------------------------- forward
 def forward(lookups, lookups_dev, table, ev_pitch, key_bufs, out_bufs, batch, my_rank=0,
             nnz_bufs=None, key_bytes=4, act_bf16=True):

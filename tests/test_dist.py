@@ -100,3 +100,23 @@ def test_hierarchical_exchange_gloo():
     """2 logical nodes x 2 ranks: node-aware two-stage embedding exchange == single process"""
     out = _run(4, ["equiv", "sgd", "2"], 29701, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "EQUIV_OK" in out
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc,extra", [(2, []), (4, ["2"])])
+def test_requester_side_shard_split_gloo(nproc, extra):
+    """HCTR_SHARD_SPLIT=1: row-sharded bags are pre-split into per-shard row lists by the requester;
+    training must still equal the single-process run (flat and hierarchical exchange)"""
+    out = _run(nproc, ["equiv", "sgd"] + extra, 29711, env={"CUDA_VISIBLE_DEVICES": "", "HCTR_SHARD_SPLIT": "1"})
+    assert "EQUIV_OK" in out
+
+
+@pytest.mark.gpu
+def test_requester_side_shard_split_multi_gpu():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    if os.environ.get("HCTR_TEST_EXPERIMENTAL", "0") != "1":
+        pytest.skip("experimental CUDA path (validated on CPU/gloo only so far): set HCTR_TEST_EXPERIMENTAL=1")
+    out = _run(min(n, 8), ["equiv", "sgd"], 29721, env={"HCTR_SHARD_SPLIT": "1"})
+    assert "EQUIV_OK" in out
