@@ -492,6 +492,8 @@ using namespace hctr;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define OK() (cudaGetLastError() == cudaSuccess ? 0 : -1)
 
+extern "C" int hctr_abi_size_dense_opt() { return static_cast<int>(sizeof(DenseOptArgs)); }
+
 extern "C" int hctr_dense_opt(const DenseOptArgs* a, int opt, void* stream) {
   if (a->n == 0) return 0;
   const int threads = 256;

@@ -721,6 +721,17 @@ __global__ void emb_bwd_finish_kernel(unsigned int* counter, unsigned int* overf
 
 using namespace hctr;
 
+// ABI self-check: the Python side mirrors these structs with ctypes (embedding/ops.py) and compares
+// the sizes at load time, so a layout drift fails loudly instead of corrupting kernel arguments.
+extern "C" int hctr_abi_sizes_emb(int* out) {
+  out[0] = static_cast<int>(sizeof(EmbLookup));
+  out[1] = static_cast<int>(sizeof(EmbParams));
+  out[2] = static_cast<int>(sizeof(UniqueTable));
+  out[3] = static_cast<int>(sizeof(BwdIndex));
+  out[4] = static_cast<int>(sizeof(OptHyper));
+  return 5;
+}
+
 extern "C" int hctr_emb_bwd_index(const EmbParams* p, const UniqueTable* ut, const BwdIndex* ix,
                                   long long total_pairs, int key_bytes, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);

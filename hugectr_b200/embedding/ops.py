@@ -86,6 +86,15 @@ def lib():
         for n in ("hctr_emb_forward", "hctr_emb_backward_accum", "hctr_emb_update",
                   "hctr_emb_gather_rows", "hctr_emb_bwd_index", "hctr_emb_bwd_reduce_update"):
             getattr(l, n).restype = i
+        # ABI self-check: ctypes mirrors vs the structs the kernels were compiled with
+        if hasattr(l, "hctr_abi_sizes_emb"):
+            sz = (C.c_int * 8)()
+            l.hctr_abi_sizes_emb(sz)
+            mine = [C.sizeof(CEmbLookup), C.sizeof(CEmbParams), C.sizeof(CUniqueTable),
+                    C.sizeof(CBwdIndex), C.sizeof(COptHyper)]
+            if list(sz[:5]) != mine:
+                raise RuntimeError(f"libhctr_cuda.so struct layout {list(sz[:5])} != python mirrors {mine}: "
+                                   "rebuild the library (python -m hugectr_b200._native)")
         _lib = l
     return _lib
 

@@ -52,6 +52,9 @@ def lib():
                   "hctr_fc1_bwd", "hctr_copy2d", "hctr_cast_pad", "hctr_elementwise",
                   "hctr_cross_bwd_ew", "hctr_add3"):
             getattr(l, n).restype = i
+        if hasattr(l, "hctr_abi_size_dense_opt") and l.hctr_abi_size_dense_opt() != C.sizeof(DenseOptArgs):
+            raise RuntimeError("libhctr_cuda.so DenseOptArgs layout differs from the python mirror: rebuild "
+                               "the library (python -m hugectr_b200._native)")
         _lib = l
     return _lib
 

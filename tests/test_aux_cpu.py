@@ -240,3 +240,11 @@ def test_native_parameter_server_index(tmp_path):
     ps2 = HostParameterServer(4, num_states=1, capacity_rows=8, ssd_path=str(tmp_path / "ssd"))
     w3, _ = ps2.pull(torch.tensor([3]))
     torch.testing.assert_close(w3[0], torch.ones(4))
+
+
+def test_native_library_abi_matches_python_mirrors():
+    """the sm_100a library loads without a GPU; its struct sizes must equal the ctypes mirrors"""
+    from hugectr_b200.embedding import ops as E
+    from hugectr_b200.ops import dense as D
+    E.lib()
+    D.lib()
