@@ -262,8 +262,72 @@ def run_legacy():
         print("LEGACY_OK")
 
 
+def run_ckpt(tmpdir):
+    """train on N ranks (row-sharded + table-wise + dp tables), save dense + embedding-collection
+    checkpoints, load them into a SINGLE-process model (different sharding) and compare weights,
+    tables and the loss on the same data (parameter_IO.cpp:262-350 re-sharding on load)"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.batch import HostBatch
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    comm = Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+    sizes = [4000, 300, 50, 9000, 1200, 77]
+    hot = [3, 1, 1, 8, 2, 1]
+    b = 64
+    kw = dict(table_sizes=sizes, multi_hot=hot, ev_size=16, lr=0.02, mixed=False, optimizer="adagrad",
+              bottom=(32, 16), top=(32, 1), cross_layers=1, projection_dim=8, use_cuda_graph=False)
+    sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]
+    sm[world - 1][3] = 1
+    plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+    m = build_dlrm_dcnv2(batchsize=b * world, num_gpus=world, comm=comm, shard_plan=plan, **kw)
+    m.compile()
+    for _ in range(4):
+        m.train()
+    prefix = os.path.join(tmpdir, "ck")
+    m.save_params_to_files(prefix, 4)
+    m.embedding_dump(os.path.join(tmpdir, "ebc"))
+    comm.barrier()
+    single = Comm.single(comm.device)
+    ref = build_dlrm_dcnv2(batchsize=b * world, num_gpus=1, comm=single, **kw)
+    ref.compile()
+    ref.load_dense_weights(prefix + "_dense_4.model")
+    ref.embedding_load(os.path.join(tmpdir, "ebc"))
+    err = float((ref.arena.weights - m.arena.weights).abs().max())
+    assert err == 0.0, f"dense weights differ after load: {err}"
+    for e_ref, e in zip(ref.ebcs_train, m.ebcs_train):
+        for name in list(e_ref.tmap.keys()):
+            ev = e_ref.tmap[name].ev_size
+            rk, rv = None, None
+            for keys, vals, col0, _, _ in e_ref.dump_table_local(name):
+                rk, rv = keys.cpu(), vals[:, :ev].cpu()
+            for keys, vals, col0, _, _ in e.dump_table_local(name):
+                if len(keys):
+                    idx = torch.searchsorted(rk, keys.cpu())
+                    assert float((rv[idx] - vals[:, :ev].cpu()).abs().max()) == 0.0, f"table {name}"
+    # same data -> same loss (eval forward of the global batch vs the ranks' shards)
+    pool = m.reader_train.pool
+    hb = pool[0]
+    allb = comm.all_gather_object((hb.label.clone(), hb.dense.clone(), hb.keys.clone()))
+    keys, off = [], 0
+    for (_, S, H, _) in m.layout.blocks:
+        n = b * S * H
+        keys.append(torch.cat([x[2][off:off + n] for x in allb]))
+        off += n
+    big = HostBatch(torch.cat([x[0] for x in allb]), torch.cat([x[1] for x in allb]), torch.cat(keys),
+                    None, b * world)
+    m.train_on_host_batch(hb)
+    ref.train_on_host_batch(big)
+    l_m, l_r = m.get_current_loss(), ref.get_current_loss()
+    assert abs(l_m - l_r) < 1e-4 * max(1.0, abs(l_r)), (l_m, l_r)
+    comm.barrier()
+    if rank == 0:
+        print("CKPT_OK", l_m, l_r)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "ckpt":
+        run_ckpt(sys.argv[2])
     if what == "legacy":
         run_legacy()
     if what == "equiv":

@@ -120,3 +120,10 @@ def test_requester_side_shard_split_multi_gpu():
         pytest.skip("experimental CUDA path (validated on CPU/gloo only so far): set HCTR_TEST_EXPERIMENTAL=1")
     out = _run(min(n, 8), ["equiv", "sgd"], 29721, env={"HCTR_SHARD_SPLIT": "1"})
     assert "EQUIV_OK" in out
+
+
+@pytest.mark.dist
+def test_checkpoint_resharding_gloo(tmp_path):
+    """2-rank checkpoint (dense + embedding collection) loads into a single-process model"""
+    out = _run(2, ["ckpt", str(tmp_path)], 29731, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "CKPT_OK" in out
