@@ -116,3 +116,34 @@ def test_dlrm_interaction_cpu():
         m.train()
     assert np.isfinite(m.get_current_loss())
     assert m.net_train.tensors["interaction1"].shape == (32, 16 + 6 + 1)
+
+
+def test_exact_resume_from_checkpoint(tmp_path):
+    """dense weights + dense optimizer state + sparse weights + sparse optimizer state: training
+    resumed from a snapshot reproduces the uninterrupted run bit for bit (Adam on both sides)"""
+    def mk():
+        m = build_dcn(batchsize=64, slot_sizes=[60] * 26, workspace_mb=1, comm=CPU(), max_eval_batches=1,
+                      seed=3)
+        for c in m.dense_layers:
+            if c.layer_type == hugectr.Layer_t.Dropout:
+                c.dropout_rate = 0.0
+        m.compile()
+        return m
+    a = mk()
+    pool = a.reader_train.pool
+    for i in range(3):
+        a.train_on_host_batch(pool[i % len(pool)])
+    pre = str(tmp_path / "r")
+    a.save_params_to_files(pre, 3)
+    for i in range(3, 5):
+        a.train_on_host_batch(pool[i % len(pool)])
+    b = mk()
+    b.load_dense_weights(pre + "_dense_3.model")
+    b.load_dense_optimizer_states(pre + "_opt_dense_3.model")
+    b.load_sparse_weights([pre + "0_sparse_3.model"])
+    b.load_sparse_optimizer_states([pre + "0_opt_sparse_3.model"])
+    b.step_t.fill_(3)                     # Adam's step count is not part of the reference's state files
+    for i in range(3, 5):
+        b.train_on_host_batch(pool[i % len(pool)])
+    assert float((a.arena.weights - b.arena.weights).abs().max()) == 0.0
+    assert a.get_current_loss() == b.get_current_loss()
