@@ -248,3 +248,59 @@ def test_native_library_abi_matches_python_mirrors():
     from hugectr_b200.ops import dense as D
     E.lib()
     D.lib()
+
+
+def test_native_raw_reader_slices_and_layout(tmp_path):
+    """csrc/host/raw_reader.cpp: per-rank slice of every global batch, feature-major keys, incomplete
+    last batch, log1p of integer dense features (Appendix A.6)"""
+    import types
+    from hugectr_b200.data.raw_reader import RawAsyncReader
+    N = 20
+    path = str(tmp_path / "t.bin")
+
+    def write(dense_float):
+        rec = []
+        for i in range(N):
+            dense = np.array([i, i + 0.5], "<f4").view("<u4") if dense_float else np.array([i, 3 * i], "<u4")
+            rec.append(np.concatenate([np.array([float(i)], "<f4").view("<u4"), dense,
+                                       np.array([i, i + 1, 2 * i], "<u4")]))
+        np.stack(rec).astype("<u4").tofile(path)
+
+    def stub(rank, dense_float):
+        m = types.SimpleNamespace()
+        m.reader_params = types.SimpleNamespace(
+            source=[path], eval_source=path, async_param=hugectr.AsyncParam(2, 2, is_dense_float=dense_float),
+            float_label_dense=False, num_samples=N, eval_num_samples=N)
+        m.b_train = m.b_eval = 4
+        m.comm = types.SimpleNamespace(rank=rank)
+        m.world = 2
+        m.input = types.SimpleNamespace(label_dim=1, dense_dim=2)
+        m.layout = types.SimpleNamespace(blocks=[("a", 1, 2, True), ("b", 1, 1, True)])
+        m.solver = types.SimpleNamespace(repeat_dataset=False, i64_input_key=False)
+        m.key_dtype = torch.int32
+        return m
+
+    write(True)
+    for rank, firsts, valid in ((0, [0, 8, 16], [4, 4, 4]), (1, [4, 12], [4, 4, 0])):
+        r = RawAsyncReader(stub(rank, True), True)
+        got = []
+        while True:
+            hb = r.read_a_batch()
+            if hb is None:
+                break
+            got.append((hb.num_valid, hb.label.reshape(-1).clone(), hb.dense.clone(), hb.keys.clone()))
+        r.stop()
+        assert [g[0] for g in got] == valid
+        for g, f in zip(got, firsts):
+            i = torch.arange(f, f + 4)
+            assert g[1].tolist() == i.float().tolist()
+            torch.testing.assert_close(g[2], torch.stack([i.float(), i.float() + 0.5], 1))
+            # feature-major: table a [4 samples x 2 hot] then table b [4 x 1]
+            exp = torch.cat([torch.stack([i, i + 1], 1).reshape(-1), 2 * i]).int()
+            assert g[3].tolist() == exp.tolist()
+    write(False)
+    r = RawAsyncReader(stub(0, False), True)
+    hb = r.read_a_batch()
+    i = torch.arange(0, 4).float()
+    torch.testing.assert_close(hb.dense, torch.stack([torch.log1p(i), torch.log1p(3 * i)], 1))
+    r.stop()
