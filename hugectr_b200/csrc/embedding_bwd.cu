@@ -335,16 +335,13 @@ __global__ void __launch_bounds__(kIdxThreads)
   const long long base = static_cast<long long>(blockIdx.x) * kPairsPerBlock;
   int slot[kPairsPerThread];
   unsigned int rank_local[kPairsPerThread];
-  int uids[kPairsPerThread];
 #pragma unroll
   for (int q = 0; q < kPairsPerThread; ++q) {
     slot[q] = -1;
-    uids[q] = -1;
     const long long pair = base + q * kIdxThreads + threadIdx.x;
     if (pair >= total_pairs) continue;
     const int uid = ix.pair_uid[pair];
     if (uid < 0) continue;
-    uids[q] = uid;
     unsigned int hslot = (static_cast<unsigned int>(uid) * 2654435761u) & (kSmemSlots - 1);
     while (true) {
       const unsigned int prev = atomicCAS(&h_uid[hslot], kInvalidVal, static_cast<unsigned int>(uid));

@@ -17,7 +17,7 @@ namespace hctr {
 
 using bf16 = __nv_bfloat16;
 constexpr int kSPT = 4;          // samples per tile
-constexpr int kRows = 32;        // padded rows per sample
+[[maybe_unused]] constexpr int kRows = 32;  // padded rows per sample (layout constant, documents kSPT * kRows == 128)
 constexpr int kHalfBytes = 128 * 128;  // one 64-column half of a 128-row tile
 
 // byte offset of 16-byte chunk `c` (0..15 over D=128) of tile row `row` in the SW128 layout
