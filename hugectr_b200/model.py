@@ -100,6 +100,9 @@ class Model:
                 loss_weights: Optional[List[float]] = None):
         assert self.input is not None, "model.add(Input) first"
         s = self.solver
+        if not s.use_algorithm_search:
+            # reference: cublasLt algorithm search off -> default heuristic; here: no tile autotuning
+            os.environ["HCTR_GEMM_AUTOTUNE"] = "0"
         self.b_train = s.batchsize // self.world
         self.b_eval = s.batchsize_eval // self.world
         inp = self.input
