@@ -244,6 +244,21 @@ class EmbeddingCollection:
                 gl["partial_w"] = k * gl["ev"] * (gl["hotness"] if gl["combiner"] == "concat" else 1)
                 poff += b * gl["partial_w"]
         self.out_slab_elems = poff
+        # Experimental (HCTR_CONCAT_ALIAS=1): spare room behind the slabs so that a downstream Concat
+        # layer can have a batch-major top written straight into ITS output buffer (alias_top): the
+        # kernels already take a row stride / offset per lookup, so the strided copy disappears.
+        import os as _os
+        self.alias_reserve = 1024 if _os.environ.get("HCTR_CONCAT_ALIAS", "0") == "1" else 0
+        self.alias_out_off, self.alias_grad_off = {}, {}
+        goff = self.top_slab_elems
+        if self.alias_reserve:
+            for tp in self.tops:
+                if tp["batch_major"]:
+                    self.alias_out_off[tp["name"]] = self.out_slab_elems
+                    self.alias_grad_off[tp["name"]] = goff
+                    self.out_slab_elems += b * (tp["width"] + self.alias_reserve)
+                    goff += b * (tp["width"] + self.alias_reserve)
+        self.grad_slab_elems = goff
 
     # ---- local storage + owner-side lookup descriptors
     def _build_storage(self, seed, share_from=None):
@@ -294,6 +309,8 @@ class EmbeddingCollection:
                             ostride = gl["out_stride"]
                             ocol = sub * gl["ev"] + sl["col0"]
                         split = "split_off" in gl and pl.kind == "mp" and sl["k"] > 1
+                        grp.lookup_gl = getattr(grp, "lookup_gl", [])
+                        grp.lookup_gl.append((gi, pl.kind == "mp" and sl["k"] > 1))
                         grp.lookups.append(E.LookupDesc(
                             table_row_off=sl["row_off"],
                             key_off=(gl["split_off"] + sl["s"] * b * H) if split else gl["key_off"] + sub,
@@ -385,7 +402,7 @@ class EmbeddingCollection:
         self.peer_nnz = None
         self.nnz_all = None
         self.out_slab = alloc(max(self.out_slab_elems, 1), self.act_dtype)
-        self.grad_slab = alloc(max(self.top_slab_elems, 1), self.act_dtype) if self.is_train else None
+        self.grad_slab = alloc(max(self.grad_slab_elems, 1), self.act_dtype) if self.is_train else None
         if self.fused:
             self.peer_keys = self.comm.peer_ptrs(self.key_slab)
             if self.nnz_slab is not None:
@@ -395,7 +412,7 @@ class EmbeddingCollection:
             if self.is_train:
                 # local staging slabs (same layout as a peer's grad slab); own slot aliases my slab
                 self.grad_stage = [self.grad_slab if r == self.rank else
-                                   torch.zeros(max(self.top_slab_elems, 1), dtype=self.act_dtype, device=dev)
+                                   torch.zeros(max(self.grad_slab_elems, 1), dtype=self.act_dtype, device=dev)
                                    for r in range(self.world)]
         elif self.world > 1:
             self.keys_all = torch.zeros(self.world, max(self.key_slab_elems, 1),
@@ -406,7 +423,7 @@ class EmbeddingCollection:
                                         dtype=self.act_dtype, device=dev)
             self.recv_out = torch.zeros_like(self.send_out)
             if self.is_train:
-                self.grads_all = torch.zeros(self.world, max(self.top_slab_elems, 1),
+                self.grads_all = torch.zeros(self.world, max(self.grad_slab_elems, 1),
                                              dtype=self.act_dtype, device=dev)
         # named views
         self.key_views = {}
@@ -420,6 +437,42 @@ class EmbeddingCollection:
             self.top_data[tp["name"]] = self.out_slab[tp["off"]:tp["off"] + b * w].view(shp)
             if self.is_train:
                 self.top_grad[tp["name"]] = self.grad_slab[tp["off"]:tp["off"] + b * w].view(shp)
+
+    def alias_top(self, name: str, total_width: int, col_off: int):
+        """Re-home the batch-major top ``name`` inside a [b, total_width] buffer carved from the slabs
+        (columns [col_off, col_off + width)): lookups write / read it with row stride total_width.
+        Returns (data [b, total_width], grad [b, total_width] or None), or None when not possible."""
+        if not getattr(self, "alias_reserve", 0) or name not in self.alias_out_off:
+            return None
+        if self.world > 1 and not self.fused:
+            return None                       # the collective path ships whole slabs
+        tp = [t for t in self.tops if t["name"] == name][0]
+        w, b = tp["width"], self.b
+        esz = 2 if self.act_dtype == torch.bfloat16 else 4
+        if tp.get("alias") or total_width > w + self.alias_reserve or col_off + w > total_width \
+                or (col_off * esz) % 16 or (total_width * esz) % 16:
+            return None
+        oo, go = self.alias_out_off[name], self.alias_grad_off[name]
+        ti = self.tops.index(tp)
+        for grp in self.groups:
+            for lk, (gi, partial) in zip(grp.lookups, grp.lookup_gl):
+                gl = self.glookups[gi]
+                if gl["top"] != ti:
+                    continue
+                if not partial:
+                    lk.out_off = oo + col_off + (lk.out_off - tp["off"])
+                    lk.out_stride = total_width
+                lk.grad_off = go + col_off + (lk.grad_off - tp["off"])
+                lk.grad_stride = total_width
+            grp.lookups_dev = E.lookups_to_device(grp.lookups, self.device)
+        tp["alias"] = {"off": oo, "goff": go, "stride": total_width, "col": col_off}
+        full = self.out_slab[oo:oo + b * total_width].view(b, total_width)
+        self.top_data[name] = full[:, col_off:col_off + w]
+        gfull = None
+        if self.is_train:
+            gfull = self.grad_slab[go:go + b * total_width].view(b, total_width)
+            self.top_grad[name] = gfull[:, col_off:col_off + w]
+        return full, gfull
 
     # ------------------------------------------------------------------ API
     def top_shapes(self):
@@ -511,7 +564,10 @@ class EmbeddingCollection:
                 part = self.out_slab[gl["partial_off"]:gl["partial_off"] + b * gl["partial_w"]] \
                     .view(b, gl["k"], w)
                 tp = self.tops[gl["top"]]
-                full = self.out_slab[tp["off"]:tp["off"] + b * tp["width"]].view(b, tp["width"])
+                if tp.get("alias"):
+                    full = self.top_data[tp["name"]]
+                else:
+                    full = self.out_slab[tp["off"]:tp["off"] + b * tp["width"]].view(b, tp["width"])
                 from ..ops import dense as D
                 D.partial_sum(part, full, gl["col"], gl["k"], w)
 

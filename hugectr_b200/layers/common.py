@@ -197,13 +197,38 @@ class ConcatLayer(Layer):
             off += w
         return res
 
+    def allocate(self):
+        """Experimental (HCTR_CONCAT_ALIAS=1): when exactly one input is a batch-major embedding
+        collection top, the output buffer is carved from the collection's slabs and that top is
+        produced (and its gradient consumed) in place -- no strided copy in either direction."""
+        import os
+        self._aliased = None
+        o = self.outputs[0]
+        if os.environ.get("HCTR_CONCAT_ALIAS", "0") == "1" and self.axis == 1 and len(o.shape) == 2:
+            cands = [i for i, t in enumerate(self.inputs)
+                     if getattr(t, "ebc", None) is not None and len(t.shape) == 2 and t.dtype == o.dtype]
+            if len(cands) == 1:
+                i = cands[0]
+                t = self.inputs[i]
+                col = sum(x.shape[1] for x in self.inputs[:i])
+                res = t.ebc.alias_top(t.ebc_top, o.shape[1], col)
+                if res is not None:
+                    o.data = res[0]
+                    if self.ctx.is_train:
+                        o.grad = res[1]
+                    t.data = t.ebc.top_data[t.ebc_top]
+                    t.grad = t.ebc.top_grad[t.ebc_top] if self.ctx.is_train else None
+                    self._aliased = i
+        super().allocate()
+
     def fprop(self, is_train):
-        for t, dst, outer, w in self._views("data"):
-            D.copy2d(t.data.reshape(outer, w), dst)
+        for i, (t, dst, outer, w) in enumerate(self._views("data")):
+            if i != getattr(self, "_aliased", None):
+                D.copy2d(t.data.reshape(outer, w), dst)
 
     def bprop(self):
-        for t, src, outer, w in self._views("grad"):
-            if t.grad is not None:
+        for i, (t, src, outer, w) in enumerate(self._views("grad")):
+            if t.grad is not None and i != getattr(self, "_aliased", None):
                 D.copy2d(src, t.grad.reshape(outer, w))
 
 

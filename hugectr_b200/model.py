@@ -200,6 +200,7 @@ class Model:
                 tb = TensorBag(name, shp, self.act_dtype)
                 tb.data = e.top_data[name]
                 tb.grad = e.top_grad[name] if is_train else None
+                tb.ebc, tb.ebc_top = e, name          # lets a Concat alias the top into its output
                 src[name] = tb
                 emb_tops.append(name)
         for rt in (self.legacy_train if is_train else self.legacy_eval):

@@ -147,3 +147,27 @@ def test_exact_resume_from_checkpoint(tmp_path):
         b.train_on_host_batch(pool[i % len(pool)])
     assert float((a.arena.weights - b.arena.weights).abs().max()) == 0.0
     assert a.get_current_loss() == b.get_current_loss()
+
+
+def test_concat_aliasing_is_bit_identical(monkeypatch):
+    """experimental HCTR_CONCAT_ALIAS=1: the embedding top is produced inside the Concat output buffer
+    (row-strided lookups) -- training must be identical to the copying path"""
+    def run(flag):
+        monkeypatch.setenv("HCTR_CONCAT_ALIAS", flag)
+        m = build_dlrm_dcnv2(batchsize=64, num_gpus=1, table_sizes=[500, 30, 2000, 40], multi_hot=[3, 1, 5, 2],
+                             ev_size=16, lr=0.05, mixed=False, optimizer="adagrad", bottom=(32, 16),
+                             top=(32, 1), cross_layers=2, projection_dim=8, comm=CPU(), use_cuda_graph=False,
+                             seed=1)
+        m.compile()
+        cat = [l for l in m.net_train.layers if type(l).__name__ == "ConcatLayer"][0]
+        pool = m.reader_train.pool
+        for i in range(4):
+            m.train_on_host_batch(pool[i % len(pool)])
+        m.eval()
+        return (m.arena.weights.clone(), [g.table.clone() for g in m.ebcs_train[0].groups],
+                m.get_current_loss(), getattr(cat, "_aliased", None))
+    w0, t0, l0, a0 = run("0")
+    w1, t1, l1, a1 = run("1")
+    assert a0 is None and a1 == 0
+    assert l0 == l1 and float((w0 - w1).abs().max()) == 0.0
+    assert all(float((x - y).abs().max()) == 0.0 for x, y in zip(t0, t1))
