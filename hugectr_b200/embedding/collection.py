@@ -51,6 +51,11 @@ class EmbeddingTableConfig:
         self.ev_size = int(ev_size)
         self.opt_params = kw.get("opt_params", opt_params_or_empty)
         self.init_param = kw.get("init_param", init_param_or_empty)
+        # max_vocabulary_size < 0: dynamic table (embedding_storage/common.hpp:78) -- arbitrary 64-bit
+        # keys, rows handed out on first sight by a per-shard hash table; ``init_capacity`` rows per
+        # shard are reserved (DynamicEmbeddingTable of the reference grows, this one is bounded)
+        self.dynamic = self.max_vocabulary_size < 0
+        self.init_capacity = int(kw.get("init_capacity", 1 << 20))
 
 
 class EmbeddingCollectionConfig:
@@ -163,6 +168,9 @@ class EmbeddingCollection:
         self.tmap = {t.name: t for t in self.tables}
         self.placement = resolve_placement(cfg, self.world)
         self.native = device.type == "cuda"
+        self.has_dynamic = any(t.dynamic for t in self.tables)
+        if self.has_dynamic:
+            fused = False      # key -> row translation runs on the gathered keys (collective path)
         self.fused = (self.native and self.world > 1 and comm.p2p_available) if fused is None else fused
         # requester-side split of row-sharded bags (see _build_layout); experimental, off by default
         import os as _os
@@ -280,10 +288,10 @@ class EmbeddingCollection:
             for (cpart, k, s) in parts:
                 key = (pl.kind, ev_part)
                 grp = groups.setdefault(key, _Group(pl.kind, ev_part))
-                rows = shard_rows(t.max_vocabulary_size, k, s)
+                rows = t.init_capacity if t.dynamic else shard_rows(t.max_vocabulary_size, k, s)
                 grp.table_slices.append({"table": t.name, "cpart": cpart, "row_off": grp.rows,
                                          "rows": rows, "k": k, "s": s, "col0": cpart * ev_part,
-                                         "ev": ev_part})
+                                         "ev": ev_part, "dynamic": t.dynamic})
                 grp.rows += rows
                 o = t.opt_params or self.default_opt
                 if grp.opt is None:
@@ -308,19 +316,21 @@ class EmbeddingCollection:
                             base = gl["out_off"]
                             ostride = gl["out_stride"]
                             ocol = sub * gl["ev"] + sl["col0"]
-                        split = "split_off" in gl and pl.kind == "mp" and sl["k"] > 1
+                        split = ("split_off" in gl and pl.kind == "mp" and sl["k"] > 1) or sl["dynamic"]
                         grp.lookup_gl = getattr(grp, "lookup_gl", [])
                         grp.lookup_gl.append((gi, pl.kind == "mp" and sl["k"] > 1))
                         grp.lookups.append(E.LookupDesc(
                             table_row_off=sl["row_off"],
-                            key_off=(gl["split_off"] + sl["s"] * b * H) if split else gl["key_off"] + sub,
+                            key_off=(gl["split_off"] + sl["s"] * b * H)
+                            if (split and not sl["dynamic"]) else gl["key_off"] + sub,
                             out_off=base + ocol, grad_off=gl["out_off"] + sub * gl["ev"] + sl["col0"],
                             hotness=1 if concat else H, key_stride=H,
                             num_shards=1 if split else sl["k"], shard_idx=0 if split else sl["s"],
                             out_stride=ostride, grad_stride=gl["out_stride"],
                             combiner=1 if gl["combiner"] in ("mean", "average") else 0,
                             ev_size=sl["ev"], rows=sl["rows"],
-                            nnz_off=(gl["split_nnz_off"] + sl["s"] * b) if split else -1))
+                            nnz_off=(gl["split_nnz_off"] + sl["s"] * b)
+                            if (split and not sl["dynamic"]) else -1))
         self.groups = list(groups.values())
         dev = self.device
         gen = torch.Generator(device="cpu")
@@ -374,7 +384,7 @@ class EmbeddingCollection:
         """default U(+-sqrt(1/max_vocabulary_size)) (ragged_static_embedding.cu:501-530)."""
         for sl in grp.table_slices:
             t = self.tmap[sl["table"]]
-            bound = math.sqrt(1.0 / max(t.max_vocabulary_size, 1))
+            bound = math.sqrt(1.0 / max(t.max_vocabulary_size if not t.dynamic else t.init_capacity, 1))
             ip = t.init_param
             if ip is not None and ip.up_bound > 0:
                 bound = ip.up_bound
@@ -385,7 +395,7 @@ class EmbeddingCollection:
                 # identical on every replica: generate by global row on host
                 gen.manual_seed(_stable_seed(seed, sl["table"], sl["cpart"]))
                 full_rows = t.max_vocabulary_size
-                if full_rows * grp.pitch <= (1 << 26):
+                if not t.dynamic and full_rows * grp.pitch <= (1 << 26):
                     full = (torch.rand(full_rows, grp.pitch, generator=gen) * 2 - 1) * bound
                     view.copy_(full[sl["s"]::sl["k"]].reshape(-1).to(view.device))
                     continue
@@ -514,6 +524,46 @@ class EmbeddingCollection:
                 self.comm.all_gather(self.keys_all, self.key_slab)
                 if self.nnz_all is not None:
                     self.comm.all_gather(self.nnz_all, self.nnz_slab)
+        if self.has_dynamic:
+            self._translate_dynamic_keys()
+
+    def _dyn_hash(self, name, sl):
+        """per (table, local shard) key -> row hash table, shared between the train and eval plans"""
+        owner = getattr(self, "_shared", self)
+        if not hasattr(owner, "_dyn_tables"):
+            owner._dyn_tables = {}
+        key = (name, sl["cpart"], sl["s"])
+        if key not in owner._dyn_tables:
+            from .hashtable import HashTable
+            owner._dyn_tables[key] = HashTable(sl["rows"], self.device)
+        return owner._dyn_tables[key]
+
+    def _translate_dynamic_keys(self):
+        """Dynamic tables: overwrite the (gathered) keys of their lookups with local row indices -- new
+        keys get the next free row while training, unknown keys read as empty (-1) in evaluation; keys
+        owned by another shard become -1.  The lookup kernels then run exactly as for static tables."""
+        b = self.b
+        buf = self.key_slab.view(1, -1) if self.world == 1 else self.keys_all
+        for gl in self.glookups:
+            t = self.tmap[gl["table"]]
+            if not t.dynamic:
+                continue
+            region = buf[:, gl["key_off"]:gl["key_off"] + b * gl["hotness"]]
+            keys = region.to(torch.int64)
+            out = torch.full_like(keys, -1)
+            for grp in self.groups:
+                for sl in grp.table_slices:
+                    if sl["table"] != t.name or sl["cpart"] != 0:
+                        continue
+                    own = (keys >= 0) & ((keys % sl["k"]) == sl["s"])
+                    ht = self._dyn_hash(t.name, sl)
+                    k = torch.where(own, keys, torch.full_like(keys, -1)).reshape(-1)
+                    rows = (ht.get_insert(k) if self.is_train else ht.get(k)).reshape(keys.shape)
+                    if self.is_train and ht.size() > sl["rows"]:
+                        raise RuntimeError(f"dynamic embedding table {t.name}: more than init_capacity="
+                                           f"{sl['rows']} distinct keys on one shard")
+                    out = torch.where(own & (rows >= 0), rows.to(torch.int64), out)
+            region.copy_(out.to(region.dtype))
 
     def forward_compute(self):
         b = self.b
@@ -687,10 +737,17 @@ class EmbeddingCollection:
             for sl in grp.table_slices:
                 if sl["table"] != name:
                     continue
-                m = (keys % sl["k"] == sl["s"]) & (keys // sl["k"] < sl["rows"]) & (keys >= 0)
-                if not bool(m.any()):
-                    continue
-                rows = (sl["row_off"] + keys[m] // sl["k"]).to(grp.table.device)
+                if sl.get("dynamic"):
+                    m = (keys % sl["k"] == sl["s"]) & (keys >= 0)
+                    if not bool(m.any()):
+                        continue
+                    ht = self._dyn_hash(name, dict(sl, cpart=0))
+                    rows = sl["row_off"] + ht.get_insert(keys[m].to(self.device)).to(grp.table.device).long()
+                else:
+                    m = (keys % sl["k"] == sl["s"]) & (keys // sl["k"] < sl["rows"]) & (keys >= 0)
+                    if not bool(m.any()):
+                        continue
+                    rows = (sl["row_off"] + keys[m] // sl["k"]).to(grp.table.device)
                 c0, ev = sl["col0"], sl["ev"]
                 grp.table.view(-1, grp.pitch)[rows] = values[m][:, c0:c0 + ev].to(grp.table.device,
                                                                                  torch.float32)
@@ -711,6 +768,12 @@ class EmbeddingCollection:
                 keys = torch.arange(sl["rows"], dtype=torch.int64) * sl["k"] + sl["s"]
                 sts = [None if t is None else t.view(-1, grp.pitch)[lo:hi].detach().float().cpu()
                        for t in (grp.s0, grp.s1)]
+                if sl.get("dynamic"):
+                    dk, dr = self._dyn_hash(name, dict(sl, cpart=0)).dump()
+                    order = torch.argsort(dk)
+                    keys, dr = dk[order].to(torch.int64), dr[order].to(torch.int64)
+                    w = w[dr]
+                    sts = [None if t is None else t[dr] for t in sts]
                 res.append((keys, w, sl["col0"], sts, grp.kind))
         return res
 

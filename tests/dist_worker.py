@@ -87,6 +87,74 @@ def run_ebc(plan, fused):
         print(f"EBC_OK plan={plan} fused={fused} world={world}")
 
 
+def run_dynamic():
+    """dynamic (hashed) tables inside the collection: arbitrary 64-bit keys, rows assigned on first
+    sight; must behave like the static tables they shadow (same values under a key bijection)"""
+    comm = Comm.init_from_env()
+    dev = comm.device
+    world, rank = comm.world_size, comm.rank
+    b, ev = 16, 8
+    sizes = [500, 40, 900]
+    hot = {"d0": 3, "d1": 1, "d2": 5}
+    scramble = lambda k: k * 1000003 + 17
+
+    def cfg_for(w, dynamic):
+        ts = [EmbeddingTableConfig(str(i), -1 if (dynamic and i != 1) else sizes[i], ev, init_capacity=1024)
+              for i in range(3)]
+        cfg = EmbeddingCollectionConfig()
+        cfg.embedding_lookup(ts, list(hot), "emb", ["sum", "sum", "mean"])
+        sm = [[0] * 3 for _ in range(w)]
+        for g in range(w):
+            sm[g][2] = 1                # table 2 row-sharded over every rank
+        sm[0][0] = 1
+        sm[w - 1][1] = 1
+        cfg.shard(sm, [("mp", ["0", "1", "2"])])
+        return cfg
+    opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.1, epsilon=1e-6)
+    e = EmbeddingCollection(cfg_for(world, True), b, hot, dev, torch.float32, comm, opt, key_dtype=torch.int64,
+                            seed=1)
+    assert e.has_dynamic and not e.fused
+    ref = EmbeddingCollection(cfg_for(1, False), b * world, hot, torch.device("cpu"), torch.float32,
+                              Comm.single(torch.device("cpu")), opt, key_dtype=torch.int64, seed=1)
+    gen = torch.Generator().manual_seed(9)
+    full = {str(i): torch.randn(sizes[i], ev, generator=gen) * 0.1 for i in range(3)}
+    for n, w in full.items():
+        k = torch.arange(w.shape[0])
+        ref.load_table_rows(n, k, w)
+        e.load_table_rows(n, scramble(k) if n != "1" else k, w)
+    lr, st = torch.tensor([0.05]), torch.tensor([1], dtype=torch.int32)
+    for it in range(3):
+        gk = [torch.randint(0, sizes[i], (b * world, h), generator=gen) for i, h in enumerate(hot.values())]
+        keys_ref = torch.cat([k.reshape(-1) for k in gk])
+        gk2 = [scramble(k) if i != 1 else k for i, k in enumerate(gk)]
+        keys_loc = torch.cat([k[rank * b:(rank + 1) * b].reshape(-1) for k in gk2])
+        grad = torch.randn(b * world, 3 * ev, generator=gen) * 0.1
+        e.set_keys(keys_loc.to(dev)); ref.set_keys(keys_ref)
+        e.forward(); ref.forward()
+        err = (e.top_data["emb"].float().cpu() - ref.top_data["emb"][rank * b:(rank + 1) * b]).abs().max().item()
+        assert err < 1e-5, f"rank {rank} it {it} fwd err {err}"
+        e.top_grad["emb"].copy_(grad[rank * b:(rank + 1) * b].to(dev))
+        ref.top_grad["emb"].copy_(grad)
+        e.backward(lr.to(dev), st.to(dev)); ref.backward(lr, st)
+    for n in full:
+        rk, rw = ref.dump_table_local(n)[0][:2]
+        for (k, w, c0, sts, kind) in e.dump_table_local(n):
+            if len(k) == 0:
+                continue
+            orig = (k - 17) // 1000003 if n != "1" else k
+            err = (w - rw[orig][:, c0:c0 + w.shape[1]]).abs().max().item()
+            assert err < 1e-5, f"rank {rank} table {n} err {err}"
+    # evaluation plan: unknown keys read as zero vectors
+    ev_e = e.eval_clone(b)
+    unk = torch.full((b * sum(hot.values()),), 987654321987, dtype=torch.int64)
+    ev_e.set_keys(unk.to(dev))
+    ev_e.forward(False)
+    assert float(ev_e.top_data["emb"][:, :ev].abs().max()) == 0.0
+    comm.barrier()
+    if rank == 0:
+        print("DYNAMIC_OK")
+
+
 def run_allreduce():
     comm = Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
@@ -328,6 +396,8 @@ if __name__ == "__main__":
     what = sys.argv[1]
     if what == "ckpt":
         run_ckpt(sys.argv[2])
+    if what == "dynamic":
+        run_dynamic()
     if what == "legacy":
         run_legacy()
     if what == "equiv":

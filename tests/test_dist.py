@@ -127,3 +127,10 @@ def test_checkpoint_resharding_gloo(tmp_path):
     """2-rank checkpoint (dense + embedding collection) loads into a single-process model"""
     out = _run(2, ["ckpt", str(tmp_path)], 29731, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "CKPT_OK" in out
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_dynamic_tables_in_collection_gloo(nproc):
+    out = _run(nproc, ["dynamic"], 29741, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "DYNAMIC_OK" in out
