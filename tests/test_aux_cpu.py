@@ -304,3 +304,53 @@ def test_native_raw_reader_slices_and_layout(tmp_path):
     i = torch.arange(0, 4).float()
     torch.testing.assert_close(hb.dense, torch.stack([torch.log1p(i), torch.log1p(3 * i)], 1))
     r.stop()
+
+
+def test_diagnose_threadpool_mlperf_and_criteo2raw(tmp_path, capsys):
+    from hugectr_b200.utils import diagnose
+    from hugectr_b200.utils.thread_pool import CPUResource, ThreadPool
+    from hugectr_b200.tools import criteo2raw
+    good = torch.randn(100)
+    assert diagnose.verify(good, "good")
+    bad = good.clone()
+    bad[3] = float("nan")
+    assert not diagnose.verify(bad, "bad", raise_on_error=False)
+    with pytest.raises(Exception):
+        diagnose.verify(bad, "bad")
+    h = diagnose.histogram(good, bins=8)
+    assert int(h.sum()) == 100 and h.numel() == 8
+    assert diagnose.sample(good, 5).numel() == 5
+    tp = ThreadPool(3)
+    fs = [tp.submit(lambda x: x * x, i) for i in range(10)]
+    tp.await_idle(fs)
+    assert [f.result() for f in fs] == [i * i for i in range(10)]
+    cr = CPUResource(7, [1, 2])
+    a, b = torch.rand(3, generator=cr.get_replica_uniform_generator()), torch.rand(3, generator=CPUResource(7, [1, 2]).get_replica_uniform_generator())
+    assert torch.equal(a, b)
+    # criteo TSV -> raw records with frequency-thresholded categorification
+    lines = []
+    rng = np.random.default_rng(0)
+    for i in range(50):
+        dense = [str(int(x)) for x in rng.integers(0, 100, 13)]
+        cats = [format(int(x), "x") for x in rng.integers(0, 5, 26)]
+        lines.append("\t".join([str(i % 2)] + dense + cats))
+    tsv = tmp_path / "day_0.tsv"
+    tsv.write_text("\n".join(lines) + "\n")
+    vocabs, sizes = criteo2raw.convert(str(tsv), str(tmp_path / "out.bin"), min_freq=2)
+    rec = np.fromfile(str(tmp_path / "out.bin"), dtype="<u4").reshape(50, 1 + 13 + 26)
+    assert rec[:, 0].tolist() == [i % 2 for i in range(50)]
+    assert all(rec[:, 14 + j].max() < sizes[j] for j in range(26)) and len(vocabs) == 26
+
+
+def test_mlperf_logging_callback_emits_events(capsys):
+    from hugectr_b200.utils.mlperf import LoggingCallback
+    cb = LoggingCallback(auc_threshold=0.8, iter_per_epoch=100.0, batchsize=64)
+    cb.on_training_start()
+    assert cb.on_eval_start(50) is False
+    assert cb.on_eval_end(50, {"AUC": 0.7}) is False
+    assert cb.on_eval_end(100, {"AUC": 0.81}) is True          # threshold reached -> stop
+    cb.on_training_end(100)
+    out = capsys.readouterr()
+    text = out.out + out.err
+    for key in ("run_start", "eval_accuracy", "run_stop", "train_samples"):
+        assert key in text
