@@ -605,6 +605,31 @@ class EmbeddingCollection:
                         E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
                                   [self.out_slab], b)
         self._reduce_partials()
+        self._rescale_mean(forward=True)
+
+    def _rescale_mean(self, forward: bool):
+        """Mean-combined bags may be shorter than the maximum hotness (padding keys are -1): the lookup
+        kernels divide by the maximum hotness, the requester -- who owns the keys -- rescales its
+        pooled vectors (forward) / their gradients (backward) by hotness / (number of valid keys), i.e.
+        the mean is over the actual bag like the reference's bucket ranges."""
+        for gi, gl in enumerate(self.glookups):
+            if gl["combiner"] not in ("mean", "average") or gl["hotness"] <= 1:
+                continue
+            tp = self.tops[gl["top"]]
+            if forward:
+                keys = self.key_views[gl["bottom"]]
+                cnt = (keys >= 0).sum(1).clamp(min=1).to(torch.float32)
+                self._mean_factor = getattr(self, "_mean_factor", {})
+                self._mean_factor[gi] = (float(gl["hotness"]) / cnt).unsqueeze(1)
+                t2d = self.top_data[tp["name"]].reshape(self.b, -1) if not tp.get("alias") \
+                    else self.top_data[tp["name"]]
+            else:
+                if gi not in getattr(self, "_mean_factor", {}):
+                    continue
+                t2d = self.top_grad[tp["name"]].reshape(self.b, -1) if not tp.get("alias") \
+                    else self.top_grad[tp["name"]]
+            col = t2d[:, gl["col"]:gl["col"] + gl["ev"]]
+            col.copy_((col.float() * self._mean_factor[gi]).to(col.dtype))
 
     def _reduce_partials(self):
         b = self.b
@@ -652,6 +677,7 @@ class EmbeddingCollection:
         if not getattr(self, "_index_done", False):
             self.backward_index()
         self._index_done = False
+        self._rescale_mean(forward=False)
         dp_groups = [g for g in self.groups if g.kind == "dp"]
         mp_groups = [g for g in self.groups if g.kind != "dp"]
         side = dp_stream is not None and self.device.type == "cuda" and bool(dp_groups)

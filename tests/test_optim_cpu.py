@@ -201,3 +201,36 @@ def test_legacy_embedding_global_update_equals_dense_optimizer(kind):
             topt.step()
     n = rt.hash.size()
     torch.testing.assert_close(rt.table.view(-1, vec)[:n], W.detach()[:n], atol=2e-5, rtol=1e-4)
+
+
+def test_mean_combiner_averages_over_the_actual_bag():
+    """padded (-1) keys: 'mean' divides by the number of valid keys of the bag, forward and backward"""
+    from hugectr_b200.embedding.collection import (EmbeddingCollection, EmbeddingCollectionConfig,
+                                                   EmbeddingTableConfig)
+    from hugectr_b200.parallel.comm import Comm
+    dev = torch.device("cpu")
+    cfg = EmbeddingCollectionConfig()
+    cfg.embedding_lookup([EmbeddingTableConfig("0", 50, 4), EmbeddingTableConfig("1", 20, 4)], ["d0", "d1"],
+                         "emb", ["mean", "sum"])
+    e = EmbeddingCollection(cfg, 3, {"d0": 4, "d1": 2}, dev, torch.float32, Comm.single(dev),
+                            hugectr.CreateOptimizer(hugectr.Optimizer_t.SGD))
+    k0 = torch.tensor([[1, 2, -1, -1], [3, 3, 3, 3], [5, -1, -1, -1]])
+    k1 = torch.tensor([[1, 2], [3, -1], [4, 4]])
+    e.set_keys(torch.cat([k0.reshape(-1), k1.reshape(-1)]).int())
+    W = e.groups[0].table.view(-1, 4).clone()
+    e.forward()
+    off1 = [sl["row_off"] for sl in e.groups[0].table_slices if sl["table"] == "1"][0]
+    torch.testing.assert_close(e.top_data["emb"][:, :4], torch.stack([(W[1] + W[2]) / 2, W[3], W[5]]))
+    g = torch.randn(3, 8)
+    e.top_grad["emb"].copy_(g)
+    e.backward(torch.tensor([1.0]), torch.tensor([1], dtype=torch.int32))
+    exp = W.clone()
+    exp[1] -= g[0, :4] / 2
+    exp[2] -= g[0, :4] / 2
+    exp[3] -= g[1, :4]
+    exp[5] -= g[2, :4]
+    exp[off1 + 1] -= g[0, 4:]
+    exp[off1 + 2] -= g[0, 4:]
+    exp[off1 + 3] -= g[1, 4:]
+    exp[off1 + 4] -= 2 * g[2, 4:]
+    torch.testing.assert_close(e.groups[0].table.view(-1, 4), exp, atol=1e-6, rtol=1e-5)
