@@ -37,20 +37,38 @@ def _as_list(v):
 
 
 class _KeyedEmbedding(nn.Module):
-    """key -> row by sorted-key binary search (arbitrary int64 keys), sum/mean combiner."""
+    """key -> row lookup with sum/mean combiner.  When the key space is small (slot-offset keys of the
+    legacy embeddings: max key < 2**24) a dense key -> row table is used (a plain Gather, exportable
+    to ONNX); otherwise a sorted-key binary search (arbitrary int64 keys, torch-only)."""
+
+    LUT_LIMIT = 1 << 24
 
     def __init__(self, keys, emb, combiner):
         super().__init__()
         order = torch.argsort(keys)
-        self.register_buffer("keys", keys[order])
+        keys = keys[order]
+        n = keys.numel()
         self.register_buffer("emb", torch.cat([emb[order], torch.zeros(1, emb.shape[1])]))
         self.combiner = combiner
+        self.n = n
+        self.use_lut = bool(n > 0 and int(keys[-1]) < self.LUT_LIMIT and int(keys[0]) >= 0)
+        if self.use_lut:
+            lut = torch.full((int(keys[-1]) + 2,), n, dtype=torch.int64)      # last entry: "missing"
+            lut[keys] = torch.arange(n, dtype=torch.int64)
+            self.register_buffer("lut", lut)
+        else:
+            self.register_buffer("keys", keys)
 
     def forward(self, k):                       # k [b, S, H], -1 padded
-        n = self.keys.numel()
-        pos = torch.searchsorted(self.keys, k.clamp(min=0)).clamp(max=max(n - 1, 0))
-        hit = (self.keys[pos] == k) & (k >= 0)
-        rows = torch.where(hit, pos, torch.full_like(pos, n))
+        n = self.n
+        if self.use_lut:
+            top = self.lut.numel() - 1
+            idx = torch.where((k >= 0) & (k < top), k, torch.full_like(k, top))
+            rows = self.lut[idx]
+        else:
+            pos = torch.searchsorted(self.keys, k.clamp(min=0)).clamp(max=max(n - 1, 0))
+            hit = (self.keys[pos] == k) & (k >= 0)
+            rows = torch.where(hit, pos, torch.full_like(pos, n))
         v = self.emb[rows]                      # [b, S, H, vec]
         out = v.sum(2)
         if self.combiner == "mean":

@@ -171,3 +171,33 @@ def test_concat_aliasing_is_bit_identical(monkeypatch):
     assert a0 is None and a1 == 0
     assert l0 == l1 and float((w0 - w1).abs().max()) == 0.0
     assert all(float((x - y).abs().max()) == 0.0 for x, y in zip(t0, t1))
+
+
+def test_onnx_converter_graph_reproduces_predictions(tmp_path):
+    """hugectr2onnx: the inference graph built from graph JSON + dense model (+ sparse model) gives the
+    model's own evaluation predictions, with the embedding inside the graph (keys in) or outside
+    (embedding vectors in).  (Serialisation itself needs the `onnx` package; without it the torch
+    graph is saved next to the requested path.)"""
+    from hugectr_b200.onnx.hugectr2onnx import convert
+    m = build_dcn(batchsize=32, slot_sizes=[60] * 26, workspace_mb=1, comm=CPU(), max_eval_batches=1,
+                  batchsize_eval=32)
+    m.compile()
+    for _ in range(3):
+        m.train()
+    pre = str(tmp_path / "dcn")
+    m.save_params_to_files(pre, 3)
+    m.graph_to_json(pre + ".json")
+    m.eval()
+    pred = [ll.pred.clone() for ll in m.net_eval.loss_layers][0].reshape(-1)
+    hb = m.reader_eval.pool[(m.reader_eval.i - 1) % len(m.reader_eval.pool)]
+    g = convert(pre + "_keys.onnx", pre + ".json", pre + "_dense_3.model", convert_embedding=True,
+                sparse_models=[pre + "0_sparse_3.model"], batch_size=32)
+    with torch.no_grad():
+        out = g(hb.dense, hb.keys.view(32, 26, 1).long()).reshape(-1)
+    torch.testing.assert_close(out, pred, atol=1e-6, rtol=1e-5)
+    assert os.path.exists(pre + "_keys.onnx") or os.path.exists(pre + "_keys.onnx.pt")
+    g2 = convert(pre + "_vec.onnx", pre + ".json", pre + "_dense_3.model", convert_embedding=False, batch_size=32)
+    emb = torch.from_numpy(m.check_out_tensor("sparse_embedding1", hugectr.Tensor_t.Evaluate))
+    with torch.no_grad():
+        out2 = g2(hb.dense, emb).reshape(-1)
+    torch.testing.assert_close(out2, pred, atol=1e-6, rtol=1e-5)
