@@ -213,8 +213,28 @@ class InferenceGraph(nn.Module):
                 else:
                     ld = l.get("leading_dim", 0) or int(np.prod(x.shape[1:]))
                     y = x.reshape(-1, ld)
-            elif ty in ("Concat",):
+            elif ty in ("Concat", "Concat3D"):
                 y = torch.cat(bots, l.get("axis", 1))
+            elif ty == "FusedReshapeConcat":            # [b, F+1, e_i] -> history [b*F, E], item [b, E]
+                xc = torch.cat(bots, 2)
+                f1 = xc.shape[1]
+                t[tops[0]] = xc[:, :f1 - 1, :].reshape(-1, xc.shape[2])
+                t[tops[1]] = xc[:, f1 - 1, :]
+                out = t[tops[1]]
+                continue
+            elif ty == "FusedReshapeConcatGeneral":
+                xc = torch.cat(bots, 2)
+                y = xc.reshape(-1, xc.shape[2])
+            elif ty == "MaskedSoftmax":
+                v = torch.where(bots[1] > 0, x, torch.full_like(x, -10000.0)) if len(bots) > 1 else x
+                y = torch.softmax(v, -1)
+            elif ty == "SequenceMask":
+                lf, lt = int(l["max_sequence_len_from"]), int(l["max_sequence_len_to"])
+                a = bots[0].reshape(-1).float()
+                b2 = bots[1].reshape(-1).float()
+                mf = torch.arange(lf).view(1, -1, 1) < a.view(-1, 1, 1)
+                mt = torch.arange(lt).view(1, 1, -1) < b2.view(-1, 1, 1)
+                y = (mf & mt).unsqueeze(1).to(bots[0].dtype)
             elif ty == "Slice":
                 ys = [x[..., a:b] for a, b in l["ranges"]]
                 for n, v in zip(tops, ys):

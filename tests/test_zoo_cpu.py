@@ -67,3 +67,49 @@ def test_graph_json_round_trip(name, tmp_path):
     assert [r[0] for r in m2.net_train.summary_rows()] == [r[0] for r in m.net_train.summary_rows()]
     assert m2.train()
     assert np.isfinite(m2.get_current_loss())
+
+
+@pytest.mark.parametrize("name", ["deepfm", "wdl", "ncf", "mmoe", "din", "bst", "dcnv2"])
+def test_onnx_converter_matches_model_predictions(name, tmp_path):
+    """hugectr2onnx inference graph (graph JSON + dense model, embedding vectors as inputs) reproduces
+    the evaluation predictions of every model family"""
+    import os
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models import build_deepfm, build_wdl
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.onnx.hugectr2onnx import convert
+    B = 16
+    kw = dict(comm=CPU(), max_eval_batches=1, batchsize_eval=B)
+    m = {"deepfm": lambda: build_deepfm(batchsize=B, slot_sizes=[30] * 26, workspace_mb=1, **kw),
+         "wdl": lambda: build_wdl(batchsize=B, wide_slot_sizes=[20, 30], deep_slot_sizes=[30] * 26,
+                                  workspace_mb=(1, 1), **kw),
+         "ncf": lambda: zoo.build_ncf("neumf", batchsize=B, num_users=100, num_items=80, **kw),
+         "mmoe": lambda: zoo.build_mmoe(batchsize=B, num_slots=4, vocab=50, ev=8, expert_dims=(16, 8),
+                                        tower_dim=8, **kw),
+         "din": lambda: zoo.build_din(batchsize=B, seq_len=3, item_vocab=60, cate_vocab=10, user_vocab=20,
+                                      ev=4, att_dims=(8, 4), mlp_dims=(8, 4), **kw),
+         "bst": lambda: zoo.build_bst(batchsize=B, seq_len=3, item_vocab=60, user_vocab=20, ev=8, heads=2,
+                                      ffn_dim=8, mlp_dims=(8, 4), **kw),
+         "dcnv2": lambda: build_dlrm_dcnv2(batchsize=B, num_gpus=1, table_sizes=[50, 30, 20],
+                                           multi_hot=[2, 1, 3], ev_size=8, mixed=False, bottom=(16, 8),
+                                           top=(16, 1), cross_layers=1, projection_dim=4,
+                                           use_cuda_graph=False, **kw)}[name]()
+    for c in m.dense_layers:
+        if c.layer_type == hugectr.Layer_t.Dropout:
+            c.dropout_rate = 0.0
+    m.compile()
+    m.train()
+    pre = str(tmp_path / name)
+    m.save_params_to_files(pre, 1)
+    m.graph_to_json(pre + ".json")
+    m.eval()
+    pred = [ll.pred.clone().reshape(-1) for ll in m.net_eval.loss_layers][-1]
+    g = convert(pre + ".onnx", pre + ".json", pre + "_dense_1.model", convert_embedding=False, batch_size=B)
+    ins = [torch.from_numpy(m.check_out_tensor(l["top"], hugectr.Tensor_t.Evaluate)) for l in g.emb_layers]
+    for e in getattr(m, "ebcs_eval", []):
+        ins += [e.top_data[tp["name"]].reshape(B, -1).float().clone() for tp in e.tops]
+    dense = m.net_eval.tensors[m.input.dense_name].data.clone() if m.input.dense_dim > 0 else torch.zeros(B, 0)
+    with torch.no_grad():
+        out = g(dense, *ins).reshape(-1)
+    torch.testing.assert_close(out, pred, atol=1e-6, rtol=1e-5)
+    assert os.path.exists(pre + ".onnx") or os.path.exists(pre + ".onnx.pt")
