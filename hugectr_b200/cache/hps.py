@@ -299,3 +299,52 @@ class OffloadedEmbedding:
             if s is not None:
                 c.update(self.uniq, s)
         self.ps.push(self.uniq, w, [s for s in (s0, s1) if s is not None])
+
+
+class HpsEmbedding:
+    """Inference-time embedding service in the shape of the reference's (removed) Hierarchical
+    Parameter Server: the full table lives in the host parameter server, a set-associative LRU cache
+    in device memory serves the hot rows; a lookup de-duplicates the batch's keys, queries the cache,
+    pulls the misses from the host table and inserts them (gpu_cache Query / Replace).  Unknown keys
+    read as zero vectors."""
+
+    def __init__(self, keys: torch.Tensor, vectors: torch.Tensor, device, cache_fraction: float = 0.2,
+                 combiner: str = "sum", min_cache_rows: int = 64):
+        from .gpu_cache import GpuCache
+        self.device = torch.device(device)
+        self.ev = int(vectors.shape[1])
+        n = int(keys.numel())
+        self.ps = HostParameterServer(self.ev, 0, capacity_rows=max(n, 1))
+        if n:
+            self.ps.push(keys.to(torch.int64), vectors.float())
+        rows = max(int(min_cache_rows), int(cache_fraction * n))
+        self.cache = GpuCache(rows, self.ev, self.device)
+        self.combiner = combiner
+        self.lookups = 0
+
+    def hit_rate(self) -> float:
+        return self.cache.hit_rate()
+
+    def lookup(self, keys: torch.Tensor) -> torch.Tensor:
+        """keys [b, S, H] (int64, -1 padded) -> pooled vectors [b, S, ev] on the cache's device"""
+        b, S, H = keys.shape
+        flat = keys.reshape(-1).to(torch.int64)
+        valid = flat >= 0
+        vec = torch.zeros(flat.numel(), self.ev, device=self.device)
+        if bool(valid.any()):
+            uniq, inv = torch.unique(flat[valid].to(self.device), return_inverse=True)
+            vals, miss_idx, miss_keys = self.cache.query(uniq)
+            if miss_idx.numel():
+                mk = miss_keys.cpu()
+                rows = self.ps._rows(mk, create=False)
+                w = self.ps._gather(self.ps.w, rows)             # absent keys -> zero rows
+                vals[miss_idx.to(self.device)] = w.to(self.device)
+                known = rows >= 0
+                if bool(known.any()):
+                    self.cache.replace(mk[known].to(self.device), w[known].to(self.device))
+            vec[valid.to(self.device)] = vals[inv]
+        self.lookups += 1
+        out = vec.view(b, S, H, self.ev).sum(2)
+        if self.combiner == "mean":
+            out = out / (keys.to(self.device) >= 0).sum(2, keepdim=True).clamp(min=1)
+        return out

@@ -48,7 +48,16 @@ class InferenceModel:
         self.model.compile()
         if params.dense_model_file:
             self.model.load_dense_weights(params.dense_model_file)
-        if params.sparse_model_files:
+        self.hps = {}
+        if params.sparse_model_files and params.use_gpu_embedding_cache and self.model.legacy_eval:
+            # HPS-style serving: tables stay in the host parameter server, hot rows in the device cache
+            from .cache import HpsEmbedding
+            from .onnx.hugectr2onnx import load_sparse_model
+            for rt, path in zip(self.model.legacy_eval, params.sparse_model_files):
+                keys, emb = load_sparse_model(path, rt.vec)
+                self.hps[rt.name] = HpsEmbedding(keys, emb, dev, params.cache_size_percentage,
+                                                 "mean" if rt.combiner == 1 else "sum")
+        elif params.sparse_model_files:
             self.model.load_sparse_weights(params.sparse_model_files)
         if params.embedding_collection_path:
             self.model.embedding_load(params.embedding_collection_path)
@@ -69,7 +78,11 @@ class InferenceModel:
         for e in m.ebcs_eval:
             e.forward(False)
         for rt in m.legacy_eval:
-            rt.forward(False)
+            if rt.name in self.hps:
+                pooled = self.hps[rt.name].lookup(rt.keys_loc.view(rt.b, rt.S, rt.H))
+                rt.top_data.copy_(pooled.to(rt.top_data.dtype))
+            else:
+                rt.forward(False)
         m.net_eval.fprop(False)
         ll = m.net_eval.loss_layers
         pred = ll[0].pred if len(ll) == 1 else torch.cat([l.pred.reshape(b, -1) for l in ll], 1)

@@ -354,3 +354,37 @@ def test_mlperf_logging_callback_emits_events(capsys):
     text = out.out + out.err
     for key in ("run_start", "eval_accuracy", "run_stop", "train_samples"):
         assert key in text
+
+
+def test_hps_inference_session_matches_direct_lookup(tmp_path):
+    """use_gpu_embedding_cache: tables in the host parameter server + device LRU cache; predictions
+    equal the plain session, repeated batches hit the cache, unknown keys read as zeros"""
+    from hugectr_b200.cache import HpsEmbedding
+    from hugectr_b200.inference import CreateInferenceSession, InferenceParams
+    from hugectr_b200.models import build_dcn
+    m = build_dcn(batchsize=32, slot_sizes=[60] * 26, workspace_mb=1, comm=Comm.single(torch.device("cpu")),
+                  max_eval_batches=1, batchsize_eval=32)
+    m.compile()
+    for _ in range(3):
+        m.train()
+    pre = str(tmp_path / "dcn")
+    m.save_params_to_files(pre, 3)
+    m.graph_to_json(pre + ".json")
+    common = dict(dense_model_file=pre + "_dense_3.model", sparse_model_files=[pre + "0_sparse_3.model"])
+    plain = CreateInferenceSession(pre + ".json", InferenceParams("dcn", 32, **common))
+    hps = CreateInferenceSession(pre + ".json", InferenceParams("dcn", 32, use_gpu_embedding_cache=True,
+                                                                cache_size_percentage=0.5, **common))
+    assert hps.hps, "HPS path not active"
+    for i in range(3):
+        hb = m.reader_eval.pool[i % len(m.reader_eval.pool)]
+        a = plain.predict(hb.dense.numpy(), hb.keys.numpy())
+        b = hps.predict(hb.dense.numpy(), hb.keys.numpy())
+        assert np.abs(a - b).max() < 1e-6
+    svc = list(hps.hps.values())[0]
+    r0 = svc.hit_rate()
+    hb = m.reader_eval.pool[0]
+    hps.predict(hb.dense.numpy(), hb.keys.numpy())          # same batch again: served from the cache
+    assert svc.hit_rate() > r0
+    e = HpsEmbedding(torch.tensor([5, 9]), torch.tensor([[1., 1.], [2., 2.]]), "cpu", combiner="mean")
+    out = e.lookup(torch.tensor([[[5, 9, -1], [777, -1, -1]]]))
+    torch.testing.assert_close(out, torch.tensor([[[1.5, 1.5], [0., 0.]]]))
