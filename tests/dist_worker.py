@@ -155,6 +155,39 @@ def run_dynamic():
         print("DYNAMIC_OK")
 
 
+def run_sok():
+    """sok.lookup_sparse over a distributed variable (rows sharded by key %% world): forward, sparse
+    backward and optimizer step must equal a dense single-process embedding"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200 import sok
+    comm = Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+    sok.init(comm)
+    torch.manual_seed(0)
+    full = torch.randn(40, 4)                               # same on every rank
+    v = sok.Variable(initial_value=full.clone(), name="dist_v")
+    gen = torch.Generator().manual_seed(11)
+    b = 6
+    ids_all = torch.randint(0, 40, (b * world, 3), generator=gen)
+    ids_all[0, 2] = -1
+    ids = ids_all[rank * b:(rank + 1) * b]
+    out = sok.lookup_sparse(v, ids, "mean")
+    W = full.clone().requires_grad_(True)
+    m = (ids_all >= 0).unsqueeze(-1).float()
+    ref = (W[ids_all.clamp(min=0)] * m).sum(1) / m.sum(1).clamp(min=1)
+    torch.testing.assert_close(out, ref[rank * b:(rank + 1) * b].detach(), atol=1e-6, rtol=1e-5)
+    gout = torch.randn(b * world, 4, generator=gen)
+    (out * gout[rank * b:(rank + 1) * b]).sum().backward()
+    (ref * gout).sum().backward()
+    sok.OptimizerWrapper(hugectr.Optimizer_t.SGD, lr=0.1).apply_gradients([v])
+    W2 = (W - 0.1 * W.grad).detach()
+    keys = v.global_keys()
+    torch.testing.assert_close(v.weight.float().cpu(), W2[keys.cpu()], atol=1e-6, rtol=1e-5)
+    comm.barrier()
+    if rank == 0:
+        print("SOK_OK")
+
+
 def run_allreduce():
     comm = Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
@@ -398,6 +431,8 @@ if __name__ == "__main__":
         run_ckpt(sys.argv[2])
     if what == "dynamic":
         run_dynamic()
+    if what == "sok":
+        run_sok()
     if what == "legacy":
         run_legacy()
     if what == "equiv":

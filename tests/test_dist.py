@@ -134,3 +134,9 @@ def test_checkpoint_resharding_gloo(tmp_path):
 def test_dynamic_tables_in_collection_gloo(nproc):
     out = _run(nproc, ["dynamic"], 29741, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "DYNAMIC_OK" in out
+
+
+@pytest.mark.dist
+def test_sok_distributed_lookup_gloo():
+    out = _run(2, ["sok"], 29751, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "SOK_OK" in out
