@@ -169,6 +169,8 @@ class SparseEmbeddingRuntime:
         hp = {"scaler": self.scaler, "beta1": self.opt.beta1, "beta2": self.opt.beta2,
               "epsilon": self.opt.epsilon, "lambda1": self.opt.lambda1, "lambda2": self.opt.lambda2,
               "ftrl_beta": self.opt.beta, "momentum": self.opt.momentum_factor}
+        if self.opt.update_type == Update_t.LazyGlobal and self.opt.optimizer_type == Optimizer_t.Adam:
+            return self._lazy_adam(lr_t, step_t)
         if self.indexed:
             E.bwd_index(self.lookups, self.lookups_dev, self.table, vec, kb, b, self.ws, self.rank)
             E.bwd_reduce_update(self.opt.optimizer_type, self.lookups, self.lookups_dev, self.table,
@@ -180,6 +182,39 @@ class SparseEmbeddingRuntime:
         if self.opt.update_type in (Update_t.Global, Update_t.LazyGlobal) and \
                 self.opt.optimizer_type in (Optimizer_t.Adam, Optimizer_t.MomentumSGD, Optimizer_t.Nesterov):
             self._global_sweep(lr_t, step_t)
+
+    def _lazy_adam(self, lr_t, step_t):
+        """Update_t.LazyGlobal with Adam (sparse_optimizer.cu:523-561, opt_adam_kernel_lazy): only the
+        touched rows are visited; a row first catches up on the weight movement of the steps it
+        skipped (geometric sum of its decaying first moment), then its moments absorb the skipped
+        decays and the new gradient -- whose own weight update is applied at the row's next visit.
+        Needs the step of the last visit per row (the extra state of model.cpp:189-192)."""
+        vec, o = self.vec, self.opt
+        if not hasattr(self, "prev_time"):
+            # initialised to 1 like the reference (sparse_optimizer.cu:137-139)
+            self.prev_time = torch.ones(self.max_rows, dtype=torch.float32, device=self.device)
+        r = self.rows_all.reshape(-1)
+        own = r >= 0
+        if not bool(own.any()):
+            return
+        # gradient of every (rank, sample, slot) bucket, repeated for its H keys
+        W, b, S, H = self.world, self.b, self.S, self.H
+        g = self.grads_all.view(W, b, S, 1, vec).float().expand(W, b, S, H, vec).reshape(-1, vec)
+        rows, inv = torch.unique(r[own], return_inverse=True)
+        gi = torch.zeros(rows.numel(), vec, device=self.device).index_add_(0, inv, g[own]) / self.scaler
+        w = self.table.view(-1, vec)
+        m, v = self.s0.view(-1, vec), self.s1.view(-1, vec)
+        t = step_t.reshape(()).float()
+        prev = self.prev_time[rows].unsqueeze(1)
+        skipped = t - prev
+        b1s = o.beta1 ** skipped
+        alpha_common = lr_t.reshape(()).float() / (1.0 - o.beta1)
+        alpha_t = alpha_common * torch.sqrt(1.0 - o.beta2 ** prev) / (1.0 - o.beta1 ** prev) * (1.0 - b1s)
+        mi, vi = m[rows], v[rows]
+        w[rows] = w[rows] - alpha_t * mi / (vi.sqrt() + o.epsilon)
+        m[rows] = b1s * mi + (1.0 - o.beta1) * gi
+        v[rows] = (o.beta2 ** skipped) * vi + (1.0 - o.beta2) * gi * gi
+        self.prev_time[rows] = t
 
     def _global_sweep(self, lr_t, step_t):
         """Update_t.Global (sparse_optimizer.cu:241-292): the touched rows were updated by the fused

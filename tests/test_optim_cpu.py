@@ -234,3 +234,47 @@ def test_mean_combiner_averages_over_the_actual_bag():
     exp[off1 + 3] -= g[1, 4:]
     exp[off1 + 4] -= 2 * g[2, 4:]
     torch.testing.assert_close(e.groups[0].table.view(-1, 4), exp, atol=1e-6, rtol=1e-5)
+
+
+def test_legacy_embedding_lazy_global_adam_follows_reference_kernel():
+    """Update_t.LazyGlobal: per-row catch-up with the skipped steps, then moment update
+    (opt_adam_kernel_lazy, sparse_optimizer.cu:523-561) -- compared with a scalar re-implementation"""
+    from hugectr_b200.data.batch import HostBatch
+    from hugectr_b200.embedding.sparse_embedding import SparseEmbeddingRuntime
+    from hugectr_b200.parallel.comm import Comm
+    torch.manual_seed(0)
+    b, S, H, vec, vocab = 4, 2, 1, 3, 12
+    opt = hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.LazyGlobal, epsilon=1e-7)
+    cfg = hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash, 0, vec, "sum",
+                                  "emb", "data", slot_size_array=[6, 6], optimizer=opt)
+    cfg.max_vocabulary_size_per_gpu = 32
+    dev = torch.device("cpu")
+    rt = SparseEmbeddingRuntime(cfg, hugectr.DataReaderSparseParam("data", H, True, S), None, b, dev,
+                                torch.float32, Comm.single(dev), opt, torch.int64)
+    W = rt.table.view(-1, vec).clone().double()
+    M, V = torch.zeros_like(W), torch.zeros_like(W)
+    P = torch.ones(W.shape[0], dtype=torch.float64)
+    lr, b1, b2, eps = 0.05, 0.9, 0.999, 1e-7
+    for step in range(1, 7):
+        keys = torch.randint(0, vocab, (b * S * H,))
+        rt.set_keys(HostBatch(torch.zeros(b, 1), torch.zeros(b, 0), keys, None, b), {"data": 0}, {})
+        rt.forward(True)
+        g = torch.randn(b, S, vec)
+        rt.top_grad.copy_(g)
+        rows = rt.rows_all.view(b, S, H).clone()
+        rt.backward(torch.tensor([lr]), torch.tensor([step], dtype=torch.int32))
+        gsum = {}
+        for i in range(b):
+            for s in range(S):
+                r = int(rows[i, s, 0])
+                gsum[r] = gsum.get(r, 0) + g[i, s].double()
+        for r, gi in gsum.items():
+            prev = P[r].item()
+            skipped = step - prev
+            alpha_t = lr / (1 - b1) * (1 - b2 ** prev) ** 0.5 / (1 - b1 ** prev) * (1 - b1 ** skipped)
+            W[r] += -alpha_t * M[r] / (V[r].sqrt() + eps)
+            M[r] = b1 ** skipped * M[r] + (1 - b1) * gi
+            V[r] = b2 ** skipped * V[r] + (1 - b2) * gi * gi
+            P[r] = step
+    n = rt.hash.size()
+    torch.testing.assert_close(rt.table.view(-1, vec)[:n].double(), W[:n], atol=1e-5, rtol=1e-4)
