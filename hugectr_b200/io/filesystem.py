@@ -132,8 +132,14 @@ class FileSystemBuilder:
             return ArrowFileSystem(FileSystemType_t.GCS)
         return LocalFileSystem()
 
+    # names of the reference (include/io/filesystem.hpp:125-152)
+    build_unique_by_path = build_by_path
+
     @staticmethod
     def build_by_type(kind: FileSystemType_t, params=None) -> FileSystem:
         if kind in (FileSystemType_t.Local, FileSystemType_t.Other):
             return LocalFileSystem()
         return ArrowFileSystem(kind, getattr(params, "server", ""), getattr(params, "port", 0))
+
+
+FileSystemBuilder.build_unique_by_type = FileSystemBuilder.build_by_type

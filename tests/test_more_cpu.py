@@ -1,0 +1,137 @@
+"""Second line of CPU tests: API corners that the end-to-end tests do not reach (found with a line
+tracer over the suite)."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import hugectr_b200 as hugectr
+from hugectr_b200.parallel.comm import Comm
+
+CPU = lambda: Comm.single(torch.device("cpu"))
+
+
+def test_sok_localized_dense_lookup_filter_and_incremental_dump(tmp_path):
+    from hugectr_b200 import sok
+    sok.init(CPU())
+    assert sok.rank() == 0 and sok.num_gpus() == 1
+    lv = sok.LocalizedVariable(shape=(30, 4), gpu=0, name="loc_v")
+    idx = torch.tensor([[1, 2, 3], [4, 4, 0]])
+    dense = sok.all2all_dense_embedding(lv, idx)
+    torch.testing.assert_close(dense, lv.weight[idx])
+    sok_vars, others = sok.filter_variables([lv, torch.nn.Parameter(torch.zeros(2))])
+    assert sok_vars == [lv] and len(others) == 1
+    d = sok.DynamicVariable(4, name="dyn_inc", init_capacity=8)
+    out = sok.lookup_sparse(d, torch.tensor([[10 ** 11, 7]]), "sum")
+    out.sum().backward()
+    t0 = time.time()
+    time.sleep(0.01)
+    sok.SGD(0.1).apply_gradients([d])                       # touches the two rows now
+    sok.lookup_sparse(d, torch.tensor([[99, -1]]), "sum")   # a third row, never updated
+    sok.incremental_model_dump([d], t0, str(tmp_path))
+    from hugectr_b200.sok import _read
+    keys = _read(str(tmp_path / "dyn_inc-key"))
+    assert sorted(keys.tolist()) == [7, 10 ** 11]
+    w = _read(str(tmp_path / "dyn_inc-weight"))
+    assert w.reshape(-1, 4).shape == (2, 4)
+
+
+def test_lr_scheduler_state_and_reset():
+    from hugectr_b200.lr_scheduler import LearningRateScheduler
+    s = LearningRateScheduler(1.0, warmup_steps=2, decay_start=4, decay_steps=4, decay_power=2.0, end_lr=0.1)
+    seq = [s.get_next() for _ in range(10)]
+    assert seq[:2] == [0.5, 1.0] and seq[2:4] == [1.0, 1.0]
+    assert abs(seq[4] - max(1.0 * (3 / 4) ** 2, 0.1)) < 1e-9 and seq[-1] == 0.1
+    st = s.state_dict()
+    s2 = LearningRateScheduler(1.0, 2, 4, 4, 2.0, 0.1)
+    s2.load_state_dict(st)
+    assert s2.get_next() == s.get_next() and abs(s.get_lr() - 0.1) < 1e-12
+    s.reset()
+    assert s.get_next() == 0.5
+
+
+def test_local_filesystem_roundtrip(tmp_path):
+    from hugectr_b200.io.filesystem import FileSystemBuilder
+    fs = FileSystemBuilder.build_unique_by_path(str(tmp_path))
+    d = str(tmp_path / "a" / "b")
+    fs.create_dir(d)
+    p = os.path.join(d, "x.bin")
+    fs.write(p, b"hello world", overwrite=True)
+    assert fs.exists(p) and fs.get_file_size(p) == 11 and fs.read(p) == b"hello world"
+    q = os.path.join(d, "y.bin")
+    fs.copy(p, q)
+    assert fs.read(q) == b"hello world"
+    fs.delete_file(p)
+    assert not fs.exists(p)
+    fs.delete_dir(str(tmp_path / "a"))
+    assert not fs.exists(d)
+
+
+def test_hmem_cache_keyset_and_training_cache(tmp_path):
+    from hugectr_b200.cache.hps import EmbeddingTrainingCache, HMemCache, HostParameterServer
+    hc = HMemCache(4, capacity_rows=2)
+    hc.put(1, torch.ones(4))
+    hc.put(2, torch.full((4,), 2.0))
+    assert torch.equal(hc.get(1), torch.ones(4))
+    hc.put(3, torch.full((4,), 3.0))                         # evicts the least recently used (2)
+    assert hc.get(2) is None and hc.get(3) is not None and 0 < hc.hit_rate() < 1
+    ps = HostParameterServer(4, num_states=1, capacity_rows=64)
+    ks = np.array([5, 6, 7], dtype="<i8")
+    ks.tofile(str(tmp_path / "keyset"))
+    keys = ps.load_keyset(str(tmp_path / "keyset"))
+    assert keys.tolist() == [5, 6, 7] and ps.size() == 3
+    etc = EmbeddingTrainingCache(ps, hugectr.TrainPSType_t.Cached, hmem_rows=8)
+    table = etc.update(keys, torch.device("cpu"))
+    assert table.shape == (3, 4)
+    table.add_(1.0)
+    etc.dump()
+    w, _ = ps.pull(keys)
+    torch.testing.assert_close(w, table)
+
+
+def test_hashtable_set_clear_and_gather_rows_and_dense_fallbacks():
+    from hugectr_b200.embedding import ops as E
+    from hugectr_b200.embedding.hashtable import HashTable
+    from hugectr_b200.ops import dense as D
+    ht = HashTable(16, "cpu")
+    ht.set(torch.tensor([10, 20]), torch.tensor([3, 1]))
+    assert ht.get(torch.tensor([20, 10, 5])).tolist() == [1, 3, -1]
+    ht.clear()
+    assert ht.size() == 0 and ht.get(torch.tensor([10])).tolist() == [-1]
+    table = torch.arange(40.).view(-1)
+    out = torch.zeros(3, 4)
+    E.gather_rows(table, 4, torch.tensor([2, 0, 9]), out)
+    torch.testing.assert_close(out, table.view(10, 4)[[2, 0, 9]])
+    src = torch.randn(3, 5)
+    dst = torch.zeros(3, 8, dtype=torch.bfloat16)
+    D.cast_pad(src, dst)
+    torch.testing.assert_close(dst[:, :5].float(), src.bfloat16().float())
+    assert float(dst[:, 5:].abs().max()) == 0.0
+    a, b, c = torch.randn(2, 8).bfloat16(), torch.randn(2, 8).bfloat16(), torch.randn(2, 8)
+    o = torch.zeros(2, 8, dtype=torch.bfloat16)
+    D.add3(a, b, c, o)
+    torch.testing.assert_close(o.float(), (a.float() + b.float() + c).bfloat16().float())
+
+
+def test_model_set_source_download_and_embedding_dump(tmp_path):
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    m = build_dlrm_dcnv2(batchsize=16, num_gpus=1, table_sizes=[30, 40], multi_hot=[2, 1], ev_size=8,
+                         mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                         comm=CPU(), use_cuda_graph=False)
+    m.compile()
+    m.train()
+    assert m.get_data_reader_train() is m.reader_train and m.get_data_reader_eval() is m.reader_eval
+    m.set_source("synthetic:1.1", "synthetic:1.1")
+    m.train()
+    m.download_params_to_files(str(tmp_path / "dl"), 2)
+    assert os.path.exists(str(tmp_path / "dl_dense_2.model"))
+    m.embedding_dump(str(tmp_path / "ebc"), ["0"])
+    before = m.ebcs_train[0].dump_table_local("0")[0][1].clone()
+    m.train()
+    m.embedding_load(str(tmp_path / "ebc"), ["0"])
+    torch.testing.assert_close(m.ebcs_train[0].dump_table_local("0")[0][1], before)
+    from hugectr_b200.utils import diagnose
+    assert diagnose.verify_model(m)
+    assert m.solver.num_nodes == 1 and "lr" in m.solver.to_json() if hasattr(m.solver, "to_json") else True
