@@ -188,6 +188,117 @@ def run_sok():
         print("SOK_OK")
 
 
+def run_fuzz(seed):
+    """randomised collection: random tables / hotness / combiners (sum, mean, concat) / batch- or
+    feature-major tops / padded bags / random sharding plan (table-wise, row-wise, column-wise, dp),
+    compared with a brute-force gather oracle (forward) and a scatter oracle (SGD backward)"""
+    import random
+    comm = Comm.init_from_env()
+    dev = comm.device
+    world, rank = comm.world_size, comm.rank
+    rnd = random.Random(int(seed))
+    b = 8
+    nt = rnd.randint(3, 5)
+    ev = [rnd.choice([4, 8]) for _ in range(nt)]
+    vocab = [rnd.randint(5, 60) for _ in range(nt)]
+    hot = [rnd.randint(1, 4) for _ in range(nt)]
+    comb = [rnd.choice(["sum", "mean", "concat"]) for _ in range(nt)]
+    ts = [EmbeddingTableConfig(str(i), vocab[i], ev[i]) for i in range(nt)]
+    cfg = EmbeddingCollectionConfig()
+    split = rnd.randint(1, nt - 1)
+    # first `split` lookups share one batch-major top, the rest are feature-major tops of their own
+    cfg.embedding_lookup(ts[:split], [f"d{i}" for i in range(split)], "bm", comb[:split])
+    for i in range(split, nt):
+        cfg.embedding_lookup(ts[i], f"d{i}", f"fm{i}", comb[i])
+    if world > 1:
+        sm = [[0] * nt for _ in range(world)]
+        strat_mp, strat_dp = [], []
+        for i in range(nt):
+            kind = rnd.choice(["table", "row", "dp", "col"])
+            if kind == "dp":
+                for g in range(world):
+                    sm[g][i] = 1
+                strat_dp.append(str(i))
+            elif kind == "table":
+                sm[rnd.randrange(world)][i] = 1
+                strat_mp.append(str(i))
+            elif kind == "row" or ev[i] % world:
+                for g in range(world):
+                    sm[g][i] = 1
+                strat_mp.append(str(i))
+            else:
+                for g in range(world):
+                    sm[g][i] = 1
+                strat_mp.append((str(i), world))
+        st = ([("mp", strat_mp)] if strat_mp else []) + ([("dp", strat_dp)] if strat_dp else [])
+        cfg.shard(sm, st)
+    opt = CreateOptimizer(Optimizer_t.SGD)
+    hotd = {f"d{i}": hot[i] for i in range(nt)}
+    e = EmbeddingCollection(cfg, b, hotd, dev, torch.float32, comm, opt, key_dtype=torch.int64, seed=3)
+    gen = torch.Generator().manual_seed(int(seed))
+    W = [torch.randn(vocab[i], ev[i], generator=gen) for i in range(nt)]
+    for i in range(nt):
+        e.load_table_rows(str(i), torch.arange(vocab[i]), W[i])
+    lr = 0.1
+    for it in range(2):
+        keys = []
+        for i in range(nt):
+            k = torch.randint(0, vocab[i], (b * world, hot[i]), generator=gen)
+            if comb[i] != "concat" and hot[i] > 1:          # padded (shorter) bags
+                n = torch.randint(1, hot[i] + 1, (b * world,), generator=gen)
+                k = torch.where(torch.arange(hot[i]).view(1, -1) < n.view(-1, 1), k, torch.full_like(k, -1))
+            keys.append(k)
+        loc = torch.cat([k[rank * b:(rank + 1) * b].reshape(-1) for k in keys])
+        e.set_keys(loc.to(dev))
+        e.forward()
+
+        def pooled(i):
+            k = keys[i]
+            v = W[i][k.clamp(min=0)] * (k >= 0).unsqueeze(-1)
+            if comb[i] == "concat":
+                return v.reshape(b * world, -1)
+            s_ = v.sum(1)
+            return s_ / (k >= 0).sum(1, keepdim=True).clamp(min=1) if comb[i] == "mean" else s_
+        exp_bm = torch.cat([pooled(i) for i in range(split)], 1)
+        got = e.top_data["bm"].float().cpu().reshape(b, -1)
+        assert (got - exp_bm[rank * b:(rank + 1) * b]).abs().max() < 1e-5, ("bm", seed, it)
+        for i in range(split, nt):
+            got = e.top_data[f"fm{i}"].float().cpu().reshape(b, -1)
+            assert (got - pooled(i)[rank * b:(rank + 1) * b]).abs().max() < 1e-5, (f"fm{i}", seed, it)
+        # backward: random top grads, SGD update == scatter of (scaled) grads
+        G = {}
+        gb = torch.randn(b * world, exp_bm.shape[1], generator=gen)
+        e.top_grad["bm"].copy_(gb[rank * b:(rank + 1) * b].view_as(e.top_grad["bm"]).to(dev))
+        off = 0
+        for i in range(split):
+            w_ = ev[i] * (hot[i] if comb[i] == "concat" else 1)
+            G[i] = gb[:, off:off + w_]
+            off += w_
+        for i in range(split, nt):
+            w_ = ev[i] * (hot[i] if comb[i] == "concat" else 1)
+            G[i] = torch.randn(b * world, w_, generator=gen)
+            e.top_grad[f"fm{i}"].copy_(G[i][rank * b:(rank + 1) * b].view_as(e.top_grad[f"fm{i}"]).to(dev))
+        e.backward(torch.tensor([lr], device=dev), torch.tensor([1], dtype=torch.int32, device=dev))
+        for i in range(nt):
+            k = keys[i]
+            valid = (k >= 0)
+            if comb[i] == "concat":
+                g_ = G[i].view(b * world, hot[i], ev[i])
+            else:
+                g_ = G[i].unsqueeze(1).expand(b * world, hot[i], ev[i])
+                if comb[i] == "mean":
+                    g_ = g_ / valid.sum(1).clamp(min=1).view(-1, 1, 1)
+            W[i].index_add_(0, k[valid], -lr * g_[valid])
+    for i in range(nt):
+        for (k, w, c0, sts, kind) in e.dump_table_local(str(i)):
+            if len(k):
+                err = (w[:, :min(w.shape[1], ev[i] - c0)] - W[i][k][:, c0:c0 + w.shape[1]]).abs().max().item()
+                assert err < 1e-4, (seed, "table", i, err)
+    comm.barrier()
+    if rank == 0:
+        print("FUZZ_OK", seed)
+
+
 def run_allreduce():
     comm = Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
@@ -433,6 +544,9 @@ if __name__ == "__main__":
         run_dynamic()
     if what == "sok":
         run_sok()
+    if what == "fuzz":
+        for sd in sys.argv[2].split(","):
+            run_fuzz(sd)
     if what == "legacy":
         run_legacy()
     if what == "equiv":

@@ -140,3 +140,21 @@ def test_dynamic_tables_in_collection_gloo(nproc):
 def test_sok_distributed_lookup_gloo():
     out = _run(2, ["sok"], 29751, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "SOK_OK" in out
+
+
+@pytest.mark.parametrize("nproc", [1, 2, 3])
+def test_randomised_collection_against_bruteforce_oracle_gloo(nproc):
+    """random tables / hotness / combiners / layouts / padded bags / sharding plans vs gather+scatter oracle"""
+    seeds = ",".join(str(100 * nproc + i) for i in range(6))
+    out = _run(nproc, ["fuzz", seeds], 29751 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert out.count("FUZZ_OK") == 6, out[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("HCTR_TEST_EXPERIMENTAL"),
+                    reason="not yet validated on a GPU box (tools_dev/next_round.sh runs it)")
+def test_randomised_collection_against_bruteforce_oracle_gpu():
+    n = min(torch.cuda.device_count(), 4)
+    seeds = ",".join(str(500 + i) for i in range(8))
+    out = _run(n, ["fuzz", seeds], 29761)
+    assert out.count("FUZZ_OK") == 8, out[-2000:]
