@@ -22,6 +22,19 @@ class HostBatch:
     keys: torch.Tensor
     nnz: Optional[torch.Tensor] = None
     num_valid: int = -1   # < b for an incomplete last batch
+    copied: object = None  # CUDA event recorded after the last async H2D copy out of this batch
+
+    def mark_copied(self):
+        """Called by the consumer right after it queued its asynchronous H2D copies: ring-buffer
+        readers wait on this before they hand the staging slot back to their producer threads."""
+        if torch.cuda.is_available():
+            self.copied = torch.cuda.Event()
+            self.copied.record()
+
+    def wait_copied(self):
+        if self.copied is not None:
+            self.copied.synchronize()
+            self.copied = None
 
     def pin(self):
         if torch.cuda.is_available():

@@ -85,6 +85,9 @@ class RawAsyncReader(IDataReader):
         if self.h is None:
             self.start()
         valid = C.c_int(0)
+        if getattr(self, "_last", None) is not None:     # its slot is recycled by the call below
+            self._last.wait_copied()
+            self._last = None
         idx = self.lib.hctr_raw_next(self.h, C.byref(valid))
         if valid.value < 0:
             return None
@@ -93,7 +96,8 @@ class RawAsyncReader(IDataReader):
         # global batch size seen by all ranks (last batch may be incomplete)
         self.current_batchsize = self.b * self.world if nv == self.b else \
             max(0, min(self.b * self.world, self.rank * self.b + nv)) if nv > 0 else self.rank * self.b
-        return HostBatch(lab, den, keys, None, nv)
+        self._last = HostBatch(lab, den, keys, None, nv)
+        return self._last
 
     def stop(self):
         if self.h is not None:

@@ -319,6 +319,7 @@ class Model:
                         hb.keys[o:o + b * gl["hotness"]].view(b, gl["hotness"]), non_blocking=nb)
             for rt in legs:
                 rt.set_keys(hb, offs, self.layout.nnz_block_offsets(b)[0])
+        hb.mark_copied()
 
     def start_data_reading(self):
         self.reader_train.start()
@@ -516,6 +517,7 @@ class Model:
             if self.input.dense_dim > 0:
                 self._stg["dense"].copy_(hb.dense, non_blocking=True)
             self._stg["keys"][:hb.keys.numel()].copy_(hb.keys, non_blocking=True)
+            hb.mark_copied()
         self._staged = hb
 
     def _commit_staged(self):
