@@ -5,18 +5,25 @@ HugeCTR/include/data_generator.hpp (Norm :189-330 with DataSetHeader + optional 
 Raw :978-1070 one binary file of fixed records [label][dense][keys], Parquet :500-660 with file list
 "<num_files>\\n<path>..." and _metadata.json {file_stats, labels, conts, cats}).  Key distribution:
 uniform or power law (alpha Long .9 / Medium 1.1 / Short 1.3 / Specific), inverse-CDF sampler :109-131.
+
+Norm and Raw files are written by the native generator (csrc/host/data_generator.cpp): counter-based
+per-record random streams (the bytes do not depend on ``num_threads``), one thread per Norm file /
+per 8 Ki-record chunk of a Raw file.  ``HCTR_DATAGEN=python`` selects the numpy writers below.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 import struct
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import List
 
 import numpy as np
 import torch
 
+from .. import _native
 from ..enums import Check_t, DataReaderType_t, Distribution_t, PowerLaw_t
 from ..utils import logger
 from .batch import power_law_keys
@@ -129,8 +136,58 @@ class DataGenerator:
         with open(file_list, "w") as fo:
             fo.write(f"{num_files}\n" + "\n".join(paths) + "\n")
 
-    # ------------------------------------------------------------------ Norm
+    # ------------------------------------------------------------------ native writers
+    SEED = 20260921
+
+    def _native_args(self):
+        p = self.p
+        L = _native.host_lib()
+        ll, ip = C.POINTER(C.c_longlong), C.POINTER(C.c_int)
+        L.hctr_gen_norm_file.argtypes = [C.c_char_p, C.c_ulonglong, C.c_longlong, C.c_longlong, C.c_int,
+                                         C.c_int, C.c_int, ll, ip, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.hctr_gen_raw_file.argtypes = [C.c_char_p, C.c_ulonglong, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                        ll, ip, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+        sizes = (C.c_longlong * p.num_slot)(*[int(v) for v in p.slot_size_array])
+        nnz = (C.c_int * p.num_slot)(*[int(v) for v in (p.nnz_array or [1] * p.num_slot)])
+        return L, sizes, nnz, 8 if p.i64_input_key else 4, int(p.dist_type == Distribution_t.PowerLaw)
+
     def _norm(self, file_list: str, num_files: int, sub: str):
+        if os.environ.get("HCTR_DATAGEN", "native") == "python":
+            return self._norm_py(file_list, num_files, sub)
+        p = self.p
+        d = os.path.join(os.path.dirname(file_list) or ".", sub)
+        os.makedirs(d, exist_ok=True)
+        L, sizes, nnz, kb, pl = self._native_args()
+        paths = [os.path.join(d, f"gen_{f}.data") for f in range(num_files)]
+        fid0 = 0 if sub == "train" else 1 << 32      # train / eval draw from different streams
+
+        def one(f):
+            return L.hctr_gen_norm_file(paths[f].encode(), self.SEED, fid0 + f, p.num_samples_per_file,
+                                        p.label_dim, p.dense_dim, p.num_slot, sizes, nnz, kb,
+                                        int(p.check_type == Check_t.Sum), pl, float(self.alpha))
+        with ThreadPoolExecutor(max_workers=max(1, min(p.num_threads, num_files or 1))) as ex:
+            rcs = list(ex.map(one, range(num_files)))
+        if any(rcs):
+            raise OSError(f"cannot write Norm files under {d}")
+        with open(file_list, "w") as fo:
+            fo.write(f"{num_files}\n" + "\n".join(paths) + "\n")
+
+    def _raw(self, path: str, num_samples: int):
+        """fixed records [label_dim x (f32|i32)][dense_dim x (f32|i32)][sum(nnz) x key]"""
+        if os.environ.get("HCTR_DATAGEN", "native") == "python":
+            return self._raw_py(path, num_samples)
+        p = self.p
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        L, sizes, nnz, kb, pl = self._native_args()
+        seed = self.SEED + (0 if path == p.source else 1)
+        rc = L.hctr_gen_raw_file(path.encode(), seed, int(num_samples), p.label_dim, p.dense_dim,
+                                 p.num_slot, sizes, nnz, kb, int(p.float_label_dense), pl,
+                                 float(self.alpha), max(1, p.num_threads))
+        if rc:
+            raise OSError(f"cannot write {path}")
+
+    # ------------------------------------------------------------------ Norm (numpy writer)
+    def _norm_py(self, file_list: str, num_files: int, sub: str):
         p = self.p
         root = os.path.dirname(file_list) or "."
         d = os.path.join(root, sub)
@@ -169,9 +226,8 @@ class DataGenerator:
         with open(file_list, "w") as fo:
             fo.write(f"{num_files}\n" + "\n".join(paths) + "\n")
 
-    # ------------------------------------------------------------------ Raw
-    def _raw(self, path: str, num_samples: int):
-        """fixed records [label_dim x (f32|i32)][dense_dim x (f32|i32)][sum(nnz) x key]"""
+    # ------------------------------------------------------------------ Raw (numpy writer)
+    def _raw_py(self, path: str, num_samples: int):
         p = self.p
         os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         nnz = p.nnz_array or [1] * p.num_slot
