@@ -1,0 +1,29 @@
+// Host-side batch assembly helpers shared by the file readers.
+// hctr_csr_to_padded: one multi-hot (list) column of a row group slice, given as CSR offsets + values,
+// scattered into the [b, S, H] key block of a batch (row stride S*H, -1 padding already in place) with
+// bags truncated to H and the per-sample counts written to the [S, b] nnz block -- the CPU counterpart
+// of the reference's dense/sparse column conversion kernels
+// (HugeCTR/src/data_readers/parquet_data_converter.cu) done before the H2D copy, so the device
+// receives the final layout.
+#include <stdint.h>
+
+extern "C" void hctr_csr_to_padded(const void* offs, int off_bytes, const long long* vals, int n, int H,
+                                   long long add, long long* out, long long row_stride, int32_t* nnz) {
+#pragma omp parallel for schedule(static) if (n > 2048)
+  for (int i = 0; i < n; ++i) {
+    long long lo, hi;
+    if (off_bytes == 4) {
+      lo = static_cast<const int32_t*>(offs)[i];
+      hi = static_cast<const int32_t*>(offs)[i + 1];
+    } else {
+      lo = static_cast<const int64_t*>(offs)[i];
+      hi = static_cast<const int64_t*>(offs)[i + 1];
+    }
+    long long c = hi - lo;
+    if (c > H) c = H;
+    if (c < 0) c = 0;
+    long long* o = out + static_cast<long long>(i) * row_stride;
+    for (long long h = 0; h < c; ++h) o[h] = vals[lo + h] + add;
+    nnz[i] = static_cast<int32_t>(c);
+  }
+}

@@ -30,6 +30,22 @@ def read_file_list(path: str):
     return files
 
 
+def _csr_to_padded(offs, vals, n, H, add, blk, s, nz):
+    """blk[i, s, :min(len_i, H)] = vals[offs[i]:...] + add ; nz[s, i] = min(len_i, H)  (native, OpenMP)"""
+    import ctypes as C
+    from .. import _native
+    L = _native.host_lib()
+    L.hctr_csr_to_padded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                                     C.c_void_p, C.c_longlong, C.c_void_p]
+    offs = np.ascontiguousarray(offs)
+    if offs.dtype not in (np.int32, np.int64):
+        offs = offs.astype(np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.int64)
+    S, Hb = blk.shape[1], blk.shape[2]
+    L.hctr_csr_to_padded(offs.ctypes.data, offs.dtype.itemsize, vals.ctypes.data, int(n), int(H), int(add),
+                         blk.ctypes.data + 8 * s * Hb, S * Hb, nz.ctypes.data + 4 * s * nz.shape[1])
+
+
 class ParquetReader(IDataReader):
     def __init__(self, model, is_train: bool):
         rp = model.reader_params
@@ -158,11 +174,7 @@ class ParquetReader(IDataReader):
                     blk[:nloc, s, 0] = vals[:nloc] + off_add
                     nz[s, :nloc] = 1
                 else:
-                    cnt = np.minimum(np.diff(offs), H)
-                    for i in range(nloc):
-                        c = cnt[i]
-                        blk[i, s, :c] = vals[offs[i]:offs[i] + c] + off_add
-                    nz[s, :nloc] = cnt
+                    _csr_to_padded(offs, vals, nloc, H, int(off_add), blk, s, nz)
                 si += 1
             blocks.append(torch.from_numpy(blk.reshape(-1)))
             nnzs.append(torch.from_numpy(nz.reshape(-1)))

@@ -102,3 +102,22 @@ def test_norm_files_are_well_formed(tmp_path, check):
     before = [_md5(f) for f in lines[1:]]
     DataGenerator(_params(tmp_path, hugectr.DataReaderType_t.Norm, 1, check_type=check)).generate()
     assert before == [_md5(f) for f in lines[1:]]
+
+
+@pytest.mark.parametrize("odt", ["int32", "int64"])
+def test_csr_to_padded_matches_python_loop(odt):
+    from hugectr_b200.data.parquet_reader import _csr_to_padded
+    rng = np.random.default_rng(3)
+    n, S, H = 5000, 3, 4
+    cnt = rng.integers(0, 7, n)
+    offs = np.concatenate([[0], np.cumsum(cnt)]).astype(odt)
+    vals = rng.integers(0, 1 << 40, int(cnt.sum()))
+    blk = np.full((n + 5, S, H), -1, dtype="int64")
+    nz = np.zeros((S, n + 5), dtype="int32")
+    _csr_to_padded(offs, vals, n, H, 17, blk, 1, nz)
+    exp = np.full_like(blk, -1)
+    for i in range(n):
+        c = min(cnt[i], H)
+        exp[i, 1, :c] = vals[offs[i]:offs[i] + c] + 17
+    assert (blk == exp).all()
+    assert (nz[1, :n] == np.minimum(cnt, H)).all() and nz[0].sum() == 0 and nz[2].sum() == 0 and nz[1, n:].sum() == 0
