@@ -782,12 +782,32 @@ class EmbeddingCollection:
                         if dst is not None and st is not None:
                             dst.view(-1, grp.pitch)[rows] = st[m][:, c0:c0 + ev].to(dst.device, dst.dtype)
 
-    def dump_table_local(self, name: str):
-        """-> list of (keys int64 [n], values fp32 [n, ev_part], col0, states list) local shards."""
+    def table_parts(self, name: str):
+        """Metadata of the local shards of table ``name`` in ``dump_table_local`` order (no data is
+        moved): rows, row shard (s of k), column window, group kind, dynamic flag, state count."""
         res = []
         for grp in self.groups:
             for sl in grp.table_slices:
                 if sl["table"] != name:
+                    continue
+                rows = sl["rows"]
+                if sl.get("dynamic"):
+                    rows = int(self._dyn_hash(name, dict(sl, cpart=0)).dump()[0].numel())
+                res.append(dict(rows=int(rows), s=int(sl["s"]), k=int(sl["k"]), col0=int(sl["col0"]),
+                                width=int(sl["ev"]), kind=grp.kind, dynamic=bool(sl.get("dynamic")),
+                                nstate=sum(t is not None for t in (grp.s0, grp.s1))))
+        return res
+
+    def dump_table_local(self, name: str, only=None):
+        """-> list of (keys int64 [n], values fp32 [n, ev_part], col0, states list) local shards.
+        ``only``: optional set of part indices to materialise (others are returned as None)."""
+        res = []
+        for grp in self.groups:
+            for sl in grp.table_slices:
+                if sl["table"] != name:
+                    continue
+                if only is not None and len(res) not in only:
+                    res.append(None)
                     continue
                 lo, hi = sl["row_off"], sl["row_off"] + sl["rows"]
                 w = grp.table.view(-1, grp.pitch)[lo:hi].detach().cpu()

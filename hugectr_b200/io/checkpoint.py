@@ -166,8 +166,87 @@ def _gather_table(model, ebc, name):
     return allkeys, W, [S[i] if has_state[i] else None for i in range(2)]
 
 
+def _parallel_plan(model, ebc, name):
+    """Layout of one table in the shared key / weight / opt files for the parallel writer: every distinct
+    local row set (static row shard s of k, or one dynamic shard) gets a contiguous row range; each
+    (row set, column window) is written by exactly one rank (the lowest that holds it: data-parallel
+    replicas are written once).  Returns None when a row set's column windows do not tile the full
+    width (the gather path handles those)."""
+    meta = ebc.table_parts(name)
+    allm = model.comm.all_gather_object(meta) if model.world > 1 else [meta]
+    ev = ebc.tmap[name].ev_size
+    rowsets, writers, seen = {}, [], set()
+    for r, m in enumerate(allm):
+        for i, p in enumerate(m):
+            rid = ("d", r, i) if p["dynamic"] else ("s", p["s"], p["k"], p["rows"])
+            if p["dynamic"] and p["width"] != ev:
+                return None
+            if rid not in rowsets:
+                rowsets[rid] = dict(rows=p["rows"], keyw=(r, i), cols=0)
+            if (rid, p["col0"]) in seen:
+                continue
+            seen.add((rid, p["col0"]))
+            rowsets[rid]["cols"] += p["width"]
+            writers.append(dict(rank=r, idx=i, rid=rid, col0=p["col0"], width=p["width"]))
+    off = 0
+    for rs in rowsets.values():
+        if rs["cols"] != ev:
+            return None
+        rs["off"] = off
+        off += rs["rows"]
+    nstate = max([p["nstate"] for m in allm for p in m] or [0])
+    return dict(n=off, ev=ev, rowsets=rowsets, writers=writers, nstate=nstate)
+
+
+def _dump_table_parallel(model, ebc, name, tid, folder, plan, kd):
+    """Every rank writes its own row / column windows straight into the shared files (the role of the
+    reference's MPI-IO writer, parameter_IO.cpp:37-250): no table is ever gathered on one rank."""
+    n, ev, ns = plan["n"], plan["ev"], plan["nstate"]
+    kb = np.dtype(kd).itemsize
+    files = {"key": (f"{folder}/key{tid}", 1, n * kb), "weight": (f"{folder}/weight{tid}", 2, n * ev * 4)}
+    if ns:
+        files["opt"] = (f"{folder}/opt{tid}", 3, ns * n * ev * 4)
+    if model.comm.rank == 0:
+        for (fp, ftype, nbytes) in files.values():
+            with open(fp, "wb") as f:
+                f.write(_file_head(ftype, tid))
+                f.truncate(FILE_HEAD_NBYTES + nbytes)
+    model.comm.barrier()
+    rank = model.comm.rank
+    mine = [w for w in plan["writers"] if w["rank"] == rank]
+    keyw = {rs["keyw"][1] for rs in plan["rowsets"].values() if rs["keyw"][0] == rank}
+    need = {w["idx"] for w in mine} | keyw
+    if need and n > 0:
+        parts = ebc.dump_table_local(name, only=need)
+        mk = np.memmap(files["key"][0], dtype=kd, mode="r+", offset=FILE_HEAD_NBYTES, shape=(n,))
+        mw = np.memmap(files["weight"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES, shape=(n, ev))
+        mo = np.memmap(files["opt"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES,
+                       shape=(ns, n, ev)) if ns else None
+        for rs in plan["rowsets"].values():
+            if rs["keyw"][0] == rank and rs["rows"]:
+                mk[rs["off"]:rs["off"] + rs["rows"]] = parts[rs["keyw"][1]][0].numpy().astype(kd)
+        for w in mine:
+            rs = plan["rowsets"][w["rid"]]
+            if not rs["rows"]:
+                continue
+            keys, W, c0, sts, kind = parts[w["idx"]]
+            lo, hi = rs["off"], rs["off"] + rs["rows"]
+            mw[lo:hi, c0:c0 + W.shape[1]] = W.numpy()
+            for i, st in enumerate(sts):
+                if st is not None and mo is not None:
+                    mo[i, lo:hi, c0:c0 + W.shape[1]] = st.numpy()
+        for m in (mk, mw, mo):
+            if m is not None:
+                m.flush()
+    model.comm.barrier()
+    return n
+
+
 def embedding_dump(model, path: str, table_names=None):
     fs = _fs(path, model)
+    from .filesystem import LocalFileSystem
+    if isinstance(fs, LocalFileSystem) and os.environ.get("HCTR_EBC_DUMP", "parallel") == "parallel":
+        return _embedding_dump_parallel(model, path, table_names, fs)
     for eid, ebc in enumerate(model.ebcs_train):
         names = [t.name for t in ebc.tables]
         sel = [n for n in names if table_names is None or n in table_names]
@@ -196,6 +275,74 @@ def embedding_dump(model, path: str, table_names=None):
                     fs.write(f"{folder}/opt{tid}", _file_head(3, tid) +
                              b"".join(s.numpy().astype("<f4").tobytes() for s in st))
         model.comm.barrier()
+
+
+def _embedding_dump_parallel(model, path, table_names, fs):
+    kd = "<i8" if model.key_dtype == torch.int64 else "<u4"
+    for eid, ebc in enumerate(model.ebcs_train):
+        names = [t.name for t in ebc.tables]
+        ids = sorted(names.index(n) for n in names if table_names is None or n in table_names)
+        folder = f"{path}/embedding_collection_{eid}"
+        if model.comm.rank == 0:
+            fs.create_dir(folder)
+        model.comm.barrier()
+        knums = {}
+        for tid in ids:
+            plan = _parallel_plan(model, ebc, names[tid])
+            logger.debug(f"embedding_dump table {names[tid]}: " + ("gather on rank 0" if plan is None else
+                         f"parallel, {plan['n']} rows, {len(plan['writers'])} windows"))
+            if plan is not None:
+                knums[tid] = _dump_table_parallel(model, ebc, names[tid], tid, folder, plan, kd)
+                continue
+            tab = _gather_table(model, ebc, names[tid])       # irregular layout: gather on rank 0
+            if model.comm.rank == 0:
+                keys, W, S = tab
+                fs.write(f"{folder}/key{tid}", _file_head(1, tid) + keys.numpy().astype(kd).tobytes())
+                fs.write(f"{folder}/weight{tid}", _file_head(2, tid) + W.numpy().astype("<f4").tobytes())
+                st = [x for x in S if x is not None]
+                if st:
+                    fs.write(f"{folder}/opt{tid}", _file_head(3, tid) +
+                             b"".join(x.numpy().astype("<f4").tobytes() for x in st))
+                knums[tid] = keys.numel()
+        if model.comm.rank == 0:
+            head = np.zeros(5, dtype="<i4")
+            head[0] = len(ids)
+            head[1] = 1 if model.key_dtype == torch.int64 else 0
+            meta = head.tobytes() + np.asarray(ids, dtype="<i4").tobytes() + \
+                np.asarray([knums[t] for t in ids], dtype="<u8").tobytes() + \
+                np.asarray([ebc.tables[t].ev_size for t in ids], dtype="<i4").tobytes()
+            fs.write(f"{folder}/meta_data", meta)
+        model.comm.barrier()
+
+
+def iter_ebc_folder(folder: str, chunk_rows: int = 1 << 22):
+    """Streams a local EBC folder: yields (table_id, keys int64 [m], W [m, ev], states|None) in chunks of
+    at most ``chunk_rows`` rows through memory maps, so a rank never holds a whole table on the host."""
+    with open(f"{folder}/meta_data", "rb") as f:
+        meta = f.read()
+    head = np.frombuffer(meta[:META_HEAD_NBYTES], dtype="<i4")
+    n, key_type = int(head[0]), int(head[1])
+    off = META_HEAD_NBYTES
+    ids = np.frombuffer(meta[off:off + 4 * n], dtype="<i4"); off += 4 * n
+    knums = np.frombuffer(meta[off:off + 8 * n], dtype="<u8"); off += 8 * n
+    evs = np.frombuffer(meta[off:off + 4 * n], dtype="<i4")
+    kd = "<i8" if key_type == 1 else "<u4"
+    for tid, kn, ev in zip(ids, knums, evs):
+        tid, kn, ev = int(tid), int(kn), int(ev)
+        if kn == 0:
+            continue
+        mk = np.memmap(f"{folder}/key{tid}", dtype=kd, mode="r", offset=FILE_HEAD_NBYTES, shape=(kn,))
+        mw = np.memmap(f"{folder}/weight{tid}", dtype="<f4", mode="r", offset=FILE_HEAD_NBYTES, shape=(kn, ev))
+        mo = None
+        op = f"{folder}/opt{tid}"
+        if os.path.exists(op):
+            ns = (os.path.getsize(op) - FILE_HEAD_NBYTES) // (kn * ev * 4)
+            mo = np.memmap(op, dtype="<f4", mode="r", offset=FILE_HEAD_NBYTES, shape=(ns, kn, ev))
+        for lo in range(0, kn, chunk_rows):
+            hi = min(kn, lo + chunk_rows)
+            S = None if mo is None else [torch.from_numpy(np.array(mo[i, lo:hi])) for i in range(mo.shape[0])]
+            yield (tid, torch.from_numpy(np.asarray(mk[lo:hi]).astype("int64")),
+                   torch.from_numpy(np.array(mw[lo:hi])), S)
 
 
 def read_ebc_folder(folder: str, fs=None):
@@ -227,8 +374,17 @@ def read_ebc_folder(folder: str, fs=None):
 
 def embedding_load(model, path: str, table_names=None):
     fs = _fs(path, model)
+    from .filesystem import LocalFileSystem
+    local = isinstance(fs, LocalFileSystem)
+    chunk = int(os.environ.get("HCTR_EBC_LOAD_CHUNK_ROWS", str(1 << 22)))
     for eid, ebc in enumerate(model.ebcs_train):
         folder = f"{path}/embedding_collection_{eid}"
+        if local:
+            names = [t.name for t in ebc.tables]
+            for tid, keys, W, S in iter_ebc_folder(folder, chunk):
+                if table_names is None or names[tid] in table_names:
+                    ebc.load_table_rows(names[tid], keys, W, S)
+            continue
         tabs = read_ebc_folder(folder, fs)
         names = [t.name for t in ebc.tables]
         for tid, (keys, W, S) in tabs.items():

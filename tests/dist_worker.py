@@ -299,6 +299,84 @@ def run_fuzz(seed):
         print("FUZZ_OK", seed)
 
 
+def run_ebcio(tmpdir, seed):
+    """parallel (every rank writes its windows) vs gather (rank 0 writes) collection dumps hold the same
+    key -> (row, optimizer state) content for a random plan incl. column-wise, data-parallel and dynamic
+    tables; a chunked load of the parallel dump restores every shard bit-exactly"""
+    import random
+    from types import SimpleNamespace as NS
+    from hugectr_b200.io.checkpoint import embedding_dump, embedding_load, read_ebc_folder
+    comm = Comm.init_from_env()
+    dev, world, rank = comm.device, comm.world_size, comm.rank
+    rnd = random.Random(int(seed))
+    b, nt = 8, 5
+    ev = [rnd.choice([4, 8]) for _ in range(nt)]
+    vocab = [rnd.randint(5, 60) for _ in range(nt)]
+    ts = [EmbeddingTableConfig(str(i), vocab[i], ev[i]) for i in range(nt - 1)]
+    ts.append(EmbeddingTableConfig(str(nt - 1), -1, ev[nt - 1], init_capacity=128))     # dynamic
+    cfg = EmbeddingCollectionConfig()
+    cfg.embedding_lookup(ts, [f"d{i}" for i in range(nt)], "bm", ["sum"] * nt)
+    if world > 1:
+        sm = [[0] * nt for _ in range(world)]
+        mp, dp = [], []
+        for i in range(nt):
+            kind = rnd.choice(["table", "row", "dp", "col"]) if i < nt - 1 else "row"
+            if kind == "table":
+                sm[rnd.randrange(world)][i] = 1
+            else:
+                for g in range(world):
+                    sm[g][i] = 1
+            if kind == "dp":
+                dp.append(str(i))
+            elif kind == "col" and ev[i] % world == 0:
+                mp.append((str(i), world))
+            else:
+                mp.append(str(i))
+        cfg.shard(sm, ([("mp", mp)] if mp else []) + ([("dp", dp)] if dp else []))
+    opt = CreateOptimizer(Optimizer_t.AdaGrad)
+    e = EmbeddingCollection(cfg, b, {f"d{i}": 2 for i in range(nt)}, dev, torch.float32, comm, opt,
+                            key_dtype=torch.int64, seed=5)
+    gen = torch.Generator().manual_seed(int(seed))
+    for it in range(3):
+        keys = [torch.randint(0, vocab[i] if i < nt - 1 else 1000, (b * world, 2), generator=gen) for i in range(nt)]
+        e.set_keys(torch.cat([k[rank * b:(rank + 1) * b].reshape(-1) for k in keys]).to(dev))
+        e.forward()
+        e.top_grad["bm"].copy_(torch.randn(e.top_grad["bm"].shape, generator=gen).to(dev))
+        e.backward(torch.tensor([0.1], device=dev), torch.tensor([1], dtype=torch.int32, device=dev))
+    model = NS(comm=comm, world=world, ebcs_train=[e], key_dtype=torch.int64, reader_params=None)
+    pa, ga = os.path.join(tmpdir, "par"), os.path.join(tmpdir, "gat")
+    embedding_dump(model, pa)
+    os.environ["HCTR_EBC_DUMP"] = "gather"
+    embedding_dump(model, ga)
+    os.environ.pop("HCTR_EBC_DUMP")
+    comm.barrier()
+    A, B = read_ebc_folder(pa + "/embedding_collection_0"), read_ebc_folder(ga + "/embedding_collection_0")
+    assert sorted(A) == sorted(B) == list(range(nt))
+    for tid in A:
+        (ka, wa, sa), (kb, wb, sb) = A[tid], B[tid]
+        oa, ob = torch.argsort(ka), torch.argsort(kb)
+        assert torch.equal(ka[oa], kb[ob]) and ka.unique().numel() == ka.numel(), tid
+        assert torch.equal(wa[oa], wb[ob]), tid
+        assert (sa is None) == (sb is None)
+        for x, y in zip(sa or [], sb or []):
+            assert torch.equal(x[oa], y[ob]), tid
+        assert sa is not None and float(sa[0].abs().sum()) > 0       # AdaGrad accumulators travelled
+    before = {str(i): e.dump_table_local(str(i)) for i in range(nt)}
+    for grp in e.groups:
+        grp.table.zero_()
+        if grp.s0 is not None:
+            grp.s0.zero_()
+    os.environ["HCTR_EBC_LOAD_CHUNK_ROWS"] = "7"
+    embedding_load(model, pa)
+    for n_, parts in before.items():
+        for (k0, w0, c0, s0, _), (k1, w1, c1, s1, _) in zip(parts, e.dump_table_local(n_)):
+            assert torch.equal(k0, k1) and torch.equal(w0, w1) and c0 == c1, n_
+            assert torch.equal(s0[0], s1[0]), n_
+    comm.barrier()
+    if rank == 0:
+        print("EBCIO_OK", seed)
+
+
 def run_allreduce():
     comm = Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
@@ -544,6 +622,11 @@ if __name__ == "__main__":
         run_dynamic()
     if what == "sok":
         run_sok()
+    if what == "ebcio":
+        for sd in sys.argv[3].split(","):
+            d = os.path.join(sys.argv[2], sd)
+            os.makedirs(d, exist_ok=True)
+            run_ebcio(d, sd)
     if what == "fuzz":
         for sd in sys.argv[2].split(","):
             run_fuzz(sd)

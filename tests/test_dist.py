@@ -158,3 +158,12 @@ def test_randomised_collection_against_bruteforce_oracle_gpu():
     seeds = ",".join(str(500 + i) for i in range(8))
     out = _run(n, ["fuzz", seeds], 29761)
     assert out.count("FUZZ_OK") == 8, out[-2000:]
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc", [1, 3])
+def test_parallel_collection_dump_equals_gather_dump_gloo(nproc, tmp_path):
+    """every rank writes its own windows of key / weight / opt files; chunked streamed load restores them"""
+    seeds = ",".join(str(40 * nproc + i) for i in range(4))
+    out = _run(nproc, ["ebcio", str(tmp_path), seeds], 29771 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert out.count("EBCIO_OK") == 4, out[-2000:]
