@@ -57,3 +57,31 @@ def create_reader(model, is_train: bool) -> IDataReader:
         from .norm_reader import NormReader
         return NormReader(model, is_train)
     raise ValueError(f"unsupported reader type {t}")
+
+
+class DataSource:
+    """hugectr.data.DataSource of older releases: stages remote files next to the job
+    (``move_to_local``) through the FileSystem layer (notebooks/training_with_remote_filesystem)."""
+
+    def __init__(self, data_source_params, remote_paths=None, local_paths=None):
+        self.params = data_source_params
+        self.remote_paths = list(remote_paths or getattr(data_source_params, "filesystem_paths", []) or [])
+        self.local_paths = list(local_paths or getattr(data_source_params, "local_paths", []) or [])
+
+    def move_to_local(self):
+        from ..io import FileSystemBuilder
+        for src, dst in zip(self.remote_paths, self.local_paths):
+            fs = FileSystemBuilder.build_by_path(src, self.params)
+            os.makedirs(os.path.dirname(dst) or ".", exist_ok=True)
+            fs.fetch(src, dst)
+        return self.local_paths
+
+
+def __getattr__(name):
+    if name == "DataSourceParams":
+        from ..solver import DataSourceParams
+        return DataSourceParams
+    if name in ("DataGenerator", "DataGeneratorParams"):
+        from . import generator
+        return getattr(generator, name)
+    raise AttributeError(name)

@@ -21,8 +21,10 @@ def lr_at(step: int, base_lr: float, warmup_steps: int = 1, decay_start: int = 0
 class LearningRateScheduler:
     def __init__(self, base_lr: float, warmup_steps: int = 1, decay_start: int = 0,
                  decay_steps: int = 1, decay_power: float = 2.0, end_lr: float = 0.0):
-        if base_lr < 0 or warmup_steps < 1 or decay_steps < 1 or decay_power < 1.0 or end_lr < 0:
-            raise ValueError("base_lr/end_lr >= 0, warmup_steps/decay_steps >= 1, decay_power >= 1")
+        # same acceptance as the reference (learning_rate_scheduler.hpp:40-46): 0 warm-up / decay steps
+        # are legal (samples/dlrm/train.py runs with warmup_steps=0)
+        if base_lr < 0 or warmup_steps < 0 or decay_steps < 0 or decay_power < 1.0 or end_lr < 0:
+            raise ValueError("base_lr < 0 || warmup_steps < 0 || decay_steps < 0 || decay_power < 1.0 || end_lr < 0")
         self.base_lr, self.warmup_steps = base_lr, warmup_steps
         self.decay_start, self.decay_steps = decay_start, decay_steps
         self.decay_power, self.end_lr = decay_power, end_lr

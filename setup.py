@@ -18,6 +18,6 @@ class BuildNative(Command):
         _native.build(force=bool(self.force), verbose=True)
 
 
-setup(name="hugectr_b200", version="25.3.1", packages=find_packages(include=["hugectr_b200*", "hugectr"]),
+setup(name="hugectr_b200", version="25.3.1", packages=find_packages(include=["hugectr_b200*", "hugectr", "hugectr2onnx"]),
       package_data={"hugectr_b200": ["csrc/*", "csrc/host/*", "lib/*.so"]},
       cmdclass={"build_ext": BuildNative}, python_requires=">=3.10")

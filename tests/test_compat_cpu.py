@@ -1,0 +1,54 @@
+"""Drop-in compatibility of the ``hugectr`` module name with scripts written for the reference."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_submodule_imports_used_by_reference_scripts():
+    sys.path.insert(0, ROOT)
+    from hugectr.data import DataSource, DataSourceParams          # noqa: F401
+    from hugectr.inference import CreateInferenceSession, InferenceParams   # noqa: F401
+    from hugectr.tools import DataGenerator, DataGeneratorParams   # noqa: F401
+    import hugectr
+    assert hugectr.tools.DataGenerator is DataGenerator
+    assert hugectr.data.DataSourceParams is DataSourceParams
+    p = DataSourceParams()
+    assert hasattr(p, "server") and hasattr(p, "port")
+
+
+def test_lr_scheduler_accepts_zero_warmup_and_decay_steps():
+    """learning_rate_scheduler.hpp:40-46 only rejects negative values; the MLPerf script passes 0"""
+    from hugectr_b200.lr_scheduler import LearningRateScheduler
+    s = LearningRateScheduler(0.5, warmup_steps=0, decay_start=0, decay_steps=0)
+    assert [s.get_next() for _ in range(3)] == [0.5, 0.5, 0.5]
+    s = LearningRateScheduler(1.0, warmup_steps=0, decay_start=2, decay_steps=0, end_lr=0.1)
+    assert [s.get_next() for _ in range(4)] == [1.0, 1.0, 0.1, 0.1]
+    with pytest.raises(ValueError):
+        LearningRateScheduler(-1.0)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/samples/dlrm/train.py"),
+                    reason="reference checkout not mounted")
+@pytest.mark.parametrize("script", ["dlrm/train.py", "wdl/wdl_1gpu.py"])
+def test_reference_sample_runs_unmodified(script):
+    """tools_dev/run_reference_samples.py execs the reference's own training script against this
+    framework (synthetic data, capped table sizes, 6 iterations, one CPU device)"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools_dev", "run_reference_samples.py"), script],
+                       capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    tail = r.stdout[-1500:] + r.stderr[-1500:]
+    assert "==== summary ====" in r.stdout, tail
+    assert r.stdout.split("==== summary ====")[1].strip().endswith("OK"), tail
+
+
+def test_hugectr2onnx_package_name():
+    sys.path.insert(0, ROOT)
+    import inspect
+    import hugectr2onnx
+    sig = inspect.signature(hugectr2onnx.converter.convert)
+    assert list(sig.parameters)[:7] == ["onnx_model_path", "graph_config", "dense_model", "convert_embedding",
+                                        "sparse_models", "ntp_file", "graph_name"]
