@@ -45,6 +45,30 @@ class IDataReader:
     def stop(self):
         pass
 
+    # ---- handle API of model.get_data_reader_train()/eval() (Core23DataReader32/64,
+    # HugeCTR/include/pybind/data_reader_wrapper.hpp:50-72)
+    def _bind(self, model, is_train: bool):
+        self._model, self._is_train, self._eof = model, is_train, False
+
+    def ready_to_collect(self):
+        """the staging slot of the previous batch may be recycled (the copy-complete handshake of the
+        ring readers does this implicitly on the next read)"""
+
+    def read_a_batch_to_device(self) -> int:
+        """next batch -> the model's input tensors; returns the global batch size read (0 at the end)"""
+        hb = self.read_a_batch()
+        if hb is None:
+            self._eof = True
+            return 0
+        self._eof = False
+        self._model._load_batch(hb, self._is_train)
+        return int(self.current_batchsize)
+
+    read_a_batch_to_device_delay_release = read_a_batch_to_device
+
+    def is_eof(self) -> bool:
+        return bool(getattr(self, "_eof", False))
+
 
 class SparseLayout:
     """Per sparse param: slot_num, max nnz per slot, fixed-length flag, per-slot vocab sizes."""

@@ -256,6 +256,8 @@ class Model:
         from .data import create_reader
         self.reader_train = create_reader(self, True)
         self.reader_eval = create_reader(self, False)
+        self.reader_train._bind(self, True)
+        self.reader_eval._bind(self, False)
 
     # ------------------------------------------------------------------ summary / json
     def summary(self):

@@ -52,3 +52,24 @@ def test_hugectr2onnx_package_name():
     sig = inspect.signature(hugectr2onnx.converter.convert)
     assert list(sig.parameters)[:7] == ["onnx_model_path", "graph_config", "dense_model", "convert_embedding",
                                         "sparse_models", "ntp_file", "graph_name"]
+
+
+def test_data_reader_handle_api():
+    """model.get_data_reader_train() handle: set_source / is_started / read_a_batch_to_device / is_eof"""
+    import torch
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.parallel.comm import Comm
+    m = build_dlrm_dcnv2(batchsize=16, num_gpus=1, table_sizes=[30, 40], multi_hot=[2, 1], ev_size=8,
+                         mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                         comm=Comm.single(torch.device("cpu")))
+    m.compile()
+    r = m.get_data_reader_train()
+    assert isinstance(r, hugectr.Core23DataReader32) and isinstance(r, hugectr.DataReader64)
+    r.set_source()
+    assert r.read_a_batch_to_device() == 16 and not r.is_eof()
+    r.ready_to_collect()
+    assert r.read_a_batch_to_device_delay_release() == 16
+    lab = m.check_out_tensor("label", hugectr.Tensor_t.Train)
+    assert lab.shape == (16, 1)
+    assert isinstance(hugectr.CreateOptimizer(), hugectr.Optimizer)
