@@ -44,6 +44,9 @@ class FileSystemType_t(Enum):
     Other = 4
 
 
+DataSourceType_t = FileSystemType_t   # name used by releases before 23.04 (notebooks/training_with_remote_filesystem)
+
+
 class SourceType_t(Enum):
     FileList = 0
     Mmap = 1

@@ -166,6 +166,11 @@ EXTRA_ARGS = {
                  "--memory_cap_for_embedding", "1"],
     "dlrm_train_ftrl.py": ["--shard_plan", "hybrid", "--optimizer", "ftrl"],
     "din_fp32.py": ["--vvgpu", "0"],
+    "benchmarks/embedding_collection/hugectr/train.py": [
+        "--batchsize", "256", "--batchsize_eval", "128", "--num_gpus_per_node", "1", "--max_iter", "6",
+        "--eval_interval", "3", "--max_eval_batches", "2", "--ev_size_per_table", "16",
+        "--vocabulary_size_per_table", ",".join(["3000"] * 26), "--memory_cap_for_embedding", "1"],
+    "embedding_collection__dlrm_train.py": ["--shard_plan", "hybrid"],
     "din_matmul_fp32_1gpu.py": ["--vvgpu", "0"],
 }
 
@@ -185,7 +190,11 @@ def main():
             for mt in ["CRITEO", "DCNV1", "DCNV2", "DEEPFM", "WDL", "BST"]:
                 runs.append((s, ["--model_type", mt, "--vvgpu", "0", "--max_iter", "6", "--auc_threshold", "0", "--eval_interval", "2", "--display", "2"], f" [{mt}]"))
         else:
-            runs.append((s, EXTRA_ARGS.get(os.path.basename(s), []), ""))
+            extra = EXTRA_ARGS.get(os.path.basename(s), [])
+            for k, v in EXTRA_ARGS.items():
+                if "/" in k and s.endswith(k):
+                    extra = v
+            runs.append((s, extra, ""))
     for s, extra, tag in runs:
         cwd = tempfile.mkdtemp()
         os.chdir(cwd)
