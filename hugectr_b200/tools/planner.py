@@ -68,6 +68,154 @@ def generate_plan(table_sizes: Sequence[int], multi_hot: Sequence[int], num_gpus
     return sm, strategy
 
 
+# ------------------------------------------------------------------------------------------------
+# heterogeneous planner: per-table widths / combiners, row- AND column-wise splits, time-based costs
+class HardwareModel:
+    """Per-GPU rates the cost model divides by (defaults: this repo's measurements on B200,
+    MEASURED_PEAKS.json / profiles/README.md): random 512-byte row gathers run at ~0.8 of the 6.5 TB/s
+    copy bandwidth, the read-modify-write sparse update at ~0.55, one NVLink direction carries
+    ~770 GB/s of payload inside the fused exchange, inter-node links 50 GB/s per GPU."""
+
+    def __init__(self, hbm_gbps: float = 6500.0, gather_eff: float = 0.8, update_eff: float = 0.55,
+                 nvlink_gbps: float = 770.0, internode_gbps: float = 50.0, hbm_capacity_gb: float = 150.0):
+        self.hbm, self.gather_eff, self.update_eff = hbm_gbps * 1e9, gather_eff, update_eff
+        self.nvlink, self.internode, self.capacity = nvlink_gbps * 1e9, internode_gbps * 1e9, hbm_capacity_gb * 1e9
+
+
+def plan_tables(table_sizes: Sequence[int], hotness: Sequence[int], ev_sizes, num_gpus: int,
+                global_batch: int = 65536, combiners: Sequence[str] = None, num_nodes: int = 1,
+                hw: HardwareModel = None, weight_bytes: int = 4, state_bytes: int = 4,
+                act_bytes: int = 2, dp_threshold_bytes: float = 4e6, min_rows_per_shard: int = 1024,
+                min_cols_per_shard: int = 32, balance_tol: float = 1.10, per_key_bytes: float = 96.0):
+    """Plan for tables of different widths and combiners (the role of the reference's larger planner,
+    benchmarks/embedding_collection/hugectr/sharding/planner.py:38-620: cost model with per-table
+    ev sizes, hot-shard / out-of-memory splits that may be column-wise, hierarchical mode).
+
+    Costs are seconds per training step on the owning GPU:
+      lookup   = keys hitting the shard * row bytes / (HBM * gather_eff)            (forward gather)
+      update   = 2 * unique-ish rows * (weight+state) bytes / (HBM * update_eff)    (backward RMW)
+      per key  = per_key_bytes of index-build / sort / key traffic for every key the shard sees
+                 (independent of the row width: NOT reduced by a column split)
+      exchange = pooled (or per-key for ``concat``) vectors of the WHOLE global batch leaving the shard
+                 and their gradients coming back, over NVLink (intra-node) or the NIC share
+    A row split by k divides lookup / update by k but every shard still sends a full-width partial
+    vector (exchange unchanged per shard -> total x k); a column split by c divides all three by c.
+    Tables whose replicated gradient all-reduce is cheaper than the exchange and that fit
+    ``dp_threshold_bytes`` become data-parallel.  The most expensive shard is split until the critical
+    GPU is within ``balance_tol`` of the mean or nothing can be split; shards are then placed
+    longest-first on the least-loaded GPU that does not hold the table yet (same node for the shards
+    of one table when ``num_nodes`` > 1) and that has memory left.
+
+    Returns (shard_matrix, shard_strategy, report); strategy entries are ``name`` or
+    ``(name, column_wise_factor)``."""
+    hw = hw or HardwareModel()
+    n = len(table_sizes)
+    evs = [int(ev_sizes)] * n if isinstance(ev_sizes, int) else [int(e) for e in ev_sizes]
+    comb = list(combiners) if combiners else ["sum"] * n
+    names = [str(i) for i in range(n)]
+    gpn = max(1, num_gpus // max(1, num_nodes))
+    link = hw.nvlink if num_nodes == 1 else (hw.nvlink * (gpn - 1) + hw.internode * (num_gpus - gpn)) / max(1, num_gpus - 1)
+
+    def mem(t, k=1, c=1):
+        return table_sizes[t] * evs[t] * (weight_bytes + state_bytes) / (k * c)
+
+    def vec_per_sample(t):
+        return hotness[t] if comb[t] == "concat" else 1
+
+    def shard_cost(t, k, c):
+        keys = global_batch * hotness[t] / k
+        row = evs[t] / c
+        lookup = keys * row * weight_bytes / (hw.hbm * hw.gather_eff)
+        update = 2.0 * min(keys, table_sizes[t] / k) * row * (weight_bytes + state_bytes) / (hw.hbm * hw.update_eff) \
+            + keys * row * act_bytes / hw.hbm
+        exch = 2.0 * global_batch * vec_per_sample(t) * row * act_bytes * (num_gpus - 1) / num_gpus / link
+        return lookup + update + exch + keys * per_key_bytes / hw.hbm
+
+    def dp_cost(t):
+        keys = global_batch / num_gpus * hotness[t]
+        lookup = keys * evs[t] * weight_bytes / (hw.hbm * hw.gather_eff)
+        allreduce = 2.0 * table_sizes[t] * evs[t] * 4 / link
+        dense_update = 3.0 * table_sizes[t] * evs[t] * (weight_bytes + state_bytes) / hw.hbm
+        return lookup + allreduce + dense_update + keys * per_key_bytes / hw.hbm
+
+    if num_gpus == 1:
+        return [[1] * n], [("mp", names)], {"step_cost_us": [sum(shard_cost(t, 1, 1) for t in range(n)) * 1e6]}
+    dp = [t for t in range(n) if mem(t) <= dp_threshold_bytes and dp_cost(t) * num_gpus <= shard_cost(t, 1, 1) * 2
+          and comb[t] != "concat"]
+    mp = [t for t in range(n) if t not in dp]
+    split = {t: [1, 1] for t in mp}                      # table -> [row shards k, column parts c]
+    dp_load = sum(dp_cost(t) for t in dp)
+
+    def can_row(t):
+        k, c = split[t]
+        return k * c * 2 <= num_gpus and table_sizes[t] / (k * 2) >= min_rows_per_shard
+
+    def can_col(t):
+        k, c = split[t]
+        return k * c * 2 <= num_gpus and evs[t] % (c * 2) == 0 and evs[t] / (c * 2) >= min_cols_per_shard \
+            and comb[t] != "concat"
+
+    def split_once(t):
+        """prefer the split with the lower resulting per-shard cost (rows when the table is big and
+        lookup-bound, columns when the exchange dominates or the table has few rows)"""
+        k, c = split[t]
+        opts = []
+        if can_row(t):
+            opts.append((shard_cost(t, k * 2, c), 0))
+        if can_col(t):
+            opts.append((shard_cost(t, k, c * 2), 1))
+        if not opts:
+            return False
+        split[t][min(opts)[1]] *= 2
+        return True
+
+    cap = hw.capacity
+    for t in mp:                                          # out-of-memory splits first
+        while mem(t, *split[t]) > cap and split_once(t):
+            pass
+    for _ in range(8 * max(1, len(mp))):
+        costs = {t: shard_cost(t, *split[t]) for t in mp}
+        total = sum(costs[t] * split[t][0] * split[t][1] for t in mp)
+        share = total / num_gpus
+        worst = max(mp, key=lambda t: costs[t]) if mp else None
+        if worst is None or costs[worst] <= balance_tol * share or not split_once(worst):
+            break
+    # placement: longest shard first
+    load = [dp_load] * num_gpus
+    used = [sum(mem(t) for t in dp)] * num_gpus
+    sm = [[0] * n for _ in range(num_gpus)]
+    order = sorted(mp, key=lambda t: -shard_cost(t, *split[t]))
+    for t in order:
+        k, c = split[t]
+        cnt, cst, mb = k * c, shard_cost(t, k, c), mem(t, k, c)
+        cand = list(range(num_gpus))
+        if num_nodes > 1 and 1 < cnt <= gpn:
+            nd = min(range(num_nodes), key=lambda i: sum(load[i * gpn:(i + 1) * gpn]))
+            cand = list(range(nd * gpn, (nd + 1) * gpn))
+        fit = [g for g in cand if used[g] + mb <= cap] or cand
+        for g in sorted(fit, key=lambda g: (load[g], used[g]))[:cnt]:
+            sm[g][t] = 1
+            load[g] += cst
+            used[g] += mb
+        if sum(sm[g][t] for g in range(num_gpus)) < cnt:           # not enough GPUs with memory left
+            for g in sorted(cand, key=lambda g: (sm[g][t], load[g]))[:cnt - sum(sm[g][t] for g in range(num_gpus))]:
+                sm[g][t] = 1
+                load[g] += cst
+                used[g] += mb
+    for t in dp:
+        for g in range(num_gpus):
+            sm[g][t] = 1
+    strategy = []
+    if mp:
+        strategy.append(("mp", [names[t] if split[t][1] == 1 else (names[t], split[t][1]) for t in mp]))
+    if dp:
+        strategy.append(("dp", [names[t] for t in dp]))
+    report = {"step_cost_us": [x * 1e6 for x in load], "memory_gb": [x / 1e9 for x in used],
+              "imbalance": max(load) / (sum(load) / num_gpus) if sum(load) else 1.0,
+              "splits": {names[t]: tuple(split[t]) for t in mp if split[t] != [1, 1]}, "dp": [names[t] for t in dp]}
+    return sm, strategy, report
+
+
 def plan_report(table_sizes: Sequence[int], multi_hot: Sequence[int], shard_matrix, ev_size: int = 128,
                 bytes_per_elem: int = 8) -> dict:
     """per-GPU lookup load (rows gathered per sample) and table memory (GB) of a plan"""
@@ -107,10 +255,23 @@ def main(argv=None):
     ap.add_argument("--slot-sizes", default="")
     ap.add_argument("--multi-hot", default="")
     ap.add_argument("--ev-size", type=int, default=128)
+    ap.add_argument("--ev-sizes", default="", help="per-table widths: selects the heterogeneous planner")
+    ap.add_argument("--combiners", default="", help="per-table sum|mean|concat (heterogeneous planner)")
+    ap.add_argument("--global-batch", type=int, default=65536)
     ap.add_argument("--out", default="")
     a = ap.parse_args(argv)
     sizes = [int(x) for x in a.slot_sizes.split(",")] if a.slot_sizes else CRITEO_TB_TABLE_SIZES
     hot = [int(x) for x in a.multi_hot.split(",")] if a.multi_hot else CRITEO_TB_MULTI_HOT
+    if a.ev_sizes or a.combiners:
+        evs = [int(x) for x in a.ev_sizes.split(",")] if a.ev_sizes else a.ev_size
+        sm, st, rep = plan_tables(sizes, hot, evs, a.num_gpus, a.global_batch,
+                                  a.combiners.split(",") if a.combiners else None, a.num_nodes)
+        print("step cost per GPU (us):", [round(x, 1) for x in rep["step_cost_us"]])
+        print("table memory per GPU (GB):", [round(x, 2) for x in rep["memory_gb"]])
+        print("imbalance (max/mean): %.3f" % rep["imbalance"], " splits (rows, cols):", rep["splits"], " dp:", rep["dp"])
+        if a.out:
+            save_plan(a.out, sm, [(k, [list(x) if isinstance(x, tuple) else x for x in v]) for k, v in st])
+        return sm, st
     sm, st = generate_plan(sizes, hot, a.num_gpus, ev_size=a.ev_size, plan=a.plan, num_nodes=a.num_nodes)
     rep = plan_report(sizes, hot, sm, a.ev_size)
     print("lookups/sample per GPU:", [round(x, 1) for x in rep["lookups_per_sample"]])

@@ -388,3 +388,50 @@ def test_hps_inference_session_matches_direct_lookup(tmp_path):
     e = HpsEmbedding(torch.tensor([5, 9]), torch.tensor([[1., 1.], [2., 2.]]), "cpu", combiner="mean")
     out = e.lookup(torch.tensor([[[5, 9, -1], [777, -1, -1]]]))
     torch.testing.assert_close(out, torch.tensor([[[1.5, 1.5], [0., 0.]]]))
+
+
+def test_heterogeneous_planner_properties():
+    """plan_tables: widths / combiners per table, row + column splits, memory cap, node locality"""
+    from hugectr_b200.embedding.collection import (EmbeddingCollectionConfig, EmbeddingTableConfig,
+                                                   resolve_placement)
+    from hugectr_b200.tools.planner import HardwareModel, plan_tables
+    nt = [5, 5, 5, 5, 20, 30, 10, 20, 10, 10, 10, 5, 40, 1, 1]
+    vs = [10000, 4000000, 4000000, 50000000, 1000, 10000, 5000000, 4000000, 10, 1000, 10000, 100000, 4000000,
+          50000000, 500000000]
+    nz = [100, 50, 30, 50, 50, 30, 20, 20, 100, 10, 100, 100, 200, 100, 100]
+    ev = [128, 64, 64, 32, 128, 128, 256, 128, 128, 64, 128, 64, 64, 128, 32]
+    S = [v for n, v in zip(nt, vs) for _ in range(n)]
+    H = [v for n, v in zip(nt, nz) for _ in range(n)]
+    E = [v for n, v in zip(nt, ev) for _ in range(n)]
+    for gpus, nodes in ((8, 1), (16, 2)):
+        sm, st, rep = plan_tables(S, H, E, gpus, num_nodes=nodes)
+        assert rep["imbalance"] < 1.15, rep["imbalance"]
+        assert max(rep["memory_gb"]) <= 150.0
+        # the plan is accepted by the collection as is
+        cfg = EmbeddingCollectionConfig()
+        ts = [EmbeddingTableConfig(str(i), S[i], E[i]) for i in range(len(S))]
+        cfg.embedding_lookup(ts, [f"d{i}" for i in range(len(S))], "top", ["sum"] * len(S))
+        cfg.shard(sm, st)
+        place = resolve_placement(cfg, gpus)
+        assert all(p is not None for p in place.values())
+        for kind, items in st:
+            for it in items:
+                if isinstance(it, tuple):
+                    t, c = int(it[0]), it[1]
+                    assert E[t] % c == 0 and E[t] // c >= 32 and sum(r[t] for r in sm) % c == 0
+    # a table that does not fit one GPU is split until it does; its shards stay inside one node
+    hw = HardwareModel(hbm_capacity_gb=20.0)
+    sm, st, rep = plan_tables([40_000_000] + [2_000_000] * 15 + [1000, 50], [3] * 16 + [1, 1], 128, 16,
+                              num_nodes=2, hw=hw)
+    owners = [g for g in range(16) if sm[g][0]]
+    assert 4 <= len(owners) <= 8 and len({g // 8 for g in owners}) == 1, owners
+    assert max(rep["memory_gb"]) <= 20.0
+    assert rep["dp"] == ["16", "17"]
+    # a tiny table looked up 200 times per sample with the concat combiner: never data-parallel, and
+    # only row-splittable (concat outputs keep whole vectors)
+    sm, st, rep = plan_tables([5000, 5000000], [200, 1], [64, 64], 8, combiners=["concat", "sum"])
+    assert "0" not in rep["dp"] and all(not isinstance(x, tuple) or x[0] != "0" for x in st[0][1])
+    # CLI
+    from hugectr_b200.tools import planner
+    sm, st = planner.main(["--num-gpus", "8", "--ev-sizes", ",".join(["128"] * 26)])
+    assert len(sm) == 8 and len(sm[0]) == 26
