@@ -348,6 +348,17 @@ class Model:
         D.lr_step(self.step_t, self.lr_t, s.lr, s.end_lr, s.decay_power, s.warmup_steps,
                   s.decay_start, s.decay_steps)
         net = self.net_train
+        # ablation switches of the reference pipeline (model_pipeline.cpp:118-286, benchmarks/
+        # embedding_collection/README.md): attribute step time by leaving a stage out
+        skip = getattr(self, "_skip", None)
+        if skip is None:
+            env = lambda k: os.environ.get(k, "0") not in ("0", "")
+            skip = self._skip = {"emb": env("SKIP_EMBEDDING"), "bottom": env("SKIP_BOTTOM_MLP"),
+                                 "top": env("SKIP_TOP_MLP"), "ar": env("SKIP_ALLREDUCE")}
+            if any(skip.values()):
+                logger.warning(f"ablation switches active, the model does not train correctly: {skip}")
+        if any(skip.values()):
+            return self._step_body_ablation(skip)
         bucketed = (self.device.type == "cuda" and not self.dense_frozen
                     and os.environ.get("HCTR_DISABLE_AR_OVERLAP", "0") == "0")
         if bucketed:
@@ -426,6 +437,37 @@ class Model:
                 if not self.embedding_frozen.get(rt.name, frozen_emb):
                     rt.backward(self.lr_t, self.step_t)
 
+    def _step_body_ablation(self, skip):
+        """Sequential step with stages left out (SKIP_EMBEDDING / SKIP_BOTTOM_MLP / SKIP_TOP_MLP /
+        SKIP_ALLREDUCE).  Timing attribution only: skipped stages leave stale activations behind."""
+        net = self.net_train
+        net.wgrad_hook = None
+        frozen_emb = self.embedding_frozen.get("*", False)
+        if not skip["emb"]:
+            for e in self.ebcs_train:
+                e.forward(True)
+            for rt in self.legacy_train:
+                rt.forward(True)
+        if not skip["bottom"]:
+            net.fprop(True, "bottom")
+        if not skip["top"]:
+            net.fprop(True, "top")
+            net.bprop("top")
+        if not skip["bottom"]:
+            net.bprop("bottom")
+        if not self.dense_frozen:
+            if not skip["ar"]:
+                self.exchange_wgrad.allreduce()
+            self._dense_opt_range(0, self.arena.weights.numel())
+        else:
+            self.arena.wgrad.zero_()
+        if not skip["emb"] and not frozen_emb:
+            for e in self.ebcs_train:
+                e.backward(self.lr_t, self.step_t)
+            for rt in self.legacy_train:
+                if not self.embedding_frozen.get(rt.name, frozen_emb):
+                    rt.backward(self.lr_t, self.step_t)
+
     def _dense_opt_range(self, lo: int, hi: int):
         """fused dense optimizer over arena elements [lo, hi) (also zeroes that wgrad range)"""
         a = self.arena
@@ -469,6 +511,12 @@ class Model:
         while step i executes (double-buffered staging; reference model_pipeline.cpp:370-418)."""
         if not self.reader_train.is_started():
             self.reader_train.start()
+        if getattr(self, "_h2d_done", False) and os.environ.get("SKIP_H2D", "0") not in ("0", ""):
+            self._run_step()                   # ablation (model.cpp:1067): keep re-using the resident batch
+            self._iter += 1
+            self.lr_sched.step = self._iter
+            return True
+        self._h2d_done = True
         prefetch = (self.device.type == "cuda" and self.solver.train_inter_iteration_overlap
                     and len(self.ebcs_train) == 1 and not self.legacy_train
                     and os.environ.get("HCTR_DISABLE_PREFETCH", "0") == "0")

@@ -66,15 +66,16 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
         label_dim=1, label_name="label", dense_dim=NUM_DENSE, dense_name="dense",
         data_reader_sparse_param_array=[
             hugectr.DataReaderSparseParam(f"data{i}", multi_hot[i], True, 1) for i in range(n)]))
+    evs = [int(ev_size)] * n if isinstance(ev_size, int) else [int(e) for e in ev_size]   # per-table widths
     tables = [hugectr.EmbeddingTableConfig(name=str(i), max_vocabulary_size=table_sizes[i],
-                                           ev_size=ev_size) for i in range(n)]
+                                           ev_size=evs[i]) for i in range(n)]
     ebc = hugectr.EmbeddingCollectionConfig(
         use_exclusive_keys=True, comm_strategy=comm_strategy or hugectr.CommunicationStrategy.Uniform)
     ebc.embedding_lookup(table_config=tables, bottom_name=[f"data{i}" for i in range(n)],
                          top_name="sparse_embedding", combiner=["sum"] * n)
     if shard_plan is None:
         from hugectr_b200.tools.planner import generate_plan
-        shard_plan = generate_plan(table_sizes, multi_hot, num_gpus, ev_size=ev_size)
+        shard_plan = generate_plan(table_sizes, multi_hot, num_gpus, ev_size=max(evs))
     ebc.shard(shard_matrix=shard_plan[0], shard_strategy=shard_plan[1])
     model.add(ebc)
     cc = hugectr.DenseLayerComputeConfig(async_wgrad=True, fuse_wb=False)

@@ -139,7 +139,9 @@ def plan_tables(table_sizes: Sequence[int], hotness: Sequence[int], ev_sizes, nu
         return lookup + allreduce + dense_update + keys * per_key_bytes / hw.hbm
 
     if num_gpus == 1:
-        return [[1] * n], [("mp", names)], {"step_cost_us": [sum(shard_cost(t, 1, 1) for t in range(n)) * 1e6]}
+        return [[1] * n], [("mp", names)], {"step_cost_us": [sum(shard_cost(t, 1, 1) for t in range(n)) * 1e6],
+                                            "memory_gb": [sum(mem(t) for t in range(n)) / 1e9],
+                                            "imbalance": 1.0, "splits": {}, "dp": []}
     dp = [t for t in range(n) if mem(t) <= dp_threshold_bytes and dp_cost(t) * num_gpus <= shard_cost(t, 1, 1) * 2
           and comb[t] != "concat"]
     mp = [t for t in range(n) if t not in dp]
