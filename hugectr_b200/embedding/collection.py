@@ -17,6 +17,7 @@ vectors travel through ``all_to_all_single``.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -516,6 +517,8 @@ class EmbeddingCollection:
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()
+            elif os.environ.get("SKIP_DATA_DISTRIBUTOR", "0") not in ("0", ""):
+                pass          # ablation (model_pipeline.cpp:118): owners keep the keys of an earlier step
             elif self.hier:
                 self.comm.hier_all_gather(self.keys_all, self.key_slab)
                 if self.nnz_all is not None:
@@ -593,6 +596,8 @@ class EmbeddingCollection:
         if self.world > 1:
             if self.fused:
                 self.comm.barrier_device()       # every owner finished writing my outputs
+            elif os.environ.get("SKIP_ALL2ALL", "0") not in ("0", ""):
+                pass          # ablation (communication.cpp:52-148): no vector exchange
             else:
                 if self.hier:
                     self.out_slab.copy_(self.comm.hier_all_to_all_sum(self.send_out))
@@ -695,6 +700,8 @@ class EmbeddingCollection:
                         E.pull_grads(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
                                      self.peer_grad, self.grad_stage, self.b, self.rank,
                                      key_bytes=self._kb, act_bf16=self._abf)
+            elif os.environ.get("SKIP_ALL2ALL", "0") not in ("0", ""):
+                pass
             elif self.hier:
                 self.comm.hier_all_gather(self.grads_all, self.grad_slab)
             else:

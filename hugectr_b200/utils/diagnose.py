@@ -74,3 +74,39 @@ def nvtx_range(name: str):
     if torch.cuda.is_available():
         return torch.cuda.nvtx.range(name)
     return contextlib.nullcontext()
+
+
+def kernel_summary(pattern: str = "", log: bool = False):
+    """Static resources of every kernel in lib/libhctr_cuda.so -- the role of HCTR_CUDA_KERNEL_SUMMARY
+    (registers / shared memory / occupancy from cudaFuncGetAttributes, cuda_debugging.hpp:44-70),
+    read from the cubin with ``cuobjdump -res-usage`` so that it also works without a GPU.
+    Returns {demangled kernel name: {"regs", "smem", "stack", "local", "max_blocks_per_sm"}}; the
+    occupancy bound is the register / static-shared-memory limit of sm_100 (64 K registers, 227 KB
+    shared memory, 2048 threads per SM) for a 256-thread block."""
+    import re
+    import shutil
+    import subprocess
+    from .. import _native
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    out = subprocess.run([exe, "-res-usage", _native.CUDA_SO], capture_output=True, text=True).stdout
+    names = re.findall(r"Function (\S+):\n\s+(.*)", out)
+    filt = shutil.which("c++filt")
+    dem = {}
+    if filt and names:
+        r = subprocess.run([filt], input="\n".join(n for n, _ in names), capture_output=True, text=True).stdout
+        dem = dict(zip([n for n, _ in names], r.split("\n")))
+    res = {}
+    for sym, line in names:
+        f = dict(kv.split(":") for kv in re.findall(r"[A-Z]+:\d+", line))
+        regs, smem = int(f.get("REG", 0)), int(f.get("SHARED", 0))
+        name = dem.get(sym, sym)
+        if pattern and pattern not in name:
+            continue
+        by_regs = 65536 // max(1, regs * 256)
+        by_smem = (227 * 1024) // smem if smem else 32
+        res[name] = {"regs": regs, "smem": smem, "stack": int(f.get("STACK", 0)), "local": int(f.get("LOCAL", 0)),
+                     "max_blocks_per_sm": max(0, min(8, by_regs, by_smem))}
+        if log:
+            logger.info(f"[kernel] {name.split('(')[0][:80]}: {regs} regs, {smem} B static smem, "
+                        f"{f.get('STACK', 0)} B stack")
+    return res

@@ -135,3 +135,16 @@ def test_model_set_source_download_and_embedding_dump(tmp_path):
     from hugectr_b200.utils import diagnose
     assert diagnose.verify_model(m)
     assert m.solver.num_nodes == 1 and "lr" in m.solver.to_json() if hasattr(m.solver, "to_json") else True
+
+
+def test_kernel_summary_reads_static_resources_without_a_gpu():
+    import shutil
+    from hugectr_b200.utils.diagnose import kernel_summary
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("no cuobjdump")
+    ks = kernel_summary()
+    assert len(ks) > 40
+    gemm = {k: v for k, v in ks.items() if "gemm_tc2_kernel" in k}
+    assert gemm and all(v["regs"] <= 255 and v["stack"] == 0 for v in gemm.values())   # no spills
+    # the register-capped (3 blocks / SM) reduce+update kernels may spill a few words, never more
+    assert all(v["stack"] <= 64 for k, v in kernel_summary("emb_bwd_reduce_update").items())
