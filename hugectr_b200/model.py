@@ -256,6 +256,10 @@ class Model:
         from .data import create_reader
         self.reader_train = create_reader(self, True)
         self.reader_eval = create_reader(self, False)
+        n_cache = int(getattr(self.reader_params, "cache_eval_data", 0) or 0)
+        if n_cache > 0 and n_cache >= self.solver.max_eval_batches:
+            from .data.readers import CachedEvalReader
+            self.reader_eval = CachedEvalReader(self.reader_eval, n_cache, self.device)
         self.reader_train._bind(self, True)
         self.reader_eval._bind(self, False)
 

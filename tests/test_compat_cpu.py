@@ -73,3 +73,27 @@ def test_data_reader_handle_api():
     lab = m.check_out_tensor("label", hugectr.Tensor_t.Train)
     assert lab.shape == (16, 1)
     assert isinstance(hugectr.CreateOptimizer(), hugectr.Optimizer)
+
+
+def test_cache_eval_data_replays_the_resident_round():
+    import torch
+    from hugectr_b200.data.readers import CachedEvalReader
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.parallel.comm import Comm
+    m = build_dlrm_dcnv2(batchsize=16, num_gpus=1, table_sizes=[30, 40], multi_hot=[2, 1], ev_size=8,
+                         mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                         comm=Comm.single(torch.device("cpu")), max_eval_batches=3)
+    m.reader_params.cache_eval_data = 3
+    m.compile()
+    r = m.get_data_reader_eval()
+    assert isinstance(r, CachedEvalReader)
+    calls = []
+    inner_read = r.inner.read_a_batch
+    r.inner.read_a_batch = lambda: (calls.append(1), inner_read())[1]
+    rounds = []
+    for _ in range(3):
+        for _ in range(3):
+            assert m.eval()
+        rounds.append(m.get_eval_metrics()[0][1])
+    assert len(calls) == 3                       # only the first round touched the source
+    assert rounds[0] == rounds[1] == rounds[2]   # identical resident data, untrained model
