@@ -23,13 +23,16 @@ class HostBatch:
     nnz: Optional[torch.Tensor] = None
     num_valid: int = -1   # < b for an incomplete last batch
     copied: object = None  # CUDA event recorded after the last async H2D copy out of this batch
+    _event: object = None  # the event object is created once per batch and re-recorded
 
     def mark_copied(self):
         """Called by the consumer right after it queued its asynchronous H2D copies: ring-buffer
         readers wait on this before they hand the staging slot back to their producer threads."""
         if torch.cuda.is_available():
-            self.copied = torch.cuda.Event()
-            self.copied.record()
+            if self._event is None:
+                self._event = torch.cuda.Event()
+            self._event.record()
+            self.copied = self._event
 
     def wait_copied(self):
         if self.copied is not None:
