@@ -66,24 +66,38 @@ class SymmetricHeap:
         """Collective: every rank must call with the same arguments in the same order."""
         esz = torch.empty(0, dtype=dtype).element_size()
         nbytes = (numel * esz + 255) // 256 * 256
+        # Every rank walks through the same collective sequence even when a local step fails, and the
+        # outcome is agreed on before anyone raises: either all ranks get the buffer or all ranks see
+        # the error (and fall back to NCCL collectives together) -- never a mix that would deadlock.
+        err = None
         p = lib().hctr_ipc_alloc(nbytes)
-        if not p:
-            raise RuntimeError("cudaMalloc failed for the symmetric heap: %s" %
-                               lib().hctr_last_cuda_error().decode())
         h = C.create_string_buffer(64)
-        if lib().hctr_ipc_get_handle(p, h) != 0:
-            raise RuntimeError("cudaIpcGetMemHandle failed")
-        handles = self.comm.all_gather_object(bytes(h.raw))
+        if not p:
+            err = "cudaMalloc failed for the symmetric heap: %s" % lib().hctr_last_cuda_error().decode()
+        elif lib().hctr_ipc_get_handle(p, h) != 0:
+            err = "cudaIpcGetMemHandle failed"
+        handles = self.comm.all_gather_object(None if err else bytes(h.raw))
         peers = []
-        for r, hb in enumerate(handles):
-            if r == self.rank:
-                peers.append(p)
-            else:
+        if err is None and all(hb is not None for hb in handles):
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    peers.append(p)
+                    continue
                 q = lib().hctr_ipc_open(C.create_string_buffer(hb, 64))
                 if not q:
-                    raise RuntimeError("cudaIpcOpenMemHandle failed: %s" %
-                                       lib().hctr_last_cuda_error().decode())
+                    err = "cudaIpcOpenMemHandle failed: %s" % lib().hctr_last_cuda_error().decode()
+                    break
                 peers.append(q)
+        errs = self.comm.all_gather_object(err)
+        if any(e is not None for e in errs) or any(hb is None for hb in handles):
+            for r, q in enumerate(peers):
+                if r != self.rank:
+                    lib().hctr_ipc_close(q)
+            if p:
+                lib().hctr_ipc_free(p)
+            bad = [(r, e) for r, e in enumerate(errs) if e is not None]
+            raise RuntimeError("symmetric heap allocation failed on rank(s) %s" %
+                               ", ".join(f"{r}: {e}" for r, e in bad))
         t = torch.as_tensor(_RawCuda(p, nbytes), device=self.device).view(dtype)[:numel]
         self._allocs[p] = {"peers": peers, "nbytes": nbytes, "tensor": t}
         return t

@@ -377,6 +377,36 @@ def run_ebcio(tmpdir, seed):
         print("EBCIO_OK", seed)
 
 
+def run_symmfail():
+    """a peer-mapping failure on ONE rank makes EVERY rank raise (agreement before the error), so the
+    job falls back to NCCL collectives as a whole instead of deadlocking in mismatched collectives"""
+    import ctypes as C
+    from hugectr_b200.parallel import symm
+    comm = Comm.init_from_env()
+
+    class FakeLib:
+        freed = closed = 0
+        def hctr_ipc_alloc(self, n): return 0x1000 * (comm.rank + 1)
+        def hctr_ipc_get_handle(self, p, h): return 0
+        def hctr_ipc_open(self, h): return 0 if comm.rank == 1 else 0x9000
+        def hctr_ipc_close(self, q): FakeLib.closed += 1; return 0
+        def hctr_ipc_free(self, p): FakeLib.freed += 1; return 0
+        def hctr_last_cuda_error(self): return b"peer access unsupported"
+    fake = FakeLib()
+    symm.lib = lambda: fake
+    heap = symm.SymmetricHeap.__new__(symm.SymmetricHeap)
+    heap.comm, heap.rank, heap.world, heap.device, heap._allocs = comm, comm.rank, comm.world_size, comm.device, {}
+    try:
+        heap.alloc(64, torch.int32)
+        raise SystemExit("alloc did not fail")
+    except RuntimeError as e:
+        assert "rank(s) 1:" in str(e) and "peer access unsupported" in str(e), str(e)
+    assert FakeLib.freed == 1 and not heap._allocs
+    comm.barrier()                       # the collective sequence is still aligned on all ranks
+    if comm.rank == 0:
+        print("SYMMFAIL_OK")
+
+
 def run_allreduce():
     comm = Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
@@ -627,6 +657,8 @@ if __name__ == "__main__":
             d = os.path.join(sys.argv[2], sd)
             os.makedirs(d, exist_ok=True)
             run_ebcio(d, sd)
+    if what == "symmfail":
+        run_symmfail()
     if what == "fuzz":
         for sd in sys.argv[2].split(","):
             run_fuzz(sd)

@@ -185,3 +185,9 @@ def test_embedding_collection_benchmark_script_gloo():
                        env=dict(env, SKIP_EMBEDDING="1", SKIP_ALLREDUCE="1", SKIP_H2D="1"))
     assert '"SKIP_EMBEDDING": "1"' in r.stdout and "ablation switches active" in (r.stdout + r.stderr), \
         r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.dist
+def test_symmetric_heap_failure_is_agreed_on_by_all_ranks_gloo():
+    out = _run(3, ["symmfail"], 29791, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "SYMMFAIL_OK" in out, out[-2000:]
