@@ -1,4 +1,5 @@
-"""MLPerf DLRM-DCNv2 sample (counterpart of samples/dlrm/train.py): single node, N GPUs.
+"""MLPerf DLRM-DCNv2 sample (counterpart of samples/dlrm/train.py): N GPUs on one or several nodes
+(scripts/launch_single_node.sh, scripts/slurm_multinode.sub).
 
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 samples/dlrm_dcnv2_train.py \
       --batchsize 55296 --max_iter 2000 [--source /data/train_data.bin --eval_source /data_val/val_data.bin]
@@ -27,13 +28,19 @@ p.add_argument("--auc_threshold", type=float, default=0.80275)
 p.add_argument("--source", default=None)
 p.add_argument("--eval_source", default=None)
 p.add_argument("--optimizer", default="adagrad", choices=["adagrad", "sgd"])
+p.add_argument("--num_nodes", type=int, default=1)
+p.add_argument("--gpus_per_node", type=int, default=0, help="0: WORLD_SIZE / num_nodes")
+p.add_argument("--cap_rows", type=int, default=0, help="cap table sizes (functional runs on small machines)")
 args = p.parse_args()
 
 num_gpus = int(os.environ.get("WORLD_SIZE", "1"))
-plan = generate_plan(CRITEO_TB_TABLE_SIZES, CRITEO_TB_MULTI_HOT, num_gpus, plan=args.sharding_plan)
+gpn = args.gpus_per_node or max(1, num_gpus // args.num_nodes)
+sizes = [min(s, args.cap_rows) if args.cap_rows else s for s in CRITEO_TB_TABLE_SIZES]
+plan = generate_plan(sizes, CRITEO_TB_MULTI_HOT, num_gpus, plan=args.sharding_plan, num_nodes=args.num_nodes)
+multi = dict(gpus_per_node=gpn, comm_strategy=hugectr.CommunicationStrategy.Hierarchical) if args.num_nodes > 1 else {}
 cb = LoggingCallback(args.auc_threshold, 4195197692 / args.batchsize, args.batchsize)
 model = build_dlrm_dcnv2(batchsize=args.batchsize, num_gpus=num_gpus, lr=args.lr, mixed=True,
-                         shard_plan=plan, optimizer=args.optimizer,
+                         shard_plan=plan, optimizer=args.optimizer, table_sizes=sizes, **multi,
                          source=[args.source] if args.source else None,
                          batchsize_eval=args.batchsize_eval, training_callbacks=[cb])
 model.compile()
