@@ -129,6 +129,10 @@ def host_lib() -> ctypes.CDLL:
     if _host_lib is None:
         with _lock:
             if _host_lib is None:
+                override = os.environ.get("HCTR_HOST_LIB")     # e.g. a sanitizer build (docs/testing.md)
+                if override:
+                    _host_lib = ctypes.CDLL(override)
+                    return _host_lib
                 if not os.path.exists(HOST_SO) or os.environ.get("HCTR_REBUILD_HOST"):
                     build_host()
                 _host_lib = ctypes.CDLL(HOST_SO)
