@@ -196,16 +196,21 @@ def _to_csr(sp_ids):
 
 class _Lookup(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, var, vals, lens, combiner):
+    def forward(ctx, anchor, var, vals, lens, combiner, wts=None):
         c = _c()
         dev = var.device
         vals = vals.to(dev)
         lens = lens.to(dev)
         b = lens.numel()
         seg = torch.repeat_interleave(torch.arange(b, device=dev), lens)
+        wts = None if wts is None else wts.to(dev).float().reshape(-1)
+        ctx.w_own = None
         if c.world_size == 1:
             rows = var.local_rows(vals)
             vec = var.weight[rows].float()
+            if wts is not None:
+                vec = vec * wts.unsqueeze(1)
+                ctx.w_own = wts
             out = torch.zeros(b, var.dim, device=dev).index_add_(0, seg, vec)
             ctx.rows, ctx.seg_owner = rows, None
         else:
@@ -223,6 +228,12 @@ class _Lookup(torch.autograd.Function):
             gs = torch.zeros(c.world_size, mx, dtype=torch.int64, device=dev)
             c.all_gather(gv, pad_v)
             c.all_gather(gs, pad_s)
+            gw = None
+            if wts is not None:
+                pad_w = torch.zeros(mx, device=dev)
+                pad_w[:vals.numel()] = wts
+                gw = torch.zeros(c.world_size, mx, device=dev)
+                c.all_gather(gw, pad_w)
             owner, _ = var.locate(gv.clamp(min=0))
             mine = (owner == c.rank) & (gv >= 0)
             partial = torch.zeros(c.world_size, b_max(c, b), var.dim, device=dev)
@@ -231,13 +242,20 @@ class _Lookup(torch.autograd.Function):
                 rws = var.local_rows(gv[mine])
                 rows_all[mine] = rws
                 src = torch.nonzero(mine)[:, 0]
-                partial.view(-1, var.dim).index_add_(0, src * partial.shape[1] + gs[mine],
-                                                     var.weight[rws].float())
+                vec = var.weight[rws].float()
+                if gw is not None:
+                    vec = vec * gw[mine].unsqueeze(1)
+                    ctx.w_own = gw[mine]
+                partial.view(-1, var.dim).index_add_(0, src * partial.shape[1] + gs[mine], vec)
             recv = torch.zeros_like(partial)
             c.all_to_all(recv, partial)
             out = recv.sum(0)[:b]
             ctx.rows, ctx.seg_owner = rows_all, (gs, mine)
-        cnt = lens.clamp(min=1).float().unsqueeze(1)
+        if wts is None:
+            cnt = lens.clamp(min=1).float().unsqueeze(1)
+        else:      # weighted mean = weighted sum / sum of weights (tf.nn.embedding_lookup_sparse)
+            cnt = torch.zeros(b, device=dev).index_add_(0, seg, wts).unsqueeze(1)
+            cnt = torch.where(cnt == 0, torch.ones_like(cnt), cnt)
         if combiner == "mean":
             out = out / cnt
         ctx.var, ctx.seg, ctx.cnt, ctx.combiner, ctx.b = var, seg, cnt, combiner, b
@@ -261,6 +279,8 @@ class _Lookup(torch.autograd.Function):
             src = torch.nonzero(mine)[:, 0]
             rows = ctx.rows[mine]
             grads = gall[src, gs[mine]]
+        if ctx.w_own is not None and rows.numel():
+            grads = grads * ctx.w_own.unsqueeze(1)
         if rows.numel():
             u, inv = torch.unique(rows, return_inverse=True)
             red = torch.zeros(u.numel(), var.dim, device=g.device).index_add_(0, inv, grads)
@@ -268,7 +288,7 @@ class _Lookup(torch.autograd.Function):
                 var.sparse_grad = (u, red)
             else:
                 var.sparse_grad = (torch.cat([var.sparse_grad[0], u]), torch.cat([var.sparse_grad[1], red]))
-        return torch.zeros((), device=g.device), None, None, None, None
+        return torch.zeros((), device=g.device), None, None, None, None, None
 
 
 def b_max(c: Comm, b: int) -> int:
@@ -281,17 +301,35 @@ def b_max(c: Comm, b: int) -> int:
 _anchor = None
 
 
-def lookup_sparse(params, sp_ids, combiners: Union[str, Sequence[str]] = "sum"):
-    """sok.lookup_sparse(params, sp_ids, combiners) -> pooled embeddings [b, dim] per variable."""
+def lookup_sparse(params, sp_ids, sp_weights=None, combiners: Union[str, Sequence[str], None] = None,
+                  use_low_frequency_filter: bool = False):
+    """sok.lookup_sparse(params, sp_ids, sp_weights=None, combiners=None) -> pooled embeddings
+    [b, dim] per variable (reference lookup.py:543).  ``sp_weights``: per-id weights in the same layout
+    as ``sp_ids`` (padded [b, H] or (values, row_lengths)); ``mean`` then divides by the sum of weights.
+    A combiner (or list of combiners) passed in the third position is accepted as ``combiners``."""
+    if isinstance(sp_weights, str) or (isinstance(sp_weights, (list, tuple)) and sp_weights
+                                       and all(isinstance(x, str) for x in sp_weights)):
+        sp_weights, combiners = None, sp_weights
     single = not isinstance(params, (list, tuple))
     ps = [params] if single else list(params)
     ids = [sp_ids] if single else list(sp_ids)
+    ws = [None] * len(ps) if sp_weights is None or (isinstance(sp_weights, (list, tuple)) and not sp_weights) \
+        else ([sp_weights] if single else list(sp_weights))
+    combiners = combiners or "sum"
     cs = [combiners] * len(ps) if isinstance(combiners, str) else list(combiners)
     outs = []
-    for p, i, cb in zip(ps, ids, cs):
+    for p, i, w, cb in zip(ps, ids, ws, cs):
         vals, lens = _to_csr(i)
+        wv = None
+        if w is not None:
+            if isinstance(w, (tuple, list)):
+                wv = w[0].float().reshape(-1)
+            else:
+                wv = w.float()[i.to(torch.int64) >= 0] if w.dim() == 2 else w.float().reshape(-1)
+            if wv.numel() != vals.numel():
+                raise ValueError("sp_ids and sp_weights must have the same shape")
         anchor = torch.zeros((), device=p.device, requires_grad=True)
-        outs.append(_Lookup.apply(anchor, p, vals, lens, cb))
+        outs.append(_Lookup.apply(anchor, p, vals, lens, cb, wv))
     return outs[0] if single else outs
 
 

@@ -183,6 +183,24 @@ def run_sok():
     W2 = (W - 0.1 * W.grad).detach()
     keys = v.global_keys()
     torch.testing.assert_close(v.weight.float().cpu(), W2[keys.cpu()], atol=1e-6, rtol=1e-5)
+    # weighted lookups (sp_weights): mean = weighted sum / sum of weights, gradients scale with the weight
+    for comb in ("sum", "mean"):
+        full2 = torch.randn(40, 4, generator=gen)
+        v2 = sok.Variable(initial_value=full2.clone(), name="dist_w_" + comb)
+        w_all = torch.rand(b * world, 3, generator=gen) + 0.1
+        out = sok.lookup_sparse(v2, ids, sp_weights=w_all[rank * b:(rank + 1) * b], combiners=comb)
+        W = full2.clone().requires_grad_(True)
+        wm = w_all * (ids_all >= 0).float()
+        ref = (W[ids_all.clamp(min=0)] * wm.unsqueeze(-1)).sum(1)
+        if comb == "mean":
+            ref = ref / wm.sum(1, keepdim=True)
+        torch.testing.assert_close(out, ref[rank * b:(rank + 1) * b].detach(), atol=1e-5, rtol=1e-5)
+        (out * gout[rank * b:(rank + 1) * b]).sum().backward()
+        (ref * gout).sum().backward()
+        sok.OptimizerWrapper(hugectr.Optimizer_t.SGD, lr=0.1).apply_gradients([v2])
+        keys = v2.global_keys()
+        torch.testing.assert_close(v2.weight.float().cpu(), (W - 0.1 * W.grad).detach()[keys.cpu()],
+                                   atol=1e-5, rtol=1e-5)
     comm.barrier()
     if rank == 0:
         print("SOK_OK")
