@@ -113,11 +113,20 @@ def LocalizedVariable(*a, gpu: int = 0, **kw):
 
 class DynamicVariable(Variable):
     """Hash-backed variable with unbounded key space (sok.DynamicVariable over HKV/DET):
-    rows are created on first lookup; capacity grows geometrically."""
+    rows are created on first lookup; capacity grows geometrically up to ``max_capacity`` rows of HBM.
+
+    HierarchicalKV semantics (third_party/HierarchicalKV, kit_src/variable/impl/hkv_variable.cu): when
+    the HBM tier is full the least recently (``evict_strategy="lru"``) or least frequently (``"lfu"``)
+    used rows are evicted -- a quarter of the table at a time, keys of the running batch are never
+    evicted.  With ``var_type="hybrid"`` evicted rows (weights and optimizer states) are demoted to a
+    host-memory tier (native key index, csrc/host/param_server.cpp) and promoted back, values intact,
+    the next time their key is looked up; with ``"hbm"`` they are dropped and a returning key starts
+    from the initializer again."""
 
     def __init__(self, dimension: int, var_type: str = "hbm", initializer: Union[str, float] = "uniform",
                  init_capacity: int = 1 << 16, max_capacity: int = 1 << 26, name: Optional[str] = None,
-                 key_type=torch.int64, dtype=torch.float32, trainable: bool = True):
+                 key_type=torch.int64, dtype=torch.float32, trainable: bool = True,
+                 evict_strategy: str = "lru", host_capacity: int = 1 << 24):
         c = _c()
         self.name = name or f"sok_dynvar_{len(_variables)}"
         self.mode = "dynamic"
@@ -134,6 +143,18 @@ class DynamicVariable(Variable):
         self.states = {}
         self.sparse_grad = None
         self.last_touch = torch.zeros(init_capacity, dtype=torch.float64)
+        init_capacity = min(init_capacity, max_capacity)
+        if self.weight.shape[0] > init_capacity:
+            self.weight = self.weight[:init_capacity].clone()
+            self.last_touch = self.last_touch[:init_capacity].clone()
+        assert evict_strategy in ("lru", "lfu") and var_type in ("hbm", "hybrid")
+        self.evict_strategy, self.host_capacity = evict_strategy, host_capacity
+        self.last_used = torch.zeros(init_capacity, dtype=torch.int64)   # lookup clock per row
+        self.freq = torch.zeros(init_capacity, dtype=torch.int64)
+        self.clock = 0
+        self.host = None            # host tier, created at the first eviction of a hybrid variable
+        self.evictions = 0
+        self.promotions = 0
         self.vocab = -1
         self.shape = (-1, self.dim)
         _variables.append(self)
@@ -163,12 +184,86 @@ class DynamicVariable(Variable):
         lt = torch.zeros(new, dtype=torch.float64)
         lt[:cap] = self.last_touch
         self.last_touch = lt
+        for nm in ("last_used", "freq"):
+            t = torch.zeros(new, dtype=torch.int64)
+            t[:cap] = getattr(self, nm)
+            setattr(self, nm, t)
         del old
+
+    def _state_names(self):
+        return sorted(self.states.keys())
+
+    def _evict(self, n_new: int, protect: torch.Tensor):
+        """make room for ``n_new`` rows: keep the best-scored 3/4 of the capacity (minus the incoming
+        rows), demote / drop the rest and rebuild the key index compactly"""
+        if self.sparse_grad is not None:
+            raise RuntimeError(f"{self.name}: gradients of an earlier lookup are pending; apply them before a "
+                               "lookup that has to evict rows (row ids change on eviction)")
+        keys_all, rows_all = self.hash.dump()                      # CPU, ordered by row
+        n = keys_all.numel()
+        score = (self.last_used if self.evict_strategy == "lru" else self.freq)[rows_all].clone().double()
+        score += self.last_used[rows_all].double() * 1e-12          # lfu ties: older first
+        prot = torch.isin(keys_all, protect.cpu())
+        score[prot] = float("inf")
+        target = max(int(prot.sum()), min(n, int(self.max_capacity * 0.75) - n_new))
+        if target + n_new > self.max_capacity:
+            raise RuntimeError(f"{self.name}: one batch needs {target + n_new} rows, max_capacity is {self.max_capacity}")
+        order = torch.argsort(score, descending=True, stable=True)
+        keep, gone = order[:target], order[target:]
+        dev_rows = lambda idx: rows_all[idx].to(self.device)
+        if gone.numel() and self.var_type == "hybrid":
+            names = self._state_names()
+            if self.host is None:
+                from ..cache.hps import HostParameterServer
+                self.host = HostParameterServer(self.dim, num_states=len(names), capacity_rows=self.host_capacity)
+                self._host_states = names
+            self.host.push(keys_all[gone], self.weight[dev_rows(gone)].float().cpu(),
+                           [self.states[nm][dev_rows(gone)].float().cpu() for nm in self._host_states
+                            if nm in self.states])
+        self.evictions += int(gone.numel())
+        old_rows = dev_rows(keep)
+        w_keep = self.weight[old_rows].clone()
+        s_keep = {nm: st[old_rows].clone() for nm, st in self.states.items()}
+        meta = {nm: getattr(self, nm)[rows_all[keep]].clone() for nm in ("last_used", "freq", "last_touch")}
+        self.hash.clear()
+        new_rows = self.hash.get_insert(keys_all[keep].to(self.device))
+        self._init_rows(0, self.weight.shape[0])
+        self.weight[new_rows] = w_keep
+        for nm, st in self.states.items():
+            st.zero_()
+            st[new_rows] = s_keep[nm]
+        for nm, val in meta.items():
+            t = getattr(self, nm)
+            t.zero_()
+            t[new_rows.cpu()] = val
 
     def local_rows(self, keys: torch.Tensor, create: bool = True) -> torch.Tensor:
         k = keys.to(self.device).to(torch.int64)
-        rows = self.hash.get_insert(k) if create else self.hash.get(k)
+        if not create:
+            return self.hash.get(k)
+        fresh = None
+        if self.hash.size() + k.numel() > self.max_capacity or self.host is not None:
+            known = self.hash.get(k)
+            fresh = torch.unique(k[(known < 0) & (k >= 0)])
+            if self.hash.size() + fresh.numel() > self.max_capacity:
+                self._evict(int(fresh.numel()), torch.unique(k[k >= 0]))
+        rows = self.hash.get_insert(k)
         self._grow(self.hash.size())
+        if self.host is not None and fresh is not None and fresh.numel():
+            hrows = self.host._rows(fresh.cpu(), create=False)        # promote demoted rows, values intact
+            hit = hrows >= 0
+            if bool(hit.any()):
+                dst = self.hash.get(fresh[hit.to(fresh.device)])
+                self.weight[dst] = self.host._gather(self.host.w, hrows[hit]).to(self.device, self.weight.dtype)
+                for j, nm in enumerate(self._host_states):
+                    if nm in self.states:
+                        self.states[nm][dst] = self.host._gather(self.host.s[j], hrows[hit]).to(
+                            self.device, self.states[nm].dtype)
+                self.promotions += int(hit.sum())
+        self.clock += 1
+        r = rows[rows >= 0].cpu()
+        self.last_used[r] = self.clock
+        self.freq.index_add_(0, r, torch.ones_like(r))
         return rows
 
     def locate(self, keys):
@@ -181,6 +276,15 @@ class DynamicVariable(Variable):
     @property
     def size(self):
         return self.hash.size()
+
+    @property
+    def total_size(self):
+        """rows in HBM + rows that only live in the host tier"""
+        if self.host is None:
+            return self.hash.size()
+        hk, _ = self.host.items()
+        in_hbm, _ = self.hash.dump()
+        return int(self.hash.size() + (~torch.isin(hk, in_hbm)).sum())
 
 
 # ----------------------------------------------------------------------------- lookup

@@ -148,3 +148,62 @@ def test_kernel_summary_reads_static_resources_without_a_gpu():
     assert gemm and all(v["regs"] <= 255 and v["stack"] == 0 for v in gemm.values())   # no spills
     # the register-capped (3 blocks / SM) reduce+update kernels may spill a few words, never more
     assert all(v["stack"] <= 64 for k, v in kernel_summary("emb_bwd_reduce_update").items())
+
+
+def test_dynamic_variable_eviction_and_host_tier():
+    """HierarchicalKV semantics of sok.DynamicVariable: bounded HBM tier, LRU / LFU eviction, rows
+    demoted to the host tier come back with weights and optimizer state intact"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200 import sok
+    from hugectr_b200.parallel.comm import Comm
+    sok.init(Comm.single(torch.device("cpu")))
+    opt = sok.OptimizerWrapper(hugectr.Optimizer_t.AdaGrad, lr=0.1, initial_accu_value=0.0)
+
+    def step(v, keys):
+        out = sok.lookup_sparse(v, keys.view(-1, 1), combiners="sum")
+        (out * torch.arange(1, out.numel() + 1).view_as(out).float()).sum().backward()
+        opt.apply_gradients([v])
+
+    def snapshot(v, keys):
+        rows = v.local_rows(keys, create=False)
+        assert bool((rows >= 0).all())
+        return v.weight[rows].clone(), v.states["s0"][rows].clone()
+
+    v = sok.DynamicVariable(4, var_type="hybrid", initializer=0.5, init_capacity=16, max_capacity=64)
+    a, b = torch.arange(0, 48), torch.arange(100, 132)
+    step(v, a)
+    wa, sa = snapshot(v, a)
+    assert float((wa - 0.5).abs().min()) > 0 and float(sa.min()) > 0      # trained
+    step(v, b)                                    # 48 + 32 > 64: evicts 32 rows of `a` to the host tier
+    assert v.size <= 64 and v.evictions == 32 and v.host is not None
+    assert v.total_size == 80
+    resident = v.local_rows(a, create=False) >= 0
+    assert int(resident.sum()) == 16
+    out = sok.lookup_sparse(v, a.view(-1, 1), combiners="sum")        # promotes the 32 demoted rows
+    assert v.promotions == 32 and v.size <= 64
+    wa2, sa2 = snapshot(v, a)
+    assert torch.equal(wa, wa2) and torch.equal(sa, sa2)                # weights + AdaGrad state intact
+    assert torch.equal(out.detach(), wa)
+    v.sparse_grad = None
+
+    # pure HBM variable: evicted keys are forgotten and start from the initializer again
+    h = sok.DynamicVariable(4, var_type="hbm", initializer=0.5, init_capacity=16, max_capacity=64)
+    step(h, a)
+    step(h, b)
+    gone = a[h.local_rows(a, create=False) < 0]
+    assert gone.numel() == 32 and h.host is None
+    out = sok.lookup_sparse(h, gone.view(-1, 1), combiners="sum")
+    assert torch.equal(out.detach(), torch.full((32, 4), 0.5))
+    h.sparse_grad = None
+
+    # LFU: frequently used keys survive a sweep of one-off keys
+    f = sok.DynamicVariable(4, var_type="hbm", initializer=0.5, init_capacity=16, max_capacity=64,
+                            evict_strategy="lfu")
+    hot = torch.arange(0, 10)
+    for _ in range(5):
+        f.local_rows(hot)
+    for i in range(6):
+        f.local_rows(torch.arange(1000 + 20 * i, 1020 + 20 * i))
+    assert f.evictions > 0 and bool((f.local_rows(hot, create=False) >= 0).all())
+    with pytest.raises(RuntimeError, match="max_capacity"):
+        f.local_rows(torch.arange(5000, 5100))      # one batch larger than the tier
