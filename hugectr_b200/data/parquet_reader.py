@@ -59,7 +59,7 @@ class ParquetReader(IDataReader):
         n_slots = model.layout.total_slots
         if rp.slot_size_array and len(rp.slot_size_array) >= n_slots and model.sparse_embeddings:
             self.slot_offsets = np.concatenate([[0], np.cumsum(rp.slot_size_array[:n_slots])[:-1]]).astype("int64")
-        self.num_workers = max(1, min(rp.num_workers, 4))
+        self.num_workers = max(1, min(int(rp.num_workers), 8))      # row-group decode threads
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.thread = None
         self._stop = threading.Event()
@@ -80,40 +80,69 @@ class ParquetReader(IDataReader):
             lab, con, cat = list(range(nl)), list(range(nl, nl + nd)), list(range(nl + nd, nl + nd + ns))
         return lab, con, cat
 
-    def _produce(self):
+    def _decode_row_group(self, fp, rg, lab_i, con_i, cat_i):
+        """one row group -> (label [n, L], dense [n, D], per-slot (offsets|None, values), n); runs on the
+        row-group worker threads (reference RowGroupReadingThread, row_group_reading_thread.cpp)"""
+        import pyarrow as pa
         import pyarrow.parquet as pq
+        tl = self._tls
+        if getattr(tl, "path", None) != fp:
+            tl.path, tl.pf = fp, pq.ParquetFile(fp)
+        tbl = tl.pf.read_row_group(rg)
+        cols = [tbl.column(i) for i in range(tbl.num_columns)]
+        n = tbl.num_rows
+        lab = np.stack([cols[i].to_numpy().astype("float32") for i in lab_i], 1) \
+            if lab_i else np.zeros((n, 0), "float32")
+        den = np.stack([cols[i].to_numpy().astype("float32") for i in con_i], 1) \
+            if con_i else np.zeros((n, 0), "float32")
+        cats = []
+        for i in cat_i:
+            c = cols[i].combine_chunks()
+            if pa.types.is_list(c.type) or pa.types.is_large_list(c.type):
+                cats.append((c.offsets.to_numpy(), c.values.to_numpy().astype("int64")))
+            else:
+                cats.append((None, c.to_numpy().astype("int64")))
+        return (lab, den, cats, n)
+
+    def _row_groups(self, files):
+        import pyarrow.parquet as pq
+        counts = {}
+        while not self._stop.is_set():
+            for fp in files:
+                if fp not in counts:
+                    counts[fp] = pq.ParquetFile(fp).num_row_groups
+                for rg in range(counts[fp]):
+                    yield fp, rg
+            if not self.repeat:
+                return
+
+    def _produce(self):
+        """``num_workers`` threads decode row groups ahead of the batch assembler, which consumes them
+        strictly in file order (so the stream of batches does not depend on the worker count)"""
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
         try:
             files = read_file_list(self.file_list)
             lab_i, con_i, cat_i = self._columns(files)
             gb = self.b * self.world
             carry = None
-            while not self._stop.is_set():
-                for fp in files:
-                    pf = pq.ParquetFile(fp)
-                    for rg in range(pf.num_row_groups):
-                        tbl = pf.read_row_group(rg)
-                        cols = [tbl.column(i) for i in range(tbl.num_columns)]
-                        n = tbl.num_rows
-                        lab = np.stack([cols[i].to_numpy().astype("float32") for i in lab_i], 1) \
-                            if lab_i else np.zeros((n, 0), "float32")
-                        den = np.stack([cols[i].to_numpy().astype("float32") for i in con_i], 1) \
-                            if con_i else np.zeros((n, 0), "float32")
-                        cats = []
-                        for i in cat_i:
-                            c = cols[i].combine_chunks()
-                            import pyarrow as pa
-                            if pa.types.is_list(c.type) or pa.types.is_large_list(c.type):
-                                offs = c.offsets.to_numpy()
-                                vals = c.values.to_numpy().astype("int64")
-                                cats.append((offs, vals))
-                            else:
-                                cats.append((None, c.to_numpy().astype("int64")))
-                        chunk = (lab, den, cats, n)
-                        carry = self._emit(chunk, carry, gb)
-                        if self._stop.is_set():
-                            return
-                if not self.repeat:
-                    break
+            self._tls = threading.local()
+            pending = deque()
+            it = self._row_groups(files)
+            with ThreadPoolExecutor(max_workers=self.num_workers) as ex:
+                while not self._stop.is_set():
+                    while len(pending) < self.num_workers + 1:
+                        nxt = next(it, None)
+                        if nxt is None:
+                            break
+                        pending.append(ex.submit(self._decode_row_group, nxt[0], nxt[1], lab_i, con_i, cat_i))
+                    if not pending:
+                        break
+                    carry = self._emit(pending.popleft().result(), carry, gb)
+                for f in pending:
+                    f.cancel()
+            if self._stop.is_set():
+                return
             if carry is not None and carry[3] > 0 and not self.drop_incomplete:
                 self._emit_batch(carry, carry[3])
             self.q.put(None)

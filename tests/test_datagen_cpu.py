@@ -121,3 +121,39 @@ def test_csr_to_padded_matches_python_loop(odt):
         exp[i, 1, :c] = vals[offs[i]:offs[i] + c] + 17
     assert (blk == exp).all()
     assert (nz[1, :n] == np.minimum(cnt, H)).all() and nz[0].sum() == 0 and nz[2].sum() == 0 and nz[1, n:].sum() == 0
+
+
+def test_parquet_reader_stream_is_independent_of_the_worker_count(tmp_path):
+    """row groups are decoded by `num_workers` threads but consumed in file order"""
+    from types import SimpleNamespace as NS
+    import torch
+    from hugectr_b200.data.parquet_reader import ParquetReader
+    from hugectr_b200.data.readers import SparseLayout
+    p = DataGeneratorParams(hugectr.DataReaderType_t.Parquet, 1, 3, 4, True, str(tmp_path / "train.txt"),
+                            str(tmp_path / "val.txt"), [1000, 7, 50, 50000], nnz_array=[3, 1, 2, 4],
+                            num_files=3, eval_num_files=1, num_samples_per_file=70000)   # 2 row groups / file
+    DataGenerator(p).generate()
+    params = [NS(top_name=f"p{i}", slot_num=1, nnz_per_slot=[h], is_fixed_length=False)
+              for i, h in enumerate([3, 1, 2, 4])]
+
+    def stream(workers, rank):
+        m = NS(reader_params=NS(source=[p.source], eval_source=p.eval_source, slot_size_array=None,
+                                num_workers=workers),
+               b_train=4096, b_eval=4096, comm=NS(rank=rank), world=2,
+               solver=NS(repeat_dataset=False, drop_incomplete_batch=False),
+               input=NS(label_dim=1, dense_dim=3), layout=SparseLayout(params), key_dtype=torch.int64,
+               sparse_embeddings=[])
+        r = ParquetReader(m, True)
+        out = []
+        while True:
+            hb = r.read_a_batch()
+            if hb is None:
+                break
+            out.append((hb.label.clone(), hb.keys.clone(), hb.nnz.clone(), hb.num_valid, r.get_current_batchsize()))
+        r.stop()
+        return out
+    a, b = stream(1, 1), stream(6, 1)
+    assert len(a) == len(b) == -(-210000 // 8192)
+    for x, y in zip(a, b):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2]) and x[3:] == y[3:]
+    assert a[-1][4] == 210000 - 8192 * (len(a) - 1)          # incomplete last batch is delivered
