@@ -56,3 +56,36 @@ def test_cli(tmp_path, capsys):
     sizes = criteo2raw.main(["--train", a, "--out-dir", str(tmp_path / "o"), "--threads", "3"])
     assert len(sizes) == 26 and (tmp_path / "o" / "day_0.bin").stat().st_size == 200 * 160
     assert "slot_size_array" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("compressed", [False, True])
+def test_mlperf_numpy_days_to_raw(tmp_path, compressed):
+    """tools/convert_to_raw.py: memory-mapped day files -> train / val / test raw records"""
+    from hugectr_b200.tools import convert_to_raw as C
+    rng = np.random.default_rng(5)
+    hot = [3, 2, 1, 2, 6, 1, 1, 1, 1, 7, 3, 8, 1, 6, 9, 5, 1, 1, 1, 12, 100, 27, 10, 3, 1, 1]
+    days, rows = 3, [50, 70, 90]
+    data = []
+    for d in range(days):
+        n = rows[d]
+        lab = rng.integers(0, 2, n).astype(np.float32)
+        den = rng.random((n, 13), dtype=np.float32)
+        sp = {str(i): rng.integers(0, 1 << 20, (n, hot[i])).astype(np.int32) for i in range(26)}
+        np.save(tmp_path / f"day_{d}_labels.npy", lab)
+        np.save(tmp_path / f"day_{d}_dense.npy", den)
+        (np.savez_compressed if compressed else np.savez)(tmp_path / f"day_{d}_sparse_multi_hot.npz", **sp)
+        data.append((lab, den, sp))
+    if not compressed:
+        assert isinstance(C.npz_member(str(tmp_path / "day_0_sparse_multi_hot.npz"), "20"), np.memmap)
+    out = tmp_path / "out"
+    counts = C.main(["--input_dir_labels_and_dense", str(tmp_path), "--input_dir_sparse_multihot", str(tmp_path),
+                     "--output_dir", str(out), "--num_days", "3", "--split_point", "60", "--chunk_size", "16"])
+    assert counts == {"train": 120, "val": 60, "test": 30}
+
+    def rows_of(lab, den, sp, lo, hi):        # the straightforward per-row writer as the oracle
+        return b"".join(lab[i].tobytes() + den[i].tobytes() + b"".join(sp[str(f)][i].tobytes() for f in range(26))
+                        for i in range(lo, hi))
+    assert (out / "train_data.bin").read_bytes() == rows_of(*data[0], 0, 50) + rows_of(*data[1], 0, 70)
+    assert (out / "val_data.bin").read_bytes() == rows_of(*data[2], 0, 60)
+    assert (out / "test_data.bin").read_bytes() == rows_of(*data[2], 60, 90)
+    assert (out / "val_data.bin").stat().st_size == 60 * 4 * (1 + 13 + sum(hot))
