@@ -89,3 +89,40 @@ def test_mlperf_numpy_days_to_raw(tmp_path, compressed):
     assert (out / "val_data.bin").read_bytes() == rows_of(*data[2], 0, 60)
     assert (out / "test_data.bin").read_bytes() == rows_of(*data[2], 60, 90)
     assert (out / "val_data.bin").stat().st_size == 60 * 4 * (1 + 13 + sum(hot))
+
+
+def test_converted_raw_data_trains_dlrm_dcnv2(tmp_path):
+    """NumPy days -> convert_to_raw -> RawAsync reader -> DLRM-DCNv2 fit with evaluation (the MLPerf data
+    path end to end on a toy data set)"""
+    import torch
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.parallel.comm import Comm
+    from hugectr_b200.tools import convert_to_raw as C
+    rng = np.random.default_rng(9)
+    sizes = [50, 30, 20, 40] + [10] * 22
+    hot = [3, 2, 1, 2] + [1] * 22
+    for d in range(2):
+        n = 256
+        sp = {str(i): rng.integers(0, sizes[i], (n, hot[i])).astype(np.int32) for i in range(26)}
+        lab = (sp["2"][:, 0] % 2).astype(np.float32)            # learnable from the one-hot feature 2
+        np.save(tmp_path / f"day_{d}_labels.npy", lab)
+        np.save(tmp_path / f"day_{d}_dense.npy", rng.random((n, 13), dtype=np.float32))
+        np.savez(tmp_path / f"day_{d}_sparse_multi_hot.npz", **sp)
+    C.convert(str(tmp_path), str(tmp_path), str(tmp_path / "raw"), num_days=2, split_point=128, log=lambda *a: None)
+    m = build_dlrm_dcnv2(batchsize=64, batchsize_eval=64, num_gpus=1, table_sizes=sizes, multi_hot=hot,
+                         ev_size=8, mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                         lr=0.05, source=[str(tmp_path / "raw" / "train_data.bin")],
+                         comm=Comm.single(torch.device("cpu")), max_eval_batches=2)
+    m.reader_params.eval_source = str(tmp_path / "raw" / "val_data.bin")
+    m.reader_params.num_samples, m.reader_params.eval_num_samples = 256, 128
+    m.compile()
+    first = None
+    for it in range(300):
+        assert m.train()
+        if it == 0:
+            first = m.get_current_loss()
+    assert m.get_current_loss() < first * 0.8
+    for _ in range(2):
+        assert m.eval()
+    auc = dict(m.get_eval_metrics())["AUC"]
+    assert auc > 0.85, auc
