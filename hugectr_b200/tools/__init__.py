@@ -6,6 +6,6 @@ def __getattr__(name):
     if name in ("DataGenerator", "DataGeneratorParams"):
         m = importlib.import_module("hugectr_b200.data.generator")
         return getattr(m, name)
-    if name in ("planner", "workspace_calculator", "criteo2raw", "convert_to_raw"):
+    if name in ("planner", "workspace_calculator", "criteo2raw", "convert_to_raw", "embedding_gen"):
         return importlib.import_module(f"hugectr_b200.tools.{name}")
     raise AttributeError(name)

@@ -207,3 +207,15 @@ def test_dynamic_variable_eviction_and_host_tier():
     assert f.evictions > 0 and bool((f.local_rows(hot, create=False) >= 0).all())
     with pytest.raises(RuntimeError, match="max_capacity"):
         f.local_rows(torch.arange(5000, 5100))      # one batch larger than the tier
+
+
+def test_embedding_gen_tool_writes_a_loadable_checkpoint(tmp_path):
+    from hugectr_b200.io.checkpoint import iter_ebc_folder, read_ebc_folder
+    from hugectr_b200.tools import embedding_gen
+    embedding_gen.main(["--embedding-size", "1000-37-5", "--dim", "8", "--output", str(tmp_path)])
+    tabs = read_ebc_folder(str(tmp_path / "embedding_collection_0"))
+    assert sorted(tabs) == [0, 1, 2]
+    k, w, s = tabs[0]
+    assert torch.equal(k, torch.arange(1000)) and w.shape == (1000, 8) and s is None
+    assert float(w.abs().max()) <= 1 / 1000 ** 0.5 + 1e-7 and float(w.std()) > 0
+    assert sum(k.numel() for _, k, _, _ in iter_ebc_folder(str(tmp_path / "embedding_collection_0"), 100)) == 1042
