@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from ..enums import Optimizer_t, TrainPSType_t
+from ..enums import TrainPSType_t
 from ..embedding import ops as E
 from .gpu_cache import GpuCache
 

@@ -18,12 +18,12 @@ from __future__ import annotations
 
 import math
 import os
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from ..enums import CommunicationStrategy, CompressionStrategy, Optimizer_t
+from ..enums import CommunicationStrategy, Optimizer_t
 from ..solver import OptParamsPy
 from . import ops as E
 

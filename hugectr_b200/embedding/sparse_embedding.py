@@ -25,7 +25,6 @@ import numpy as np
 import torch
 
 from ..enums import Embedding_t, Optimizer_t, Update_t
-from ..utils import logger
 from . import ops as E
 from .hashtable import HashTable
 

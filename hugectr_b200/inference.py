@@ -5,7 +5,6 @@ and embedding tables and runs the eval network; embeddings may optionally be ser
 GPU hot-row cache (``use_gpu_embedding_cache`` + ``cache_size_percentage``)."""
 from __future__ import annotations
 
-import json
 from dataclasses import dataclass, field
 from typing import List, Optional
 

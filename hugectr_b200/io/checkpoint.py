@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import json
 import os
-import struct
 
 import numpy as np
 import torch

@@ -10,7 +10,6 @@ import math
 import torch
 import torch.nn.functional as F
 
-from ..enums import Initializer_t
 from ..ops import dense as D
 from .base import Layer, TorchLayer, make_init
 

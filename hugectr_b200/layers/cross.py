@@ -10,11 +10,10 @@ from __future__ import annotations
 
 import torch
 
-from ..enums import Initializer_t
 from ..ops import dense as D
 from ..ops import gemm as G
 from ..ops import interaction as I
-from .base import Layer, TorchLayer, make_init
+from .base import Layer, make_init
 
 
 class MultiCrossLayer(Layer):

@@ -11,10 +11,10 @@ from typing import List
 
 import torch
 
-from ..enums import Activation_t, Initializer_t
+from ..enums import Activation_t
 from ..ops import dense as D
 from ..ops import gemm as G
-from .base import Layer, TensorBag, make_init
+from .base import Layer, make_init
 
 
 def _ceil8(n):

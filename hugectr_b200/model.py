@@ -18,11 +18,10 @@ import torch
 
 from . import metrics as M
 from .data.batch import HostBatch
-from .data.readers import SparseLayout, SyntheticReader
+from .data.readers import SparseLayout
 from .embedding.collection import EmbeddingCollection, EmbeddingCollectionConfig
-from .enums import (DataReaderType_t, Embedding_t, Layer_t, MetricsRawType, MetricsType,
-                    Optimizer_t, Tensor_t, Update_t)
-from .layers import LOSS_LAYERS, BuildCtx, ParamArena, TensorBag
+from .enums import MetricsRawType, MetricsType, Optimizer_t, Tensor_t
+from .layers import BuildCtx, ParamArena, TensorBag
 from .lr_scheduler import LearningRateScheduler
 from .network import Network, insert_fanout_slices
 from .ops import dense as D

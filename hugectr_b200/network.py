@@ -10,9 +10,8 @@ from typing import Dict, List
 
 import torch
 
-from .enums import Layer_t, Regularizer_t
-from .layers import (LAYER_REGISTRY, LOSS_LAYERS, BuildCtx, Layer, ParamArena, Regularizer,
-                     TensorBag)
+from .enums import Layer_t
+from .layers import LAYER_REGISTRY, LOSS_LAYERS, BuildCtx, Layer, Regularizer, TensorBag
 from .solver import DenseLayer
 
 

@@ -9,7 +9,7 @@ Parity with the reference pybind wrappers:
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Sequence, Union
 
 from .enums import (Activation_t, Alignment_t, AllReduceAlgo, Check_t, DataReaderType_t,
                     DeviceLayout, Embedding_t, FcPosition_t, Initializer_t, Layer_t, LrPolicy_t,

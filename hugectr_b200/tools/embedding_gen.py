@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from ..io.checkpoint import FILE_HEAD_NBYTES, _file_head
+from ..io.checkpoint import _file_head
 
 
 def generate(table_sizes, dim, out_dir: str, i64_keys: bool = True, seed: int = 0, chunk_rows: int = 1 << 20):

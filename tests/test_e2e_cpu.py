@@ -1,5 +1,4 @@
 """End-to-end CPU smoke trainings of the BASELINE configs at reduced size + format round trips."""
-import json
 import os
 
 import numpy as np

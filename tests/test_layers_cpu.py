@@ -1,6 +1,5 @@
 """CPU numerics: every layer's fprop/bprop vs an independent PyTorch autograd oracle
 (pattern of test/utest/core23_layer_test/*.cpp: random host data -> op -> reference)."""
-import math
 
 import pytest
 import torch

@@ -1,5 +1,4 @@
 """GPU: native embedding kernels + full DLRM-DCNv2 step vs the fp32 PyTorch/CPU oracle."""
-import copy
 
 import pytest
 import torch

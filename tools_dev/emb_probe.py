@@ -1,5 +1,5 @@
 """Isolated embedding fwd/bwd timing on the DLRM-DCNv2 lookup shapes (1 GPU)."""
-import sys, time, torch
+import sys, torch
 sys.path.insert(0, ".")
 from hugectr_b200.embedding.collection import EmbeddingCollection, EmbeddingCollectionConfig, EmbeddingTableConfig
 from hugectr_b200.models.dlrm import CRITEO_TB_MULTI_HOT as H, CRITEO_TB_TABLE_SIZES as T
