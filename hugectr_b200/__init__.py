@@ -24,7 +24,7 @@ __version__ = "25.03.b200.1"
 def __getattr__(name):
     # lazy sub-namespaces: hugectr.tools / hugectr.data / hugectr.sok / hugectr.inference
     import importlib
-    if name in ("tools", "data", "sok", "onnx", "cache", "io", "parallel", "utils", "models", "inference"):
+    if name in ("tools", "data", "sok", "onnx", "cache", "io", "parallel", "utils", "models", "inference", "core23"):
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("Core23DataReader32", "Core23DataReader64", "DataReader32", "DataReader64"):
         from .data.readers import IDataReader     # reader handle classes (data_reader_wrapper.hpp:50-72)
