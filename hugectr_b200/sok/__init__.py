@@ -277,6 +277,28 @@ class DynamicVariable(Variable):
     def size(self):
         return self.hash.size()
 
+    def export(self):
+        """-> (keys, weights, {state name: rows}) of every row this rank holds: the HBM tier plus the rows
+        that currently live only in the host tier"""
+        k, r = self.hash.dump()
+        rd = r.to(self.device)
+        w = self.weight[rd].float().cpu()
+        sts = {nm: st[rd].float().cpu() for nm, st in self.states.items()}
+        if self.host is not None:
+            hk, hr = self.host.items()
+            only = ~torch.isin(hk, k)
+            if bool(only.any()):
+                hk, hr = hk[only], hr[only]
+                k = torch.cat([k, hk])
+                w = torch.cat([w, self.host._gather(self.host.w, hr)])
+                for j, nm in enumerate(self._host_states):
+                    if nm in sts:
+                        sts[nm] = torch.cat([sts[nm], self.host._gather(self.host.s[j], hr)])
+                for nm in sts:
+                    if nm not in self._host_states:      # state created after the tier: demoted rows have none
+                        sts[nm] = torch.cat([sts[nm], torch.zeros(int(only.sum()), self.dim)])
+        return k, w, sts
+
     @property
     def total_size(self):
         """rows in HBM + rows that only live in the host tier"""
@@ -518,9 +540,8 @@ def dump(path: str, variables: Sequence[Variable], optimizer: Optional[Optimizer
     for v in variables:
         keys = v.global_keys()
         if isinstance(v, DynamicVariable):
-            k, r = v.hash.dump()
-            keys, w = k, v.weight[r.to(v.device)].float().cpu()
-            sts = [v.states[s][r.to(v.device)].cpu() for s in ("s0", "s1") if s in v.states]
+            keys, w, sts = v.export()
+            sts = [sts[s] for s in ("s0", "s1") if s in sts]
         else:
             w = v.weight.float().cpu()
             sts = [v.states[s].cpu() for s in ("s0", "s1") if s in v.states]

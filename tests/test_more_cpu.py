@@ -185,6 +185,20 @@ def test_dynamic_variable_eviction_and_host_tier():
     assert torch.equal(wa, wa2) and torch.equal(sa, sa2)                # weights + AdaGrad state intact
     assert torch.equal(out.detach(), wa)
     v.sparse_grad = None
+    # a dump contains the HBM rows AND the rows that only live in the host tier (weights + slots)
+    import tempfile
+    d = tempfile.mkdtemp()
+    sok.dump(d, [v], opt)
+    from hugectr_b200.sok import _read
+    K = torch.from_numpy(_read(f"{d}/{v.name}-key").astype("int64"))
+    W = torch.from_numpy(_read(f"{d}/{v.name}-weight").copy())
+    S0 = torch.from_numpy(_read(f"{d}/{v.name}-slot0").copy())
+    assert K.numel() == v.total_size == 80 and torch.equal(K, torch.cat([a, b]))
+    assert torch.equal(W[:48], wa) and torch.equal(S0[:48], sa)
+    fresh = sok.DynamicVariable(4, var_type="hbm", initializer=0.0, init_capacity=16, max_capacity=128,
+                                name=v.name)
+    sok.load(d, [fresh], opt)
+    assert torch.equal(fresh.weight[fresh.local_rows(a, create=False)], wa)
 
     # pure HBM variable: evicted keys are forgotten and start from the initializer again
     h = sok.DynamicVariable(4, var_type="hbm", initializer=0.5, init_capacity=16, max_capacity=64)
