@@ -436,6 +436,7 @@ class EmbeddingCollection:
             if self.is_train:
                 self.grads_all = torch.zeros(self.world, max(self.grad_slab_elems, 1),
                                              dtype=self.act_dtype, device=dev)
+            self._build_packed_exchange()
         # named views
         self.key_views = {}
         for gl in self.glookups:
@@ -489,6 +490,39 @@ class EmbeddingCollection:
     def top_shapes(self):
         return {tp["name"]: ((self.b, tp["width"]) if tp["batch_major"] else (self.b, 1, tp["width"]))
                 for tp in self.tops}
+
+    def _build_packed_exchange(self):
+        """Collective (NCCL / gloo) path: every element of a requester's output slab is produced by
+        exactly one owner, and an owner needs only the gradient columns of its own lookups.  Instead
+        of shipping whole slabs (all-to-all of ``world`` full slabs forward, all-gather of full gradient
+        slabs backward -- ``world`` times the useful bytes) the owners' regions are packed: rank o sends
+        requester r the ``n_o`` elements it owns, r returns the ``n_o`` matching gradient elements.
+        The region lists are exchanged once here; ``HCTR_PACKED_EXCHANGE=0`` keeps the full-slab path."""
+        self.packed = None
+        if os.environ.get("HCTR_PACKED_EXCHANGE", "1") == "0" or self.hier:
+            return
+        mine = [(int(d.out_off), int(d.out_stride), int(d.grad_off), int(d.grad_stride), int(d.ev_size))
+                for grp in self.groups if grp.kind == "mp" for d in grp.lookups]
+        regions = self.comm.all_gather_object(mine)
+        dev, b = self.device, self.b
+        rows = torch.arange(b, dtype=torch.int64).view(b, 1)
+
+        def flat(off, stride, ev):
+            return (off + rows * stride + torch.arange(ev, dtype=torch.int64).view(1, ev)).reshape(-1)
+        oidx, gidx = [], []
+        for regs in regions:
+            oidx.append(torch.cat([flat(o, s, e) for (o, s, _, _, e) in regs]) if regs
+                        else torch.zeros(0, dtype=torch.int64))
+            gidx.append(torch.cat([flat(g, gs, e) for (_, _, g, gs, e) in regs]) if regs
+                        else torch.zeros(0, dtype=torch.int64))
+        n = [int(x.numel()) for x in oidx]
+        self.packed = {
+            "n": n, "n_me": n[self.rank],
+            "out_me": oidx[self.rank].to(dev), "out_all": torch.cat(oidx).to(dev),
+            "grad_me": gidx[self.rank].to(dev), "grad_all": torch.cat(gidx).to(dev),
+            "fwd_recv": torch.zeros(max(sum(n), 1), dtype=self.act_dtype, device=dev),
+            "bwd_recv": torch.zeros(max(self.world * n[self.rank], 1), dtype=self.act_dtype, device=dev),
+        }
 
     def set_keys(self, feature_major_keys: torch.Tensor):
         """Copy a whole feature-major key batch into the key slab (H2D lands here directly)."""
@@ -601,6 +635,12 @@ class EmbeddingCollection:
             else:
                 if self.hier:
                     self.out_slab.copy_(self.comm.hier_all_to_all_sum(self.send_out))
+                elif self.packed is not None:
+                    pk = self.packed
+                    send = self.send_out.index_select(1, pk["out_me"]).reshape(-1)        # [world * n_me]
+                    recv = pk["fwd_recv"][:sum(pk["n"])]
+                    self.comm.all_to_all_v(recv, send, pk["n"], [pk["n_me"]] * self.world)
+                    self.out_slab.index_copy_(0, pk["out_all"], recv)
                 else:
                     self.comm.all_to_all(self.recv_out, self.send_out)
                     # each (rank, lookup) region of my slab is written by exactly one owner
@@ -704,6 +744,13 @@ class EmbeddingCollection:
                 pass
             elif self.hier:
                 self.comm.hier_all_gather(self.grads_all, self.grad_slab)
+            elif getattr(self, "packed", None) is not None:
+                pk = self.packed
+                send = self.grad_slab.index_select(0, pk["grad_all"])                    # chunks per owner
+                recv = pk["bwd_recv"][:self.world * pk["n_me"]]
+                self.comm.all_to_all_v(recv, send, [pk["n_me"]] * self.world, pk["n"])
+                if pk["n_me"]:
+                    self.grads_all.index_copy_(1, pk["grad_me"], recv.view(self.world, pk["n_me"]))
             else:
                 self.comm.all_gather(self.grads_all, self.grad_slab)
         for grp in mp_groups:

@@ -121,6 +121,34 @@ class Comm:
             for j in range(n):
                 out[j].copy_(gl[j][self.rank].to(out.dtype))
 
+    def all_to_all_v(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits):
+        """variable-size all-to-all of flat tensors: ``inp`` = concatenation of the chunks for ranks
+        0..n-1 (``in_splits`` elements each), ``out`` = concatenation of the chunks received from them
+        (``out_splits``).  NCCL: one ``all_to_all_single`` with split sizes; gloo: padded all-gather."""
+        if self.world_size == 1:
+            out.copy_(inp)
+        elif inp.is_cuda:
+            dist.all_to_all_single(out, inp.contiguous(), [int(x) for x in out_splits],
+                                   [int(x) for x in in_splits], group=self.group)
+        else:
+            # every rank broadcasts its chunks padded to its own widest one; receivers keep their row
+            src = inp.float() if inp.dtype == torch.bfloat16 else inp
+            mx = torch.tensor([int(max(max(in_splits), 1))])
+            widths = [torch.zeros_like(mx) for _ in range(self.world_size)]
+            dist.all_gather(widths, mx, group=self.group)
+            o_out = 0
+            for r in range(self.world_size):
+                blk = torch.zeros(self.world_size, int(widths[r]), dtype=src.dtype)
+                if r == self.rank:
+                    o = 0
+                    for dst, n in enumerate(in_splits):
+                        blk[dst, :n] = src[o:o + n]
+                        o += n
+                dist.broadcast(blk, r, group=self.group)
+                n = int(out_splits[r])
+                out[o_out:o_out + n].copy_(blk[self.rank, :n].to(out.dtype))
+                o_out += n
+
     def reduce_scatter(self, out: torch.Tensor, inp: torch.Tensor):
         if self.world_size == 1:
             out.copy_(inp.view_as(out))

@@ -191,3 +191,10 @@ def test_embedding_collection_benchmark_script_gloo():
 def test_symmetric_heap_failure_is_agreed_on_by_all_ranks_gloo():
     out = _run(3, ["symmfail"], 29791, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "SYMMFAIL_OK" in out, out[-2000:]
+
+
+@pytest.mark.dist
+def test_full_slab_exchange_still_selectable_gloo():
+    """HCTR_PACKED_EXCHANGE=0: whole-slab all-to-all / all-gather instead of the packed owner regions"""
+    out = _run(2, ["fuzz", "301,302,303"], 29795, env={"CUDA_VISIBLE_DEVICES": "", "HCTR_PACKED_EXCHANGE": "0"})
+    assert out.count("FUZZ_OK") == 3, out[-2000:]
