@@ -503,7 +503,11 @@ class EmbeddingCollection:
             return
         mine = [(int(d.out_off), int(d.out_stride), int(d.grad_off), int(d.grad_stride), int(d.ev_size))
                 for grp in self.groups if grp.kind == "mp" for d in grp.lookups]
-        regions = self.comm.all_gather_object(mine)
+        # key blocks [key_off, key_off + b * hotness) of the lookups this rank serves
+        kmine = sorted({(int(self.glookups[gi]["key_off"]), int(self.b * self.glookups[gi]["hotness"]))
+                        for grp in self.groups if grp.kind == "mp" for (gi, _) in getattr(grp, "lookup_gl", [])})
+        both = self.comm.all_gather_object((mine, kmine))
+        regions, kregions = [x[0] for x in both], [x[1] for x in both]
         dev, b = self.device, self.b
         rows = torch.arange(b, dtype=torch.int64).view(b, 1)
 
@@ -516,7 +520,12 @@ class EmbeddingCollection:
             gidx.append(torch.cat([flat(g, gs, e) for (_, _, g, gs, e) in regs]) if regs
                         else torch.zeros(0, dtype=torch.int64))
         n = [int(x.numel()) for x in oidx]
+        kidx = [torch.cat([torch.arange(o, o + ln, dtype=torch.int64) for (o, ln) in regs]) if regs
+                else torch.zeros(0, dtype=torch.int64) for regs in kregions]
+        kn = [int(x.numel()) for x in kidx]
         self.packed = {
+            "kn": kn, "kn_me": kn[self.rank], "key_me": kidx[self.rank].to(dev), "key_all": torch.cat(kidx).to(dev),
+            "key_recv": torch.zeros(max(self.world * kn[self.rank], 1), dtype=self.key_dtype, device=dev),
             "n": n, "n_me": n[self.rank],
             "out_me": oidx[self.rank].to(dev), "out_all": torch.cat(oidx).to(dev),
             "grad_me": gidx[self.rank].to(dev), "grad_all": torch.cat(gidx).to(dev),
@@ -557,6 +566,13 @@ class EmbeddingCollection:
                 self.comm.hier_all_gather(self.keys_all, self.key_slab)
                 if self.nnz_all is not None:
                     self.comm.hier_all_gather(self.nnz_all, self.nnz_slab)
+            elif getattr(self, "packed", None) is not None and self.nnz_all is None:
+                pk = self.packed        # every owner receives only the key blocks of the lookups it serves
+                send = self.key_slab.index_select(0, pk["key_all"])
+                recv = pk["key_recv"][:self.world * pk["kn_me"]]
+                self.comm.all_to_all_v(recv, send, [pk["kn_me"]] * self.world, pk["kn"])
+                if pk["kn_me"]:
+                    self.keys_all.index_copy_(1, pk["key_me"], recv.view(self.world, pk["kn_me"]))
             else:
                 self.comm.all_gather(self.keys_all, self.key_slab)
                 if self.nnz_all is not None:
