@@ -75,6 +75,11 @@ class Model:
         self._iter = 0
         self.mixed = bool(solver.use_mixed_precision)
         self.act_dtype = torch.bfloat16 if self.mixed else torch.float32
+        if solver.enable_tf32_compute and not self.mixed:
+            # fp32 models: GEMMs of the fp32 path (library matmul) may use TF32 tensor cores, as the
+            # reference's enable_tf32_compute does for cuBLAS (fully_connected_layer.cu compute types)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
         self.key_dtype = torch.int64 if solver.i64_input_key else torch.int32
         self.launches_per_step = 0
 
