@@ -159,6 +159,23 @@ class Model:
         t[inp.dense_name] = den
         return t
 
+    def _apply_device_layout(self, cfg):
+        """``DeviceLayout.NodeFirst`` (device_map.hpp:76-115): row ``local * num_nodes + node`` of a
+        shard matrix describes GPU ``local`` of node ``node``.  Ranks here are node-major
+        (``node * gpus_per_node + local``), so the rows are permuted once into rank order."""
+        s = self.solver
+        if getattr(s.device_layout, "name", s.device_layout) != "NodeFirst" or len(s.vvgpu) < 2 \
+                or cfg.shard_matrix is None or getattr(cfg, "_layout_applied", False):
+            return cfg
+        from .parallel.comm import DeviceMap
+        dm = DeviceMap(s.vvgpu, "NodeFirst")
+        gpn = len(s.vvgpu[0])
+        rows = [cfg.shard_matrix[dm.get_global_id(r % gpn, r // gpn)] for r in range(len(cfg.shard_matrix))]
+        import copy
+        out = copy.copy(cfg)
+        out.shard_matrix, out._layout_applied = rows, True
+        return out
+
     def _build_embeddings(self):
         s = self.solver
         hot = {p.top_name: max(p.nnz_per_slot) for p in self.input.data_reader_sparse_param_array}
@@ -174,6 +191,7 @@ class Model:
                         raise KeyError(f"embedding_lookup bottom '{bname}' is not a sparse input")
                     if prm[0].slot_num != 1:
                         raise ValueError("EmbeddingCollection requires slot_num == 1 per sparse param")
+            cfg = self._apply_device_layout(cfg)
             e = EmbeddingCollection(cfg, self.b_train, hot, self.device, self.act_dtype, self.comm,
                                     self.opt_params, self.key_dtype,
                                     scaler=s.scaler if self.mixed else 1.0, state_dtype=state_dtype,

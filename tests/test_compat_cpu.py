@@ -97,3 +97,18 @@ def test_cache_eval_data_replays_the_resident_round():
         rounds.append(m.get_eval_metrics()[0][1])
     assert len(calls) == 3                       # only the first round touched the source
     assert rounds[0] == rounds[1] == rounds[2]   # identical resident data, untrained model
+
+
+def test_node_first_device_layout_permutes_the_shard_matrix():
+    import hugectr_b200 as hugectr
+    from types import SimpleNamespace as NS
+    from hugectr_b200.model import Model
+    sm = [[g] for g in range(6)]                       # row g marks "global id g"
+    cfg = NS(shard_matrix=sm)
+    fake = NS(solver=NS(device_layout=hugectr.DeviceLayout.NodeFirst, vvgpu=[[0, 1, 2], [0, 1, 2]]))
+    out = Model._apply_device_layout(fake, cfg)
+    # rank r = node * 3 + local  ->  NodeFirst global id = local * 2 + node
+    assert [row[0] for row in out.shard_matrix] == [0, 2, 4, 1, 3, 5]
+    assert Model._apply_device_layout(fake, out) is out                         # applied once
+    fake.solver.device_layout = hugectr.DeviceLayout.LocalFirst
+    assert Model._apply_device_layout(fake, cfg) is cfg
