@@ -187,6 +187,12 @@ def _parallel_plan(model, ebc, name):
             seen.add((rid, p["col0"]))
             rowsets[rid]["cols"] += p["width"]
             writers.append(dict(rank=r, idx=i, rid=rid, col0=p["col0"], width=p["width"]))
+    # column windows are written through a shared memory map; across hosts (network file systems flush
+    # whole pages of a mapping) only contiguous full-width row windows, written with pwrite, are safe
+    multi_host = int(getattr(model.comm, "num_nodes", 1) or 1) > 1 or \
+        os.environ.get("HCTR_EBC_DUMP_MULTIHOST", "0") == "1"
+    if multi_host and any(w["width"] != ev for w in writers):
+        return None
     off = 0
     for rs in rowsets.values():
         if rs["cols"] != ev:
@@ -217,24 +223,43 @@ def _dump_table_parallel(model, ebc, name, tid, folder, plan, kd):
     need = {w["idx"] for w in mine} | keyw
     if need and n > 0:
         parts = ebc.dump_table_local(name, only=need)
-        mk = np.memmap(files["key"][0], dtype=kd, mode="r+", offset=FILE_HEAD_NBYTES, shape=(n,))
-        mw = np.memmap(files["weight"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES, shape=(n, ev))
-        mo = np.memmap(files["opt"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES,
-                       shape=(ns, n, ev)) if ns else None
+
+        def pwrite_rows(path, arr, row_off, row_bytes):
+            """contiguous rows [row_off, ...) of a [n, row_bytes] payload: plain positional writes"""
+            buf = memoryview(np.ascontiguousarray(arr)).cast("B")
+            fd = os.open(path, os.O_WRONLY)
+            try:
+                pos, off0 = 0, FILE_HEAD_NBYTES + row_off * row_bytes
+                while pos < len(buf):
+                    pos += os.pwrite(fd, buf[pos:pos + (1 << 30)], off0 + pos)
+            finally:
+                os.close(fd)
         for rs in plan["rowsets"].values():
             if rs["keyw"][0] == rank and rs["rows"]:
-                mk[rs["off"]:rs["off"] + rs["rows"]] = parts[rs["keyw"][1]][0].numpy().astype(kd)
+                pwrite_rows(files["key"][0], parts[rs["keyw"][1]][0].numpy().astype(kd), rs["off"], kb)
+        strided = [w for w in mine if w["width"] != ev and plan["rowsets"][w["rid"]]["rows"]]
+        mw = mo = None
+        if strided:        # column windows of a column-sharded table (single host): strided map writes
+            mw = np.memmap(files["weight"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES, shape=(n, ev))
+            mo = np.memmap(files["opt"][0], dtype="<f4", mode="r+", offset=FILE_HEAD_NBYTES,
+                           shape=(ns, n, ev)) if ns else None
         for w in mine:
             rs = plan["rowsets"][w["rid"]]
             if not rs["rows"]:
                 continue
             keys, W, c0, sts, kind = parts[w["idx"]]
             lo, hi = rs["off"], rs["off"] + rs["rows"]
-            mw[lo:hi, c0:c0 + W.shape[1]] = W.numpy()
-            for i, st in enumerate(sts):
-                if st is not None and mo is not None:
-                    mo[i, lo:hi, c0:c0 + W.shape[1]] = st.numpy()
-        for m in (mk, mw, mo):
+            if w["width"] == ev:
+                pwrite_rows(files["weight"][0], W.numpy().astype("<f4"), lo, ev * 4)
+                for i, st in enumerate(sts):
+                    if st is not None and ns:
+                        pwrite_rows(files["opt"][0], st.numpy().astype("<f4"), i * n + lo, ev * 4)
+            else:
+                mw[lo:hi, c0:c0 + W.shape[1]] = W.numpy()
+                for i, st in enumerate(sts):
+                    if st is not None and mo is not None:
+                        mo[i, lo:hi, c0:c0 + W.shape[1]] = st.numpy()
+        for m in (mw, mo):
             if m is not None:
                 m.flush()
     model.comm.barrier()
