@@ -2,8 +2,9 @@
 NCF (GMF / MLP / NeuMF), MMoE (multi-task), DIN-style target attention and BST-style transformer
 over a behaviour sequence.
 
-Reference architectures: samples/ncf/{gmf,ncf,neumf}.py, samples/mmoe/mmoe_parquet.py,
-samples/din/din_parquet.py, samples/bst/bst_avg_pooling.py.  Every builder returns an un-compiled
+Reference architectures: samples/ncf/{gmf,ncf,neumf}.py, samples/mmoe/{mmoe_parquet,shared_bottom}.py,
+samples/din/din_parquet.py, samples/bst/bst_avg_pooling.py, samples/criteo/criteo_parquet.py (plain DNN),
+samples/ftrl/dlrm_train_ftrl.py (DLRM-DCNv2 over an embedding collection trained with FTRL).  Every builder returns an un-compiled
 ``Model``; ``source="synthetic"`` trains on generated batches (no files needed).
 """
 from __future__ import annotations
@@ -129,6 +130,72 @@ def build_mmoe(batchsize: int = 1024, num_slots: int = 32, vocab: int = 2000, ev
         model.add(hugectr.DenseLayer(L.InnerProduct, [cur], [f"logit{t}"], num_output=1))
         model.add(hugectr.DenseLayer(L.BinaryCrossEntropyLoss, [f"logit{t}", names[t]], [f"loss{t}"]))
     return model
+
+
+def build_shared_bottom(batchsize: int = 1024, num_slots: int = 32, vocab: int = 2000, ev: int = 16,
+                        shared_dims: Sequence[int] = (128, 256), tower_dim: int = 64, num_tasks: int = 2,
+                        source="synthetic", eval_source="synthetic", fmt=hugectr.DataReaderType_t.Parquet,
+                        lr: float = 0.001, vvgpu=None, mixed: bool = False, comm=None,
+                        **solver_kw) -> "hugectr.Model":
+    """Shared-bottom multi-task baseline of the MMoE sample: one shared MLP, fanned out (the graph
+    compiler inserts the Slice) into one tower + BCE loss per task."""
+    slots = [vocab] * num_slots
+    solver = _solver(batchsize, lr, vvgpu, mixed, **solver_kw)
+    opt = hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.Global)
+    model = hugectr.Model(solver, _reader(source, eval_source, fmt, slots), opt, comm=comm)
+    names = [f"label{t}" for t in range(num_tasks)]
+    model.add(hugectr.Input(label_dim=[1] * num_tasks, label_name=names, dense_dim=0, dense_name="dense",
+                            data_reader_sparse_param_array=[
+                                hugectr.DataReaderSparseParam("data", 1, True, num_slots)]))
+    model.add(hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash,
+                                      workspace_size_per_gpu_in_mb=max(1, (sum(slots) * ev * 4 * 3) >> 20),
+                                      embedding_vec_size=ev, combiner="sum", sparse_embedding_name="emb",
+                                      bottom_name="data", slot_size_array=slots, optimizer=opt))
+    model.add(hugectr.DenseLayer(L.Reshape, ["emb"], ["x"], leading_dim=num_slots * ev))
+    cur = "x"
+    for i, n in enumerate(shared_dims):
+        cur = _fc(model, cur, f"shared{i}", n, dropout=0.1)
+    for t in range(num_tasks):
+        tw = _fc(model, cur, f"tower{t}", tower_dim, dropout=0.1)
+        model.add(hugectr.DenseLayer(L.InnerProduct, [tw], [f"logit{t}"], num_output=1))
+        model.add(hugectr.DenseLayer(L.BinaryCrossEntropyLoss, [f"logit{t}", names[t]], [f"loss{t}"]))
+    return model
+
+
+def build_criteo_dnn(batchsize: int = 16384, num_slots: int = 26, vocab: int = 10000, ev: int = 64,
+                     hidden: Sequence[int] = (200, 200, 200), source="synthetic", eval_source="synthetic",
+                     fmt=hugectr.DataReaderType_t.Parquet, lr: float = 0.001, vvgpu=None, mixed: bool = False,
+                     comm=None, **solver_kw) -> "hugectr.Model":
+    """The plain Criteo DNN sample: categorical features only -> summed embeddings per slot -> MLP."""
+    slots = [vocab] * num_slots
+    solver = _solver(batchsize, lr, vvgpu, mixed, **solver_kw)
+    opt = hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.Global)
+    model = hugectr.Model(solver, _reader(source, eval_source, fmt, slots), opt, comm=comm)
+    model.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=0, dense_name="dense",
+                            data_reader_sparse_param_array=[
+                                hugectr.DataReaderSparseParam("data1", 1, True, num_slots)]))
+    model.add(hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash,
+                                      workspace_size_per_gpu_in_mb=max(1, (sum(slots) * ev * 4 * 3) >> 20),
+                                      embedding_vec_size=ev, combiner="sum",
+                                      sparse_embedding_name="sparse_embedding1", bottom_name="data1",
+                                      slot_size_array=slots, optimizer=opt))
+    model.add(hugectr.DenseLayer(L.Reshape, ["sparse_embedding1"], ["reshape1"], leading_dim=num_slots * ev))
+    cur = "reshape1"
+    for i, n in enumerate(hidden):
+        cur = _fc(model, cur, f"fc{i + 1}", n)
+    model.add(hugectr.DenseLayer(L.InnerProduct, [cur], ["logit"], num_output=1))
+    model.add(hugectr.DenseLayer(L.BinaryCrossEntropyLoss, ["logit", "label"], ["loss"]))
+    return model
+
+
+def build_dlrm_ftrl(batchsize: int = 8192, num_gpus: int = 1, **kw) -> "hugectr.Model":
+    """DLRM-DCNv2 over an embedding collection with the FTRL sparse / dense optimizer (samples/ftrl)."""
+    from .dlrm import build_dlrm_dcnv2
+    m = build_dlrm_dcnv2(batchsize=batchsize, num_gpus=num_gpus, **kw)
+    ftrl = hugectr.CreateOptimizer(hugectr.Optimizer_t.Ftrl, hugectr.Update_t.Global, beta=0.9,
+                                   lambda1=0.1, lambda2=0.1)
+    m.opt_params = ftrl
+    return m
 
 
 # ----------------------------------------------------------------------------------------- DIN

@@ -113,3 +113,27 @@ def test_onnx_converter_matches_model_predictions(name, tmp_path):
         out = g(dense, *ins).reshape(-1)
     torch.testing.assert_close(out, pred, atol=1e-6, rtol=1e-5)
     assert os.path.exists(pre + ".onnx") or os.path.exists(pre + ".onnx.pt")
+
+
+def test_shared_bottom_multitask_uses_an_automatic_fanout():
+    m = zoo.build_shared_bottom(batchsize=64, num_slots=6, vocab=100, ev=8, shared_dims=(32, 16), tower_dim=8,
+                                comm=CPU(), max_eval_batches=1)
+    losses = _train(m, 12)
+    assert len(m.net_train.loss_layers) == 2 and len(losses) == 12
+    assert any(l.cfg.layer_type.name == "Slice" for l in m.net_train.layers)     # inserted by the compiler
+
+
+def test_criteo_dnn():
+    losses = _train(zoo.build_criteo_dnn(batchsize=64, num_slots=5, vocab=200, ev=8, hidden=(32, 16),
+                                         comm=CPU(), max_eval_batches=1), 12)
+    assert len(losses) == 12          # random synthetic labels: finite losses are what _train checks
+
+
+def test_dlrm_dcnv2_with_ftrl():
+    import hugectr_b200 as hugectr
+    m = zoo.build_dlrm_ftrl(batchsize=32, num_gpus=1, table_sizes=[50, 40, 30], multi_hot=[2, 1, 1], ev_size=8,
+                            mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                            comm=CPU(), max_eval_batches=1)
+    assert m.opt_params.optimizer_type == hugectr.Optimizer_t.Ftrl
+    losses = _train(m, 10)
+    assert np.isfinite(losses).all()
