@@ -1,6 +1,6 @@
 """Train one of the sample model families on synthetic data.
 
-  python samples/model_zoo_train.py {ncf-gmf,ncf-mlp,ncf-neumf,mmoe,din,bst,dcn,deepfm,wdl} [--iters N]
+  python samples/model_zoo_train.py {ncf-gmf,ncf-mlp,ncf-neumf,mmoe,shared-bottom,din,bst,dcn,deepfm,wdl,criteo-dnn,dlrm-ftrl} [--iters N]
 
 (reference: samples/ncf, samples/mmoe, samples/din, samples/bst, samples/dcn, samples/deepfm, samples/wdl)
 """
@@ -24,7 +24,10 @@ builders = {"ncf-gmf": lambda: models.build_ncf("gmf", batchsize=a.batchsize),
             "bst": lambda: models.build_bst(batchsize=a.batchsize),
             "dcn": lambda: models.build_dcn(batchsize=a.batchsize),
             "deepfm": lambda: models.build_deepfm(batchsize=a.batchsize),
-            "wdl": lambda: models.build_wdl(batchsize=a.batchsize)}
+            "wdl": lambda: models.build_wdl(batchsize=a.batchsize),
+            "shared-bottom": lambda: models.build_shared_bottom(batchsize=a.batchsize),
+            "criteo-dnn": lambda: models.build_criteo_dnn(batchsize=a.batchsize),
+            "dlrm-ftrl": lambda: models.build_dlrm_ftrl(batchsize=a.batchsize, table_sizes=[100000] * 26)}
 m = builders[a.model]()
 m.compile()
 m.summary()
