@@ -286,7 +286,6 @@ def dense_opt_reference(opt, w, g, w16, s0, s1, lr, step, hp, zero_grad=True):
         n_new = s1 + gg * gg
         s0.add_(gg + ((s1 + fb).sqrt() - (n_new + fb).sqrt()) * w / lr)
         s1.copy_(n_new)
-        p = torch.sign(s0) * l1 - s0
         p = torch.where(s0 > 0, l1 - s0, -l1 - s0)
         q = (n_new + fb).sqrt() / lr + l2
         w.copy_(torch.where(s0.abs() > l1, p / q, torch.zeros_like(w)))

@@ -250,7 +250,10 @@ def run_fuzz(seed):
                 strat_mp.append((str(i), world))
         st = ([("mp", strat_mp)] if strat_mp else []) + ([("dp", strat_dp)] if strat_dp else [])
         cfg.shard(sm, st)
-    opt = CreateOptimizer(Optimizer_t.SGD)
+    adagrad = rnd.random() < 0.5          # non-linear rule: exercises the reduce-then-update order and
+    opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.0, epsilon=1e-7) if adagrad \
+        else CreateOptimizer(Optimizer_t.SGD)    # the optimizer-state windows of column / row shards
+    S = [torch.zeros(vocab[i], ev[i]) for i in range(nt)]
     hotd = {f"d{i}": hot[i] for i in range(nt)}
     e = EmbeddingCollection(cfg, b, hotd, dev, torch.float32, comm, opt, key_dtype=torch.int64, seed=3)
     gen = torch.Generator().manual_seed(int(seed))
@@ -306,7 +309,12 @@ def run_fuzz(seed):
                 g_ = G[i].unsqueeze(1).expand(b * world, hot[i], ev[i])
                 if comb[i] == "mean":
                     g_ = g_ / valid.sum(1).clamp(min=1).view(-1, 1, 1)
-            W[i].index_add_(0, k[valid], -lr * g_[valid])
+            if not adagrad:
+                W[i].index_add_(0, k[valid], -lr * g_[valid])
+            else:
+                Gr = torch.zeros_like(W[i]).index_add_(0, k[valid], g_[valid])      # reduce per row first
+                S[i] += Gr * Gr
+                W[i] -= lr * Gr / (S[i].sqrt() + 1e-7)
     for i in range(nt):
         for (k, w, c0, sts, kind) in e.dump_table_local(str(i)):
             if len(k):
@@ -514,6 +522,26 @@ def run_equiv(optimizer="sgd", gpus_per_node=0):
     sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]
     sm[world - 1][3] = 1
     plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+    if os.environ.get("HCTR_TEST_PLAN_SEED"):
+        # random placement per table: table-wise, row-wise, column-wise (x row-wise) or data-parallel
+        import random
+        rnd = random.Random(int(os.environ["HCTR_TEST_PLAN_SEED"]))
+        sm = [[0] * len(sizes) for _ in range(world)]
+        mp, dp = [], []
+        for t in range(len(sizes)):
+            kind = rnd.choice(["table", "row", "col", "dp"])
+            if kind == "table":
+                sm[rnd.randrange(world)][t] = 1
+            else:
+                for g in range(world):
+                    sm[g][t] = 1
+            if kind == "dp":
+                dp.append(str(t))
+            elif kind == "col" and world % 2 == 0:
+                mp.append((str(t), 2))
+            else:
+                mp.append(str(t))
+        plan = (sm, ([("mp", mp)] if mp else []) + ([("dp", dp)] if dp else []))
     hkw = {}
     if gpus_per_node:
         # logical nodes: hierarchical two-stage exchange (intra-node reduce, inter-node same-local-id)
@@ -566,7 +594,8 @@ def run_equiv(optimizer="sgd", gpus_per_node=0):
                 if len(keys) == 0:
                     continue
                 idx = torch.searchsorted(rk, keys.cpu())
-                d = (rv[idx] - vals[:, :ev].cpu()).abs().max().item()
+                w = min(vals.shape[1], ev - col0)
+                d = (rv[idx][:, col0:col0 + w] - vals[:, :w].cpu()).abs().max().item()
                 assert d < 2e-3, f"table {name} differs: {d}"
     comm.barrier()
     if rank == 0:

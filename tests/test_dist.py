@@ -198,3 +198,12 @@ def test_full_slab_exchange_still_selectable_gloo():
     """HCTR_PACKED_EXCHANGE=0: whole-slab all-to-all / all-gather instead of the packed owner regions"""
     out = _run(2, ["fuzz", "301,302,303"], 29795, env={"CUDA_VISIBLE_DEVICES": "", "HCTR_PACKED_EXCHANGE": "0"})
     assert out.count("FUZZ_OK") == 3, out[-2000:]
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc,seed", [(2, 11), (4, 12)])
+def test_multi_rank_equals_single_process_random_plan_gloo(nproc, seed):
+    """whole-model training under a random table / row / column / dp placement == single process (AdaGrad)"""
+    out = _run(nproc, ["equiv", "adagrad"], 29800 + seed,
+               env={"CUDA_VISIBLE_DEVICES": "", "HCTR_TEST_PLAN_SEED": str(seed)})
+    assert "EQUIV_OK" in out, out[-2000:]
