@@ -435,3 +435,47 @@ def test_heterogeneous_planner_properties():
     from hugectr_b200.tools import planner
     sm, st = planner.main(["--num-gpus", "8", "--ev-sizes", ",".join(["128"] * 26)])
     assert len(sm) == 8 and len(sm[0]) == 26
+
+
+def test_planners_property_based():
+    """hypothesis: any table set -> both planners return a plan the collection accepts, every table is
+    placed, column factors divide widths and shard counts, data-parallel tables sit on every GPU"""
+    from hypothesis import given, settings, strategies as st
+    from hugectr_b200.embedding.collection import (EmbeddingCollectionConfig, EmbeddingTableConfig,
+                                                   resolve_placement)
+    from hugectr_b200.tools.planner import generate_plan, plan_tables
+
+    tables = st.lists(st.tuples(st.integers(1, 50_000_000), st.integers(1, 120), st.sampled_from([8, 16, 32, 64, 128, 256])),
+                      min_size=1, max_size=40)
+
+    @settings(max_examples=60, deadline=None)
+    @given(tables, st.sampled_from([1, 2, 4, 8, 16]), st.booleans())
+    def check(tabs, gpus, hetero):
+        S, H, E = [t[0] for t in tabs], [t[1] for t in tabs], [t[2] for t in tabs]
+        nodes = 2 if gpus == 16 else 1
+        if hetero:
+            sm, strat, rep = plan_tables(S, H, E, gpus, num_nodes=nodes)
+            assert len(rep["step_cost_us"]) == gpus
+        else:
+            E = [128] * len(S)
+            sm, strat = generate_plan(S, H, gpus, ev_size=128, num_nodes=nodes)
+        assert len(sm) == gpus and all(len(r) == len(S) for r in sm)
+        listed = set()
+        for kind, items in strat:
+            for it in items:
+                name, c = (it[0], it[1]) if isinstance(it, tuple) else (it, 1)
+                t = int(name)
+                listed.add(t)
+                owners = sum(r[t] for r in sm)
+                assert owners >= 1
+                if kind == "dp":
+                    assert owners == gpus
+                else:
+                    assert owners % c == 0 and E[t] % c == 0
+        assert listed == set(range(len(S)))
+        cfg = EmbeddingCollectionConfig()
+        ts = [EmbeddingTableConfig(str(i), S[i], E[i]) for i in range(len(S))]
+        cfg.embedding_lookup(ts, [f"d{i}" for i in range(len(S))], "top", ["sum"] * len(S))
+        cfg.shard(sm, strat)
+        assert all(p is not None for p in resolve_placement(cfg, gpus).values())
+    check()
