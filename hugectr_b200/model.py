@@ -531,6 +531,18 @@ class Model:
         self._graph.replay()
 
     def train(self) -> bool:
+        """One iteration on the next batch; with ``HCTR_STEP_TIMEOUT`` set a watchdog dumps all Python
+        stacks (and optionally aborts the rank) when the call does not return in time."""
+        wd = getattr(self, "_watchdog", False)
+        if wd is False:
+            from .utils.watchdog import StepWatchdog
+            wd = self._watchdog = StepWatchdog.from_env()
+        if wd is None:
+            return self._train_step()
+        with wd:
+            return self._train_step()
+
+    def _train_step(self) -> bool:
         """One iteration on the next batch (Model::train, model.cpp:1048-1138).
 
         With train_inter_iteration_overlap on a GPU the H2D copy of batch i+1 runs on a copy stream

@@ -92,6 +92,10 @@ class Comm:
             kw = {}
             if use_cuda:
                 kw["device_id"] = device
+            t = float(os.environ.get("HCTR_STEP_TIMEOUT", "0") or 0)
+            if t > 0:       # collectives give up with the step watchdog (utils/watchdog.py)
+                import datetime
+                kw["timeout"] = datetime.timedelta(seconds=max(t, 10.0))
             dist.init_process_group("nccl" if use_cuda else "gloo", **kw)
         return Comm(device)
 

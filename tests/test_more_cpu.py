@@ -233,3 +233,34 @@ def test_embedding_gen_tool_writes_a_loadable_checkpoint(tmp_path):
     assert torch.equal(k, torch.arange(1000)) and w.shape == (1000, 8) and s is None
     assert float(w.abs().max()) <= 1 / 1000 ** 0.5 + 1e-7 and float(w.std()) > 0
     assert sum(k.numel() for _, k, _, _ in iter_ebc_folder(str(tmp_path / "embedding_collection_0"), 100)) == 1042
+
+
+def test_step_watchdog_dumps_stacks_of_a_hung_step(tmp_path):
+    import time
+    from hugectr_b200.utils.watchdog import StepWatchdog
+    log = open(tmp_path / "wd.txt", "w+")
+    wd = StepWatchdog(0.2, file=log)
+    with wd:
+        pass                                   # fast step: nothing is written
+    time.sleep(0.4)
+    log.seek(0)
+    assert log.read() == ""
+    with wd:
+        time.sleep(0.6)                        # "hung" step
+    log.seek(0)
+    txt = log.read()
+    assert "Timeout" in txt and "test_step_watchdog" in txt
+    assert StepWatchdog.from_env() is None
+    os.environ["HCTR_STEP_TIMEOUT"] = "30"
+    try:
+        assert StepWatchdog.from_env().timeout == 30.0
+        # a model step runs under the watchdog without side effects
+        from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+        from hugectr_b200.parallel.comm import Comm
+        m = build_dlrm_dcnv2(batchsize=16, num_gpus=1, table_sizes=[30, 40], multi_hot=[2, 1], ev_size=8,
+                             mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1,
+                             comm=Comm.single(torch.device("cpu")))
+        m.compile()
+        assert m.train() and m._watchdog is not None and not m._watchdog.armed
+    finally:
+        del os.environ["HCTR_STEP_TIMEOUT"]
