@@ -119,7 +119,70 @@ def load_sparse_opt_states(model, paths):
             rt.load_opt_states(p)
 
 
+def train_state_path(prefix: str, it: int):
+    return f"{prefix}_train_state_{it}.json"
+
+
+def save_train_state(model, prefix: str, it: int):
+    """What the reference's snapshot leaves out: optimizer step count, iteration and
+    learning-rate schedule position, so that ``Model.resume`` continues exactly where the run stopped."""
+    if model.comm.rank != 0:
+        return
+    st = {"iteration": int(getattr(model, "_iter", it)), "snapshot": int(it),
+          "optimizer_step": int(model.step_t.item()) if hasattr(model, "step_t") else int(it),
+          "lr_scheduler": model.lr_sched.state_dict() if hasattr(model, "lr_sched") else {},
+          "world_size": int(model.world)}
+    _fs(prefix, model).write(train_state_path(prefix, it), json.dumps(st).encode())
+
+
+def latest_snapshot(prefix: str):
+    """largest <it> for which <prefix>_dense_<it>.model exists (local file systems), or None"""
+    import glob
+    import re
+    its = []
+    for p in glob.glob(f"{glob.escape(prefix)}_dense_*.model"):
+        m = re.fullmatch(re.escape(prefix) + r"_dense_(\d+)\.model", p)
+        if m:
+            its.append(int(m.group(1)))
+    return max(its) if its else None
+
+
+def resume(model, prefix: str, it=None) -> int:
+    """Load everything ``save_params_to_files(prefix, it)`` wrote -- dense weights + optimizer state,
+    legacy sparse models + their optimizer states, embedding collections (weights + optimizer state) and
+    the training counters -- and return the iteration to continue from.  ``it=None``: latest snapshot."""
+    if it is None:
+        it = latest_snapshot(prefix)
+        if it is None:
+            raise FileNotFoundError(f"no snapshot with prefix {prefix}")
+    fs = _fs(prefix, model)
+    d, o = dense_paths(prefix, it)
+    load_dense_weights(model, d)
+    if fs.exists(o):
+        load_dense_opt_states(model, o)
+    sp = [sparse_paths(prefix, i, it) for i in range(len(model.legacy_train))]
+    if sp:
+        load_sparse_weights(model, [a for a, _ in sp])
+        if all(fs.exists(b) for _, b in sp):
+            load_sparse_opt_states(model, [b for _, b in sp])
+    if model.ebcs_train and fs.exists(f"{prefix}_ebc_{it}"):
+        embedding_load(model, f"{prefix}_ebc_{it}")
+    sp_state = train_state_path(prefix, it)
+    if fs.exists(sp_state):
+        st = json.loads(fs.read(sp_state).decode())
+        model._iter = int(st["iteration"])
+        model.step_t.fill_(int(st["optimizer_step"]))
+        model.lr_sched.step = max(int(st.get("lr_scheduler", {}).get("step", 0)), model._iter)
+    else:                                   # a snapshot written by the reference: counters from its name
+        model._iter = int(it)
+        model.step_t.fill_(int(it))
+        model.lr_sched.step = int(it)
+    model._graph = None
+    return model._iter
+
+
 def save_model(model, prefix: str, it: int):
+    save_train_state(model, prefix, it)
     save_sparse(model, prefix, it)
     save_dense(model, prefix, it)
     if model.ebcs_train:

@@ -793,6 +793,13 @@ class Model:
         from .io.checkpoint import save_model
         save_model(self, prefix, iter)
 
+    def resume(self, prefix: str, iter: Optional[int] = None) -> int:
+        """Continue a run from the snapshot ``save_params_to_files(prefix, iter)`` / ``fit(snapshot=...)``
+        wrote (latest one when ``iter`` is None): weights, every optimizer state and the training
+        counters.  Returns the iteration to continue from (call after ``compile()``)."""
+        from .io.checkpoint import resume
+        return resume(self, prefix, iter)
+
     def download_params_to_files(self, prefix: str, iter: int = 0):
         self.save_params_to_files(prefix, iter)
 
