@@ -85,10 +85,12 @@ class ParquetReader(IDataReader):
         row-group worker threads (reference RowGroupReadingThread, row_group_reading_thread.cpp)"""
         import pyarrow as pa
         import pyarrow.parquet as pq
+        from ..utils.diagnose import nvtx_range
         tl = self._tls
         if getattr(tl, "path", None) != fp:
             tl.path, tl.pf = fp, pq.ParquetFile(fp)
-        tbl = tl.pf.read_row_group(rg)
+        with nvtx_range("parquet_read_row_group"):      # the reference annotates its reader threads too
+            tbl = tl.pf.read_row_group(rg)
         cols = [tbl.column(i) for i in range(tbl.num_columns)]
         n = tbl.num_rows
         lab = np.stack([cols[i].to_numpy().astype("float32") for i in lab_i], 1) \
