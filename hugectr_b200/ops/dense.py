@@ -119,7 +119,8 @@ def fc1_fwd(x, w, b, y, relu=False):
                                 y.data_ptr(), x.shape[0], x.shape[1], x.stride(0), int(relu),
                                 _isbf(x), _st(x)), "fc1_fwd")
         return
-    v = x.float() @ w.float().reshape(-1, 1)
+    K = w.numel()          # x may be the zero-padded staging copy (K rounded up to 8 in mixed precision)
+    v = x[:, :K].float() @ w.float().reshape(-1, 1)
     if b is not None:
         v = v + b.float()
     if relu:
@@ -137,14 +138,18 @@ def fc1_bwd(x, w, dy, dx, dw, db, mask_relu=False):
                                 _isbf(x), _st(x)), "fc1_bwd")
         return
     g = dy.float().reshape(-1, 1)
-    dw.add_((x.float() * g).sum(0).reshape(dw.shape))
+    K = w.numel()
+    xk = x[:, :K].float()
+    dw.add_((xk * g).sum(0).reshape(dw.shape))
     if db is not None:
         db.add_(g.sum().reshape(db.shape))
     if dx is not None:
         d = g * w.float().reshape(1, -1)
         if mask_relu:
-            d = d * (x.float() > 0)
-        dx.copy_(d.to(dx.dtype))
+            d = d * (xk > 0)
+        if dx.shape[1] > K:
+            dx[:, K:].zero_()
+        dx[:, :K].copy_(d.to(dx.dtype))
 
 
 # ----------------------------------------------------------------------------- copies / casts

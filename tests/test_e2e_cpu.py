@@ -234,3 +234,17 @@ def test_model_resume_restores_weights_states_and_counters(tmp_path):
     assert c.resume(pre, 3) == 3
     with pytest.raises(FileNotFoundError):
         mk().resume(str(tmp_path / "nothing"))
+
+
+def test_mixed_precision_single_output_fc_with_unaligned_input_width():
+    """bf16 models pad the first GEMM operand to a multiple of 8 columns; the num_output == 1 fast path
+    (fc1) must use the logical width (DCN's last layer: 1024 + 6 * 16 + 13 = 1133 inputs)"""
+    m = build_dcn(batchsize=32, slot_sizes=[50] * 6, num_slots=6, workspace_mb=1, comm=CPU(), max_eval_batches=1,
+                  mixed=True)
+    m.compile()
+    losses = []
+    for _ in range(4):
+        assert m.train()
+        losses.append(m.get_current_loss())
+    assert np.isfinite(losses).all()
+    assert m.eval()

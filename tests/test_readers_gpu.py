@@ -24,7 +24,7 @@ def test_file_readers_feed_a_cuda_model(tmp_path, fmt):
     p = DataGeneratorParams(fmt, 1, 13, 6, False, str(tmp_path / ("t.bin" if raw else "t.txt")),
                             str(tmp_path / ("v.bin" if raw else "v.txt")), slots, num_files=2, eval_num_files=1,
                             num_samples_per_file=2048, num_samples=4096, eval_num_samples=1024,
-                            float_label_dense=True)
+                            float_label_dense=True, check_type=hugectr.Check_t.Non)
     DataGenerator(p).generate()
     m = build_dcn(batchsize=256, source=p.source, eval_source=p.eval_source, slot_sizes=slots, num_slots=6,
                   fmt=fmt, workspace_mb=4, max_eval_batches=4, mixed=True)
