@@ -171,16 +171,16 @@ def test_parallel_collection_dump_equals_gather_dump_gloo(nproc, tmp_path):
 
 @pytest.mark.dist
 def test_embedding_collection_benchmark_script_gloo():
-    """benchmarks/embedding_collection/benchmark.py: 200 tables of mixed width, planned by plan_tables,
-    2 gloo ranks; then the SKIP_* ablation switches on one rank"""
+    """benchmarks/embedding_collection/benchmark.py: the 7-table mixed-width workload (ev 32..256, hotness up
+    to 80) planned by plan_tables on 2 gloo ranks; then the SKIP_* ablation switches on one rank"""
     script = os.path.join(os.path.dirname(HERE), "benchmarks", "embedding_collection", "benchmark.py")
-    args = ["--workload", "200table_100B_hotness20", "--batch_per_gpu", "16", "--iters", "2", "--warmup", "1",
+    args = ["--workload", "7table_470B_hotness20", "--batch_per_gpu", "16", "--iters", "2", "--warmup", "1",
             "--cap_rows", "300", "--fp32"]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29781", script] + args
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-    assert '"gpus": 2' in r.stdout and '"tables": 200' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert '"gpus": 2' in r.stdout and '"tables": 7' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
     r = subprocess.run([sys.executable, script] + args, capture_output=True, text=True, timeout=600,
                        env=dict(env, SKIP_EMBEDDING="1", SKIP_ALLREDUCE="1", SKIP_H2D="1"))
     assert '"SKIP_EMBEDDING": "1"' in r.stdout and "ablation switches active" in (r.stdout + r.stderr), \
