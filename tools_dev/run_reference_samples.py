@@ -36,19 +36,6 @@ class _Comm:
 
 # the samples import mpi4py only to initialise MPI before hugectr; torch.distributed does that here
 _stub("mpi4py", MPI=types.SimpleNamespace(COMM_WORLD=_Comm(), SUM=None))
-try:
-    import mlperf_logging  # noqa: F401
-except ImportError:
-    class _ML:
-        def __getattr__(self, k):
-            return lambda *a, **kw: None
-    consts = types.SimpleNamespace()
-    _stub("mlperf_logging", mllog=types.SimpleNamespace(get_mllogger=lambda: _ML(), config=lambda **kw: None,
-                                                       constants=type("C", (), {"__getattr__": lambda s, k: k})()))
-    _stub("mlperf_logging.mllog", get_mllogger=lambda: _ML(), config=lambda **kw: None,
-          constants=type("C", (), {"__getattr__": lambda s, k: k})())
-
-
 
 class _Any:
     """accepts any attribute access / call (mlperf logging stand-in)"""
@@ -56,10 +43,6 @@ class _Any:
     def __getattr__(self, k): return _Any()
     def __call__(self, *a, **kw): return _Any()
     def __str__(self): return "stub"
-
-
-class _Consts:
-    def __getattr__(self, k): return k.lower()
 
 
 _stub("mlperf_logging", mllog=_stub("mlperf_logging.mllog", constants=_stub("mlperf_logging.mllog.constants")))
