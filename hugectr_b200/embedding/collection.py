@@ -112,6 +112,13 @@ def resolve_placement(cfg: EmbeddingCollectionConfig, num_gpus: int) -> Dict[str
         return place
     sm = cfg.shard_matrix
     assert len(sm) == num_gpus, "shard_matrix must have one row per GPU"
+    if any(isinstance(x, str) for row in sm for x in row):
+        # the reference's form (embedding_collection.hpp:55-90, samples/dlrm/sharding/generate_plan.py):
+        # row g lists the NAMES of the tables GPU g holds -> 0/1 matrix over the table order
+        unknown = {x for row in sm for x in row} - set(names)
+        if unknown:
+            raise ValueError(f"shard_matrix names unknown tables: {sorted(unknown)}")
+        sm = [[1 if n in set(map(str, row)) else 0 for n in names] for row in sm]
     for n in names:
         place[n] = None
     for kind, items in cfg.shard_strategy:

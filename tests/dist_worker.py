@@ -249,6 +249,8 @@ def run_fuzz(seed):
                     sm[g][i] = 1
                 strat_mp.append((str(i), world))
         st = ([("mp", strat_mp)] if strat_mp else []) + ([("dp", strat_dp)] if strat_dp else [])
+        if rnd.random() < 0.5:          # the reference's form: per GPU the list of table NAMES it holds
+            sm = [[str(i) for i in range(nt) if row[i]] for row in sm]
         cfg.shard(sm, st)
     adagrad = rnd.random() < 0.5          # non-linear rule: exercises the reduce-then-update order and
     opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.0, epsilon=1e-7) if adagrad \

@@ -112,3 +112,25 @@ def test_node_first_device_layout_permutes_the_shard_matrix():
     assert Model._apply_device_layout(fake, out) is out                         # applied once
     fake.solver.device_layout = hugectr.DeviceLayout.LocalFirst
     assert Model._apply_device_layout(fake, cfg) is cfg
+
+
+def test_shard_matrix_as_lists_of_table_names():
+    """the documented reference form (hugectr_layer_book.md: "each row stores the name of embedding table
+    that user want to place on row-th GPU") and the 0/1 matrix resolve to the same placement"""
+    from hugectr_b200.embedding.collection import (EmbeddingCollectionConfig, EmbeddingTableConfig,
+                                                   resolve_placement)
+
+    def cfg(sm):
+        c = EmbeddingCollectionConfig()
+        ts = [EmbeddingTableConfig(n, 100, 8) for n in ("t0", "t1", "t2", "t3")]
+        c.embedding_lookup(ts, ["a", "b", "c", "d"], "top", ["sum"] * 4)
+        c.shard(sm, [("mp", ["t0", ("t1", 2)]), ("dp", ["t2", "t3"])])
+        return resolve_placement(c, 4)
+    names = [["t0", "t1", "t2", "t3"], ["t1", "t2", "t3"], ["t3", "t2", "t1"], ["t2", "t1", "t3"]]
+    ints = [[1, 1, 1, 1], [0, 1, 1, 1], [0, 1, 1, 1], [0, 1, 1, 1]]
+    pa, pb = cfg(names), cfg(ints)
+    for n in ("t0", "t1", "t2", "t3"):
+        assert (pa[n].kind, pa[n].shard_gpus, pa[n].col_factor) == (pb[n].kind, pb[n].shard_gpus, pb[n].col_factor)
+    assert pa["t0"].shard_gpus == [0] and pa["t1"].shard_gpus == [0, 1, 2, 3] and pa["t1"].col_factor == 2
+    with pytest.raises(ValueError, match="unknown tables"):
+        cfg([["t0", "nope"], [], [], []])

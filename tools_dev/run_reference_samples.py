@@ -63,7 +63,8 @@ _solver = hugectr_b200.CreateSolver
 
 
 def _small_solver(*a, **kw):
-    kw["vvgpu"] = [[0]]
+    world = int(os.environ.get("WORLD_SIZE", "1"))      # under torchrun: one list entry per rank
+    kw["vvgpu"] = [list(range(world))]
     kw["batchsize"] = min(int(kw.get("batchsize", 2048)), 256)
     kw["batchsize_eval"] = min(int(kw.get("batchsize_eval", 2048)), 256)
     kw["max_eval_batches"] = 2
@@ -100,7 +101,13 @@ _shard = hugectr_b200.EmbeddingCollectionConfig.shard
 
 
 def _one_gpu_shard(self, shard_matrix, shard_strategy, *a, **kw):
-    if len(shard_matrix) > 1:           # the script planned for its own GPU count: fold onto the one device
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if len(shard_matrix) != world and world > 1:      # planned for another GPU count: round-robin the tables
+        names = sorted({t for row in shard_matrix for t in row}, key=int) if isinstance(shard_matrix[0][0], str) \
+            else [str(i) for i in range(len(shard_matrix[0]))]
+        shard_matrix = [[n for j, n in enumerate(names) if j % world == r] for r in range(world)]
+        shard_strategy = [("mp", names)]
+    elif len(shard_matrix) > 1 and world == 1:   # the script planned for its own GPU count: fold onto the one device
         if isinstance(shard_matrix[0][0], str):
             shard_matrix = [sorted({t for row in shard_matrix for t in row}, key=int)]
         else:
@@ -191,6 +198,8 @@ def main():
         except BaseException as e:  # noqa: BLE001
             tb = traceback.extract_tb(e.__traceback__)
             res[s + tag] = f"{type(e).__name__}: {str(e)[:300]}  @ {tb[-1].filename.split('/')[-1]}:{tb[-1].lineno}"
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     print("\n==== summary ====")
     for s, r in res.items():
         print(f"{s.replace('/root/reference/', ''):60s} {r}")
