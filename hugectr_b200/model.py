@@ -303,8 +303,8 @@ class Model:
             print("%-36s%-30s%-30s" % (se.embedding_type.name, se.bottom_name, se.sparse_embedding_name))
         for e in getattr(self, "ebcs_train", []):
             for tp in e.tops:
-                print("%-36s%-30s%-30s%-20s" % ("EmbeddingCollection", "", tp["name"],
-                                                f"(None, {tp['width']})"))
+                shp = f"(None, {tp['width']})" if tp["batch_major"] else f"(None, 1, {tp['width']})"
+                print("%-36s%-30s%-30s%-20s" % ("EmbeddingCollection", "", tp["name"], shp))
         if self.compiled:
             for (t, i, o, shp) in self.net_train.summary_rows():
                 print("%-36s%-30s%-30s%-20s" % (t, i[:29], o[:29], shp))
