@@ -317,6 +317,7 @@ class Model:
     def graph_to_json(self, graph_config_file: str):
         from .graph_json import model_to_json
         if self.comm.rank == 0:
+            os.makedirs(os.path.dirname(graph_config_file) or ".", exist_ok=True)
             with open(graph_config_file, "w") as f:
                 json.dump(model_to_json(self), f, indent=2)
 

@@ -156,6 +156,7 @@ EXTRA_ARGS = {
                  "--memory_cap_for_embedding", "1"],
     "dlrm_train_ftrl.py": ["--shard_plan", "hybrid", "--optimizer", "ftrl"],
     "din_fp32.py": ["--vvgpu", "0"],
+    "hugectr_e2e_demo_with_nvtabular__18.py": ["--data_path", "./data", "--model_path", "./model"],
     "benchmarks/embedding_collection/hugectr/train.py": [
         "--batchsize", "256", "--batchsize_eval", "128", "--num_gpus_per_node", "1", "--max_iter", "6",
         "--eval_interval", "3", "--max_eval_batches", "2", "--ev_size_per_table", "16",
