@@ -134,3 +134,24 @@ def test_shard_matrix_as_lists_of_table_names():
     assert pa["t0"].shard_gpus == [0] and pa["t1"].shard_gpus == [0, 1, 2, 3] and pa["t1"].col_factor == 2
     with pytest.raises(ValueError, match="unknown tables"):
         cfg([["t0", "nope"], [], [], []])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test/utest/simple_sparse_embedding_fp32.json"),
+                    reason="reference checkout not mounted")
+@pytest.mark.parametrize("cfg", ["simple_sparse_embedding_fp32.json", "simple_sparse_embedding_sgd.json"])
+def test_reference_graph_json_constructs_and_trains(cfg, monkeypatch):
+    """graph JSON files shipped with the reference (legacy layout with solver / optimizer sections around the
+    layer list) load through construct_from_json and train"""
+    import torch
+    import hugectr_b200 as hugectr
+    from hugectr_b200.parallel.comm import Comm
+    monkeypatch.setenv("HCTR_FORCE_SYNTHETIC", "1")
+    solver = hugectr.CreateSolver(batchsize=64, batchsize_eval=64, vvgpu=[[0]], max_eval_batches=1)
+    reader = hugectr.DataReaderParams(hugectr.DataReaderType_t.Norm, source=["x"], eval_source="x",
+                                      check_type=hugectr.Check_t.Sum)
+    m = hugectr.Model(solver, reader, hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam),
+                      comm=Comm.single(torch.device("cpu")))
+    m.construct_from_json("/root/reference/test/utest/" + cfg, True)
+    m.compile()
+    assert m.train() and m.get_current_loss() == m.get_current_loss()
+    assert len(m.legacy_train) == 2           # one Distributed + one Localized embedding in the file
