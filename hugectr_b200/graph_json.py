@@ -65,10 +65,17 @@ def dense_layer_to_json(c: DenseLayer) -> dict:
     elif t == Layer_t.Reshape:
         if c.selected:
             j["selected"] = c.selected_slots
-        if c.shape:
-            j["shape"] = c.shape
         j["leading_dim"] = c.leading_dim
         j["time_step"] = c.time_step
+        if c.shape:
+            j["shape"] = c.shape
+            # the reference's converter only understands leading_dim / time_step: spell [-1, d] and
+            # [-1, t, d] shapes that way too (hugectr_loader.py:473-491)
+            sh = list(c.shape)
+            if len(sh) == 2 and sh[0] == -1:
+                j["leading_dim"], j["time_step"] = sh[1], 0
+            elif len(sh) == 3 and sh[0] == -1:
+                j["leading_dim"], j["time_step"] = sh[2], sh[1]
     elif t in (Layer_t.Concat, Layer_t.ReduceSum, Layer_t.ReduceMean):
         j["axis"] = c.axis
     elif t == Layer_t.Slice:
@@ -179,7 +186,14 @@ def model_to_json(model) -> dict:
                                "nnz_per_slot": p.nnz_per_slot, "is_fixed_length": p.is_fixed_length,
                                "slot_num": p.slot_num} for p in inp.data_reader_sparse_param_array]})
     for se in model.sparse_embeddings:
+        o = se.optimizer or model.opt_params
+        per_gpu = getattr(se, "max_vocabulary_size_per_gpu", 0)
+        if per_gpu <= 0 and se.workspace_size_per_gpu_in_mb > 0:      # model.cpp:186-196
+            per_gpu = int(se.workspace_size_per_gpu_in_mb * 1024 * 1024 // ((1 + o.num_states) * 4 * se.embedding_vec_size))
+        if per_gpu <= 0:
+            per_gpu = max(1024, sum(se.slot_size_array or [0]) // max(1, model.world) + 1024)
         hp = {"workspace_size_per_gpu_in_mb": se.workspace_size_per_gpu_in_mb,
+              "max_vocabulary_size_global": int(per_gpu * model.world),      # read by hugectr2onnx
               "embedding_vec_size": se.embedding_vec_size, "combiner": se.combiner}
         if se.slot_size_array:
             hp["slot_size_array"] = se.slot_size_array

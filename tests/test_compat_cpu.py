@@ -155,3 +155,41 @@ def test_reference_graph_json_constructs_and_trains(cfg, monkeypatch):
     m.compile()
     assert m.train() and m.get_current_loss() == m.get_current_loss()
     assert len(m.legacy_train) == 2           # one Distributed + one Localized embedding in the file
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/onnx_converter/hugectr2onnx/hugectr_loader.py"),
+                    reason="reference checkout not mounted")
+@pytest.mark.parametrize("family", ["dcn", "deepfm", "wdl", "ncf", "mmoe", "din", "bst"])
+def test_reference_onnx_loader_parses_our_graph_json_and_dense_model(family, tmp_path):
+    """graph_to_json + <prefix>_dense_<it>.model written here are read layer by layer by the reference's own
+    converter front end (onnx_converter/hugectr2onnx/hugectr_loader.py), consuming the weight file exactly"""
+    import importlib.util
+    import torch
+    from hugectr_b200 import models
+    from hugectr_b200.parallel.comm import Comm
+    spec = importlib.util.spec_from_file_location("ref_loader",
+                                                  "/root/reference/onnx_converter/hugectr2onnx/hugectr_loader.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    c = Comm.single(torch.device("cpu"))
+    kw = dict(comm=c, max_eval_batches=1)
+    m = {"dcn": lambda: models.build_dcn(batchsize=32, slot_sizes=[50] * 5, num_slots=5, vec=8, workspace_mb=1, **kw),
+         "deepfm": lambda: models.build_deepfm(batchsize=32, **kw),
+         "wdl": lambda: models.build_wdl(batchsize=32, **kw),
+         "ncf": lambda: models.build_ncf("neumf", batchsize=64, num_users=300, num_items=200, **kw),
+         "mmoe": lambda: models.build_mmoe(batchsize=64, num_slots=6, vocab=100, ev=8, expert_dims=(32, 16),
+                                           tower_dim=8, **kw),
+         "din": lambda: models.build_din(batchsize=32, seq_len=5, item_vocab=200, cate_vocab=30, user_vocab=50,
+                                         ev=6, att_dims=(16, 8), mlp_dims=(24, 12), **kw),
+         "bst": lambda: models.build_bst(batchsize=32, **kw)}[family]()
+    m.compile()
+    m.train()
+    m.graph_to_json(str(tmp_path / "g.json"))
+    m.save_params_to_files(str(tmp_path / "m"), 1)
+    ntp = str(tmp_path / "m_dense_1.model.ntp.json")
+    loader = ref.HugeCTRLoader(str(tmp_path / "g.json"), str(tmp_path / "m_dense_1.model"), False, None,
+                               ntp if os.path.exists(ntp) else None)
+    for _ in range(loader.layers):
+        loader.load_layer()
+    consumed = getattr(loader, "_HugeCTRLoader__offset")
+    assert consumed == os.path.getsize(tmp_path / "m_dense_1.model"), (consumed, m.arena.num_params * 4)
