@@ -3,6 +3,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -193,3 +194,40 @@ def test_reference_onnx_loader_parses_our_graph_json_and_dense_model(family, tmp
         loader.load_layer()
     consumed = getattr(loader, "_HugeCTRLoader__offset")
     assert consumed == os.path.getsize(tmp_path / "m_dense_1.model"), (consumed, m.arena.num_params * 4)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/onnx_converter/hugectr2onnx/hugectr_loader.py"),
+                    reason="reference checkout not mounted")
+def test_reference_onnx_loader_reads_our_sparse_model_directories(tmp_path):
+    """<prefix><i>_sparse_<it>.model/{key, emb_vector[, slot_id]} written here load into the reference
+    converter's embedding tables (Distributed + Localized embeddings of the W&D sample)"""
+    import importlib.util
+    import torch
+    from hugectr_b200 import models
+    from hugectr_b200.parallel.comm import Comm
+    spec = importlib.util.spec_from_file_location("ref_loader",
+                                                  "/root/reference/onnx_converter/hugectr2onnx/hugectr_loader.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    m = models.build_wdl(batchsize=32, comm=Comm.single(torch.device("cpu")), max_eval_batches=1)
+    m.compile()
+    for _ in range(3):
+        m.train()
+    m.graph_to_json(str(tmp_path / "g.json"))
+    m.save_params_to_files(str(tmp_path / "m"), 3)
+    sparse = [str(tmp_path / f"m{i}_sparse_3.model") for i in range(len(m.legacy_train))]
+    loader = ref.HugeCTRLoader(str(tmp_path / "g.json"), str(tmp_path / "m_dense_3.model"), True, sparse, None)
+    tables = []
+    for _ in range(loader.layers):
+        _, w, _ = loader.load_layer()
+        tables += [v for k, v in w.items() if "embedding" in k.lower() and hasattr(v, "shape")]
+    assert [t.shape[1] for t in tables] == [rt.vec for rt in m.legacy_train]
+    # every key trained here is known to the converter's key -> row hash, with the trained row behind it
+    rt = m.legacy_train[0]
+    keys, rows = rt.hash.dump()
+    hsh = loader.key_to_indice_hash_all_tables[0]
+    assert int((hsh[keys.numpy()] > 0).sum()) >= keys.numel() - 1
+    k0 = int(keys[0])
+    got = tables[0][hsh[k0]]
+    exp = rt.table.view(-1, rt.vec)[int(rows[0])].numpy()
+    assert np.allclose(got, exp)
