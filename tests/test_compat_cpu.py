@@ -231,3 +231,33 @@ def test_reference_onnx_loader_reads_our_sparse_model_directories(tmp_path):
     got = tables[0][hsh[k0]]
     exp = rt.table.view(-1, rt.vec)[int(rows[0])].numpy()
     assert np.allclose(got, exp)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/tools/embedding_workspace_calculator"),
+                    reason="reference checkout not mounted")
+def test_workspace_calculator_matches_the_reference_tool():
+    import importlib.util
+    import hugectr_b200 as hugectr
+    from hugectr_b200.tools import workspace_calculator as W
+    spec = importlib.util.spec_from_file_location(
+        "ref_ws", "/root/reference/tools/embedding_workspace_calculator/"
+                  "cal_vocabulary_size_per_gpu_and_workspace_size_per_gpu.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    slots = [39884, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532, 2953546, 403346, 10]
+    for gpus in (1, 2, 8):
+        for opt in ("adam", "adagrad", "momentumsgd", "nesterov", "sgd"):
+            for upd in ("local", "global", "lazy_global"):
+                for vec in (16, 128):
+                    vd = ref.cal_vocabulary_size_per_gpu_for_distributed_slot(sum(slots), gpus)
+                    vl = ref.cal_vocabulary_size_per_gpu_for_localized_slot(slots, gpus)
+                    assert vd == W.cal_vocabulary_size_per_gpu_for_distributed_slot(sum(slots), gpus)
+                    assert vl == W.cal_vocabulary_size_per_gpu_for_localized_slot(slots, gpus)
+                    for v in (vd, vl):
+                        assert ref.cal_workspace_size_per_gpu_from_vocabulary_size_per_gpu(v, vec, gpus, opt, upd) \
+                            == W.cal_workspace_size_per_gpu_from_vocabulary_size_per_gpu(v, vec, gpus, opt, upd)
+                    assert W.calculate(slots, vec, W._OPT[opt], W._UPD[upd], gpus) == \
+                        ref.cal_workspace_size_per_gpu_from_vocabulary_size_per_gpu(vd, vec, gpus, opt, upd)
+                    assert W.calculate(slots, vec, W._OPT[opt], W._UPD[upd], gpus,
+                                       hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash) == \
+                        ref.cal_workspace_size_per_gpu_from_vocabulary_size_per_gpu(vl, vec, gpus, opt, upd)
