@@ -4,7 +4,8 @@
 AdaGrad) training throughput in samples/s on N B200 GPUs of one node, bf16, synthetic power-law data.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (unmodified reference)
+  python bench.py --impl reference ...                     (unmodified reference built by baseline/build_reference.py)
+  python bench.py --impl nccl_cublas ...                   (stand-in baseline: our model on NCCL collectives + cuBLAS GEMMs)
 
 Prints ONE JSON line on rank 0 (contract in the task description).  Weak scaling: 6912 samples per
 GPU (the MLPerf 8-GPU global batch 55296 / 8).
@@ -20,7 +21,9 @@ import threading
 import time
 
 PER_GPU_BATCH = 6912
-BASELINE_SAMPLES_PER_S = 14.7e6   # implied HugeCTR MLPerf v3.1 rate on 8 x H100
+BASELINE_SAMPLES_PER_S = 14.7e6   # implied (derived) HugeCTR MLPerf v3.1 rate on 8 x H100
+ROW_CAP_1GPU = 22_000_000         # N == 1 only: fp32 tables + fp32 AdaGrad state must fit 180 GB (see run_arm)
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def clocks_sampler(stop_evt, out, gpu_index):
@@ -84,59 +87,85 @@ def summarize_clocks(samples):
             "samples": len(samples)}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--per-gpu-batch", type=int, default=PER_GPU_BATCH)
-    ap.add_argument("--small", action="store_true", help="tiny tables (debug only; not a valid number)")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--plan", default="auto")
-    ap.add_argument("--cap-rows", type=int, default=0,
-                    help="cap every table at this many rows (profiling under ncu only; INVALID as a bench number)")
-    ap.add_argument("--profile", default="", help="dump a torch.profiler kernel table (rank 0) here")
-    args = ap.parse_args()
-
-    if args.impl == "reference":
-        # see DESIGN.md "Reference arm": /root/reference has no setup.py/pyproject.toml (pip refuses),
-        # and its CMake build needs libaio, numa, tbb, cuDF/RMM and a network fetch of pybind11.
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "reference is a CMake project without setup.py/pyproject.toml; pip install "
-                          "fails offline and its build deps (libaio, numa, tbb, cuDF, MPI, pybind11 "
-                          "FetchContent) are absent from this image"}))
+def reference_arm(args):
+    """`--impl reference`: rank 0 runs the unmodified reference (one process driving all N GPUs, its own
+    execution model) in a clean subprocess; the other torchrun ranks have nothing to do."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
         return 0
-
-    import torch
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from hugectr_b200.models.dlrm import (CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES,
-                                          build_dlrm_dcnv2)
-    from hugectr_b200.ops import dense as D
-    from hugectr_b200.parallel.comm import Comm
-    from hugectr_b200.tools.planner import generate_plan
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    comm = Comm.init_from_env()
-    rank = comm.rank
+    so = os.path.join(HERE, "baseline", "_ref", "hugectr.so")
+    if not os.path.exists(so):
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "baseline/_ref/hugectr.so missing: run `python baseline/build_reference.py` "
+                          "(offline build of /root/reference; pip install fails, no setup.py/pyproject.toml)"}))
+        return 0
     n = args.gpus
-    b = args.per_gpu_batch
+    sys.path.insert(0, HERE)
+    plan_path = ""
+    try:      # sharding plan = configuration data; the reference's own planner lives in samples/, not in the library
+        from hugectr_b200.models.dlrm import CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES
+        from hugectr_b200.tools.planner import generate_plan
+        cap = ROW_CAP_1GPU if n == 1 else 0
+        tabs = [min(t, cap) if cap else t for t in CRITEO_TB_TABLE_SIZES]
+        sm, ss = generate_plan(tabs, CRITEO_TB_MULTI_HOT, n, plan=args.plan)
+        names = [[str(i) for i, v in enumerate(row) if v] for row in sm]
+        import tempfile
+        fd, plan_path = tempfile.mkstemp(suffix=".json")
+        with os.fdopen(fd, "w") as f:
+            json.dump({"shard_matrix": names, "shard_strategy": [[k, [list(x) if isinstance(x, tuple) else x
+                                                                      for x in v]] for k, v in ss]}, f)
+    except Exception as e:                       # round-robin plan inside the script
+        sys.stderr.write(f"plan generation failed ({e}); reference uses its round-robin plan\n")
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "CUDA_VISIBLE_DEVICES",
+                        "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE")}
+    cmd = [sys.executable, os.path.join(HERE, "baseline", "ref_dlrm_dcnv2.py"), "--gpus", str(n),
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--per-gpu-batch", str(args.per_gpu_batch)]
+    if n == 1:
+        cmd += ["--table-cap", str(ROW_CAP_1GPU)]
+    if plan_path:
+        cmd += ["--plan", plan_path]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=args.ref_timeout)
+    except subprocess.TimeoutExpired:
+        print(json.dumps({"impl": "reference", "unavailable": f"reference run exceeded {args.ref_timeout}s"}))
+        return 0
+    line = next((l for l in reversed(r.stdout.splitlines()) if l.startswith("{") and '"impl"' in l), None)
+    if line is None:
+        tail = (r.stderr or r.stdout)[-600:].replace("\n", " | ")
+        print(json.dumps({"impl": "reference", "unavailable": f"reference run failed rc={r.returncode}: {tail}"}))
+        return 0
+    print(line, flush=True)
+    return 0
+
+
+def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, sustained_s=2.0, label="b200"):
+    """Build the model for one configuration, time it, tear it down.  Returns the measurements (rank 0: dict)."""
+    import gc
+    import torch
+    from hugectr_b200.models.dlrm import (CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES, build_dlrm_dcnv2)
+    from hugectr_b200.ops import gemm as G
+    from hugectr_b200.tools.planner import generate_plan
+    import hugectr_b200 as hugectr
+
+    rank, n, b = comm.rank, args.gpus, args.per_gpu_batch
     tables = CRITEO_TB_TABLE_SIZES if not args.small else [min(t, 100000) for t in CRITEO_TB_TABLE_SIZES]
-    if args.cap_rows > 0:
-        tables = [min(t, args.cap_rows) for t in tables]
-    # 104 GB of fp32 tables + 104 GB of fp32 AdaGrad state do not fit one 180 GB GPU: at N == 1 the
-    # AdaGrad accumulators are stored in bf16 (weights stay fp32, math fp32); N >= 2 keeps fp32 state
-    state = "fp32"
-    if n == 1 and not args.small and not args.cap_rows:
-        os.environ["HCTR_EMB_STATE_BF16"] = "1"
-        state = "bf16"
-    os.environ.setdefault("HCTR_SYNTH_POOL", "8")
+    if cap_rows > 0:
+        tables = [min(t, cap_rows) for t in tables]
+    os.environ["HCTR_EMB_STATE_BF16"] = "1" if state == "bf16" else "0"
+    os.environ.setdefault("HCTR_SYNTH_POOL", "64")
+    kw = {}
+    if standin:
+        # stand-in baseline: same model / optimizer / data, embedding exchange through NCCL collectives,
+        # dense all-reduce through NCCL, every GEMM through torch.mm (cuBLAS / cuBLASLt)
+        comm.disable_p2p()
+        G.set_impl("library")
+        kw = dict(fused_embedding_comm=False, all_reduce_algo=hugectr.AllReduceAlgo.NCCL)
+    else:
+        G.set_impl("tc")
     plan = generate_plan(tables, CRITEO_TB_MULTI_HOT, n, plan=args.plan)
-    model = build_dlrm_dcnv2(batchsize=b * n, num_gpus=n, table_sizes=tables, mixed=True,
-                             lr=0.004, scaler=1.0, shard_plan=plan, comm=comm,
-                             use_cuda_graph=not args.no_graph)
+    model = build_dlrm_dcnv2(batchsize=b * n, num_gpus=n, table_sizes=tables, mixed=True, lr=0.004, scaler=1.0,
+                             shard_plan=plan, comm=comm, use_cuda_graph=not args.no_graph, **kw)
     model.compile()
     dev = model.device
     pool = model.reader_train.pool
@@ -146,16 +175,19 @@ def main():
         comm.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- warm-up (>= 3; includes the 2 eager iterations + graph capture)
-    W = max(args.warmup, 3)
-    for i in range(W + 2):
+    def maxr(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if n > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    for i in range(W + 2):                      # W untimed steps (+ 2 eager iterations before graph capture)
         model.train()
     sync_all()
     launches_per_step = model.launches_per_step
     loss_trace = [model.get_current_loss()]
 
-    if args.profile:
-        # kernel-level breakdown with CUPTI (never used for reported numbers)
+    if args.profile and not standin:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for i in range(5):
@@ -166,7 +198,6 @@ def main():
             with open(args.profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60,
                                                   max_name_column_width=90))
-            # compact per-stream timeline (start us, dur us, stream, kernel) for overlap analysis
             evs = []
             for e in prof.events():
                 if str(e.device_type).endswith("CUDA"):
@@ -177,100 +208,194 @@ def main():
             with open(args.profile + ".timeline", "w") as f:
                 for st, du, sid, nm in evs:
                     f.write(f"{st - t0:10.1f} {du:8.1f} {sid} {nm}\n")
-    # ---------------- device-timed steps: inputs pre-staged on device, exactly K steps
-    K = args.steps
+
     stop_evt, samples = threading.Event(), []
     th = threading.Thread(target=clocks_sampler, args=(stop_evt, samples, dev.index or 0), daemon=True)
     th.start()
-    # device-resident copies of the batch pool: every timed step trains a different batch (a D2D
-    # refresh of label / dense / keys, ~6 MB, is part of the timed region)
+    # ---- device-timed: the whole pool resident on the device, every timed step trains a different batch
+    # (the D2D refresh of label / dense / keys, ~6 MB, is inside the timed region), exactly K steps
     inp = model.input
     t_label = model.net_train.tensors[inp.label_name].data
     t_dense = model.net_train.tensors[inp.dense_name].data
     ebc0 = model.ebcs_train[0]
     dev_pool = [(hb.label.to(dev).view_as(t_label), hb.dense.to(dev).view_as(t_dense).to(t_dense.dtype),
-                 hb.keys.to(dev)) for hb in pool[:8]]
+                 hb.keys.to(dev)) for hb in pool]
 
     def load_resident(i):
         lab, den, keys = dev_pool[i % len(dev_pool)]
         t_label.copy_(lab, non_blocking=True)
         t_dense.copy_(den, non_blocking=True)
         ebc0.key_slab[:keys.numel()].copy_(keys, non_blocking=True)
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        load_resident(i)
-        model._run_step()
-    e1.record()
-    sync_all()
-    ms_dev = e0.elapsed_time(e1)
-    loss_trace.append(model.get_current_loss())
-    t_ms = torch.tensor([ms_dev], device=dev)
-    if n > 1:
-        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
-    ms_dev = float(t_ms.item())
 
-    # ---------------- end-to-end through the public API: H2D of every batch from pinned host
-    # memory + the step + a D2H read of the loss, every step
+    def timed(nsteps, i0=0):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            load_resident(i0 + i)
+            model._run_step()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+    sync_all()
+    ms_dev = timed(K)
+    sync_all()
+    ms_dev = maxr([ms_dev])[0]
+    n_clk_short = len(samples)
+    loss_trace.append(model.get_current_loss())
+    # ---- sustained: >= sustained_s seconds of back-to-back steps (clocks settle below boost)
+    sus = None
+    if sustained_s > 0:
+        est = max(ms_dev / K, 1e-3)
+        chunk = max(10, int(sustained_s * 1e3 / est / 4) + 1)
+        tot_ms, tot_steps = 0.0, 0
+        sync_all()
+        while tot_ms < sustained_s * 1e3 and tot_steps < 100000:
+            ms = maxr([timed(chunk, tot_steps)])[0]      # same chunk count on every rank (max is shared)
+            tot_ms += ms
+            tot_steps += chunk
+        sync_all()
+        sus = {"value": b * n * tot_steps / (tot_ms / 1e3), "unit": "samples/s", "steps": tot_steps,
+               "seconds": tot_ms / 1e3, "ms_per_step": tot_ms / tot_steps,
+               "clocks": summarize_clocks(samples[n_clk_short:])}
+    n_clk_dev = len(samples)
+    # ---- end to end through the public API: reader -> pinned host batch -> H2D -> step, every step, plus an
+    # asynchronous D2H read of the loss every step
     loss_host = torch.zeros(1).pin_memory()
     sync_all()
     w0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(K):
-        model.train()                                   # reader -> pinned host batch -> H2D -> step
+        model.train()
         loss_host.copy_(model.net_train.loss_value(), non_blocking=True)
     e3.record()
     sync_all()
     wall_ms = (time.perf_counter() - w0) * 1e3
-    ms_e2e = max(e2.elapsed_time(e3), 0.0)
-    t_ms = torch.tensor([ms_e2e, wall_ms], device=dev)
-    if n > 1:
-        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
-    ms_e2e, wall_ms = float(t_ms[0].item()), float(t_ms[1].item())
+    ms_e2e, wall_ms = maxr([max(e2.elapsed_time(e3), 0.0), wall_ms])
     stop_evt.set()
     th.join(timeout=2)
     loss = model.get_current_loss()
+    hb = pool[0]
+    gb = b * n
+    res = {
+        "value": gb * K / (ms_dev / 1e3), "ms_per_step": ms_dev / K,
+        "e2e": {"value": gb * K / (max(ms_e2e, wall_ms) / 1e3), "unit": "samples/s",
+                "ms_per_step": max(ms_e2e, wall_ms) / K, "h2d_bytes_per_step": hb.h2d_bytes(),
+                "d2h_bytes_per_step": 4},
+        "sustained": sus, "clocks": summarize_clocks(samples[:n_clk_short] or samples),
+        "clocks_all": summarize_clocks(samples),
+        "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
+        "final_loss": loss, "loss_trace": [round(x, 5) for x in loss_trace + [loss]],
+        "state": state, "cap_rows": cap_rows, "pool_batches": len(pool),
+        "table_bytes": int(sum(e.memory_bytes() for e in model.ebcs_train)),
+    }
+    # ---- teardown of this arm: graph, streams, reader threads, tables
+    model.close()
+    del model, dev_pool, pool, t_label, t_dense, ebc0, inp, hb
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    G.set_impl("tc")
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "nccl_cublas"])
+    ap.add_argument("--per-gpu-batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--small", action="store_true", help="tiny tables (debug only; not a valid number)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--plan", default="auto")
+    ap.add_argument("--cap-rows", type=int, default=0,
+                    help="cap every table at this many rows (profiling under ncu only; INVALID as a bench number)")
+    ap.add_argument("--profile", default="", help="dump a torch.profiler kernel table (rank 0) here")
+    ap.add_argument("--no-standin", action="store_true", help="skip the NCCL+cuBLAS stand-in arm")
+    ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the bf16-state full-size run")
+    ap.add_argument("--sustained-sec", type=float, default=2.0)
+    ap.add_argument("--ref-timeout", type=int, default=1500)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import faulthandler
+    import torch
+    sys.path.insert(0, HERE)
+    from hugectr_b200.parallel.comm import Comm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    comm = Comm.init_from_env()
+    rank, n = comm.rank, args.gpus
+    W, K = max(args.warmup, 3), args.steps
+    # 104 GB of fp32 tables + 104 GB of fp32 AdaGrad state do not fit one 180 GB GPU.  N == 1 therefore runs
+    # fp32 state (the reference's precision) with the six 40 M-row tables capped at ROW_CAP_1GPU rows (declared
+    # in config.row_cap; same random-access pattern, 146 GB resident), and reports the full-size run with bf16
+    # AdaGrad accumulators as `secondary`.  N >= 2: full tables, fp32 state.
+    cap = args.cap_rows or (ROW_CAP_1GPU if (n == 1 and not args.small) else 0)
+    standin_only = args.impl == "nccl_cublas"
+    main_res = run_arm(args, comm, standin=standin_only, state="fp32", cap_rows=cap, K=K, W=W,
+                       sustained_s=args.sustained_sec)
+    secondary = None
+    if n == 1 and not args.small and not args.cap_rows and not args.no_secondary and not standin_only:
+        try:
+            r2 = run_arm(args, comm, state="bf16", cap_rows=0, K=K, W=W, sustained_s=0.0)
+            secondary = {"bf16_adagrad_state_full_tables": {
+                "value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"]["value"],
+                "table_bytes": r2["table_bytes"], "final_loss": r2["final_loss"]}}
+        except Exception as e:       # noqa: BLE001 -- a secondary figure must not take the headline down
+            secondary = {"bf16_adagrad_state_full_tables": {"error": repr(e)[:300]}}
+    standin = None
+    if not args.no_standin and not standin_only:
+        try:
+            r3 = run_arm(args, comm, standin=True, state="fp32", cap_rows=cap, K=K, W=W, sustained_s=0.0)
+            standin = {"impl": "nccl_cublas (our model: NCCL all-to-all / all-reduce + torch.mm GEMMs; NOT the reference)",
+                       "value": r3["value"], "ms_per_step": r3["ms_per_step"], "e2e": r3["e2e"]["value"],
+                       "gpu_launches_per_step": r3["gpu_launches_per_step"], "final_loss": r3["final_loss"]}
+        except Exception as e:       # noqa: BLE001
+            standin = {"impl": "nccl_cublas", "error": repr(e)[:300]}
 
     if rank == 0:
-        gb = b * n
-        value = gb * K / (ms_dev / 1e3)
-        e2e = gb * K / (max(ms_e2e, wall_ms) / 1e3)
-        hb = pool[0]
+        gb = args.per_gpu_batch * n
+        r = main_res
         out = {
             "metric": "DLRM-DCNv2 Criteo-TB training samples/sec (device-timed, max over ranks)",
-            "value": value, "unit": "samples/s", "n_gpus": n, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / BASELINE_SAMPLES_PER_S, "dtype": "bf16", "data": "synthetic",
-            "impl": "b200",
+            "value": r["value"], "unit": "samples/s", "n_gpus": n, "steps": K, "warmup": W,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            # anchor: BASELINE.md's only throughput figure is the DERIVED 14.7 M samples/s on 8 x H100;
+            # scaled to N GPUs (per-GPU share) so the ratio means the same thing at every N
+            "vs_baseline": r["value"] / (BASELINE_SAMPLES_PER_S * n / 8.0),
+            "baseline_anchor": "derived 14.7e6 samples/s @ 8xH100 (BASELINE.md) x N/8",
+            "dtype": "bf16", "data": "synthetic", "impl": args.impl,
             "config": {"model": "DLRM-DCNv2 (MLPerf v3.1: 26 Criteo-TB tables, multi-hot 214 keys/sample, "
                                 "ev 128, bottom 512-256-128, 3x cross p=512, top 1024-1024-512-256-1, AdaGrad)",
-                       "global_batch": gb, "per_gpu_batch": b, "seq_len": None,
+                       "global_batch": gb, "per_gpu_batch": args.per_gpu_batch, "seq_len": None,
                        "parallelism": f"dp{n} dense + model-parallel embeddings (plan={args.plan})",
-                       "embedding_weights": "fp32", "embedding_opt_state": state,
-                       "l2_hygiene": "inputs_exceed_L2 (>=100 GB tables random access, ~1 GB activations/step)",
+                       "embedding_weights": "fp32", "embedding_opt_state": r["state"],
+                       "row_cap": r["cap_rows"], "embedding_bytes_resident_per_gpu": r["table_bytes"],
+                       "l2_hygiene": "inputs_exceed_L2 (>=50 GB of tables per GPU under random access, "
+                                     "~1 GB activations/step, a different batch every step)",
+                       "synthetic_pool_batches": r["pool_batches"],
                        "cuda_graph": not args.no_graph, "small_tables_debug": bool(args.small or args.cap_rows),
-                       "final_loss": loss,
-                       "loss_after_warmup_timed_e2e": [round(x, 5) for x in loss_trace + [loss]]},
-            "clocks": summarize_clocks(samples),
-            "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": max(ms_e2e, wall_ms) / K,
-                    "h2d_bytes_per_step": hb.h2d_bytes() * 1, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches_per_step * K),
-            "gpu_launches_per_step": int(launches_per_step),
+                       "final_loss": r["final_loss"], "loss_after_warmup_timed_e2e": r["loss_trace"]},
+            "clocks": r["clocks"], "e2e": r["e2e"], "sustained": r["sustained"],
+            "gpu_launches": r["gpu_launches"], "gpu_launches_per_step": r["gpu_launches_per_step"],
         }
+        if secondary is not None:
+            out["secondary"] = secondary
+        if standin is not None:
+            out["standin"] = standin
         print(json.dumps(out), flush=True)
-    # orderly teardown: drop the captured graph (it references NCCL kernels and peer mappings) before
-    # the process group goes away, then leave without running interpreter finalizers that can block
-    # on IPC-mapped memory of ranks that are already gone
-    model._graph = None
-    torch.cuda.synchronize()
-    if n > 1:
-        torch.distributed.barrier()
-        torch.cuda.synchronize()
+    # orderly teardown: symmetric heap unmapped on every rank, process group destroyed, then a NORMAL interpreter
+    # exit (atexit hooks and finalizers run).  The watchdog only fires if that exit wedges.
     sys.stdout.flush()
-    sys.stderr.flush()
-    os._exit(0)
+    faulthandler.dump_traceback_later(120, exit=True)
+    comm.shutdown()
+    return 0
 
 
 if __name__ == "__main__":

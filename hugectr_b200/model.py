@@ -506,7 +506,7 @@ class Model:
     def _run_step(self):
         use_graph = (self.solver.use_cuda_graph and self.device.type == "cuda"
                      and os.environ.get("HCTR_DISABLE_CUDA_GRAPH", "0") == "0"
-                     and not self.legacy_train)
+                     and self._graph_safe())
         if not use_graph:
             c0 = D.launch_count
             self._step_body()
@@ -530,6 +530,34 @@ class Model:
             self.comm.barrier()                # pipeline.cpp:111-125 barrier after first capture
             # capture does not execute: run the captured step now
         self._graph.replay()
+
+    def _graph_safe(self) -> bool:
+        """The step can be captured when nothing in it needs the host: legacy embeddings whose hash
+        insert is checked on the host and collections with dynamic tables on the translate-on-host
+        path (their overflow check reads a device counter) run eagerly."""
+        if any(not getattr(rt, "graph_safe", False) for rt in self.legacy_train):
+            return False
+        if any(getattr(e, "has_dynamic", False) and not getattr(e, "dynamic_graph_safe", False)
+               for e in self.ebcs_train):
+            return False
+        return True
+
+    def close(self):
+        """Release what outlives a Python reference drop: the captured graph (it pins NCCL kernels and
+        peer mappings), side streams, reader worker threads.  The model is unusable afterwards."""
+        self._graph = None
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        for r in (getattr(self, "reader_train", None), getattr(self, "reader_eval", None)):
+            try:
+                if r is not None:
+                    r.stop()
+            except Exception:
+                pass
+        for n in ("_s_emb", "_s_idx", "_copy_stream", "_stg", "_staged", "exchange_wgrad"):
+            if hasattr(self, n):
+                setattr(self, n, None)
+        self.compiled = False
 
     def train(self) -> bool:
         """One iteration on the next batch; with ``HCTR_STEP_TIMEOUT`` set a watchdog dumps all Python

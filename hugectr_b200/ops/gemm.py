@@ -91,6 +91,61 @@ def gemm_reference(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, 
 
 _bn_override = {}
 
+# "tc": the hand-written tcgen05 kernels (product path).  "library": bf16 GEMMs through torch.mm
+# (cuBLAS / cuBLASLt) with eager epilogues -- the stand-in baseline arm of bench.py, never a default.
+IMPL = "tc"
+_fallback_logged = set()
+
+
+def set_impl(name: str):
+    global IMPL
+    assert name in ("tc", "library")
+    IMPL = name
+
+
+def gemm_library(a, b, a_mn=False, b_mn=False, bias=None, mask=None, x0=None, xl=None,
+                 alpha=1.0, flags=0, out=None, aux=None, addf=None):
+    """Same contract as ``gemm_reference`` with the matmul in the operands' dtype on the vendor
+    library (what a cuBLASLt-based framework runs): bias through addmm, the rest eager."""
+    A = a.t() if a_mn else a
+    B = b if b_mn else b.t()
+    f32 = bool(flags & (EPI_OUT_F32 | EPI_ATOMIC | EPI_ACCUM))
+    if f32:
+        v = torch.mm(A, B).float()
+        if alpha != 1.0:
+            v = v * alpha
+        if bias is not None:
+            v = v + bias.float()
+    elif bias is not None and alpha == 1.0:
+        v = torch.addmm(bias.to(A.dtype), A, B)
+    else:
+        v = torch.mm(A, B)
+        if alpha != 1.0:
+            v = v * alpha
+        if bias is not None:
+            v = v + bias.to(v.dtype)
+    if flags & EPI_CROSS:
+        if aux is not None:
+            aux.copy_(v)
+        v = torch.addcmul(xl.to(v.dtype), x0.to(v.dtype), v)
+    if flags & EPI_ADD:
+        v = v + xl.to(v.dtype)
+        if addf is not None:
+            v = v + addf.to(v.dtype)
+    if flags & EPI_MASK:
+        v = v * (mask > 0).to(v.dtype)
+    if flags & EPI_RELU:
+        v = torch.relu(v)
+    if flags & EPI_SIGMOID:
+        v = torch.sigmoid(v)
+    if flags & (EPI_ATOMIC | EPI_ACCUM):
+        out.add_(v.to(out.dtype))
+        return out
+    if out is None:
+        return v
+    out.copy_(v)
+    return out
+
 
 def _pick_block_n(M, N, K, splits):
     """Tile / cluster choice.  1000 + BN selects the 2-CTA cluster kernel that multicasts the B tile
@@ -131,7 +186,22 @@ def gemm_bf16(a, b, out=None, *, a_mn=False, b_mn=False, bias=None, mask=None, x
     f32_out = bool(flags & (EPI_OUT_F32 | EPI_ATOMIC | EPI_ACCUM))
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else a.dtype)
+    if IMPL == "library" and a.is_cuda:
+        r = gemm_library(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux, addf)
+        if colsum is not None:
+            colsum.add_(out.float().sum(0))
+        return r
     if not tc_eligible(a, b, a_mn, b_mn) or out.stride(1) != 1:
+        if a.is_cuda:
+            # never silent: a misaligned / non-bf16 operand moves this GEMM off the tcgen05 kernel
+            sig = (M, N, K, str(a.dtype), tuple(a.stride()), tuple(b.stride()), a.data_ptr() % 16,
+                   b.data_ptr() % 16)
+            if sig not in _fallback_logged:
+                _fallback_logged.add(sig)
+                from ..utils import logger
+                logger.warning(f"gemm_bf16: M={M} N={N} K={K} dtype={a.dtype} strides a={tuple(a.stride())} "
+                               f"b={tuple(b.stride())} is not TMA-addressable (16-byte base / pitch, bf16): "
+                               "running the library matmul instead of the tcgen05 kernel")
         r = gemm_reference(a, b, a_mn, b_mn, bias, mask, x0, xl, alpha, flags, out, aux, addf)
         if colsum is not None:
             colsum.add_(out.float().sum(0))

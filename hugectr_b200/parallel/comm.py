@@ -271,6 +271,26 @@ class Comm:
     def peer_ptrs(self, t: torch.Tensor) -> List[int]:
         return self.heap.peer_ptrs(t)
 
+    def disable_p2p(self):
+        """Force the NCCL / gloo collective paths on this communicator (the stand-in baseline arm)."""
+        if self._heap is not None:
+            self._heap.close()
+            self._heap = None
+        self._p2p = False
+
+    def shutdown(self, destroy_process_group: bool = True):
+        """Orderly teardown (collective): close the symmetric heap, then the process group.  After
+        this the interpreter exits through its normal finalizers."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        if self._heap is not None:
+            self._heap.close()
+            self._heap = None
+            self._p2p = False
+        if destroy_process_group and self.group is None and dist.is_available() and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+
     def barrier_device(self):
         """Device-side all-GPU barrier on the current stream (no host sync, graph capturable)."""
         if self.world_size > 1:

@@ -110,6 +110,28 @@ class SymmetricHeap:
                 return [q + off for q in info["peers"]]
         raise KeyError("tensor is not part of the symmetric heap")
 
+    def close(self):
+        """Collective, idempotent: unmap every peer's buffers and free the local ones.  Called from
+        ``Comm.shutdown`` after the last kernel that touches peer memory has completed on EVERY rank
+        (device sync + process-group barrier on both sides), so no rank unmaps memory a peer still
+        reads and interpreter exit never waits on a mapping whose exporter is already gone."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
+        self.comm.barrier()
+        for p, info in self._allocs.items():
+            for r, q in enumerate(info["peers"]):
+                if r != self.rank and q:
+                    lib().hctr_ipc_close(q)
+            info["peers"] = []
+        torch.cuda.synchronize(self.device)
+        self.comm.barrier()                  # every importer has closed before any exporter frees
+        for p, info in self._allocs.items():
+            info["tensor"] = None
+            lib().hctr_ipc_free(p)
+        self._allocs = {}
+
     def barrier(self):
         rc = lib().hctr_peer_barrier(self.flag_ptrs, self.epoch.data_ptr(), self.rank, self.world,
                                      torch.cuda.current_stream(self.device).cuda_stream)
