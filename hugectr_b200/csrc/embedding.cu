@@ -394,45 +394,9 @@ __global__ void emb_gather_rows_kernel(const float* __restrict__ table, const lo
     out[w * ev + c] = from_f<OutT>(r < 0 ? 0.f : table[r * ev + c]);
 }
 
-// Bulk pull of the gradient rows this rank needs from every peer's top-grad slab into a local
-// staging slab with the SAME layout (the "all-to-all" of the backward pass issued as coalesced
-// 16-byte peer loads over NVLink; afterwards the reduce kernel only touches local memory / L2).
-// grid = (row blocks, src * L + l); a half-warp copies one 256-byte gradient row.
-template <typename T>
-__global__ void __launch_bounds__(256)
-    emb_pull_grads_kernel(const EmbParams p, PeerStage st) {
-  const int l = blockIdx.y % p.num_lookups;
-  const int src = blockIdx.y / p.num_lookups;
-  if (src == p.my_rank) return;            // own gradients are read in place
-  const EmbLookup lk = p.lookups[l];
-  const int chunks = (lk.ev_size * static_cast<int>(sizeof(T)) + 15) / 16;   // 16-byte chunks per row
-  const int rows_per_block = (blockDim.x * 1) / max(chunks, 1);
-  const int r_in = threadIdx.x / max(chunks, 1), c = threadIdx.x % max(chunks, 1);
-  if (r_in >= rows_per_block) return;
-  const T* gsrc = reinterpret_cast<const T*>(p.grad[src]) + lk.grad_off;
-  T* gdst = reinterpret_cast<T*>(st.dst[src]) + lk.grad_off;
-  for (int s = blockIdx.x * rows_per_block + r_in; s < p.batch; s += gridDim.x * rows_per_block) {
-    const long long off = static_cast<long long>(s) * lk.grad_stride;
-    const int4 v = ld_nc_v4(reinterpret_cast<const int4*>(gsrc + off) + c);
-    reinterpret_cast<int4*>(gdst + off)[c] = v;
-  }
-}
-
 }  // namespace hctr
 
 using namespace hctr;
-
-extern "C" int hctr_emb_pull_grads(const EmbParams* p, void* const* stage, int grad_bf16,
-                                   void* stream_) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (p->num_ranks <= 1 || p->num_lookups == 0) return 0;
-  PeerStage ps;
-  for (int i = 0; i < p->num_ranks; ++i) ps.dst[i] = stage[i];
-  const dim3 grid(32, p->num_ranks * p->num_lookups);
-  if (grad_bf16) emb_pull_grads_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*p, ps);
-  else emb_pull_grads_kernel<float><<<grid, 256, 0, st>>>(*p, ps);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
 
 static inline int pick_group(int ev, int vec) {
   int g = (ev + vec - 1) / vec;

@@ -18,8 +18,12 @@ struct HashTableView {
   long long max_rows;         // rows beyond this are an overflow (check_overflow)
 };
 
+// Bounded: a full table can neither spin (probe count <= capacity) nor hand out rows past max_rows --
+// both cases return -1 and raise the sticky ``overflow`` flag that check_overflow() reads on the host
+// outside the step (no per-step host sync; the step stays graph capturable).
 __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restrict__ keys,
-                                     long long* __restrict__ out, long long n, int insert) {
+                                     long long* __restrict__ out, long long n, int insert,
+                                     unsigned int* __restrict__ overflow) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long key = keys[i];
@@ -29,10 +33,18 @@ __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restric
   }
   const unsigned long long k = static_cast<unsigned long long>(key);
   unsigned long long h = hash64(k) & t.capacity_mask;
-  while (true) {
-    unsigned long long prev;
-    if (insert) prev = atomicCAS(&t.keys[h], kEmptyKey, k);
-    else prev = t.keys[h];
+  for (unsigned long long probes = 0; probes <= t.capacity_mask; ++probes) {
+    unsigned long long prev = *reinterpret_cast<volatile unsigned long long*>(&t.keys[h]);
+    if (prev == kEmptyKey && insert) {
+      // rows are exhausted: do not consume another key slot (the table would fill up and probing
+      // would never terminate), report the overflow instead
+      if (static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(t.counter)) >= t.max_rows) {
+        if (overflow) atomicMax(overflow, 1u);
+        out[i] = -1;
+        return;
+      }
+      prev = atomicCAS(&t.keys[h], kEmptyKey, k);
+    }
     if (prev == kEmptyKey) {
       if (!insert) {
         out[i] = -1;
@@ -40,7 +52,9 @@ __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restric
       }
       const unsigned long long row = atomicAdd(t.counter, 1ull);
       atomicExch(reinterpret_cast<unsigned long long*>(&t.vals[h]), row);
-      out[i] = (static_cast<long long>(row) < t.max_rows) ? static_cast<long long>(row) : -1;
+      const bool ok = static_cast<long long>(row) < t.max_rows;
+      if (!ok && overflow) atomicMax(overflow, 1u);
+      out[i] = ok ? static_cast<long long>(row) : -1;
       return;
     }
     if (prev == k) {
@@ -53,6 +67,8 @@ __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restric
     }
     h = (h + 1) & t.capacity_mask;
   }
+  if (overflow) atomicMax(overflow, 1u);
+  out[i] = -1;
 }
 
 __global__ void ht_set_kernel(HashTableView t, const long long* __restrict__ keys,
@@ -91,12 +107,12 @@ using namespace hctr;
 extern "C" int hctr_ht_get_insert(void* keys_tab, void* vals_tab, void* counter,
                                   unsigned long long capacity, long long max_rows,
                                   const long long* keys, long long* out, long long n, int insert,
-                                  void* stream) {
+                                  void* stream, void* overflow) {
   if (n == 0) return 0;
   HashTableView t{(unsigned long long*)keys_tab, (long long*)vals_tab, (unsigned long long*)counter,
                   capacity - 1, max_rows};
-  ht_get_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t, keys, out, n,
-                                                                                     insert);
+  ht_get_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      t, keys, out, n, insert, reinterpret_cast<unsigned int*>(overflow));
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -177,12 +177,15 @@ class EmbeddingCollection:
         self.placement = resolve_placement(cfg, self.world)
         self.native = device.type == "cuda"
         self.has_dynamic = any(t.dynamic for t in self.tables)
-        if self.has_dynamic:
-            fused = False      # key -> row translation runs on the gathered keys (collective path)
         self.fused = (self.native and self.world > 1 and comm.p2p_available) if fused is None else fused
-        # requester-side split of row-sharded bags (see _build_layout); experimental, off by default
+        # requester-side split of row-sharded bags (see _build_layout): part of the key dispatch on the
+        # fused path (default on there, HCTR_SHARD_SPLIT=0 disables); opt-in on the collective path
         import os as _os
-        self.shard_split = _os.environ.get("HCTR_SHARD_SPLIT", "0") == "1" and self.world > 1
+        ss = _os.environ.get("HCTR_SHARD_SPLIT", "")
+        self.shard_split = self.world > 1 and (ss == "1" or (ss != "0" and bool(self.fused)))
+        # dynamic tables translate keys with a device hash table and flag overflow on the device: the
+        # step has no host sync (graph capturable); check_overflow() reads the flags on demand
+        self.dynamic_graph_safe = True
         # node-aware two-stage exchange (collective path only; inside one NVSwitch box the fused
         # peer-memory kernels are used instead)
         self.hier = (not self.fused and self.world > 1
@@ -412,38 +415,45 @@ class EmbeddingCollection:
             view.uniform_(-bound, bound, generator=g2)
 
     def _alloc_buffers(self):
-        dev, b = self.device, self.b
-        alloc = self.comm.symm_alloc if self.fused else \
-            (lambda n, dt: torch.zeros(n, dtype=dt, device=dev))
-        self.key_slab = alloc(max(self.key_slab_elems, 1), self.key_dtype)
-        self.nnz_slab = alloc(max(self.nnz_slab_elems, 1), torch.int32) if self.nnz_slab_elems else None
+        dev, b, W = self.device, self.b, self.world
+        z = lambda n, dt: torch.zeros(max(int(n), 1), dtype=dt, device=dev)
         self.peer_nnz = None
         self.nnz_all = None
-        self.out_slab = alloc(max(self.out_slab_elems, 1), self.act_dtype)
-        self.grad_slab = alloc(max(self.grad_slab_elems, 1), self.act_dtype) if self.is_train else None
+        self.key_slab = z(self.key_slab_elems, self.key_dtype)
+        self.nnz_slab = z(self.nnz_slab_elems, torch.int32) if self.nnz_slab_elems else None
         if self.fused:
-            self.peer_keys = self.comm.peer_ptrs(self.key_slab)
-            if self.nnz_slab is not None:
-                self.peer_nnz = self.comm.peer_ptrs(self.nnz_slab)
+            # Inboxes in the peer-mapped heap, one slot per source rank, same layout as a key / grad
+            # slab: requesters scatter their key blocks and gradient rows into them with posted peer
+            # stores (csrc/emb_dispatch.cu); owners write pooled vectors into the requesters' out slabs.
+            # Every owner-side kernel then reads LOCAL memory only.
+            sa = self.comm.symm_alloc
+            ks, ns, gs = max(self.key_slab_elems, 1), self.nnz_slab_elems, max(self.grad_slab_elems, 1)
+            self.keys_all = sa(W * ks, self.key_dtype).view(W, ks)
+            self.peer_keys_all = self.comm.peer_ptrs(self.keys_all)
+            if ns:
+                self.nnz_all = sa(W * ns, torch.int32).view(W, ns)
+                self.peer_nnz = self.comm.peer_ptrs(self.nnz_all)
+            self.out_slab = sa(max(self.out_slab_elems, 1), self.act_dtype)
             self.peer_out = self.comm.peer_ptrs(self.out_slab)
-            self.peer_grad = self.comm.peer_ptrs(self.grad_slab) if self.is_train else None
+            self.grad_slab = z(self.grad_slab_elems, self.act_dtype) if self.is_train else None
             if self.is_train:
-                # local staging slabs (same layout as a peer's grad slab); own slot aliases my slab
-                self.grad_stage = [self.grad_slab if r == self.rank else
-                                   torch.zeros(max(self.grad_slab_elems, 1), dtype=self.act_dtype, device=dev)
-                                   for r in range(self.world)]
-        elif self.world > 1:
-            self.keys_all = torch.zeros(self.world, max(self.key_slab_elems, 1),
-                                        dtype=self.key_dtype, device=dev)
-            if self.nnz_slab is not None:
-                self.nnz_all = torch.zeros(self.world, self.nnz_slab_elems, dtype=torch.int32, device=dev)
-            self.send_out = torch.zeros(self.world, max(self.out_slab_elems, 1),
-                                        dtype=self.act_dtype, device=dev)
-            self.recv_out = torch.zeros_like(self.send_out)
-            if self.is_train:
-                self.grads_all = torch.zeros(self.world, max(self.grad_slab_elems, 1),
-                                             dtype=self.act_dtype, device=dev)
-            self._build_packed_exchange()
+                self.grads_all = sa(W * gs, self.act_dtype).view(W, gs)
+                self.peer_grads_all = self.comm.peer_ptrs(self.grads_all)
+            self._build_key_routes()
+            self._grad_routes = None
+        else:
+            self.out_slab = z(self.out_slab_elems, self.act_dtype)
+            self.grad_slab = z(self.grad_slab_elems, self.act_dtype) if self.is_train else None
+            if W > 1:
+                self.keys_all = torch.zeros(W, max(self.key_slab_elems, 1), dtype=self.key_dtype, device=dev)
+                if self.nnz_slab is not None:
+                    self.nnz_all = torch.zeros(W, self.nnz_slab_elems, dtype=torch.int32, device=dev)
+                self.send_out = torch.zeros(W, max(self.out_slab_elems, 1), dtype=self.act_dtype, device=dev)
+                self.recv_out = torch.zeros_like(self.send_out)
+                if self.is_train:
+                    self.grads_all = torch.zeros(W, max(self.grad_slab_elems, 1), dtype=self.act_dtype,
+                                                 device=dev)
+                self._build_packed_exchange()
         # named views
         self.key_views = {}
         for gl in self.glookups:
@@ -456,6 +466,65 @@ class EmbeddingCollection:
             self.top_data[tp["name"]] = self.out_slab[tp["off"]:tp["off"] + b * w].view(shp)
             if self.is_train:
                 self.top_grad[tp["name"]] = self.grad_slab[tp["off"]:tp["off"] + b * w].view(shp)
+
+    def _mp_owners(self, gl):
+        """[(rank, column part, row shards k, row shard s)] of the table behind a lookup (mp only)"""
+        pl = self.placement[gl["table"]]
+        if pl.kind != "mp":
+            return []
+        kk = len(pl.shard_gpus) // pl.col_factor
+        return [(g, idx // kk, kk, idx % kk) for idx, g in enumerate(pl.shard_gpus)]
+
+    def _build_key_routes(self):
+        """Forward dispatch plan of THIS rank's batch: per model-parallel lookup one route per owner --
+        the whole key block, or (row-sharded, split on) the owner's compacted shard list + lengths."""
+        b, me = self.b, self.rank
+        ks, ns = max(self.key_slab_elems, 1), self.nnz_slab_elems
+        routes = []
+        for gl in self.glookups:
+            H = gl["hotness"]
+            seen = set()
+            for (g, cpart, kk, s_) in self._mp_owners(gl):
+                if "split_off" in gl:
+                    if (g, s_) in seen:
+                        continue
+                    seen.add((g, s_))
+                    routes.append(E.Route(src_off=gl["key_off"], dst_off=me * ks + gl["split_off"] + s_ * b * H,
+                                          rows=b, row_elems=H, src_stride=H, dst_stride=H, dst_rank=g, kind=1,
+                                          k=kk, shard=s_, nnz_off=me * ns + gl["split_nnz_off"] + s_ * b))
+                else:
+                    if g in seen:
+                        continue
+                    seen.add(g)
+                    routes.append(E.Route(src_off=gl["key_off"], dst_off=me * ks + gl["key_off"], rows=1,
+                                          row_elems=b * H, src_stride=b * H, dst_stride=b * H, dst_rank=g))
+        self._key_routes = routes
+        self._key_routes_dev = E.routes_to_device(routes, self.device)
+        # bytes this rank stores into peers per step (roofline accounting, see profiles/)
+        kb = self._kb
+        self.dispatch_key_bytes = sum(r.rows * r.row_elems * kb for r in routes if r.dst_rank != me)
+
+    def _build_grad_routes(self):
+        """Backward push plan: the gradient columns of every model-parallel lookup go to each rank that
+        owns (a shard of) its table.  Built at the first backward, after any alias_top() re-homing."""
+        b, me = self.b, self.rank
+        gs = max(self.grad_slab_elems, 1)
+        routes = []
+        for gl in self.glookups:
+            tp = self.tops[gl["top"]]
+            w = gl["ev"] * (gl["hotness"] if gl["combiner"] == "concat" else 1)
+            al = tp.get("alias")
+            if al:
+                base, stride = al["goff"] + al["col"] + (gl["out_off"] - tp["off"]), al["stride"]
+            else:
+                base, stride = gl["out_off"], gl["out_stride"]
+            for g in sorted({o[0] for o in self._mp_owners(gl)}):
+                routes.append(E.Route(src_off=base, dst_off=me * gs + base, rows=b, row_elems=w,
+                                      src_stride=stride, dst_stride=stride, dst_rank=g))
+        self._grad_routes = routes
+        self._grad_routes_dev = E.routes_to_device(routes, self.device)
+        esz = 2 if self._abf else 4
+        self.push_grad_bytes = sum(r.rows * r.row_elems * esz for r in routes if r.dst_rank != me)
 
     def alias_top(self, name: str, total_width: int, col_off: int):
         """Re-home the batch-major top ``name`` inside a [b, total_width] buffer carved from the slabs
@@ -551,21 +620,23 @@ class EmbeddingCollection:
 
     def _nnz_bufs(self, grp):
         """per-source-rank bag-length buffers of the split lists (None when the split is off)"""
-        if self.nnz_slab is None or grp.kind != "mp":
+        if self.nnz_all is None or grp.kind != "mp":
             return None
-        if self.fused:
-            return self.peer_nnz
         return list(self.nnz_all.unbind(0))
 
     def forward_begin(self):
         """every rank's keys are in place (fused mode: device-side barrier; collective: all-gather)"""
-        if self.nnz_slab is not None:
+        if self.nnz_slab is not None and not self.fused:
             for gl in self.glookups:
                 if "split_off" in gl:
                     E.shard_split(self.key_slab, gl["key_off"], self.b, gl["hotness"], gl["k"],
                                   gl["split_off"], self.nnz_slab, gl["split_nnz_off"])
         if self.world > 1:
             if self.fused:
+                # forward all-to-all of keys: posted peer stores into the owners' inboxes, then ONE
+                # device barrier (also orders the previous step's readers of these inboxes)
+                E.dispatch(self.key_slab, self._key_routes, self._key_routes_dev, self.peer_keys_all,
+                           self.peer_nnz)
                 self.comm.barrier_device()
             elif os.environ.get("SKIP_DATA_DISTRIBUTOR", "0") not in ("0", ""):
                 pass          # ablation (model_pipeline.cpp:118): owners keep the keys of an earlier step
@@ -618,12 +689,20 @@ class EmbeddingCollection:
                     own = (keys >= 0) & ((keys % sl["k"]) == sl["s"])
                     ht = self._dyn_hash(t.name, sl)
                     k = torch.where(own, keys, torch.full_like(keys, -1)).reshape(-1)
+                    # bounded insert: a key that finds no free row reads as empty (-1) and raises the
+                    # table's sticky device flag -- no host sync here, see check_overflow()
                     rows = (ht.get_insert(k) if self.is_train else ht.get(k)).reshape(keys.shape)
-                    if self.is_train and ht.size() > sl["rows"]:
-                        raise RuntimeError(f"dynamic embedding table {t.name}: more than init_capacity="
-                                           f"{sl['rows']} distinct keys on one shard")
                     out = torch.where(own & (rows >= 0), rows.to(torch.int64), out)
             region.copy_(out.to(region.dtype))
+
+    def check_overflow(self):
+        """Raise if a dynamic table ran out of rows (reads device flags: a host sync -- called by
+        ``Model`` at display / evaluation / checkpoint time, never inside the captured step)."""
+        owner = getattr(self, "_shared", self)
+        for (name, cpart, s_), ht in getattr(owner, "_dyn_tables", {}).items():
+            if ht.overflowed():
+                raise RuntimeError(f"dynamic embedding table {name}: more than init_capacity="
+                                   f"{ht.max_rows} distinct keys on one shard (shard {s_})")
 
     def forward_compute(self):
         b = self.b
@@ -634,9 +713,9 @@ class EmbeddingCollection:
         elif self.fused:
             for grp in self.groups:
                 if grp.kind == "mp":
-                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
-                              self.peer_out, b, self.rank, nnz_bufs=self._nnz_bufs(grp),
-                              key_bytes=self._kb, act_bf16=self._abf)
+                    E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch,
+                              list(self.keys_all.unbind(0)), self.peer_out, b, self.rank,
+                              nnz_bufs=self._nnz_bufs(grp), key_bytes=self._kb, act_bf16=self._abf)
                 else:
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
                               [self.out_slab], b, key_bytes=self._kb, act_bf16=self._abf)
@@ -717,14 +796,7 @@ class EmbeddingCollection:
     def _bwd_bufs(self, grp):
         if self.world == 1 or grp.kind == "dp":
             return [self.key_slab], [self.grad_slab]
-        if self.fused:
-            return self.peer_keys, (self.grad_stage if self._stage_ok(grp) else self.peer_grad)
         return list(self.keys_all.unbind(0)), list(self.grads_all.unbind(0))
-
-    def _stage_ok(self, grp) -> bool:
-        esz = 2 if self._abf else 4
-        return (grp.pitch * esz) % 16 == 0 and all((l.grad_off * esz) % 16 == 0 and
-                                                   (l.grad_stride * esz) % 16 == 0 for l in grp.lookups)
 
     def backward_index(self):
         """gradient-independent part of the backward (unique rows + bucket lists); may run on a
@@ -757,12 +829,14 @@ class EmbeddingCollection:
                     self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
         if self.world > 1:
             if self.fused:
-                self.comm.barrier_device()           # all top-grads are final
-                for grp in mp_groups:                # backward "all-to-all": bulk peer loads
-                    if grp.lookups and self._stage_ok(grp):
-                        E.pull_grads(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, self.peer_keys,
-                                     self.peer_grad, self.grad_stage, self.b, self.rank,
-                                     key_bytes=self._kb, act_bf16=self._abf)
+                # backward all-to-all of gradients: every rank pushes the gradient columns of each
+                # lookup to the owner's inbox (posted peer stores), one barrier, then the owners'
+                # reduce + optimizer kernels read local memory only
+                if self._grad_routes is None:
+                    self._build_grad_routes()
+                E.dispatch(self.grad_slab, self._grad_routes, self._grad_routes_dev, self.peer_grads_all,
+                           blocks_x=16)
+                self.comm.barrier_device()
             elif os.environ.get("SKIP_ALL2ALL", "0") not in ("0", ""):
                 pass
             elif self.hier:
@@ -784,8 +858,11 @@ class EmbeddingCollection:
         else:
             for grp in dp_groups:
                 self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
-        if self.world > 1 and self.fused:
-            self.comm.barrier_device()               # keys / grads may now be overwritten
+        if self.world > 1 and self.fused and os.environ.get("HCTR_EMB_END_BARRIER", "0") == "1":
+            # not needed for correctness: a rank can only overwrite an owner's inbox after that owner
+            # passed the NEXT step's dispatch barrier, i.e. after its reduce of this step was queued
+            # on the same stream ahead of it
+            self.comm.barrier_device()
 
     def _hp(self, o: OptParamsPy):
         return {"scaler": self.scaler, "beta1": o.beta1, "beta2": o.beta2, "epsilon": o.epsilon,

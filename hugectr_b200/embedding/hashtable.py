@@ -20,7 +20,7 @@ def lib():
     if _lib is None:
         l = _native.cuda_lib()
         vp, ull, ll, i = C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int
-        l.hctr_ht_get_insert.argtypes = [vp, vp, vp, ull, ll, vp, vp, ll, i, vp]
+        l.hctr_ht_get_insert.argtypes = [vp, vp, vp, ull, ll, vp, vp, ll, i, vp, vp]
         l.hctr_ht_set.argtypes = [vp, vp, vp, ull, vp, vp, ll, vp]
         l.hctr_ht_dump.argtypes = [vp, vp, ull, vp, vp, vp, vp]
         for n in ("hctr_ht_get_insert", "hctr_ht_set", "hctr_ht_dump"):
@@ -43,8 +43,10 @@ class HashTable:
             self.keys = torch.full((cap,), -1, dtype=torch.int64, device=self.device)
             self.vals = torch.full((cap,), -1, dtype=torch.int64, device=self.device)
             self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=self.device)   # sticky device flag
         else:
             self.map = {}
+            self._overflowed = False
 
     def _st(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -65,7 +67,7 @@ class HashTable:
             rc = lib().hctr_ht_get_insert(self.keys.data_ptr(), self.vals.data_ptr(),
                                           self.counter.data_ptr(), self.capacity, self.max_rows,
                                           k.data_ptr(), out.data_ptr(), k.numel(), int(insert),
-                                          self._st())
+                                          self._st(), self.overflow.data_ptr())
             if rc:
                 raise RuntimeError("hash get_insert failed")
             D._count()
@@ -81,8 +83,12 @@ class HashTable:
                 res.append(v if v < self.max_rows else -1)
             elif insert:
                 v = len(self.map)
+                if v >= self.max_rows:          # rows exhausted: no insertion, sticky overflow
+                    self._overflowed = True
+                    res.append(-1)
+                    continue
                 self.map[x] = v
-                res.append(v if v < self.max_rows else -1)
+                res.append(v)
             else:
                 res.append(-1)
         return torch.tensor(res, dtype=torch.int64).view(keys.shape)
@@ -99,6 +105,12 @@ class HashTable:
         else:
             for a, b in zip(k.tolist(), v.tolist()):
                 self.map[a] = b
+
+    def overflowed(self) -> bool:
+        """True once a key could not get a row (host sync on CUDA: call it outside the step)."""
+        if self.device.type == "cuda":
+            return bool(int(self.overflow.item()))
+        return self._overflowed
 
     def size(self) -> int:
         if self.device.type == "cuda":
@@ -127,5 +139,7 @@ class HashTable:
             self.keys.fill_(-1)
             self.vals.fill_(-1)
             self.counter.zero_()
+            self.overflow.zero_()
         else:
             self.map = {}
+            self._overflowed = False

@@ -81,8 +81,6 @@ def lib():
         l.hctr_emb_bwd_reduce_update.argtypes = [C.POINTER(CEmbParams), C.POINTER(CUniqueTable),
                                                  C.POINTER(CBwdIndex), vp, vp, i, i,
                                                  C.POINTER(COptHyper), f, i, vp, i, vp]
-        l.hctr_emb_pull_grads.argtypes = [C.POINTER(CEmbParams), C.POINTER(vp), i, vp]
-        l.hctr_emb_pull_grads.restype = i
         for n in ("hctr_emb_forward", "hctr_emb_backward_accum", "hctr_emb_update",
                   "hctr_emb_gather_rows", "hctr_emb_bwd_index", "hctr_emb_bwd_reduce_update"):
             getattr(l, n).restype = i
@@ -171,6 +169,84 @@ def shard_split(key_slab, key_off, batch, hotness, k, split_off, nnz_slab, nnz_o
         cnt = m.sum(1)
         out[j].copy_(torch.where(pos < cnt.view(-1, 1), rows, torch.full_like(rows, -1)).to(out.dtype))
         cnts[j].copy_(cnt.to(torch.int32))
+
+
+# ----------------------------------------------------------------------------- dispatch (peer stores)
+class CDispatchRoute(C.Structure):
+    _fields_ = [("src_off", C.c_longlong), ("dst_off", C.c_longlong), ("nnz_off", C.c_longlong),
+                ("rows", C.c_int), ("row_elems", C.c_int), ("src_stride", C.c_int),
+                ("dst_stride", C.c_int), ("dst_rank", C.c_int), ("kind", C.c_int), ("k", C.c_int),
+                ("shard", C.c_int)]
+
+
+@dataclass
+class Route:
+    """One block a rank sends to one destination rank's inbox (csrc/emb_dispatch.cu).  kind 0: 2-D
+    copy of [rows, row_elems]; kind 1: key-bag split for shard ``shard`` of ``k`` (+ list lengths)."""
+    src_off: int
+    dst_off: int
+    rows: int
+    row_elems: int
+    src_stride: int
+    dst_stride: int
+    dst_rank: int
+    kind: int = 0
+    k: int = 1
+    shard: int = 0
+    nnz_off: int = 0
+
+
+def routes_to_device(routes: List[Route], device) -> torch.Tensor:
+    arr = (CDispatchRoute * max(1, len(routes)))()
+    for i, r in enumerate(routes):
+        arr[i] = CDispatchRoute(r.src_off, r.dst_off, r.nnz_off, r.rows, r.row_elems, r.src_stride,
+                                r.dst_stride, r.dst_rank, r.kind, r.k, r.shard)
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(device)
+
+
+def dispatch(src: torch.Tensor, routes: List[Route], routes_dev, dst_bufs, nnz_bufs=None, blocks_x: int = 8):
+    """Scatter blocks of the local 1-D buffer ``src`` into the per-rank inboxes ``dst_bufs`` (tensor or
+    int peer pointer per destination rank; element type of ``src``).  Posted peer stores on CUDA."""
+    if not routes:
+        return
+    if src.is_cuda:
+        l = lib()
+        if not hasattr(l, "_dispatch_ready"):
+            l.hctr_emb_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]
+            l.hctr_emb_dispatch.restype = C.c_int
+            if l.hctr_abi_size_dispatch_route() != C.sizeof(CDispatchRoute):
+                raise RuntimeError("libhctr_cuda.so DispatchRoute layout differs from the python mirror: rebuild")
+            l._dispatch_ready = True
+        n = len(dst_bufs)
+        dp = (C.c_void_p * n)(*[d if isinstance(d, int) else d.data_ptr() for d in dst_bufs])
+        np_ = None
+        if nnz_bufs is not None:
+            np_ = (C.c_void_p * n)(*[d if isinstance(d, int) else d.data_ptr() for d in nnz_bufs])
+        rc = l.hctr_emb_dispatch(src.data_ptr(), routes_dev.data_ptr(), len(routes), dp, np_, n,
+                                 src.element_size(), blocks_x, _st(src.device))
+        if rc:
+            raise RuntimeError(f"hctr_emb_dispatch failed rc={rc}")
+        D._count()
+        return
+    for r in routes:
+        dst = dst_bufs[r.dst_rank].reshape(-1)
+        if r.kind == 0:
+            s2 = torch.as_strided(src, (r.rows, r.row_elems), (r.src_stride, 1), src.storage_offset() + r.src_off)
+            d2 = torch.as_strided(dst, (r.rows, r.row_elems), (r.dst_stride, 1), dst.storage_offset() + r.dst_off)
+            d2.copy_(s2)
+            continue
+        keys = torch.as_strided(src, (r.rows, r.row_elems), (r.src_stride, 1),
+                                src.storage_offset() + r.src_off).long()
+        m = (keys >= 0) & (keys % r.k == r.shard)
+        order = torch.argsort((~m).to(torch.int8), dim=1, stable=True)
+        rows = torch.div(keys, r.k, rounding_mode="floor").gather(1, order)
+        cnt = m.sum(1)
+        pos = torch.arange(r.row_elems).view(1, -1)
+        d2 = torch.as_strided(dst, (r.rows, r.row_elems), (r.dst_stride, 1), dst.storage_offset() + r.dst_off)
+        d2.copy_(torch.where(pos < cnt.view(-1, 1), rows, torch.full_like(rows, -1)).to(dst.dtype))
+        nn = nnz_bufs[r.dst_rank].reshape(-1)
+        nn[r.nnz_off:r.nnz_off + r.rows].copy_(cnt.to(torch.int32))
 
 
 # ----------------------------------------------------------------------------- forward
@@ -513,16 +589,3 @@ def bwd_reduce_update(opt: Optimizer_t, lookups, lookups_dev, table, s0, s1, ev_
     if rc:
         raise RuntimeError(f"hctr_emb_bwd_reduce_update failed rc={rc}")
     D._count(3)
-
-
-def pull_grads(lookups, lookups_dev, table, ev_pitch, key_bufs, peer_grad_ptrs, stage_tensors, batch,
-               my_rank, key_bytes=4, act_bf16=True):
-    """Copy the gradient rows of this rank's lookups from every peer's grad slab into local staging
-    slabs (same layout) with coalesced peer loads."""
-    p, _, gbf = _fill_params(lookups, lookups_dev, table, ev_pitch, key_bufs, peer_grad_ptrs, batch,
-                             my_rank, None, key_bytes, act_bf16)
-    arr = (C.c_void_p * len(stage_tensors))(*[t.data_ptr() for t in stage_tensors])
-    rc = lib().hctr_emb_pull_grads(C.byref(p), arr, gbf, _st(table.device))
-    if rc:
-        raise RuntimeError("hctr_emb_pull_grads failed")
-    D._count()

@@ -131,9 +131,9 @@ class SparseEmbeddingRuntime:
         return valid & ((keys_all % self.world) == self.rank)
 
     def check_overflow(self):
-        n = self.hash.size()
-        if n > self.max_rows:
-            raise RuntimeError(f"Runtime vocabulary size ({n}) exceeds max_vocabulary_size_per_gpu "
+        if self.hash.overflowed():
+            n = self.hash.size()
+            raise RuntimeError(f"Runtime vocabulary size (>= {n}) exceeds max_vocabulary_size_per_gpu "
                                f"({self.max_rows}) of {self.name}, new feature insertion failed.")
 
     # ------------------------------------------------------------------ forward / backward

@@ -767,6 +767,8 @@ class Model:
                 continue
             it += 1
             if display > 0 and it % display == 0:
+                for e in self.ebcs_train:
+                    e.check_overflow()
                 loss = self.get_current_loss()
                 if math.isnan(loss):
                     raise RuntimeError("Train Runtime error: Loss cannot converge")  # model.cpp:889
@@ -819,6 +821,8 @@ class Model:
 
     # ------------------------------------------------------------------ checkpoints
     def save_params_to_files(self, prefix: str, iter: int = 0):
+        for e in getattr(self, "ebcs_train", []):
+            e.check_overflow()
         from .io.checkpoint import save_model
         save_model(self, prefix, iter)
 

@@ -137,7 +137,19 @@ class Network:
         for layer in reversed(layers):
             layer.bprop()
             if hook is not None and layer.params:
-                hook(min(p.offset for p in layer.params))
+                lo = min(p.offset for p in layer.params)
+                hook(lo, self._range_end(max(p.offset for p in layer.params)))
+
+    def _range_end(self, last_offset: int) -> int:
+        """arena offset where the parameter after ``last_offset`` starts (padding belongs to the
+        parameter in front of it), or the arena size"""
+        import bisect
+        offs = getattr(self, "_arena_offsets", None)
+        arena = self.ctx.arena
+        if offs is None:
+            offs = self._arena_offsets = sorted(p.offset for p in arena.params)
+        i = bisect.bisect_right(offs, last_offset)
+        return offs[i] if i < len(offs) else int(arena.wgrad.numel())
 
     def loss_value(self) -> torch.Tensor:
         tot = None

@@ -15,6 +15,19 @@ import torch
 from ..enums import AllReduceAlgo
 
 
+def advance_final(final_lo: int, pending):
+    """Move ``final_lo`` down over finished ranges that touch it; returns (final_lo, still pending)."""
+    moved = True
+    while moved:
+        moved = False
+        for (a, b) in pending:
+            if a < final_lo <= b:
+                final_lo = a
+                moved = True
+        pending = [(a, b) for (a, b) in pending if a < final_lo]
+    return final_lo, pending
+
+
 class ExchangeWgrad:
     def __init__(self, comm, wgrad: torch.Tensor, algo: AllReduceAlgo = AllReduceAlgo.NCCL):
         self.comm = comm
@@ -36,18 +49,29 @@ class ExchangeWgrad:
         """``after_bucket(lo, hi)``: optional callback run on the communication stream right after
         the bucket's all-reduce (the fused dense optimizer of that parameter range), so neither the
         reduction nor the update of the big upper layers sits at the tail of the step."""
-        self._done_lo = self.wgrad.numel()
+        self._done_lo = self.wgrad.numel()      # everything in [_done_lo, end) has been flushed
+        self._final_lo = self.wgrad.numel()     # everything in [_final_lo, end) is final (bprop done)
+        self._pending = []                      # finished layer ranges below _final_lo (out of order)
         self._after = after_bucket
         if self.wgrad.is_cuda and not hasattr(self, "_stream"):
             self._stream = torch.cuda.Stream()       # all-reduces, back to back
             self._opt_stream = torch.cuda.Stream()   # per-bucket optimizer slices, behind their bucket
 
-    def layer_done(self, lo: int, bucket_elems: int = 2 << 20):
-        """called after a trainable layer's bprop; lo = arena offset of its first parameter"""
+    def layer_done(self, lo: int, hi: int = None, bucket_elems: int = 2 << 20):
+        """called after a trainable layer's bprop; [lo, hi) = arena range of its parameters.
+
+        Layers need not finish back to front (the overlapped step runs the embedding-dependent "top"
+        pass before the "bottom" pass, and a bottom layer may have been declared after a top layer):
+        a range is flushed only when every parameter above it is final, i.e. ``_final_lo`` moves down
+        over CONTIGUOUS finished ranges (a range ends where the next parameter of the arena starts); out-of-order ranges wait in ``_pending``."""
         if not self.wgrad.is_cuda:
             return
-        if self._done_lo - lo >= bucket_elems:
-            self._flush(lo)
+        if hi is None:
+            hi = self._final_lo
+        self._final_lo, self._pending = advance_final(self._final_lo, self._pending + [(lo, hi)])
+        if self._done_lo - self._final_lo >= bucket_elems:
+            self._flush(self._final_lo)
+
 
     def _flush(self, lo: int):
         hi = self._done_lo

@@ -36,8 +36,8 @@ def make_cfg(world, plan):
     return cfg, sizes, hot, ev
 
 
-def run_ebc(plan, fused):
-    comm = Comm.init_from_env()
+def run_ebc(plan, fused, comm=None):
+    comm = comm or Comm.init_from_env()
     dev = comm.device
     world, rank = comm.world_size, comm.rank
     b = 32
@@ -87,10 +87,10 @@ def run_ebc(plan, fused):
         print(f"EBC_OK plan={plan} fused={fused} world={world}")
 
 
-def run_dynamic():
+def run_dynamic(comm=None):
     """dynamic (hashed) tables inside the collection: arbitrary 64-bit keys, rows assigned on first
     sight; must behave like the static tables they shadow (same values under a key bijection)"""
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     dev = comm.device
     world, rank = comm.world_size, comm.rank
     b, ev = 16, 8
@@ -113,7 +113,7 @@ def run_dynamic():
     opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.1, epsilon=1e-6)
     e = EmbeddingCollection(cfg_for(world, True), b, hot, dev, torch.float32, comm, opt, key_dtype=torch.int64,
                             seed=1)
-    assert e.has_dynamic and not e.fused
+    assert e.has_dynamic
     ref = EmbeddingCollection(cfg_for(1, False), b * world, hot, torch.device("cpu"), torch.float32,
                               Comm.single(torch.device("cpu")), opt, key_dtype=torch.int64, seed=1)
     gen = torch.Generator().manual_seed(9)
@@ -155,12 +155,12 @@ def run_dynamic():
         print("DYNAMIC_OK")
 
 
-def run_sok():
+def run_sok(comm=None):
     """sok.lookup_sparse over a distributed variable (rows sharded by key %% world): forward, sparse
     backward and optimizer step must equal a dense single-process embedding"""
     import hugectr_b200 as hugectr
     from hugectr_b200 import sok
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     world, rank = comm.world_size, comm.rank
     sok.init(comm)
     torch.manual_seed(0)
@@ -206,12 +206,12 @@ def run_sok():
         print("SOK_OK")
 
 
-def run_fuzz(seed):
+def run_fuzz(seed, comm=None):
     """randomised collection: random tables / hotness / combiners (sum, mean, concat) / batch- or
     feature-major tops / padded bags / random sharding plan (table-wise, row-wise, column-wise, dp),
     compared with a brute-force gather oracle (forward) and a scatter oracle (SGD backward)"""
     import random
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     dev = comm.device
     world, rank = comm.world_size, comm.rank
     rnd = random.Random(int(seed))
@@ -327,14 +327,14 @@ def run_fuzz(seed):
         print("FUZZ_OK", seed)
 
 
-def run_ebcio(tmpdir, seed):
+def run_ebcio(tmpdir, seed, comm=None):
     """parallel (every rank writes its windows) vs gather (rank 0 writes) collection dumps hold the same
     key -> (row, optimizer state) content for a random plan incl. column-wise, data-parallel and dynamic
     tables; a chunked load of the parallel dump restores every shard bit-exactly"""
     import random
     from types import SimpleNamespace as NS
     from hugectr_b200.io.checkpoint import embedding_dump, embedding_load, read_ebc_folder
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     dev, world, rank = comm.device, comm.world_size, comm.rank
     rnd = random.Random(int(seed))
     b, nt = 8, 5
@@ -405,12 +405,12 @@ def run_ebcio(tmpdir, seed):
         print("EBCIO_OK", seed)
 
 
-def run_symmfail():
+def run_symmfail(comm=None):
     """a peer-mapping failure on ONE rank makes EVERY rank raise (agreement before the error), so the
     job falls back to NCCL collectives as a whole instead of deadlocking in mismatched collectives"""
     import ctypes as C
     from hugectr_b200.parallel import symm
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
 
     class FakeLib:
         freed = closed = 0
@@ -435,8 +435,8 @@ def run_symmfail():
         print("SYMMFAIL_OK")
 
 
-def run_allreduce():
-    comm = Comm.init_from_env()
+def run_allreduce(comm=None):
+    comm = comm or Comm.init_from_env()
     from hugectr_b200.parallel.p2p import P2PAllReduce
     n = 4 * comm.world_size * 100003
     buf = comm.symm_alloc(n, torch.float32)
@@ -445,7 +445,7 @@ def run_allreduce():
         g = torch.Generator(device="cuda").manual_seed(it * 10 + comm.rank)
         x = torch.randn(n, device="cuda", generator=g)
         exp = x.clone()
-        dist.all_reduce(exp)
+        comm.all_reduce(exp)
         buf.copy_(x)
         ar.run()
         torch.cuda.synchronize()
@@ -456,12 +456,12 @@ def run_allreduce():
         print("ALLREDUCE_OK")
 
 
-def run_model():
+def run_model(comm=None):
     """whole-model data-parallel step: (NCCL all-reduce, no overlap, eager) vs (bucketed P2P
     all-reduce overlapped with backward, side streams, CUDA graph) must train to the same weights"""
     import hugectr_b200 as hugectr
     from hugectr_b200.models.dlrm import build_dlrm_dcnv2
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     world = comm.world_size
     cuda = comm.device.type == "cuda"
     sizes = [4000, 300, 50, 9000, 1200, 77]
@@ -471,11 +471,13 @@ def run_model():
         m = build_dlrm_dcnv2(batchsize=256 * world, num_gpus=world, table_sizes=sizes, multi_hot=hot,
                              ev_size=16, lr=0.05, mixed=cuda, optimizer="sgd", bottom=(64, 32, 16),
                              top=(64, 32, 1), cross_layers=2, projection_dim=16, comm=comm,
-                             all_reduce_algo=algo, use_cuda_graph=cuda)
+                             all_reduce_algo=algo,
+                             use_cuda_graph=cuda and not getattr(comm, "emulated", False))
         m.compile()
         return m
 
     flags = ("HCTR_DISABLE_AR_OVERLAP", "HCTR_DISABLE_OVERLAP", "HCTR_DISABLE_CUDA_GRAPH")
+    comm.barrier()
     for f in flags:
         os.environ[f] = "1"
     ma = build(hugectr.AllReduceAlgo.NCCL)
@@ -484,6 +486,7 @@ def run_model():
         ma.train_on_host_batch(pool[i % len(pool)])
     wa = ma.arena.weights.clone()
     la = ma.get_current_loss()
+    comm.barrier()                      # (emulated ranks share the process environment)
     for f in flags:
         os.environ[f] = "0"
     mb = build(hugectr.AllReduceAlgo.OneShot if cuda else hugectr.AllReduceAlgo.NCCL)
@@ -504,13 +507,13 @@ def run_model():
         print("MODEL_OK", err, la, lb)
 
 
-def run_equiv(optimizer="sgd", gpus_per_node=0):
+def run_equiv(optimizer="sgd", gpus_per_node=0, comm=None):
     """N-rank training (data-parallel dense, model-parallel / data-parallel embeddings) must equal
     single-process training on the concatenation of the ranks' batches."""
     import hugectr_b200 as hugectr
     from hugectr_b200.data.batch import HostBatch
     from hugectr_b200.models.dlrm import build_dlrm_dcnv2
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     world, rank = comm.world_size, comm.rank
     cuda = comm.device.type == "cuda"
     sizes = [4000, 300, 50, 9000, 1200, 77]
@@ -604,12 +607,12 @@ def run_equiv(optimizer="sgd", gpus_per_node=0):
         print("EQUIV_OK", err)
 
 
-def run_legacy():
+def run_legacy(comm=None):
     """legacy embeddings (Distributed = row-sharded over all ranks, Localized = slot s on rank s % N)
     trained data-parallel: replicas stay identical and the loss is finite"""
     import hugectr_b200 as hugectr
     from hugectr_b200.models import build_dcn, build_deepfm
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     world = comm.world_size
     slots = [120] * 26
     for build, kw in ((build_dcn, {}),
@@ -631,14 +634,14 @@ def run_legacy():
         print("LEGACY_OK")
 
 
-def run_ckpt(tmpdir):
+def run_ckpt(tmpdir, comm=None):
     """train on N ranks (row-sharded + table-wise + dp tables), save dense + embedding-collection
     checkpoints, load them into a SINGLE-process model (different sharding) and compare weights,
     tables and the loss on the same data (parameter_IO.cpp:262-350 re-sharding on load)"""
     import hugectr_b200 as hugectr
     from hugectr_b200.data.batch import HostBatch
     from hugectr_b200.models.dlrm import build_dlrm_dcnv2
-    comm = Comm.init_from_env()
+    comm = comm or Comm.init_from_env()
     world, rank = comm.world_size, comm.rank
     sizes = [4000, 300, 50, 9000, 1200, 77]
     hot = [3, 1, 1, 8, 2, 1]

@@ -264,3 +264,15 @@ def test_step_watchdog_dumps_stacks_of_a_hung_step(tmp_path):
         assert m.train() and m._watchdog is not None and not m._watchdog.armed
     finally:
         del os.environ["HCTR_STEP_TIMEOUT"]
+
+
+def test_bucket_finality_out_of_order():
+    """a bottom layer declared after a top layer must not be flushed before its bprop ran."""
+    from hugectr_b200.parallel.allreduce import advance_final
+    # arena: A [0,100) (top), B [100,200) (bottom, declared later), C [200,300) (top); top pass runs C then A
+    f, pend = advance_final(300, [(200, 300)])
+    assert (f, pend) == (200, [])
+    f, pend = advance_final(f, pend + [(0, 100)])        # A done, B not yet: nothing below 200 is final
+    assert f == 200 and pend == [(0, 100)]
+    f, pend = advance_final(f, pend + [(100, 200)])      # bottom pass: B done -> everything final
+    assert (f, pend) == (0, [])
