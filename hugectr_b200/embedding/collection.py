@@ -381,7 +381,7 @@ class EmbeddingCollection:
                                                need_scale=any(l.combiner == 1 for l in grp.lookups))
                 else:
                     n_pad = (n + 4 * self.world - 1) // (4 * self.world) * (4 * self.world)
-                    if self.fused and self.world > 1:
+                    if self.fused and self.world > 1 and not getattr(self.comm, "emulated", False):
                         from ..parallel.p2p import P2PAllReduce
                         grp.dense_wgrad_full = self.comm.symm_alloc(n_pad, torch.float32)
                         grp.p2p_ar = P2PAllReduce(self.comm, grp.dense_wgrad_full, blocks=32)

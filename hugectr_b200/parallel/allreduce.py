@@ -36,7 +36,9 @@ class ExchangeWgrad:
         self.extra = []     # grouped all-reduce: extra buffers (DP embedding wgrads)
         self._p2p = None
         if comm.world_size > 1 and algo in (AllReduceAlgo.OneShot, AllReduceAlgo.TwoShot) \
-                and comm.p2p_available:
+                and comm.p2p_available and not getattr(comm, "emulated", False):
+            # (emulated ranks share one device: a spinning kernel and a device-wide sync of another rank
+            # thread could deadlock; the kernel has its own emulated-rank test)
             from .p2p import P2PAllReduce
             self._p2p = P2PAllReduce(comm, wgrad)
 

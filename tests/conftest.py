@@ -21,3 +21,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_collection_modifyitems(config, items):
+    """emulated-rank tests run rank threads that rendezvous: a bug must fail fast instead of hanging the
+    (metered) GPU box until the outer timeout"""
+    import pytest as _pt
+    for it in items:
+        if "test_emu_ranks" in it.nodeid or "test_metrics_dist" in it.nodeid:
+            it.add_marker(_pt.mark.timeout(180))
