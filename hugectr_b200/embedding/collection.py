@@ -263,11 +263,11 @@ class EmbeddingCollection:
                 gl["partial_w"] = k * gl["ev"] * (gl["hotness"] if gl["combiner"] == "concat" else 1)
                 poff += b * gl["partial_w"]
         self.out_slab_elems = poff
-        # Experimental (HCTR_CONCAT_ALIAS=1): spare room behind the slabs so that a downstream Concat
+        # Default (HCTR_CONCAT_ALIAS=0 disables): spare room behind the slabs so that a downstream Concat
         # layer can have a batch-major top written straight into ITS output buffer (alias_top): the
         # kernels already take a row stride / offset per lookup, so the strided copy disappears.
         import os as _os
-        self.alias_reserve = 1024 if _os.environ.get("HCTR_CONCAT_ALIAS", "0") == "1" else 0
+        self.alias_reserve = 1024 if _os.environ.get("HCTR_CONCAT_ALIAS", "1") == "1" else 0
         self.alias_out_off, self.alias_grad_off = {}, {}
         goff = self.top_slab_elems
         if self.alias_reserve:

@@ -262,13 +262,13 @@ class ConcatLayer(Layer):
         return res
 
     def allocate(self):
-        """Experimental (HCTR_CONCAT_ALIAS=1): when exactly one input is a batch-major embedding
+        """Default (HCTR_CONCAT_ALIAS=0 disables): when exactly one input is a batch-major embedding
         collection top, the output buffer is carved from the collection's slabs and that top is
         produced (and its gradient consumed) in place -- no strided copy in either direction."""
         import os
         self._aliased = None
         o = self.outputs[0]
-        if os.environ.get("HCTR_CONCAT_ALIAS", "0") == "1" and self.axis == 1 and len(o.shape) == 2:
+        if os.environ.get("HCTR_CONCAT_ALIAS", "1") == "1" and self.axis == 1 and len(o.shape) == 2:
             cands = [i for i, t in enumerate(self.inputs)
                      if getattr(t, "ebc", None) is not None and len(t.shape) == 2 and t.dtype == o.dtype]
             if len(cands) == 1:

@@ -13,6 +13,11 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # emulated-rank tests run rank threads that rendezvous: a bug must fail fast instead of hanging the
+    # (metered) GPU box until the outer timeout
+    for it in items:
+        if "test_emu_ranks" in it.nodeid or "test_metrics_dist" in it.nodeid:
+            it.add_marker(pytest.mark.timeout(180))
     # HCTR_GPU_TESTS_ON_CPU=1: development aid -- run the bodies of the gpu-marked tests on the CPU
     # reference paths (those that do not address a cuda device explicitly) to find CPU-path regressions
     if torch.cuda.is_available() or os.environ.get("HCTR_GPU_TESTS_ON_CPU") == "1":
@@ -22,11 +27,3 @@ def pytest_collection_modifyitems(config, items):
         if "gpu" in item.keywords:
             item.add_marker(skip)
 
-
-def pytest_collection_modifyitems(config, items):
-    """emulated-rank tests run rank threads that rendezvous: a bug must fail fast instead of hanging the
-    (metered) GPU box until the outer timeout"""
-    import pytest as _pt
-    for it in items:
-        if "test_emu_ranks" in it.nodeid or "test_metrics_dist" in it.nodeid:
-            it.add_marker(_pt.mark.timeout(180))
