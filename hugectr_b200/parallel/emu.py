@@ -178,6 +178,9 @@ def run_ranks(world: int, fn: Callable[[EmuComm], object], device=None, p2p: boo
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
             else torch.device("cpu")
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     fab = EmuFabric(world, device)
     res: List[object] = [None] * world
     errs: List[object] = [None] * world
