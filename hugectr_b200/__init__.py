@@ -11,9 +11,9 @@ from .enums import (Activation_t, Alignment_t, AllReduceAlgo, Check_t, Communica
                     Embedding_t, Error_t, FcPosition_t, FileSystemType_t, Initializer_t, Layer_t,
                     LrPolicy_t, MetricsRawType, MetricsType, Optimizer_t, PowerLaw_t,
                     Regularizer_t, SourceType_t, Tensor_t, TrainPSType_t, Update_t)
-from .solver import (AsyncParam, CreateOptimizer, CreateSolver, DataReaderParams,
+from .solver import (AsyncParam, CreateETC, CreateHMemCache, CreateOptimizer, CreateSolver, DataReaderParams,
                      DataReaderSparseParam, DataSourceParams, DenseLayer, DenseLayerComputeConfig,
-                     Input, OptParamsPy, Solver, SparseEmbedding)
+                     EmbeddingTrainingCacheParams, HMemCacheConfig, Input, OptParamsPy, Solver, SparseEmbedding)
 from .embedding.collection import (EmbeddingCollectionConfig, EmbeddingTableConfig, InitParams)
 from .lr_scheduler import LearningRateScheduler
 from .model import Model, TrainingCallback

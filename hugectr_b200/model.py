@@ -46,8 +46,9 @@ class TrainingCallback:
 
 class Model:
     def __init__(self, solver: Solver, reader_params: DataReaderParams,
-                 opt_params: Optional[OptParamsPy] = None, comm: Optional[Comm] = None):
+                 opt_params: Optional[OptParamsPy] = None, etc=None, comm: Optional[Comm] = None):
         self.solver = solver
+        self.etc = etc                 # hugectr.CreateETC(...): host parameter server + gpu_cache per embedding
         self.reader_params = reader_params
         self.opt_params = opt_params or OptParamsPy()
         self.comm = comm or Comm.init_from_env()
@@ -205,10 +206,18 @@ class Model:
             for se in self.sparse_embeddings:
                 prm = [p for p in self.input.data_reader_sparse_param_array
                        if p.top_name == se.bottom_name][0]
-                rt = SparseEmbeddingRuntime(se, prm, self.layout, self.b_train, self.device,
-                                            self.act_dtype, self.comm, se.optimizer or self.opt_params,
-                                            self.key_dtype, scaler=s.scaler if self.mixed else 1.0,
-                                            seed=s.seed)
+                idx = len(self.legacy_train)
+                kw = dict(scaler=s.scaler if self.mixed else 1.0, seed=s.seed)
+                cls = SparseEmbeddingRuntime
+                if self.etc is not None and idx < len(self.etc.ps_types):
+                    from .embedding.offloaded import CachedSparseEmbeddingRuntime as cls   # noqa: N813
+                    kw.update(ps_type=self.etc.ps_types[idx], host_capacity=self.etc.host_capacity_rows,
+                              local_path=(self.etc.local_paths[idx] if idx < len(self.etc.local_paths) else None))
+                rt = cls(se, prm, self.layout, self.b_train, self.device, self.act_dtype, self.comm,
+                         se.optimizer or self.opt_params, self.key_dtype, **kw)
+                if cls is not SparseEmbeddingRuntime and idx < len(self.etc.sparse_models) \
+                        and self.etc.sparse_models[idx] and os.path.isdir(self.etc.sparse_models[idx]):
+                    rt.load_parameters(self.etc.sparse_models[idx])
                 self.legacy_train.append(rt)
                 self.legacy_eval.append(rt.eval_clone(self.b_eval))
 

@@ -89,7 +89,9 @@ def build_deepfm(batchsize=16384, vvgpu=None, source="synthetic", eval_source="s
 
 def build_wdl(batchsize=16384, vvgpu=None, source="synthetic", eval_source="synthetic",
               fmt=hugectr.DataReaderType_t.Parquet, wide_slot_sizes=None, deep_slot_sizes=None,
-              lr=0.001, workspace_mb=(23, 358), mixed=False, comm=None, **solver_kw):
+              lr=0.001, workspace_mb=(23, 358), mixed=False, comm=None, etc=None, **solver_kw):
+    """``etc=hugectr.CreateETC([TrainPSType_t.Cached, TrainPSType_t.Cached], ...)`` puts both tables on the
+    host parameter server behind the HBM gpu_cache (BASELINE config 5)."""
     wide = list(wide_slot_sizes or [1000, 1000])
     deep = list(deep_slot_sizes or [1000] * 26)
     solver = hugectr.CreateSolver(max_eval_batches=solver_kw.pop("max_eval_batches", 10),
@@ -97,7 +99,7 @@ def build_wdl(batchsize=16384, vvgpu=None, source="synthetic", eval_source="synt
                                   batchsize=batchsize, lr=lr, vvgpu=vvgpu or [[0]],
                                   repeat_dataset=True, use_mixed_precision=mixed, **solver_kw)
     opt = hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.Global)
-    model = hugectr.Model(solver, _reader(source, eval_source, fmt, wide + deep), opt, comm=comm)
+    model = hugectr.Model(solver, _reader(source, eval_source, fmt, wide + deep), opt, etc=etc, comm=comm)
     model.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=13, dense_name="dense",
                             data_reader_sparse_param_array=[
                                 hugectr.DataReaderSparseParam("wide_data", 1, True, len(wide)),

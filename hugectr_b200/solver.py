@@ -299,6 +299,39 @@ class SparseEmbedding:
         self.max_vocabulary_size_per_gpu = int(max_vocabulary_size_per_gpu)
 
 
+class HMemCacheConfig:
+    """hugectr.CreateHMemCache(num_blocks, target_hit_rate, max_num_evict) of the 22.x releases: sizing hints of
+    the host-memory cache; the host parameter server here keeps the whole table, the hints are recorded."""
+
+    def __init__(self, num_blocks: int = 1, target_hit_rate: float = 0.5, max_num_evict: int = 0):
+        self.num_blocks, self.target_hit_rate, self.max_num_evict = num_blocks, target_hit_rate, max_num_evict
+
+
+def CreateHMemCache(num_blocks: int = 1, target_hit_rate: float = 0.5, max_num_evict: int = 0) -> HMemCacheConfig:
+    return HMemCacheConfig(num_blocks, target_hit_rate, max_num_evict)
+
+
+class EmbeddingTrainingCacheParams:
+    """``hugectr.CreateETC(ps_types, sparse_models, local_paths, hmem_cache_configs)`` (embedding training cache,
+    HugeCTR/include/embedding_training_cache/*.hpp): one entry per SparseEmbedding, in model.add order.
+    ``TrainPSType_t.Cached``: table on the host parameter server, hot rows in the HBM gpu_cache;
+    ``TrainPSType_t.Staged``: host table, every step stages its rows.  ``sparse_models[i]``: directory the
+    table is initialised from / saved to ("" = fresh)."""
+
+    def __init__(self, ps_types, sparse_models, local_paths=None, hmem_cache_configs=None, host_capacity_rows=0):
+        self.ps_types = list(ps_types)
+        self.sparse_models = list(sparse_models)
+        self.local_paths = list(local_paths or [])
+        self.hmem_cache_configs = list(hmem_cache_configs or [])
+        self.host_capacity_rows = int(host_capacity_rows)
+        if len(self.sparse_models) not in (0, len(self.ps_types)):
+            raise ValueError("CreateETC: one sparse model path per ps_type")
+
+
+def CreateETC(ps_types, sparse_models=(), local_paths=None, hmem_cache_configs=None, host_capacity_rows=0):
+    return EmbeddingTrainingCacheParams(ps_types, sparse_models, local_paths, hmem_cache_configs, host_capacity_rows)
+
+
 @dataclass
 class DenseLayerComputeConfig:
     async_wgrad: bool = False
