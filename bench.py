@@ -299,6 +299,83 @@ def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, s
     return res
 
 
+CRITEO_KAGGLE_SLOTS = [1461, 558, 335378, 211710, 306, 20, 12136, 634, 4, 51298, 5302, 332600, 3179, 27, 12191,
+                       301211, 11, 4841, 2086, 4, 324273, 17, 16, 79734, 96, 58622]     # samples/deepfm (Criteo Kaggle)
+
+
+def run_secondary(args, comm):
+    """Secondary configurations of BASELINE.json through the public API (`--model`): every step = reader ->
+    pinned host batch -> H2D -> step (model.train()), device-timed with CUDA events, max over ranks.
+      deepfm     DeepFM, Criteo-shaped synthetic data, DistributedSlotSparseEmbeddingHash (config 2)
+      dlrm       MLPerf-v1 DLRM: Criteo-TB table sizes, 128-dim one-hot lookups, dot Interaction, SGD, bf16 (config 3)
+      wdl_cache  Wide&Deep, both tables on the host parameter server behind the HBM gpu_cache (config 5)"""
+    import torch
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.dlrm import CRITEO_TB_TABLE_SIZES, build_dlrm
+    from hugectr_b200.models.legacy import build_deepfm, build_wdl
+    n, rank = args.gpus, comm.rank
+    os.environ.setdefault("HCTR_SYNTH_POOL", "16")
+    vv = [list(range(n))]
+    if args.model == "deepfm":
+        b = 16384
+        m = build_deepfm(batchsize=b * n, vvgpu=vv, slot_sizes=CRITEO_KAGGLE_SLOTS, workspace_mb=2000, mixed=True,
+                         comm=comm, use_cuda_graph=not args.no_graph)
+        desc = "DeepFM (samples/deepfm): 26 Criteo slots, vec 11, DistributedSlotSparseEmbeddingHash, 3x400 MLP, Adam"
+    elif args.model == "dlrm":
+        b = 6912
+        tables = [min(t, args.cap_rows) for t in CRITEO_TB_TABLE_SIZES] if args.cap_rows else CRITEO_TB_TABLE_SIZES
+        m = build_dlrm(batchsize=b * n, num_gpus=n, table_sizes=tables, mixed=True, lr=0.5, comm=comm,
+                       use_cuda_graph=not args.no_graph)
+        desc = "DLRM (MLPerf v1): 26 Criteo-TB tables, ev 128, one-hot, dot Interaction, top 1024-1024-512-256-1, SGD"
+    elif args.model == "wdl_cache":
+        b = 16384
+        etc = hugectr.CreateETC(ps_types=[hugectr.TrainPSType_t.Cached] * 2, sparse_models=["", ""],
+                                host_capacity_rows=8 << 20)
+        m = build_wdl(batchsize=b * n, vvgpu=vv, wide_slot_sizes=CRITEO_KAGGLE_SLOTS[:2],
+                      deep_slot_sizes=CRITEO_KAGGLE_SLOTS, workspace_mb=(64, 1024), mixed=True, comm=comm, etc=etc)
+        desc = ("Wide&Deep (samples/wdl): 2 + 26 Criteo slots, tables on the host parameter server, hot rows in the "
+                "HBM gpu_cache (TrainPSType_t.Cached), Adam")
+    else:
+        raise SystemExit(f"unknown --model {args.model}")
+    m.compile()
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W + 2):
+        m.train()
+    torch.cuda.synchronize(); comm.barrier()
+    c0 = __import__("hugectr_b200.ops.dense", fromlist=["x"]).launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loss_host = torch.zeros(1).pin_memory()
+    e0.record()
+    for _ in range(K):
+        m.train()
+        loss_host.copy_(m.net_train.loss_value(), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(); comm.barrier()
+    launches = __import__("hugectr_b200.ops.dense", fromlist=["x"]).launch_count - c0
+    t = torch.tensor([e0.elapsed_time(e1)], device=m.device)
+    if n > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        hb = m.reader_train.pool[0]
+        v = b * n * K / (ms / 1e3)
+        extra = {}
+        if args.model == "wdl_cache":
+            rt = m.legacy_train[1]
+            extra = {"cache_hit_rate": rt.cache.hits / max(1, rt.cache.queries), "host_rows": rt.ps.size()}
+        print(json.dumps({
+            "metric": f"{args.model} training samples/sec (device-timed, max over ranks, end to end through model.train())",
+            "value": v, "unit": "samples/s", "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "impl": "b200", "secondary": True,
+            "config": {"model": desc, "global_batch": b * n, "per_gpu_batch": b, "seq_len": None,
+                       "parallelism": f"dp{n} dense + model-parallel embeddings",
+                       "cuda_graph": bool(m._graph is not None), "final_loss": m.get_current_loss(), **extra},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches // max(K, 1))}), flush=True)
+    m.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,6 +393,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the bf16-state full-size run")
     ap.add_argument("--sustained-sec", type=float, default=2.0)
     ap.add_argument("--ref-timeout", type=int, default=1500)
+    ap.add_argument("--model", default="dlrm_dcnv2",
+                    help="dlrm_dcnv2 (headline) | deepfm | dlrm | wdl_cache (secondary configurations)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -332,6 +411,12 @@ def main():
     comm = Comm.init_from_env()
     rank, n = comm.rank, args.gpus
     W, K = max(args.warmup, 3), args.steps
+    if args.model != "dlrm_dcnv2":
+        run_secondary(args, comm)
+        sys.stdout.flush()
+        faulthandler.dump_traceback_later(120, exit=True)
+        comm.shutdown()
+        return 0
     # 104 GB of fp32 tables + 104 GB of fp32 AdaGrad state do not fit one 180 GB GPU.  N == 1 therefore runs
     # fp32 state (the reference's precision) with the six 40 M-row tables capped at ROW_CAP_1GPU rows (declared
     # in config.row_cap; same random-access pattern, 146 GB resident), and reports the full-size run with bf16

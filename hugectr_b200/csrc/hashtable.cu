@@ -71,6 +71,72 @@ __global__ void ht_get_insert_kernel(HashTableView t, const long long* __restric
   out[i] = -1;
 }
 
+// Ownership filter + translation in one pass over an inbox of gathered keys [ranks x n_per_rank]
+// (legacy embeddings on the fused path): a key is translated iff this rank owns it,
+//   Distributed  key % key_mod == key_rem
+//   Localized    ((position / slot_div) % slot_num) % key_mod == key_rem     (slot of the key's position)
+// everything else becomes -1.  Same bounded insert as ht_get_insert_kernel.
+struct OwnFilter {
+  long long n_per_rank;
+  int key_mod, key_rem;      // key_mod <= 1: no key filter
+  int slot_div, slot_num;    // slot_num <= 0: no slot filter
+};
+__global__ void ht_translate_kernel(HashTableView t, const long long* __restrict__ keys,
+                                    long long* __restrict__ out, long long n, int insert,
+                                    unsigned int* __restrict__ overflow, OwnFilter f) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long key = keys[i];
+  bool own = key >= 0;
+  if (own && f.slot_num > 0) {
+    const long long pos = i % f.n_per_rank;
+    own = (((pos / f.slot_div) % f.slot_num) % f.key_mod) == f.key_rem;
+  } else if (own && f.key_mod > 1) {
+    own = static_cast<int>(static_cast<unsigned long long>(key) % static_cast<unsigned long long>(f.key_mod)) ==
+          f.key_rem;
+  }
+  if (!own) {
+    out[i] = -1;
+    return;
+  }
+  const unsigned long long k = static_cast<unsigned long long>(key);
+  unsigned long long h = hash64(k) & t.capacity_mask;
+  for (unsigned long long probes = 0; probes <= t.capacity_mask; ++probes) {
+    unsigned long long prev = *reinterpret_cast<volatile unsigned long long*>(&t.keys[h]);
+    if (prev == kEmptyKey && insert) {
+      if (static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(t.counter)) >= t.max_rows) {
+        if (overflow) atomicMax(overflow, 1u);
+        out[i] = -1;
+        return;
+      }
+      prev = atomicCAS(&t.keys[h], kEmptyKey, k);
+    }
+    if (prev == kEmptyKey) {
+      if (!insert) {
+        out[i] = -1;
+        return;
+      }
+      const unsigned long long row = atomicAdd(t.counter, 1ull);
+      atomicExch(reinterpret_cast<unsigned long long*>(&t.vals[h]), row);
+      const bool ok = static_cast<long long>(row) < t.max_rows;
+      if (!ok && overflow) atomicMax(overflow, 1u);
+      out[i] = ok ? static_cast<long long>(row) : -1;
+      return;
+    }
+    if (prev == k) {
+      long long v;
+      do {
+        v = *reinterpret_cast<volatile long long*>(&t.vals[h]);
+      } while (v < 0);
+      out[i] = v < t.max_rows ? v : -1;
+      return;
+    }
+    h = (h + 1) & t.capacity_mask;
+  }
+  if (overflow) atomicMax(overflow, 1u);
+  out[i] = -1;
+}
+
 __global__ void ht_set_kernel(HashTableView t, const long long* __restrict__ keys,
                               const long long* __restrict__ vals, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -113,6 +179,19 @@ extern "C" int hctr_ht_get_insert(void* keys_tab, void* vals_tab, void* counter,
                   capacity - 1, max_rows};
   ht_get_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       t, keys, out, n, insert, reinterpret_cast<unsigned int*>(overflow));
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int hctr_ht_translate(void* keys_tab, void* vals_tab, void* counter, unsigned long long capacity,
+                                 long long max_rows, const long long* keys, long long* out, long long n,
+                                 int insert, void* overflow, long long n_per_rank, int key_mod, int key_rem,
+                                 int slot_div, int slot_num, void* stream) {
+  if (n == 0) return 0;
+  HashTableView t{(unsigned long long*)keys_tab, (long long*)vals_tab, (unsigned long long*)counter,
+                  capacity - 1, max_rows};
+  OwnFilter f{n_per_rank, key_mod, key_rem, slot_div, slot_num};
+  ht_translate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      t, keys, out, n, insert, reinterpret_cast<unsigned int*>(overflow), f);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -636,7 +636,7 @@ class EmbeddingCollection:
                 # forward all-to-all of keys: posted peer stores into the owners' inboxes, then ONE
                 # device barrier (also orders the previous step's readers of these inboxes)
                 E.dispatch(self.key_slab, self._key_routes, self._key_routes_dev, self.peer_keys_all,
-                           self.peer_nnz)
+                           self.peer_nnz, blocks_x=48)
                 self.comm.barrier_device()
             elif os.environ.get("SKIP_DATA_DISTRIBUTOR", "0") not in ("0", ""):
                 pass          # ablation (model_pipeline.cpp:118): owners keep the keys of an earlier step
@@ -835,7 +835,7 @@ class EmbeddingCollection:
                 if self._grad_routes is None:
                     self._build_grad_routes()
                 E.dispatch(self.grad_slab, self._grad_routes, self._grad_routes_dev, self.peer_grads_all,
-                           blocks_x=16)
+                           blocks_x=24)
                 self.comm.barrier_device()
             elif os.environ.get("SKIP_ALL2ALL", "0") not in ("0", ""):
                 pass

@@ -23,6 +23,8 @@ def lib():
         l.hctr_ht_get_insert.argtypes = [vp, vp, vp, ull, ll, vp, vp, ll, i, vp, vp]
         l.hctr_ht_set.argtypes = [vp, vp, vp, ull, vp, vp, ll, vp]
         l.hctr_ht_dump.argtypes = [vp, vp, ull, vp, vp, vp, vp]
+        l.hctr_ht_translate.argtypes = [vp, vp, vp, ull, ll, vp, vp, ll, i, vp, ll, i, i, i, i, vp]
+        l.hctr_ht_translate.restype = i
         for n in ("hctr_ht_get_insert", "hctr_ht_set", "hctr_ht_dump"):
             getattr(l, n).restype = i
         _lib = l
@@ -92,6 +94,31 @@ class HashTable:
             else:
                 res.append(-1)
         return torch.tensor(res, dtype=torch.int64).view(keys.shape)
+
+    def translate(self, keys: torch.Tensor, out: torch.Tensor, insert: bool, n_per_rank: int, key_mod: int = 1,
+                  key_rem: int = 0, slot_div: int = 1, slot_num: int = 0):
+        """out = row of every OWNED key of ``keys`` (int64, any shape; -1 elsewhere) in one launch, no host
+        sync.  Ownership: ``key % key_mod == key_rem`` or, with ``slot_num`` > 0, the slot of the key's
+        position ``((pos % n_per_rank) // slot_div) % slot_num) % key_mod == key_rem``."""
+        k = keys.reshape(-1)
+        if self.device.type == "cuda":
+            rc = lib().hctr_ht_translate(self.keys.data_ptr(), self.vals.data_ptr(), self.counter.data_ptr(),
+                                         self.capacity, self.max_rows, k.data_ptr(), out.data_ptr(), k.numel(),
+                                         int(insert), self.overflow.data_ptr(), int(n_per_rank), int(key_mod),
+                                         int(key_rem), int(slot_div), int(slot_num), self._st())
+            if rc:
+                raise RuntimeError("hash translate failed")
+            D._count()
+            return out
+        pos = torch.arange(k.numel()) % max(int(n_per_rank), 1)
+        own = k >= 0
+        if slot_num > 0:
+            own &= ((pos // slot_div) % slot_num) % key_mod == key_rem
+        elif key_mod > 1:
+            own &= (k % key_mod) == key_rem
+        kk = torch.where(own, k, torch.full_like(k, -1))
+        out.reshape(-1).copy_(self._lookup(kk, insert))
+        return out
 
     def set(self, keys: torch.Tensor, vals: torch.Tensor):
         k, v = keys.reshape(-1).to(torch.int64), vals.reshape(-1).to(torch.int64)

@@ -147,7 +147,7 @@ class CachedSparseEmbeddingRuntime(SparseEmbeddingRuntime):
         order = torch.argsort(keys)
         keys, rows = keys[order], rows[order]
         w = self.ps.w[rows].clone()
-        return self.comm.all_gather_object((keys, w))
+        return self.comm.all_gather_object((keys, w, self._slot_ids(keys) if self.localized else None))
 
     def load_parameters(self, path: str):
         keys = torch.from_numpy(np.fromfile(os.path.join(path, "key"), dtype="<i8").astype("int64"))

@@ -11,9 +11,16 @@ Reference semantics:
   eval uses lookup-only (get_mark): unseen keys contribute zero vectors
   check_overflow: "Runtime vocabulary size ... exceeds max_vocabulary_size_per_gpu"
 
-Implementation: keys are translated to dense rows by the GPU HashTable, then the SAME owner-side
-pool / accumulate / fused-update kernels as the EmbeddingCollection run on the row buffer; the
-exchange uses the collective back-end (all-gather of keys, all-to-all of pooled vectors).
+Implementation: keys are translated to dense rows by the GPU HashTable (ownership filter + bounded insert
+in ONE kernel, overflow raised through a device flag), then the SAME owner-side pool / accumulate /
+fused-update kernels as the EmbeddingCollection run on the row buffer.  Exchange:
+  fused       (CUDA, world > 1, peer-mapped heap) every rank scatters its key block into all owners'
+              inboxes and its top-gradients into their gradient inboxes with posted peer stores
+              (csrc/emb_dispatch.cu); owners write their partial pooled vectors straight into the
+              requesters' receive slabs.  Device barriers only: no NCCL, no host sync -- the whole step is
+              captured in the model's CUDA graph like the EmbeddingCollection path.
+  collective  (CPU / gloo, HCTR_DISABLE_P2P) all-gather of keys, all-to-all of pooled vectors, all-gather
+              of gradients through torch.distributed.
 """
 from __future__ import annotations
 
@@ -75,11 +82,39 @@ class SparseEmbeddingRuntime:
         self.top_data = torch.zeros(b, S, vec, dtype=act_dtype, device=device)
         self.top_grad = torch.zeros(b, S, vec, dtype=act_dtype, device=device) if self.is_train else None
         self.keys_loc = torch.full((b * S * H,), -1, dtype=torch.int64, device=device)
-        self.keys_all = torch.full((W, b * S * H), -1, dtype=torch.int64, device=device)
         self.rows_all = torch.full((W, b * S * H), -1, dtype=torch.int64, device=device)
-        self.partial = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device)
-        self.recv = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device)
-        self.grads_all = torch.zeros(W, b * S * vec, dtype=act_dtype, device=device) if self.is_train else None
+        nk, nv = b * S * H, b * S * vec
+        self.fused = (device.type == "cuda" and W > 1 and comm.p2p_available
+                      and os.environ.get("HCTR_LEGACY_FUSED", "1") == "1")
+        if self.fused:
+            sa = comm.symm_alloc
+            self.keys_all = sa(W * nk, torch.int64).view(W, nk)
+            self.keys_all.fill_(-1)
+            self.recv = sa(W * nv, act_dtype).view(W, nv)            # slot o: partial sums from owner o
+            self.peer_keys_all = comm.peer_ptrs(self.keys_all)
+            esz = 2 if act_dtype == torch.bfloat16 else 4
+            self.peer_recv_me = [p + self.rank * nv * esz for p in comm.peer_ptrs(self.recv)]
+            self.partial = None
+            me = self.rank
+            self._key_routes = [E.Route(0, me * nk, 1, nk, nk, nk, g) for g in range(W)]
+            self._key_routes_dev = E.routes_to_device(self._key_routes, device)
+            if self.is_train:
+                self.grads_all = sa(W * nv, act_dtype).view(W, nv)
+                self.peer_grads_all = comm.peer_ptrs(self.grads_all)
+                self._grad_routes = [E.Route(0, me * nv, 1, nv, nv, nv, g) for g in range(W)]
+                self._grad_routes_dev = E.routes_to_device(self._grad_routes, device)
+            else:
+                self.grads_all = None
+            self._out_sum = torch.zeros(nv, dtype=act_dtype, device=device)
+        else:
+            self.keys_all = torch.full((W, nk), -1, dtype=torch.int64, device=device)
+            self.partial = torch.zeros(W, nv, dtype=act_dtype, device=device)
+            self.recv = torch.zeros(W, nv, dtype=act_dtype, device=device)
+            self.grads_all = torch.zeros(W, nv, dtype=act_dtype, device=device) if self.is_train else None
+        # no per-step host work (device-side overflow flag): the step is graph capturable unless the
+        # optimizer variant needs torch.unique (LazyGlobal Adam)
+        self.graph_safe = (W == 1 or self.fused) and device.type == "cuda" and not (
+            opt.update_type == Update_t.LazyGlobal and opt.optimizer_type == Optimizer_t.Adam)
         # one lookup per slot over the row buffer: keys [b, S, H] sample-major
         self.lookups: List[E.LookupDesc] = []
         for s in range(S):
@@ -137,24 +172,52 @@ class SparseEmbeddingRuntime:
                                f"({self.max_rows}) of {self.name}, new feature insertion failed.")
 
     # ------------------------------------------------------------------ forward / backward
+    def _translate(self, is_train: bool):
+        """keys_all -> rows_all: rows of the keys this rank owns, -1 elsewhere (one kernel, no host sync)"""
+        n = self.b * self.S * self.H
+        if self.localized:
+            self.hash.translate(self.keys_all, self.rows_all, is_train, n, key_mod=self.world, key_rem=self.rank,
+                                slot_div=self.H, slot_num=self.S)
+        else:
+            self.hash.translate(self.keys_all, self.rows_all, is_train, n, key_mod=self.world, key_rem=self.rank)
+        if self.localized and is_train and self.slot_of_row is not None:
+            # remember the slot of every row (dumped as slot_id; the reference stores it per hash value)
+            r = self.rows_all.reshape(-1)
+            slot = (torch.arange(r.numel(), device=r.device) % n) // self.H % self.S
+            self.slot_of_row.index_put_((r.clamp(min=0),), torch.where(r >= 0, slot, self.slot_of_row[r.clamp(min=0)]))
+
     def forward(self, is_train: bool):
         W, b, S, H, vec = self.world, self.b, self.S, self.H, self.vec
-        self.comm.all_gather(self.keys_all, self.keys_loc)
-        own = self._owner_mask(self.keys_all)
-        k = torch.where(own, self.keys_all, torch.full_like(self.keys_all, -1))
-        rows = self.hash.get_insert(k) if is_train else self.hash.get(k)
-        self.rows_all.copy_(rows)
-        if is_train and os.environ.get("HUGECTR_DISABLE_OVERFLOW_CHECK", "0") != "1":
+        if self.fused:
+            # key all-gather by posted peer stores into every owner's inbox, one device barrier
+            E.dispatch(self.keys_loc, self._key_routes, self._key_routes_dev, self.peer_keys_all)
+            self.comm.barrier_device()
+        else:
+            self.comm.all_gather(self.keys_all, self.keys_loc)
+        self._translate(is_train)
+        if is_train and not self.graph_safe and os.environ.get("HUGECTR_DISABLE_OVERFLOW_CHECK", "0") != "1":
             self.check_overflow()
-        self.partial.zero_()
-        E.forward(self.lookups, self.lookups_dev, self.table, vec, list(self.rows_all.unbind(0)),
-                  list(self.partial.unbind(0)), b, self.rank)
-        self.comm.all_to_all(self.recv, self.partial)
-        out = self.recv.float().sum(0).view(b, S, vec)
+        if self.fused:
+            # partial pooled vectors of MY rows go straight into slot [me] of every requester's slab
+            E.forward(self.lookups, self.lookups_dev, self.table, vec, list(self.rows_all.unbind(0)),
+                      self.peer_recv_me, b, self.rank, key_bytes=8, act_bf16=self.act_dtype == torch.bfloat16)
+            self.comm.barrier_device()
+            if self.recv.is_cuda and self.recv.dtype in (torch.float32, torch.bfloat16):
+                from ..ops import layer_ops as LO
+                LO.reduce_mid(self.recv, self._out_sum, 1, W, b * S * vec, 1.0, False)
+                out = self._out_sum.view(b, S, vec)
+            else:
+                out = self.recv.float().sum(0).view(b, S, vec)
+        else:
+            self.partial.zero_()
+            E.forward(self.lookups, self.lookups_dev, self.table, vec, list(self.rows_all.unbind(0)),
+                      list(self.partial.unbind(0)), b, self.rank)
+            self.comm.all_to_all(self.recv, self.partial)
+            out = self.recv.float().sum(0).view(b, S, vec)
         if self.combiner == 1:
             cnt = (self.keys_loc.view(b, S, H) >= 0).sum(-1).clamp(min=1).float()
             self._nnz_cnt = cnt
-            out = out / cnt.unsqueeze(-1)
+            out = out.float() / cnt.unsqueeze(-1)
         self.top_data.copy_(out.to(self.top_data.dtype))
 
     def backward(self, lr_t, step_t):
@@ -162,7 +225,16 @@ class SparseEmbeddingRuntime:
         g = self.top_grad
         if self.combiner == 1:
             g = (g.float() / self._nnz_cnt.unsqueeze(-1)).to(self.top_grad.dtype)
-        self.comm.all_gather(self.grads_all, g.reshape(-1))
+        if self.fused:
+            # gradient all-gather by posted peer stores, one device barrier; no end-of-step barrier is
+            # needed (the next step's key dispatch barrier orders the inbox reuse)
+            gsrc = g.reshape(-1)
+            if not gsrc.is_contiguous():
+                gsrc = gsrc.contiguous()
+            E.dispatch(gsrc, self._grad_routes, self._grad_routes_dev, self.peer_grads_all)
+            self.comm.barrier_device()
+        else:
+            self.comm.all_gather(self.grads_all, g.reshape(-1))
         kb = list(self.rows_all.unbind(0))
         gb = list(self.grads_all.unbind(0))
         hp = {"scaler": self.scaler, "beta1": self.opt.beta1, "beta2": self.opt.beta2,
@@ -171,9 +243,11 @@ class SparseEmbeddingRuntime:
         if self.opt.update_type == Update_t.LazyGlobal and self.opt.optimizer_type == Optimizer_t.Adam:
             return self._lazy_adam(lr_t, step_t)
         if self.indexed:
-            E.bwd_index(self.lookups, self.lookups_dev, self.table, vec, kb, b, self.ws, self.rank)
+            abf = self.act_dtype == torch.bfloat16
+            E.bwd_index(self.lookups, self.lookups_dev, self.table, vec, kb, b, self.ws, self.rank, key_bytes=8)
             E.bwd_reduce_update(self.opt.optimizer_type, self.lookups, self.lookups_dev, self.table,
-                                self.s0, self.s1, vec, kb, gb, b, self.ws, hp, lr_t, step_t, 1.0, self.rank)
+                                self.s0, self.s1, vec, kb, gb, b, self.ws, hp, lr_t, step_t, 1.0, self.rank,
+                                key_bytes=8, act_bf16=abf)
         else:
             E.backward_accum(self.lookups, self.lookups_dev, self.table, vec, kb, gb, b, self.ws, 1.0,
                              self.rank)
@@ -222,12 +296,15 @@ class SparseEmbeddingRuntime:
         update mathematically identical to the dense optimizer.  LazyGlobal (the reference's cheaper
         approximation of the same thing) takes this exact path too."""
         vec = self.vec
-        n = min(int(self.hash.size()), self.max_rows)
-        if n == 0:
-            return
+        n = self.max_rows                      # (allocated rows only, masked on the device: no host sync)
+        if self.device.type == "cuda":
+            alive = torch.arange(n, device=self.device) < self.hash.counter
+        else:
+            alive = torch.arange(n) < int(self.hash.size())
         touched = torch.zeros(self.max_rows, dtype=torch.bool, device=self.device)
         r = self.rows_all.reshape(-1)
-        touched[r[r >= 0]] = True
+        touched.index_put_((r.clamp(min=0),), (r >= 0), accumulate=False)
+        touched |= ~alive                       # never-allocated rows are left alone
         unt = (~touched[:n]).unsqueeze(1)
         w = self.table.view(-1, vec)[:n]
         s0 = self.s0.view(-1, vec)[:n]
@@ -257,8 +334,13 @@ class SparseEmbeddingRuntime:
     def _gather_all(self):
         keys, rows = self.hash.dump()
         w = self.table.view(-1, self.vec)[rows.to(self.device)].cpu()
-        parts = self.comm.all_gather_object((keys, w))
-        return parts
+        slots = None
+        if self.localized:
+            # the slot recorded when the row was created (forward); rows that only exist through
+            # load_parameters fall back to the slot_size_array ranges
+            rec = self.slot_of_row[rows.to(self.device)].cpu()
+            slots = torch.where(rec >= 0, rec, self._slot_ids(keys))
+        return self.comm.all_gather_object((keys, w, slots))
 
     def dump_parameters(self, path: str):
         parts = self._gather_all()
@@ -269,7 +351,7 @@ class SparseEmbeddingRuntime:
             keys.numpy().astype("<i8").tofile(os.path.join(path, "key"))
             w.numpy().astype("<f4").tofile(os.path.join(path, "emb_vector"))
             if self.localized:
-                slots = self._slot_ids(keys)
+                slots = torch.cat([p[2] for p in parts])
                 slots.numpy().astype("<u8").tofile(os.path.join(path, "slot_id"))
         self.comm.barrier()
 
@@ -292,6 +374,9 @@ class SparseEmbeddingRuntime:
         rows = self.hash.get_insert(k.to(self.device))
         self.check_overflow()
         self.table.view(-1, self.vec)[rows] = w[m].to(self.device)
+        self._loaded_keys = keys                 # file order: optimizer states are matched by key
+        if self.localized and self.slot_of_row is not None and os.path.exists(os.path.join(path, "slot_id")):
+            self.slot_of_row[rows] = slot[m].to(self.device)
 
     def dump_opt_states(self, path: str):
         keys, rows = self.hash.dump()
@@ -304,15 +389,26 @@ class SparseEmbeddingRuntime:
         self.comm.barrier()
 
     def load_opt_states(self, path: str):
+        """States are stored in the order of the sparse model's ``key`` file (all ranks' rows concatenated).
+        They are matched BY KEY: the hash table hands out rows in arbitrary order within a launch, so the
+        row order of this process says nothing about the file order."""
         raw = np.fromfile(path, dtype="<f4")
         states = [s for s in (self.s0, self.s1) if s is not None]
         if not states:
             return
-        keys, rows = self.hash.dump()
-        parts = self.comm.all_gather_object(int(keys.numel()))
-        tot = sum(parts)
-        off = sum(parts[:self.rank])
+        keys = getattr(self, "_loaded_keys", None)
+        if keys is None:
+            # no sparse model loaded in this process: the file order is the order a dump would write now
+            kd, _ = self.hash.dump()
+            keys = torch.cat([p for p in self.comm.all_gather_object(kd)])
+        tot = keys.numel()
+        if raw.size != len(states) * tot * self.vec:
+            raise RuntimeError(f"optimizer state file {path} holds {raw.size} values, expected "
+                               f"{len(states)} x {tot} x {self.vec} for the loaded sparse model")
+        rows = self.hash.get(keys.to(self.device))           # -1: key lives on another rank
+        mine = (rows >= 0).cpu()
+        r = rows[mine.to(rows.device)]
         per = tot * self.vec
         for i, s in enumerate(states):
             blk = torch.from_numpy(raw[i * per:(i + 1) * per].copy()).view(tot, self.vec)
-            s.view(-1, self.vec)[rows.to(self.device)] = blk[off:off + keys.numel()].to(self.device)
+            s.view(-1, self.vec)[r] = blk[mine].to(self.device)

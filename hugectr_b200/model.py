@@ -417,6 +417,11 @@ class Model:
                 # so forward CTAs are scheduled ahead of its still-pending blocks.
                 self._s_emb = torch.cuda.Stream(priority=int(os.environ.get("HCTR_PRIO_EMB", "-1")))
                 self._s_idx = torch.cuda.Stream(priority=int(os.environ.get("HCTR_PRIO_IDX", "0")))
+                # The bottom-MLP backward (a chain of small kernels) and the last all-reduce bucket end the
+                # step: above the embedding update's priority, so their blocks take the first SM slots that
+                # free up instead of queueing behind a GPU-filling update kernel (measured: the chain took
+                # ~180 us beside the update at priority 0, ~80 us of work)
+                self._s_bot = torch.cuda.Stream(priority=int(os.environ.get("HCTR_PRIO_BOTTOM", "-3")))
             s_emb, s_idx = self._s_emb, self._s_idx
             for e in self.ebcs_train:
                 e.forward_begin()
@@ -447,7 +452,10 @@ class Model:
                 with torch.cuda.stream(s_emb):
                     for e in self.ebcs_train:
                         e.backward(self.lr_t, self.step_t, dp_stream=s_idx)
-            net.bprop("bottom")
+            self._s_bot.wait_stream(main)
+            with torch.cuda.stream(self._s_bot):
+                net.bprop("bottom")
+            main.wait_stream(self._s_bot)
         else:
             for e in self.ebcs_train:
                 e.forward(True)

@@ -56,8 +56,10 @@ class ExchangeWgrad:
         self._pending = []                      # finished layer ranges below _final_lo (out of order)
         self._after = after_bucket
         if self.wgrad.is_cuda and not hasattr(self, "_stream"):
-            self._stream = torch.cuda.Stream()       # all-reduces, back to back
-            self._opt_stream = torch.cuda.Stream()   # per-bucket optimizer slices, behind their bucket
+            import os
+            prio = int(os.environ.get("HCTR_PRIO_COMM", "-3"))
+            self._stream = torch.cuda.Stream(priority=prio)       # all-reduces, back to back
+            self._opt_stream = torch.cuda.Stream(priority=prio)   # per-bucket optimizer slices, behind their bucket
 
     def layer_done(self, lo: int, hi: int = None, bucket_elems: int = 2 << 20):
         """called after a trainable layer's bprop; [lo, hi) = arena range of its parameters.
