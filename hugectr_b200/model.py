@@ -523,6 +523,7 @@ class Model:
     def _run_step(self):
         use_graph = (self.solver.use_cuda_graph and self.device.type == "cuda"
                      and os.environ.get("HCTR_DISABLE_CUDA_GRAPH", "0") == "0"
+                     and not getattr(self.comm, "emulated", False)     # (rank threads share one device)
                      and self._graph_safe())
         if not use_graph:
             c0 = D.launch_count

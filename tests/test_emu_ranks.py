@@ -97,3 +97,14 @@ def test_emu_dynamic_tables_fused_gpu():
 
 def test_emu_dynamic_tables_cpu():
     run_ranks(2, lambda c: W.run_dynamic(comm=c), device=CPU)
+
+
+def test_emu_legacy_embeddings_cpu():
+    run_ranks(2, lambda c: W.run_legacy(comm=c), device=CPU)
+
+
+@pytest.mark.gpu
+def test_emu_legacy_embeddings_fused_gpu():
+    """Distributed / Localized hash embeddings on the fused path (peer-store key / gradient exchange,
+    one-kernel ownership filter + hash translation): replicas stay identical, loss finite"""
+    run_ranks(4, lambda c: W.run_legacy(comm=c))

@@ -1,0 +1,55 @@
+"""Block-scaled fp8 (MX) GEMM: quantiser against the PyTorch reference (bit exact), tensor-core GEMM
+(tcgen05.mma.kind::mxf8f6f4.block_scale, scales in TMEM) against the fp32 product of the de-quantised operands."""
+import pytest
+import torch
+
+from hugectr_b200.ops import gemm as G
+from hugectr_b200.ops import mxfp8 as MX
+
+
+def test_mx_quantize_reference_roundtrip_cpu():
+    torch.manual_seed(0)
+    x = torch.randn(200, 256) * torch.logspace(-3, 2, 256).unsqueeze(0)
+    q, sf = MX.mx_quantize_reference(x)
+    xd = MX.mx_dequantize(q, sf, 200, 256)
+    rel = (xd - x).abs() / x.abs().clamp(min=1e-6)
+    assert rel.median() < 0.04                                # e4m3: 3 mantissa bits
+    blk = (xd - x).view(200, 8, 32).abs().amax(-1) / x.view(200, 8, 32).abs().amax(-1)
+    assert blk.max() < 0.07                                  # error relative to the block's largest element
+    y = MX.gemm_mxfp8(q, sf, q, sf, 200, 200, 256, flags=G.EPI_OUT_F32)
+    assert torch.allclose(y, xd @ xd.t(), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transposed", [False, True])
+def test_mx_quantize_kernel_matches_reference(transposed):
+    torch.manual_seed(1)
+    x = (torch.randn(300, 384) * torch.logspace(-2, 1, 384).unsqueeze(0)).to(torch.bfloat16)
+    xin = x.t().contiguous().cuda() if transposed else x.cuda()
+    q, sf = MX.mx_quantize(xin, transposed=transposed)
+    qr, sfr = MX.mx_quantize_reference(x)
+    assert torch.equal(sf.cpu(), sfr)
+    # fp8 rounding of the scaled value: allow 1 ulp disagreements from fast-math exp2
+    a, b = q.cpu().view(torch.float8_e4m3fn).float(), qr.view(torch.float8_e4m3fn).float()
+    assert (a != b).float().mean() < 1e-3
+    assert torch.allclose(a, b, rtol=0.13, atol=1e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(128, 128, 128), (256, 384, 512), (6912, 1024, 3456), (300, 200, 640)])
+def test_gemm_mxfp8_matches_dequantised_product(shape):
+    M, N, K = shape
+    torch.manual_seed(2)
+    a = (torch.randn(M, K) * 0.5).to(torch.bfloat16).cuda()
+    b = (torch.randn(N, K) * 0.1).to(torch.bfloat16).cuda()
+    bias = torch.randn(N).cuda()
+    aq, sfa = MX.mx_quantize(a)
+    bq, sfb = MX.mx_quantize(b)
+    out = MX.gemm_mxfp8(aq, sfa, bq, sfb, M, N, K, bias=bias, flags=G.EPI_RELU)
+    ref = torch.relu(MX.mx_dequantize(aq, sfa, M, K).cuda() @ MX.mx_dequantize(bq, sfb, N, K).cuda().t() + bias)
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 2e-2 * max(scale, 1.0), (err, scale)       # bf16 output rounding only
+    full = torch.relu(a.float() @ b.float().t() + bias)
+    rel = (out.float() - full).norm() / full.norm()
+    assert rel < 0.06, rel                                   # quantisation error of the MX format
