@@ -155,12 +155,14 @@ def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, s
     os.environ["HCTR_EMB_STATE_BF16"] = "1" if state == "bf16" else "0"
     os.environ.setdefault("HCTR_SYNTH_POOL", "64")
     kw = {}
+    if getattr(args, "fp8_mlp", False) and not standin:
+        kw["use_fp8_mlp"] = True
     if standin:
         # stand-in baseline: same model / optimizer / data, embedding exchange through NCCL collectives,
         # dense all-reduce through NCCL, every GEMM through torch.mm (cuBLAS / cuBLASLt)
         comm.disable_p2p()
         G.set_impl("library")
-        kw = dict(fused_embedding_comm=False, all_reduce_algo=hugectr.AllReduceAlgo.NCCL)
+        kw.update(fused_embedding_comm=False, all_reduce_algo=hugectr.AllReduceAlgo.NCCL)
     else:
         G.set_impl("tc")
     plan = generate_plan(tables, CRITEO_TB_MULTI_HOT, n, plan=args.plan)
@@ -393,6 +395,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the bf16-state full-size run")
     ap.add_argument("--sustained-sec", type=float, default=2.0)
     ap.add_argument("--ref-timeout", type=int, default=1500)
+    ap.add_argument("--fp8-mlp", action="store_true",
+                    help="forward MLP GEMMs in MX block-scaled fp8 (Solver.use_fp8_mlp); reported in config.fp8_mlp")
     ap.add_argument("--model", default="dlrm_dcnv2",
                     help="dlrm_dcnv2 (headline) | deepfm | dlrm | wdl_cache (secondary configurations)")
     args = ap.parse_args()
@@ -466,6 +470,7 @@ def main():
                                      "~1 GB activations/step, a different batch every step)",
                        "synthetic_pool_batches": r["pool_batches"],
                        "cuda_graph": not args.no_graph, "small_tables_debug": bool(args.small or args.cap_rows),
+                       "fp8_mlp": bool(args.fp8_mlp),
                        "final_loss": r["final_loss"], "loss_after_warmup_timed_e2e": r["loss_trace"]},
             "clocks": r["clocks"], "e2e": r["e2e"], "sustained": r["sustained"],
             "gpu_launches": r["gpu_launches"], "gpu_launches_per_step": r["gpu_launches_per_step"],

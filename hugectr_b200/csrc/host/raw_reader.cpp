@@ -210,3 +210,140 @@ extern "C" void hctr_raw_close(void* h) {
   if (r->fd >= 0) close(r->fd);
   delete r;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-split mode: the workers only move BYTES -- this rank's slice of a batch is read with O_DIRECT
+// (page-cache bypass, aligned offset / length / buffer like the reference's libaio reader,
+// HugeCTR/src/data_readers/multi_hot/detail/{aio_context,batch_file_reader}.cpp) straight into a pinned,
+// page-aligned staging slot; the consumer copies the slot to the device in one H2D transfer and a device
+// kernel (csrc/reader_split.cu) splits it into label / dense / feature-major keys.  `depth` reads are in
+// flight (one positional read per worker thread at a time).
+namespace {
+
+struct RawSlotD {
+  char* buf;
+  std::atomic<int> state{0};
+  long long seq{-1};
+  int valid{0};
+  int skew{0};          // byte offset of the first record inside buf
+};
+
+struct RawReaderD {
+  int fd{-1};
+  bool direct{false};
+  long long num_samples{0}, rec_bytes{0}, slot_bytes{0};
+  int batch_global, batch_local, rank;
+  bool repeat;
+  long long batches_per_epoch;
+  std::vector<RawSlotD> slots;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<bool> stop{false};
+  std::atomic<long long> next_seq{0};
+  long long consume_seq{0};
+
+  void fill(RawSlotD& s, long long seq) {
+    const long long it = repeat ? (seq % batches_per_epoch) : seq;
+    const long long first = it * batch_global + static_cast<long long>(rank) * batch_local;
+    int n = batch_local;
+    if (first + n > num_samples) n = static_cast<int>(std::max(0ll, num_samples - first));
+    s.valid = n;
+    s.skew = 0;
+    if (n <= 0) return;
+    const long long beg = first * rec_bytes, end = beg + static_cast<long long>(n) * rec_bytes;
+    const long long A = 4096;
+    const long long abeg = direct ? (beg / A) * A : beg;
+    const long long aend = direct ? ((end + A - 1) / A) * A : end;
+    s.skew = static_cast<int>(beg - abeg);
+    long long off = 0;
+    const long long total = aend - abeg;
+    while (off < total) {
+      ssize_t r = pread(fd, s.buf + off, static_cast<size_t>(total - off), abeg + off);
+      if (r <= 0) break;          // (the tail of the file may be shorter than the aligned length)
+      off += r;
+    }
+  }
+
+  void worker() {
+    while (!stop.load()) {
+      const long long seq = next_seq.fetch_add(1);
+      RawSlotD& s = slots[seq % slots.size()];
+      const bool eof = !repeat && seq >= batches_per_epoch;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop.load() || (s.state.load() == 0 && consume_seq + (long long)slots.size() > seq); });
+        if (stop.load()) return;
+        s.state.store(1);
+      }
+      if (eof) s.valid = -1; else fill(s, seq);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        s.seq = seq;
+        s.state.store(2);
+      }
+      cv.notify_all();
+      if (eof) return;
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" void* hctr_rawd_open(const char* path, long long rec_bytes, int batch_global, int batch_local, int rank,
+                                int repeat, long long num_samples_hint, int use_direct) {
+  RawReaderD* r = new RawReaderD();
+  r->fd = -1;
+  if (use_direct) {
+    r->fd = open(path, O_RDONLY | O_DIRECT);
+    r->direct = r->fd >= 0;
+  }
+  if (r->fd < 0) r->fd = open(path, O_RDONLY);
+  if (r->fd < 0) { delete r; return nullptr; }
+  struct stat st;
+  fstat(r->fd, &st);
+  r->rec_bytes = rec_bytes;
+  r->num_samples = st.st_size / rec_bytes;
+  if (num_samples_hint > 0 && num_samples_hint < r->num_samples) r->num_samples = num_samples_hint;
+  r->batch_global = batch_global; r->batch_local = batch_local; r->rank = rank; r->repeat = repeat != 0;
+  r->batches_per_epoch = std::max(1ll, (r->num_samples + batch_global - 1) / batch_global);
+  r->slot_bytes = ((static_cast<long long>(batch_local) * rec_bytes + 4095) / 4096 + 2) * 4096;
+  return r;
+}
+extern "C" long long hctr_rawd_slot_bytes(void* h) { return static_cast<RawReaderD*>(h)->slot_bytes; }
+extern "C" long long hctr_rawd_num_samples(void* h) { return static_cast<RawReaderD*>(h)->num_samples; }
+extern "C" int hctr_rawd_is_direct(void* h) { return static_cast<RawReaderD*>(h)->direct ? 1 : 0; }
+extern "C" int hctr_rawd_start(void* h, int num_threads, int depth, void** bufs) {
+  RawReaderD* r = static_cast<RawReaderD*>(h);
+  r->slots = std::vector<RawSlotD>(depth);
+  for (int i = 0; i < depth; ++i) r->slots[i].buf = static_cast<char*>(bufs[i]);
+  r->stop.store(false);
+  r->next_seq.store(0);
+  r->consume_seq = 0;
+  for (int t = 0; t < num_threads; ++t) r->workers.emplace_back([r] { r->worker(); });
+  return 0;
+}
+// returns the slot index; *valid = samples in the slot (-1: end of data), *skew = byte offset of record 0
+extern "C" int hctr_rawd_next(void* h, int* valid, int* skew) {
+  RawReaderD* r = static_cast<RawReaderD*>(h);
+  std::unique_lock<std::mutex> lk(r->mu);
+  if (r->consume_seq > 0) {
+    r->slots[(r->consume_seq - 1) % r->slots.size()].state.store(0);
+    r->cv.notify_all();
+  }
+  const long long seq = r->consume_seq;
+  RawSlotD& s = r->slots[seq % r->slots.size()];
+  r->cv.wait(lk, [&] { return s.state.load() == 2 && s.seq == seq; });
+  *valid = s.valid;
+  *skew = s.skew;
+  r->consume_seq = seq + 1;
+  return static_cast<int>(seq % r->slots.size());
+}
+extern "C" void hctr_rawd_close(void* h) {
+  RawReaderD* r = static_cast<RawReaderD*>(h);
+  r->stop.store(true);
+  r->cv.notify_all();
+  for (auto& t : r->workers) if (t.joinable()) t.join();
+  if (r->fd >= 0) close(r->fd);
+  delete r;
+}

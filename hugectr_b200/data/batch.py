@@ -24,6 +24,9 @@ class HostBatch:
     num_valid: int = -1   # < b for an incomplete last batch
     copied: object = None  # CUDA event recorded after the last async H2D copy out of this batch
     _event: object = None  # the event object is created once per batch and re-recorded
+    raw: Optional[torch.Tensor] = None   # device-split readers: the batch's raw records (pinned uint8) ...
+    raw_skew: int = 0                    # ... starting at this byte offset; label / dense / keys are None
+    splitter: object = None              # RawSplit: knows how to turn ``raw`` into the three tensors on the device
 
     def mark_copied(self):
         """Called by the consumer right after it queued its asynchronous H2D copies: ring-buffer
@@ -48,6 +51,8 @@ class HostBatch:
         return self
 
     def h2d_bytes(self) -> int:
+        if self.raw is not None:
+            return int(self.splitter.batch * self.splitter.rec_bytes)
         return sum(t.numel() * t.element_size() for t in (self.label, self.dense, self.keys, self.nnz)
                    if t is not None)
 

@@ -13,6 +13,53 @@ from .batch import HostBatch
 from .readers import IDataReader
 
 
+class RawSplit:
+    """Device split of a raw batch (csrc/reader_split.cu): column tables + destination offsets."""
+
+    def __init__(self, batch, label_dim, dense_dim, hot, key_in, key_dtype, dense_float, device):
+        self.batch, self.label_dim, self.dense_dim = batch, label_dim, dense_dim
+        self.hot, self.key_in, self.key_dtype, self.dense_float = list(hot), key_in, key_dtype, dense_float
+        self.device = device
+        self.sparse_cols = sum(hot)
+        self.rec_bytes = (label_dim + dense_dim) * 4 + self.sparse_cols * key_in
+        feat, pos, off, o = [], [], [], 0
+        for f, h in enumerate(hot):
+            feat += [f] * h
+            pos += list(range(h))
+            off.append(o)
+            o += batch * h
+        self.total_keys = o
+        i32 = dict(dtype=torch.int32, device=device)
+        self.col_feat, self.col_pos = torch.tensor(feat or [0], **i32), torch.tensor(pos or [0], **i32)
+        self.key_off = torch.tensor(off or [0], dtype=torch.int64, device=device)
+        self.hot_t = torch.tensor(hot or [1], **i32)
+        self.stage = None
+
+    def run(self, raw_host: torch.Tensor, skew: int, valid: int, label, dense, keys):
+        """H2D of the raw block (async, from pinned memory) + the split kernel on the current stream"""
+        n = self.batch * self.rec_bytes
+        if self.stage is None:
+            self.stage = torch.empty(n + 16, dtype=torch.uint8, device=self.device)
+        if not hasattr(self, "_lib"):
+            l = _native.cuda_lib()
+            vp, i = C.c_void_p, C.c_int
+            l.hctr_raw_split.argtypes = [vp] * 8 + [i] * 9 + [vp]
+            l.hctr_raw_split.restype = i
+            self._lib = l
+        nv = max(valid, 0)
+        self.stage[:nv * self.rec_bytes].copy_(raw_host[skew:skew + nv * self.rec_bytes], non_blocking=True)
+        rc = self._lib.hctr_raw_split(self.stage.data_ptr(), label.data_ptr(), dense.data_ptr() if dense is not None and dense.numel() else 0,
+                                      keys.data_ptr(), self.col_feat.data_ptr(), self.col_pos.data_ptr(),
+                                      self.key_off.data_ptr(), self.hot_t.data_ptr(), self.batch, nv, self.label_dim,
+                                      self.dense_dim, self.sparse_cols, self.rec_bytes, self.key_in,
+                                      8 if self.key_dtype == torch.int64 else 4, int(self.dense_float),
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            raise RuntimeError("hctr_raw_split failed")
+        from ..ops import dense as D
+        D._count()
+
+
 class RawAsyncReader(IDataReader):
     def __init__(self, model, is_train: bool):
         rp = model.reader_params
@@ -31,7 +78,21 @@ class RawAsyncReader(IDataReader):
         self.num_samples_hint = rp.num_samples if is_train else rp.eval_num_samples
         self.h = None
         self.lib = _native.host_lib()
+        # device-split mode (default on CUDA): workers move raw bytes with O_DIRECT into pinned slots, ONE H2D
+        # per batch, a device kernel splits label / dense / keys.  HCTR_RAW_READER=host keeps the CPU split.
+        import os
+        self.device_split = (model.device.type == "cuda" and os.environ.get("HCTR_RAW_READER", "device") == "device")
+        self.model_device = model.device
+        self.use_direct = os.environ.get("HCTR_RAW_ODIRECT", "1") == "1"
         L = self.lib
+        L.hctr_rawd_open.restype = C.c_void_p
+        L.hctr_rawd_open.argtypes = [C.c_char_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]
+        L.hctr_rawd_slot_bytes.restype = C.c_longlong
+        L.hctr_rawd_slot_bytes.argtypes = [C.c_void_p]
+        L.hctr_rawd_is_direct.argtypes = [C.c_void_p]
+        L.hctr_rawd_start.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.hctr_rawd_next.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hctr_rawd_close.argtypes = [C.c_void_p]
         L.hctr_raw_open.restype = C.c_void_p
         L.hctr_raw_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong]
@@ -41,7 +102,11 @@ class RawAsyncReader(IDataReader):
         L.hctr_raw_close.argtypes = [C.c_void_p]
         L.hctr_raw_num_samples.restype = C.c_longlong
         L.hctr_raw_num_samples.argtypes = [C.c_void_p]
-        self._alloc()
+        if self.device_split:
+            self.split = RawSplit(b, self.label_dim, self.dense_dim, self.hot, self.key_in, self.key_dtype,
+                                  self.dense_float, model.device)
+        else:
+            self._alloc()
 
     def _alloc(self):
         b = self.b
@@ -57,9 +122,25 @@ class RawAsyncReader(IDataReader):
                 lab, den, keys = lab.pin_memory(), den.pin_memory(), keys.pin_memory()
             self.slots.append((lab, den, keys))
 
+    def _start_device(self):
+        sp = self.split
+        self.h = self.lib.hctr_rawd_open(self.path.encode(), sp.rec_bytes, self.b * self.world, self.b, self.rank,
+                                         int(self.repeat), int(self.num_samples_hint), int(self.use_direct))
+        if not self.h:
+            raise FileNotFoundError(self.path)
+        self.o_direct = bool(self.lib.hctr_rawd_is_direct(self.h))
+        nb = int(self.lib.hctr_rawd_slot_bytes(self.h))
+        if not getattr(self, "raw_slots", None) or self.raw_slots[0].numel() != nb:
+            self.raw_slots = [torch.empty(nb, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        bufs = (C.c_void_p * self.depth)(*[t.data_ptr() for t in self.raw_slots])
+        self.lib.hctr_rawd_start(self.h, self.threads, self.depth, bufs)
+        self.started = True
+
     def start(self):
         if self.h is not None:
             return
+        if self.device_split:
+            return self._start_device()
         hot = (C.c_int * len(self.hot))(*self.hot)
         self.h = self.lib.hctr_raw_open(self.path.encode(), self.label_dim, self.dense_dim, hot,
                                         len(self.hot), self.key_in, 8 if self.key_dtype == torch.int64 else 4,
@@ -88,6 +169,17 @@ class RawAsyncReader(IDataReader):
         if getattr(self, "_last", None) is not None:     # its slot is recycled by the call below
             self._last.wait_copied()
             self._last = None
+        if self.device_split:
+            skew = C.c_int(0)
+            idx = self.lib.hctr_rawd_next(self.h, C.byref(valid), C.byref(skew))
+            if valid.value < 0:
+                return None
+            nv = valid.value
+            self.current_batchsize = self.b * self.world if nv == self.b else \
+                max(0, min(self.b * self.world, self.rank * self.b + nv)) if nv > 0 else self.rank * self.b
+            self._last = HostBatch(None, None, None, None, nv, raw=self.raw_slots[idx], raw_skew=skew.value,
+                                   splitter=self.split)
+            return self._last
         idx = self.lib.hctr_raw_next(self.h, C.byref(valid))
         if valid.value < 0:
             return None
@@ -101,7 +193,7 @@ class RawAsyncReader(IDataReader):
 
     def stop(self):
         if self.h is not None:
-            self.lib.hctr_raw_close(self.h)
+            (self.lib.hctr_rawd_close if self.device_split else self.lib.hctr_raw_close)(self.h)
             self.h = None
             self.started = False
 

@@ -61,6 +61,10 @@ class MLPLayer(Layer):
             kin = nout
         self._out(0, self.lead + (self.dims_out[-1],))
         self._side = None
+        # Solver.use_fp8_mlp: forward GEMMs in block-scaled fp8 (OCP MX: e4m3 values, one UE8M0 scale per 32
+        # K elements, applied inside tcgen05.mma.kind::mxf8f6f4.block_scale); backward stays bf16 on the
+        # bf16 activations.  Layers whose K is not a multiple of 128 (or N == 1) keep the bf16 GEMM.
+        self.fp8 = bool(getattr(ctx.solver, "use_fp8_mlp", False)) and ctx.mixed and ctx.native
 
     # ------------------------------------------------------------------ buffers
     def allocate(self):
@@ -106,10 +110,28 @@ class MLPLayer(Layer):
             out = self.acts[i]
             if nout == 1 and W.shape[0] >= 8:
                 D.fc1_fwd(h, self.W[i].w.reshape(-1), bias, out, relu=self.relu[i])
+            elif self.fp8 and h.shape[1] % 128 == 0 and h.dtype == torch.bfloat16 and out.stride(1) == 1:
+                self._fprop_fp8(i, h, W, bias, out)
             else:
                 G.gemm_bf16(h, W, out, b_mn=True, bias=bias,
                             flags=G.EPI_RELU if self.relu[i] else 0)
             h = out
+
+    def _fprop_fp8(self, i, h, W, bias, out):
+        """out = act(deq(Q(h)) @ deq(Q(W)) + bias): activations and weights are quantised to MX fp8 (the
+        weights from their transposed view, so both operands are K-major)"""
+        from ..ops import mxfp8 as MX
+        K, N = h.shape[1], W.shape[1]
+        bufs = getattr(self, "_fp8_bufs", None)
+        if bufs is None:
+            bufs = self._fp8_bufs = {}
+        if i not in bufs:
+            bufs[i] = (MX.mx_buffers(h.shape[0], K, h.device), MX.mx_buffers(N, K, h.device))
+        (aq, sfa), (bq, sfb) = bufs[i]
+        MX.mx_quantize(h, aq, sfa)
+        MX.mx_quantize(W[:K], bq, sfb, transposed=True)          # W is [K, N] row-major: quantise W^T
+        MX.gemm_mxfp8(aq, sfa, bq, sfb, h.shape[0], N, K, out=out, bias=bias,
+                      flags=G.EPI_RELU if self.relu[i] else 0)
 
     # ------------------------------------------------------------------ backward
     def bprop(self):

@@ -340,6 +340,17 @@ class Model:
         net = self.net_train if is_train else self.net_eval
         inp = self.input
         nb = True
+        if getattr(hb, "raw", None) is not None:
+            # device-split reader: ONE H2D of the raw records, the split kernel writes label / dense and
+            # the feature-major keys straight into the input tensors / the key slab
+            ebcs = self.ebcs_train if is_train else self.ebcs_eval
+            legs = self.legacy_train if is_train else self.legacy_eval
+            if len(ebcs) == 1 and not legs and ebcs[0].key_slab.dtype == hb.splitter.key_dtype:
+                hb.splitter.run(hb.raw, hb.raw_skew, hb.num_valid, net.tensors[inp.label_name].data,
+                                net.tensors[inp.dense_name].data if inp.dense_dim > 0 else None, ebcs[0].key_slab)
+                hb.mark_copied()
+                return
+            hb = self._materialize_raw(hb)
         net.tensors[inp.label_name].data.copy_(hb.label, non_blocking=nb)
         if inp.dense_dim > 0:
             net.tensors[inp.dense_name].data.copy_(hb.dense, non_blocking=nb)
@@ -358,6 +369,20 @@ class Model:
             for rt in legs:
                 rt.set_keys(hb, offs, self.layout.nnz_block_offsets(b)[0])
         hb.mark_copied()
+
+    def _materialize_raw(self, hb: HostBatch) -> HostBatch:
+        """raw batch -> device label / dense / keys tensors (models with several collections or legacy
+        embeddings copy from these)"""
+        sp = hb.splitter
+        dev = self.device
+        if not hasattr(self, "_raw_tmp"):
+            self._raw_tmp = (torch.empty(sp.batch, sp.label_dim, device=dev),
+                             torch.empty(sp.batch, max(sp.dense_dim, 1), device=dev)[:, :sp.dense_dim].contiguous(),
+                             torch.empty(max(sp.total_keys, 1), dtype=sp.key_dtype, device=dev))
+        lab, den, keys = self._raw_tmp
+        sp.run(hb.raw, hb.raw_skew, hb.num_valid, lab, den, keys)
+        hb.mark_copied()
+        return HostBatch(lab, den, keys, None, hb.num_valid)
 
     def start_data_reading(self):
         self.reader_train.start()
@@ -647,6 +672,15 @@ class Model:
             self._stg_free.record()
         cs = self._copy_stream
         cs.wait_event(self._stg_free)           # previous D2D commit has consumed the staging area
+        if getattr(hb, "raw", None) is not None and self._stg["keys"].dtype == hb.splitter.key_dtype:
+            with torch.cuda.stream(cs):
+                hb.splitter.run(hb.raw, hb.raw_skew, hb.num_valid, self._stg["label"],
+                                self._stg["dense"] if self.input.dense_dim > 0 else None, self._stg["keys"])
+                hb.mark_copied()
+            self._staged = hb
+            return
+        if getattr(hb, "raw", None) is not None:
+            hb = self._materialize_raw(hb)
         with torch.cuda.stream(cs):
             self._stg["label"].copy_(hb.label, non_blocking=True)
             if self.input.dense_dim > 0:

@@ -90,11 +90,8 @@ def CreateSolver(model_name: str = "", seed: int = 0, lr_policy=LrPolicy_t.fixed
         raise RuntimeError("use_mixed_precision and enable_tf32_compute cannot be true at the same time")
     if use_mixed_precision and scaler not in (1.0, 128.0, 256.0, 512.0, 1024.0) and scaler <= 0:
         raise RuntimeError("scaler must be positive")
-    if use_fp8_mlp:
-        # extension hook (block-scaled fp8 MLP GEMMs, tcgen05 kind::f8f6f4): not wired into the layers
-        # yet -- the bf16 path is used and the request is reported instead of silently ignored
-        from .utils import logger
-        logger.warning("use_fp8_mlp=True is not implemented in this build; MLP layers run in bf16")
+    if use_fp8_mlp and not use_mixed_precision:
+        raise RuntimeError("use_fp8_mlp needs use_mixed_precision=True (bf16 activations, fp8 forward GEMMs)")
     return Solver(
         model_name=model_name, seed=seed, lr_policy=lr_policy, lr=lr, warmup_steps=warmup_steps,
         decay_start=decay_start, decay_steps=decay_steps, decay_power=decay_power, end_lr=end_lr,

@@ -278,6 +278,7 @@ def test_native_raw_reader_slices_and_layout(tmp_path):
         m.layout = types.SimpleNamespace(blocks=[("a", 1, 2, True), ("b", 1, 1, True)])
         m.solver = types.SimpleNamespace(repeat_dataset=False, i64_input_key=False)
         m.key_dtype = torch.int32
+        m.device = torch.device("cpu")
         return m
 
     write(True)

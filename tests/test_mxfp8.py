@@ -53,3 +53,35 @@ def test_gemm_mxfp8_matches_dequantised_product(shape):
     full = torch.relu(a.float() @ b.float().t() + bias)
     rel = (out.float() - full).norm() / full.norm()
     assert rel < 0.06, rel                                   # quantisation error of the MX format
+
+
+@pytest.mark.gpu
+def test_mlp_layer_fp8_forward_close_to_bf16():
+    """Solver.use_fp8_mlp: the MLP forward runs on the MX fp8 GEMM and stays within the format's error of the
+    bf16 layer; backward (bf16) is unchanged"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.layers import LAYER_REGISTRY, BuildCtx, ParamArena, TensorBag
+    from hugectr_b200.solver import CreateSolver, DenseLayer
+    outs = {}
+    for fp8 in (False, True):
+        arena = ParamArena()
+        solver = CreateSolver(use_mixed_precision=True, use_fp8_mlp=fp8)
+        ctx = BuildCtx(arena, torch.device("cuda"), torch.bfloat16, 512, True, solver, True)
+        x = TensorBag("x", (512, 256), torch.bfloat16)
+        g = torch.Generator().manual_seed(5)
+        x.data = (torch.randn(512, 256, generator=g) * 0.5).to(torch.bfloat16).cuda()
+        x.grad = torch.zeros(512, 256, dtype=torch.bfloat16, device="cuda")
+        cfg = DenseLayer(hugectr.Layer_t.MLP, ["x"], ["y"], num_outputs=[384, 128, 1],
+                         activations=[hugectr.Activation_t.Relu, hugectr.Activation_t.Relu, hugectr.Activation_t.Non])
+        layer = LAYER_REGISTRY[hugectr.Layer_t.MLP](cfg, [x], ctx)
+        arena.finalize(torch.device("cuda"), True)
+        layer.allocate()
+        arena.init_params(3)
+        layer.fprop(True)
+        assert bool(getattr(layer, "_fp8_bufs", None)) == fp8
+        layer.outputs[0].grad.fill_(0.01)
+        layer.bprop()
+        outs[fp8] = (layer.outputs[0].data.float().clone(), x.grad.float().clone())
+    y0, y1 = outs[False][0], outs[True][0]
+    assert (y0 - y1).norm() / y0.norm() < 0.08
+    assert (outs[False][1] - outs[True][1]).norm() / outs[False][1].norm() < 0.15

@@ -9,9 +9,65 @@ import torch
 
 import hugectr_b200 as hugectr
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("HCTR_TEST_EXPERIMENTAL"),
-                                 reason="not yet validated on a GPU box (tools_dev/next_round.sh runs it)")]
+pytestmark = [pytest.mark.gpu]
+
+
+def test_raw_reader_device_split_equals_host_split(tmp_path):
+    """RawAsync device mode (O_DIRECT byte mover + csrc/reader_split.cu) produces exactly the tensors of the
+    host-split mode: per-rank slices, feature-major keys, incomplete last batch, log1p of integer dense"""
+    import types
+    from hugectr_b200.data.raw_reader import RawAsyncReader
+    N, hot = 1000, [3, 1, 7, 2]
+    rng = np.random.default_rng(0)
+    for dense_float in (True, False):
+        path = str(tmp_path / f"t{int(dense_float)}.bin")
+        lab = rng.integers(0, 2, (N, 1)).astype("<f4" if dense_float else "<u4")
+        den = rng.random((N, 5)).astype("<f4") if dense_float else rng.integers(0, 1000, (N, 5)).astype("<u4")
+        keys = rng.integers(0, 1 << 20, (N, sum(hot))).astype("<u4")
+        np.concatenate([lab.view("<u4"), den.view("<u4"), keys], 1).astype("<u4").tofile(path)
+
+        def stub(dev):
+            m = types.SimpleNamespace()
+            m.reader_params = types.SimpleNamespace(
+                source=[path], eval_source=path, async_param=hugectr.AsyncParam(2, 3, is_dense_float=dense_float),
+                float_label_dense=False, num_samples=N, eval_num_samples=N)
+            m.b_train = m.b_eval = 96
+            m.comm = types.SimpleNamespace(rank=1)
+            m.world = 3
+            m.input = types.SimpleNamespace(label_dim=1, dense_dim=5)
+            m.layout = types.SimpleNamespace(blocks=[(f"f{i}", 1, h, True) for i, h in enumerate(hot)])
+            m.solver = types.SimpleNamespace(repeat_dataset=False, i64_input_key=False)
+            m.key_dtype = torch.int32
+            m.device = torch.device(dev)
+            return m
+        host = RawAsyncReader(stub("cpu"), True)
+        devr = RawAsyncReader(stub("cuda"), True)
+        assert devr.device_split and not host.device_split
+        n = 0
+        while True:
+            a, b = host.read_a_batch(), devr.read_a_batch()
+            assert (a is None) == (b is None)
+            if a is None:
+                break
+            assert a.num_valid == b.num_valid
+            sp = b.splitter
+            lab_d = torch.empty(96, 1, device="cuda")
+            den_d = torch.empty(96, 5, device="cuda")
+            key_d = torch.empty(sp.total_keys, dtype=torch.int32, device="cuda")
+            sp.run(b.raw, b.raw_skew, b.num_valid, lab_d, den_d, key_d)
+            b.mark_copied()
+            torch.cuda.synchronize()
+            nv = a.num_valid
+            torch.testing.assert_close(lab_d.cpu()[:nv], a.label[:nv])
+            torch.testing.assert_close(den_d.cpu()[:nv], a.dense[:nv], atol=1e-6, rtol=1e-6)
+            ka, kb = a.keys, key_d.cpu()
+            off = 0
+            for h in hot:
+                assert torch.equal(ka[off:off + 96 * h].view(96, h)[:nv], kb[off:off + 96 * h].view(96, h)[:nv])
+                off += 96 * h
+            n += 1
+        assert n == 4                      # ceil(1000 / 288)
+        host.stop(); devr.stop()
 
 
 @pytest.mark.parametrize("fmt", [hugectr.DataReaderType_t.Norm, hugectr.DataReaderType_t.Parquet,
