@@ -159,9 +159,11 @@ def GetBuffer(params: BufferParams, device: Device) -> Buffer:
 
 def AllocateBuffers(device: Optional[Device] = None) -> bool:
     """allocate every declared-but-unallocated buffer (of one device)"""
-    for (dev, _), buf in list(_buffers.items()):
-        if device is None or dev == device:
+    for key, buf in list(_buffers.items()):
+        if device is None or key[0] == device:
             buf.allocate()
+            if key[1].name.find("#") >= 0:        # per-arena channels are single use: drop the registry entry,
+                del _buffers[key]                 # the tensors keep the storage alive
     return True
 
 

@@ -71,7 +71,7 @@ struct RawReader {
       for (int j = 0; j < label_dim; ++j) {
         float v = 0.f;
         if (ok) {
-          if (dense_is_float) memcpy(&v, ld + j, 4);
+          if (dense_is_float & 2) memcpy(&v, ld + j, 4);      // bit 1: labels stored as floats
           else v = static_cast<float>(static_cast<int32_t>(ld[j]));
         }
         s.label[static_cast<size_t>(i) * label_dim + j] = v;
@@ -79,7 +79,7 @@ struct RawReader {
       for (int j = 0; j < dense_dim; ++j) {
         float v = 0.f;
         if (ok) {
-          if (dense_is_float) memcpy(&v, ld + label_dim + j, 4);
+          if (dense_is_float & 1) memcpy(&v, ld + label_dim + j, 4);   // bit 0: dense stored as floats
           else v = logf(static_cast<float>(ld[label_dim + j]) + 1.f);   // log(x+1) of uint features
         }
         s.dense[static_cast<size_t>(i) * dense_dim + j] = v;

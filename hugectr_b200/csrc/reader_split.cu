@@ -1,8 +1,8 @@
 // Device side of the RawAsync reader (C13): one kernel splits a batch of raw fixed-size records that was copied to
 // the device as ONE contiguous block into the model's input tensors
 //   record = [label_dim x 4 B][dense_dim x 4 B][sum(hotness) x key bytes]
-//   label [b, L] fp32 (int32 -> float unless the file stores floats), dense [b, D] fp32 (log(x + 1) of integer
-//   features, or the stored floats), keys FEATURE-major: feature f at keys[key_off[f] + s * hot[f] + h]
+//   label [b, L] fp32 (int32 -> float; stored floats when flag bit 1 is set), dense [b, D] fp32 (log(x + 1) of
+//   integer features; the stored floats when flag bit 0 is set), keys FEATURE-major: feature f at keys[key_off[f] + s * hot[f] + h]
 // Reference: HugeCTR/src/data_readers/multi_hot/split_batch.cu:43-88 (one thread per record column, per-column
 // bucket tables); here the column -> (feature, position) tables sit in shared memory and the keys land directly in
 // the embedding collection's key slab (no per-feature tensors, no second copy).
@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(256) raw_split_kernel(const SplitDesc d) {
       float v = 0.f;
       if (ok) {
         const uint32_t w = *reinterpret_cast<const uint32_t*>(rec + 4 * c);
-        v = d.dense_is_float ? __uint_as_float(w) : static_cast<float>(static_cast<int>(w));
+        v = (d.dense_is_float & 2) ? __uint_as_float(w) : static_cast<float>(static_cast<int>(w));
       }
       d.label[static_cast<long long>(s) * d.label_dim + c] = v;
     } else if (c < d.label_dim + d.dense_dim) {
       float v = 0.f;
       if (ok) {
         const uint32_t w = *reinterpret_cast<const uint32_t*>(rec + 4 * c);
-        v = d.dense_is_float ? __uint_as_float(w) : logf(static_cast<float>(w) + 1.f);
+        v = (d.dense_is_float & 1) ? __uint_as_float(w) : logf(static_cast<float>(w) + 1.f);
       }
       d.dense[static_cast<long long>(s) * d.dense_dim + (c - d.label_dim)] = v;
     } else {

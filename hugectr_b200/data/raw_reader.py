@@ -70,7 +70,11 @@ class RawAsyncReader(IDataReader):
         self.hot = [s * h for (_, s, h, _) in model.layout.blocks]
         self.label_dim, self.dense_dim = inp.label_dim, inp.dense_dim
         ap = rp.async_param
-        self.dense_float = bool(ap.is_dense_float or rp.float_label_dense)
+        # flag word of the native readers: bit 0 = dense features stored as floats (AsyncParam.is_dense_float,
+        # the MLPerf raw format), bit 1 = labels stored as floats too (DataGenerator float_label_dense files);
+        # integer labels are cast, integer dense features go through log(x + 1) (split_batch.cu:43-88)
+        self.dense_float = (1 if (ap.is_dense_float or rp.float_label_dense) else 0) | \
+            (2 if rp.float_label_dense else 0)
         self.key_in = 8 if model.solver.i64_input_key else 4
         self.key_dtype = model.key_dtype
         self.depth = max(2, min(64, ap.num_threads * ap.num_batches_per_thread))

@@ -105,10 +105,27 @@ class ParamArena:
         peer-mapped heap when the P2P all-reduce is used)."""
         n = max(self._size, 1)
         n = (n + pad_to - 1) // pad_to * pad_to  # model_compile.cpp:853-869 pads wgrad to 16*N bytes
-        self.weights = torch.zeros(n, dtype=torch.float32, device=device)
-        self.wgrad = (wgrad_alloc(n, torch.float32) if wgrad_alloc is not None
-                      else torch.zeros(n, dtype=torch.float32, device=device))
-        self.weights16 = torch.zeros(n, dtype=torch.bfloat16, device=device) if mixed else None
+        # The flat arrays are core23 unitary buffers, one per channel like the reference's network buffer
+        # channels (include/network_buffer_channels.hpp: "Weight", "WeightHalf", "Wgrad"): a lazily allocated
+        # core23.Tensor is declared per channel, AllocateBuffers() materialises them, decay() gives the flat
+        # view the fused optimizer / in-place all-reduce / raw checkpoint dump work on.  The peer-mapped wgrad
+        # of the P2P all-reduce is external memory bound into a core23.Tensor.
+        from .. import core23
+        cdev = core23.Device(core23.DeviceType.GPU, device.index or 0) if device.type == "cuda" else core23.Device()
+        tag = f"#{id(self):x}"
+
+        def chan(name, dtype):
+            tp = core23.TensorParams(shape=(n,), data_type=dtype, device=cdev,
+                                     buffer_params=core23.BufferParams(channel=core23.BufferChannel(name + tag)))
+            return core23.Tensor(tp)
+        self.c23_weights = chan("Weight", torch.float32)
+        self.c23_weights16 = chan("WeightHalf", torch.bfloat16) if mixed else None
+        self.c23_wgrad = (core23.Tensor.bind(wgrad_alloc(n, torch.float32)) if wgrad_alloc is not None
+                          else chan("Wgrad", torch.float32))
+        core23.AllocateBuffers(cdev)
+        self.weights = self.c23_weights.data()
+        self.wgrad = self.c23_wgrad.data()
+        self.weights16 = self.c23_weights16.data() if mixed else None
         for p in self.params:
             p.w = self.weights[p.offset:p.offset + p.numel].view(p.shape)
             p.g = self.wgrad[p.offset:p.offset + p.numel].view(p.shape)

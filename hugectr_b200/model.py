@@ -712,16 +712,38 @@ class Model:
         if hb is None:
             return False
         self._load_batch(hb, False)
-        for e in self.ebcs_eval:
-            e.forward(False)
-        for rt in self.legacy_eval:
-            rt.forward(False)
-        self.net_eval.fprop(False)
+        self._eval_pipeline().run_graph() if self._eval_graph_ok() else self._eval_pipeline().run()
         raw = self._raw_metrics()
         for (_, _, m) in self.metrics:
             m.set_current_batch_size(self.reader_eval.get_current_batchsize())
             m.local_reduce(raw)
         return True
+
+    def _eval_graph_ok(self) -> bool:
+        return (self.solver.use_cuda_graph and self.device.type == "cuda" and self._graph_safe()
+                and os.environ.get("HCTR_DISABLE_CUDA_GRAPH", "0") == "0"
+                and os.environ.get("HCTR_EVAL_GRAPH", "1") == "1"
+                and not getattr(self.comm, "emulated", False))
+
+    def _eval_pipeline(self):
+        """The evaluation step as a ``Pipeline`` (pipeline.py, the reference's scheduler of
+        HugeCTR/include/pipeline.hpp:28-108 / model_pipeline.cpp:420-520): embedding forward on its own
+        stream beside the embedding-independent bottom layers, the top network behind both; with
+        ``use_cuda_graph`` the whole pipeline is captured once and replayed (GraphScheduleable)."""
+        if getattr(self, "_eval_pipe", None) is None:
+            from .pipeline import Pipeline, StreamContextScheduleable
+
+            def emb():
+                for e in self.ebcs_eval:
+                    e.forward(False)
+                for rt in self.legacy_eval:
+                    rt.forward(False)
+            s_emb = StreamContextScheduleable(emb, "embedding_forward").set_stream("eval_emb")
+            s_bot = StreamContextScheduleable(lambda: self.net_eval.fprop(False, "bottom"), "bottom_network")
+            s_top = StreamContextScheduleable(lambda: self.net_eval.fprop(False, "top"), "top_network") \
+                .wait_event([s_emb, s_bot])
+            self._eval_pipe = Pipeline("evaluate", self.device, [s_emb, s_bot, s_top])
+        return self._eval_pipe
 
     def _raw_metrics(self):
         net = self.net_eval

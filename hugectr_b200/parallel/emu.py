@@ -47,7 +47,8 @@ class EmuComm:
         self.fabric, self.rank, self.world_size = fabric, rank, fabric.world
         self.device = fabric.device
         self.group = None
-        self._p2p = bool(p2p) and self.device.type == "cuda" and self.world_size > 1
+        # p2p="force": fused data flow on CPU tensors too (logic tests of the peer-memory paths)
+        self._p2p = (p2p == "force" or (bool(p2p) and self.device.type == "cuda")) and self.world_size > 1
         self.num_nodes = 1
         self.emulated = True
 
@@ -157,6 +158,13 @@ class EmuComm:
             lo = a.data_ptr()
             if lo <= base < lo + a.numel() * a.element_size():
                 off = base - lo
+                if not t.is_cuda:
+                    # CPU fabric: the "peer pointers" are the peers' tensors themselves (the reference
+                    # implementations of the kernels take tensors), so the FUSED data flow -- routes,
+                    # inbox layouts, barrier placement -- can be exercised without a GPU
+                    e0 = off // a.element_size()
+                    return [self.fabric.allocs[r][i].view(-1)[e0:e0 + t.numel()].view(t.shape)
+                            for r in range(self.world_size)]
                 return [self.fabric.allocs[r][i].data_ptr() + off for r in range(self.world_size)]
         raise KeyError("tensor is not part of the (emulated) symmetric heap")
 

@@ -2,8 +2,9 @@
 capture.  API parity with HugeCTR/include/pipeline.hpp:28-108 (Scheduleable,
 StreamContextScheduleable{set_stream, set_absolute_stream, wait_event, record_done},
 GraphScheduleable, Pipeline{run, run_graph}); implementation on torch streams / events / CUDAGraph.
-``Model._step_body`` is the built-in instance of such a pipeline; this module exposes the mechanism
-for custom schedules and for the tests.
+``Model.eval`` runs through it (embedding forward beside the bottom network, top network behind both, the
+whole evaluation step captured as one CUDA graph); ``Model._step_body`` is the hand-scheduled training
+instance of the same idea (it additionally interleaves the bucketed all-reduce hooks).
 """
 from __future__ import annotations
 
@@ -48,7 +49,10 @@ class StreamContextScheduleable(Scheduleable):
         if not cuda:
             self.fn()
             return
-        stream = ctx.stream(self.stream_name) if self.stream_name else torch.cuda.current_stream()
+        cur = torch.cuda.current_stream()
+        stream = ctx.stream(self.stream_name) if self.stream_name else cur
+        if stream is not cur and not self.absolute:
+            stream.wait_stream(cur)          # a side stage starts after everything queued before the pipeline
         for w in self.waits:
             if w.done_event is not None:
                 stream.wait_event(w.done_event)

@@ -270,7 +270,7 @@ def test_native_raw_reader_slices_and_layout(tmp_path):
         m = types.SimpleNamespace()
         m.reader_params = types.SimpleNamespace(
             source=[path], eval_source=path, async_param=hugectr.AsyncParam(2, 2, is_dense_float=dense_float),
-            float_label_dense=False, num_samples=N, eval_num_samples=N)
+            float_label_dense=dense_float, num_samples=N, eval_num_samples=N)
         m.b_train = m.b_eval = 4
         m.comm = types.SimpleNamespace(rank=rank)
         m.world = 2

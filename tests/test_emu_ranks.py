@@ -108,3 +108,74 @@ def test_emu_legacy_embeddings_fused_gpu():
     """Distributed / Localized hash embeddings on the fused path (peer-store key / gradient exchange,
     one-kernel ownership filter + hash translation): replicas stay identical, loss finite"""
     run_ranks(4, lambda c: W.run_legacy(comm=c))
+
+
+def _real_plan_body(world, device, p2p):
+    """fused collection with the sharding plan the BENCHMARK uses at this GPU count (capped tables): hot table
+    row-split over a subset of the ranks (requester-side shard split), table-wise giants, data-parallel small
+    tables; forward and AdaGrad backward against a single-process collection"""
+    from hugectr_b200.embedding.collection import (EmbeddingCollection, EmbeddingCollectionConfig,
+                                                   EmbeddingTableConfig)
+    from hugectr_b200.enums import Optimizer_t
+    from hugectr_b200.models.dlrm import CRITEO_TB_MULTI_HOT, CRITEO_TB_TABLE_SIZES
+    from hugectr_b200.parallel.comm import Comm
+    from hugectr_b200.solver import CreateOptimizer
+    from hugectr_b200.tools.planner import generate_plan
+    b, ev = 8, 8
+    sizes = [min(s, 4000) for s in CRITEO_TB_TABLE_SIZES]
+    hot = list(CRITEO_TB_MULTI_HOT)
+    plan = generate_plan(CRITEO_TB_TABLE_SIZES, hot, world)
+    n = len(sizes)
+
+    def cfg_for(pl):
+        cfg = EmbeddingCollectionConfig()
+        cfg.embedding_lookup([EmbeddingTableConfig(str(i), sizes[i], ev) for i in range(n)],
+                             [f"d{i}" for i in range(n)], "emb", ["sum"] * n)
+        if pl:
+            cfg.shard(pl[0], pl[1])
+        return cfg
+    gen = torch.Generator().manual_seed(0)
+    full = {str(i): torch.randn(sizes[i], ev, generator=gen) * 0.1 for i in range(n)}
+    keys = [torch.randint(0, sizes[i], (b * world, hot[i]), generator=gen) for i in range(n)]
+    grad = torch.randn(b * world, n * ev, generator=gen) * 0.1
+    opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.1, epsilon=1e-6)
+    hotd = {f"d{i}": hot[i] for i in range(n)}
+    cpu = torch.device("cpu")
+    ref = EmbeddingCollection(cfg_for(None), b * world, hotd, cpu, torch.float32, Comm.single(cpu), opt, seed=1)
+    for nm, w in full.items():
+        ref.load_table_rows(nm, torch.arange(w.shape[0]), w)
+    ref.set_keys(torch.cat([k.reshape(-1) for k in keys]).int())
+    ref.forward()
+    ref.top_grad["emb"].copy_(grad)
+    lr, st = torch.tensor([0.05]), torch.tensor([1], dtype=torch.int32)
+    ref.backward(lr, st)
+
+    def body(c):
+        e = EmbeddingCollection(cfg_for(plan), b, hotd, device, torch.float32, c, opt, seed=1, fused=True)
+        assert e.fused and e.shard_split
+        for nm, w in full.items():
+            e.load_table_rows(nm, torch.arange(w.shape[0]), w)
+        r = c.rank
+        e.set_keys(torch.cat([k[r * b:(r + 1) * b].reshape(-1) for k in keys]).int().to(device))
+        e.forward()
+        err = (e.top_data["emb"].float().cpu() - ref.top_data["emb"][r * b:(r + 1) * b]).abs().max().item()
+        assert err < 1e-5, ("forward", r, err)
+        e.top_grad["emb"].copy_(grad[r * b:(r + 1) * b].to(device))
+        e.backward(lr.to(device), st.to(device))
+        for nm in full:
+            rk, rw = ref.dump_table_local(nm)[0][:2]
+            for (k, w, c0, sts, kind) in e.dump_table_local(nm):
+                if len(k):
+                    assert (w - rw[k][:, c0:c0 + w.shape[1]]).abs().max().item() < 2e-4, ("table", nm, r)
+    run_ranks(world, body, device=device, p2p=p2p)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_emu_fused_benchmark_plan_cpu(world):
+    _real_plan_body(world, CPU, "force")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [4, 8])
+def test_emu_fused_benchmark_plan_gpu(world):
+    _real_plan_body(world, torch.device("cuda"), True)

@@ -30,7 +30,7 @@ def test_raw_reader_device_split_equals_host_split(tmp_path):
             m = types.SimpleNamespace()
             m.reader_params = types.SimpleNamespace(
                 source=[path], eval_source=path, async_param=hugectr.AsyncParam(2, 3, is_dense_float=dense_float),
-                float_label_dense=False, num_samples=N, eval_num_samples=N)
+                float_label_dense=dense_float, num_samples=N, eval_num_samples=N)
             m.b_train = m.b_eval = 96
             m.comm = types.SimpleNamespace(rank=1)
             m.world = 3
