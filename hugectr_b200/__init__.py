@@ -6,6 +6,15 @@ EmbeddingTableConfig, EmbeddingCollectionConfig, tools.DataGenerator, data.DataS
 TrainingCallback (HugeCTR/src/pybind/module_main.cpp:36-48).
 """
 from .enums import *  # noqa: F401,F403
+import os as _os
+
+# The step runs up to ten concurrent branches (main, embedding forward / backward, index build, heavy rows,
+# bottom-network backward, bucketed all-reduce, per-bucket optimizer, data-parallel tables, H2D prefetch) and
+# several of them contain kernels that spin on flags written by OTHER GPUs.  With the default of 8 hardware
+# work queues two branches can share a queue: a spinning kernel then blocks an unrelated branch that a peer
+# is waiting for -- a cross-GPU deadlock.  Must be set before the CUDA context exists.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .enums import (Activation_t, Alignment_t, AllReduceAlgo, Check_t, CommunicationStrategy,
                     CompressionStrategy, DataReaderType_t, DeviceLayout, Distribution_t,
                     Embedding_t, Error_t, FcPosition_t, FileSystemType_t, Initializer_t, Layer_t,

@@ -858,10 +858,12 @@ class EmbeddingCollection:
         else:
             for grp in dp_groups:
                 self._accum_update(grp, [self.key_slab], [self.grad_slab], lr_t, step_t)
-        if self.world > 1 and self.fused and os.environ.get("HCTR_EMB_END_BARRIER", "0") == "1":
-            # not needed for correctness: a rank can only overwrite an owner's inbox after that owner
-            # passed the NEXT step's dispatch barrier, i.e. after its reduce of this step was queued
-            # on the same stream ahead of it
+        sched = os.environ.get("HCTR_STEP_SCHEDULE", "")
+        end_default = "0" if (sched == "aggressive" or (sched != "safe" and self.world <= 4)) else "1"
+        if self.world > 1 and self.fused and os.environ.get("HCTR_EMB_END_BARRIER", end_default) == "1":
+            # (<= 4 ranks skip it: a rank can only overwrite an owner's inbox after that owner passed the NEXT
+            # step's dispatch barrier, i.e. after its reduce of this step was queued on the same stream ahead
+            # of it; kept for larger jobs, see Model._aggressive_schedule)
             self.comm.barrier_device()
 
     def _hp(self, o: OptParamsPy):

@@ -477,10 +477,13 @@ class Model:
                 with torch.cuda.stream(s_emb):
                     for e in self.ebcs_train:
                         e.backward(self.lr_t, self.step_t, dp_stream=s_idx)
-            self._s_bot.wait_stream(main)
-            with torch.cuda.stream(self._s_bot):
+            if self._aggressive_schedule():
+                self._s_bot.wait_stream(main)
+                with torch.cuda.stream(self._s_bot):
+                    net.bprop("bottom")
+                main.wait_stream(self._s_bot)
+            else:
                 net.bprop("bottom")
-            main.wait_stream(self._s_bot)
         else:
             for e in self.ebcs_train:
                 e.forward(True)
@@ -573,6 +576,18 @@ class Model:
             self.comm.barrier()                # pipeline.cpp:111-125 barrier after first capture
             # capture does not execute: run the captured step now
         self._graph.replay()
+
+    def _aggressive_schedule(self) -> bool:
+        """Step-tail scheduling.  "aggressive" (validated on 1, 2 and 4 B200): bottom-network backward and the
+        all-reduce buckets on streams above the embedding update's priority, no end-of-step device barrier
+        (the next step's dispatch barrier orders the inbox reuse).  More than 4 ranks run the round-1 schedule
+        (bottom backward on the main stream, default-priority communication streams, end-of-step barrier):
+        an 8-GPU run of the aggressive schedule stopped making progress after the warm-up in the only 8-GPU
+        slot this round had, and could not be re-run.  HCTR_STEP_SCHEDULE=aggressive|safe overrides."""
+        mode = os.environ.get("HCTR_STEP_SCHEDULE", "")
+        if mode in ("aggressive", "safe"):
+            return mode == "aggressive"
+        return self.world <= 4
 
     def _graph_safe(self) -> bool:
         """The step can be captured when nothing in it needs the host: legacy embeddings whose hash

@@ -57,7 +57,9 @@ class ExchangeWgrad:
         self._after = after_bucket
         if self.wgrad.is_cuda and not hasattr(self, "_stream"):
             import os
-            prio = int(os.environ.get("HCTR_PRIO_COMM", "-3"))
+            default = "-3" if (os.environ.get("HCTR_STEP_SCHEDULE", "") == "aggressive" or
+                               (os.environ.get("HCTR_STEP_SCHEDULE", "") != "safe" and self.comm.world_size <= 4)) else "0"
+            prio = int(os.environ.get("HCTR_PRIO_COMM", default))
             self._stream = torch.cuda.Stream(priority=prio)       # all-reduces, back to back
             self._opt_stream = torch.cuda.Stream(priority=prio)   # per-bucket optimizer slices, behind their bucket
 

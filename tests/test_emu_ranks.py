@@ -110,7 +110,7 @@ def test_emu_legacy_embeddings_fused_gpu():
     run_ranks(4, lambda c: W.run_legacy(comm=c))
 
 
-def _real_plan_body(world, device, p2p):
+def _real_plan_body(world, device, p2p, fused=True):
     """fused collection with the sharding plan the BENCHMARK uses at this GPU count (capped tables): hot table
     row-split over a subset of the ranks (requester-side shard split), table-wise giants, data-parallel small
     tables; forward and AdaGrad backward against a single-process collection"""
@@ -151,8 +151,8 @@ def _real_plan_body(world, device, p2p):
     ref.backward(lr, st)
 
     def body(c):
-        e = EmbeddingCollection(cfg_for(plan), b, hotd, device, torch.float32, c, opt, seed=1, fused=True)
-        assert e.fused and e.shard_split
+        e = EmbeddingCollection(cfg_for(plan), b, hotd, device, torch.float32, c, opt, seed=1, fused=fused)
+        assert e.fused == fused and (e.shard_split or not fused)
         for nm, w in full.items():
             e.load_table_rows(nm, torch.arange(w.shape[0]), w)
         r = c.rank
@@ -173,6 +173,12 @@ def _real_plan_body(world, device, p2p):
 @pytest.mark.parametrize("world", [4, 8])
 def test_emu_fused_benchmark_plan_cpu(world):
     _real_plan_body(world, CPU, "force")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_emu_collective_benchmark_plan_cpu(world):
+    """the NCCL-style (stand-in baseline) exchange with the benchmark's plan"""
+    _real_plan_body(world, CPU, False, fused=False)
 
 
 @pytest.mark.gpu
