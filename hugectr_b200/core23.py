@@ -162,9 +162,12 @@ def AllocateBuffers(device: Optional[Device] = None) -> bool:
     for key, buf in list(_buffers.items()):
         if device is None or key[0] == device:
             buf.allocate()
-            if key[1].name.find("#") >= 0:        # per-arena channels are single use: drop the registry entry,
-                del _buffers[key]                 # the tensors keep the storage alive
     return True
+
+
+def ForgetChannel(device: Device, channel: BufferChannel):
+    """drop a (single-use) channel from the registry; its tensors keep the storage alive"""
+    _buffers.pop((device, channel), None)
 
 
 def ReleaseBuffers():

@@ -79,6 +79,7 @@ class RawAsyncReader(IDataReader):
         self.key_dtype = model.key_dtype
         self.depth = max(2, min(64, ap.num_threads * ap.num_batches_per_thread))
         self.threads = max(1, min(8, ap.num_threads))
+        self._threads_cfg = self.threads
         self.num_samples_hint = rp.num_samples if is_train else rp.eval_num_samples
         self.h = None
         self.lib = _native.host_lib()
@@ -107,6 +108,9 @@ class RawAsyncReader(IDataReader):
         L.hctr_raw_num_samples.restype = C.c_longlong
         L.hctr_raw_num_samples.argtypes = [C.c_void_p]
         if self.device_split:
+            # byte movers: each worker has ONE positional read in flight, so the IO depth the reference gets
+            # from libaio (io_depth requests per thread) comes from a few more threads here
+            self.threads = max(4, self._threads_cfg)
             self.split = RawSplit(b, self.label_dim, self.dense_dim, self.hot, self.key_in, self.key_dtype,
                                   self.dense_float, model.device)
         else:

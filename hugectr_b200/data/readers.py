@@ -103,8 +103,17 @@ class CachedEvalReader(IDataReader):
         if hb is None:
             self._inner_done = True
             return None if not self.cache else self.read_a_batch()
-        mv = lambda t: None if t is None else t.to(self.device, copy=True)
-        kept = HostBatch(mv(hb.label), mv(hb.dense), mv(hb.keys), mv(hb.nnz), hb.num_valid)
+        if getattr(hb, "raw", None) is not None:
+            # device-split reader: split the raw records into fresh device tensors and keep those
+            sp = hb.splitter
+            lab = torch.empty(sp.batch, sp.label_dim, device=self.device)
+            den = torch.empty(sp.batch, max(sp.dense_dim, 1), device=self.device)[:, :sp.dense_dim].contiguous()
+            keys = torch.empty(max(sp.total_keys, 1), dtype=sp.key_dtype, device=self.device)
+            sp.run(hb.raw, hb.raw_skew, hb.num_valid, lab, den, keys)
+            kept = HostBatch(lab, den, keys, None, hb.num_valid)
+        else:
+            mv = lambda t: None if t is None else t.to(self.device, copy=True)
+            kept = HostBatch(mv(hb.label), mv(hb.dense), mv(hb.keys), mv(hb.nnz), hb.num_valid)
         hb.mark_copied()
         self.cache.append(kept)
         self.current_batchsize = self.inner.current_batchsize

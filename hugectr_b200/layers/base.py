@@ -122,10 +122,13 @@ class ParamArena:
         self.c23_weights16 = chan("WeightHalf", torch.bfloat16) if mixed else None
         self.c23_wgrad = (core23.Tensor.bind(wgrad_alloc(n, torch.float32)) if wgrad_alloc is not None
                           else chan("Wgrad", torch.float32))
-        core23.AllocateBuffers(cdev)
+        # data() allocates the tensor's own buffer (AllocateBuffers() would walk every channel of the process,
+        # including those other rank threads are declaring); the per-arena channels are single use
         self.weights = self.c23_weights.data()
         self.wgrad = self.c23_wgrad.data()
         self.weights16 = self.c23_weights16.data() if mixed else None
+        for nm in ("Weight", "WeightHalf", "Wgrad"):
+            core23.ForgetChannel(cdev, core23.BufferChannel(nm + tag))
         for p in self.params:
             p.w = self.weights[p.offset:p.offset + p.numel].view(p.shape)
             p.g = self.wgrad[p.offset:p.offset + p.numel].view(p.shape)
