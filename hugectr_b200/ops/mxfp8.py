@@ -68,8 +68,11 @@ def mx_quantize_reference(x: torch.Tensor):
     xf[:rows] = x.float().cpu()
     blk = xf.view(rp, cols // 32, 32)
     amax = blk.abs().amax(-1)
-    e = torch.where(amax > 0, torch.ceil(torch.log2(amax / 448.0)), torch.full_like(amax, -127.0)).clamp(-127, 127)
-    qv = (blk * torch.exp2(-e).unsqueeze(-1)).reshape(rp, cols).to(torch.float8_e4m3fn)
+    # smallest power of two 2^e with amax / 2^e <= 448, computed exactly like the kernel (fp32 frexp)
+    m, ex = torch.frexp(amax * torch.tensor(1.0 / 448.0, dtype=torch.float32))
+    e = torch.where(m > 0.5, ex, ex - 1).to(torch.float32)
+    e = torch.where(amax > 0, e, torch.full_like(e, -127.0)).clamp(-127, 127)
+    qv = (blk * torch.ldexp(torch.ones_like(e), (-e).to(torch.int32)).unsqueeze(-1)).reshape(rp, cols).to(torch.float8_e4m3fn)
     q = qv.view(torch.uint8)
     sfb = (e + 127).to(torch.uint8)                                   # [rp, cols / 32]
     # block layout: [rp/128][cols/128][32][4][4] <- [r%32][(r%128)//32][k]
