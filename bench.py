@@ -209,7 +209,8 @@ def _note(comm, msg):
         sys.stderr.flush()
 
 
-def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, sustained_s=2.0, label="b200"):
+def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, sustained_s=2.0, label="b200",
+            on_partial=None):
     """Build the model for one configuration, time it, tear it down.  Returns the measurements (rank 0: dict)."""
     _note(comm, f"arm standin={standin} state={state} cap={cap_rows}: building")
     import gc
@@ -319,23 +320,7 @@ def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, s
     ms_dev = maxr([ms_dev])[0]
     n_clk_short = len(samples)
     loss_trace.append(model.get_current_loss())
-    # ---- sustained: >= sustained_s seconds of back-to-back steps (clocks settle below boost)
-    sus = None
-    if sustained_s > 0:
-        est = max(ms_dev / K, 1e-3)
-        chunk = max(10, int(sustained_s * 1e3 / est / 4) + 1)
-        tot_ms, tot_steps = 0.0, 0
-        sync_all()
-        while tot_ms < sustained_s * 1e3 and tot_steps < 100000:
-            ms = maxr([timed(chunk, tot_steps)])[0]      # same chunk count on every rank (max is shared)
-            tot_ms += ms
-            tot_steps += chunk
-        sync_all()
-        sus = {"value": b * n * tot_steps / (tot_ms / 1e3), "unit": "samples/s", "steps": tot_steps,
-               "seconds": tot_ms / 1e3, "ms_per_step": tot_ms / tot_steps,
-               "clocks": summarize_clocks(samples[n_clk_short:])}
-    n_clk_dev = len(samples)
-    _note(comm, "sustained done; end-to-end loop")
+    _note(comm, "end-to-end loop")
     # ---- end to end through the public API: reader -> pinned host batch -> H2D -> step, every step, plus an
     # asynchronous D2H read of the loss every step
     loss_host = torch.zeros(1).pin_memory()
@@ -350,18 +335,6 @@ def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, s
     sync_all()
     wall_ms = (time.perf_counter() - w0) * 1e3
     ms_e2e, wall_ms = maxr([max(e2.elapsed_time(e3), 0.0), wall_ms])
-    # ---- end to end from a FILE: the same public API with the RawAsync reader (O_DIRECT byte movers -> pinned
-    # slots -> one H2D per batch -> device split kernel) on a synthetic Criteo-TB shaped raw file -- what the
-    # reference arm measures (its reader is libaio based), so the two e2e numbers are like for like
-    e2e_file = None
-    if args.e2e_file and not standin:
-        try:
-            e2e_file = _e2e_from_file(args, comm, model, tables, K, sync_all, maxr, loss_host)
-        except Exception as e:       # noqa: BLE001 -- secondary figure
-            e2e_file = {"error": repr(e)[:300]}
-    stop_evt.set()
-    th.join(timeout=2)
-    loss = model.get_current_loss()
     hb = pool[0]
     gb = b * n
     res = {
@@ -369,14 +342,46 @@ def run_arm(args, comm, *, standin=False, state="fp32", cap_rows=0, K=30, W=5, s
         "e2e": {"value": gb * K / (max(ms_e2e, wall_ms) / 1e3), "unit": "samples/s",
                 "ms_per_step": max(ms_e2e, wall_ms) / K, "h2d_bytes_per_step": hb.h2d_bytes(),
                 "d2h_bytes_per_step": 4},
-        "e2e_file": e2e_file,
-        "sustained": sus, "clocks": summarize_clocks(samples[:n_clk_short] or samples),
-        "clocks_all": summarize_clocks(samples),
+        "e2e_file": None, "sustained": None, "clocks": summarize_clocks(samples[:n_clk_short] or samples),
         "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
-        "final_loss": loss, "loss_trace": [round(x, 5) for x in loss_trace + [loss]],
+        "final_loss": model.get_current_loss(), "loss_trace": [round(x, 5) for x in loss_trace],
         "state": state, "cap_rows": cap_rows, "pool_batches": len(pool),
         "table_bytes": int(sum(e.memory_bytes() for e in model.ebcs_train)),
     }
+    res["loss_trace"].append(round(res["final_loss"], 5))
+    if on_partial is not None:
+        on_partial(res)        # the headline (K device-timed steps + end-to-end) exists: everything below is extra
+    n_clk_e2e = len(samples)
+    # ---- sustained: >= sustained_s seconds of back-to-back steps (clocks settle below boost)
+    sus = None
+    if sustained_s > 0:
+        est = max(ms_dev / K, 1e-3)
+        chunk = max(10, int(sustained_s * 1e3 / est / 4) + 1)
+        tot_ms, tot_steps = 0.0, 0
+        sync_all()
+        while tot_ms < sustained_s * 1e3 and tot_steps < 100000:
+            ms = maxr([timed(chunk, tot_steps)])[0]      # same chunk count on every rank (max is shared)
+            tot_ms += ms
+            tot_steps += chunk
+        sync_all()
+        sus = {"value": b * n * tot_steps / (tot_ms / 1e3), "unit": "samples/s", "steps": tot_steps,
+               "seconds": tot_ms / 1e3, "ms_per_step": tot_ms / tot_steps,
+               "clocks": summarize_clocks(samples[n_clk_e2e:])}
+    res["sustained"] = sus
+    _note(comm, "sustained done")
+    # ---- end to end from a FILE: the same public API with the RawAsync reader (O_DIRECT byte movers -> pinned
+    # slots -> one H2D per batch -> device split kernel) on a synthetic Criteo-TB shaped raw file -- what the
+    # reference arm measures (its reader is libaio based), so the two e2e numbers are like for like
+    if args.e2e_file and not standin:
+        try:
+            res["e2e_file"] = _e2e_from_file(args, comm, model, tables, K, sync_all, maxr, loss_host)
+        except Exception as e:       # noqa: BLE001 -- secondary figure
+            res["e2e_file"] = {"error": repr(e)[:300]}
+    stop_evt.set()
+    th.join(timeout=2)
+    res["clocks_all"] = summarize_clocks(samples)
+    res["final_loss"] = model.get_current_loss()
+    res["loss_trace"].append(round(res["final_loss"], 5))
     # ---- teardown of this arm: graph, streams, reader threads, tables
     _note(comm, "arm measured; teardown")
     model.close()
@@ -554,26 +559,37 @@ def main():
     # AdaGrad accumulators as `secondary`.  N >= 2: full tables, fp32 state.
     cap = args.cap_rows or (ROW_CAP_1GPU if (n == 1 and not args.small) else 0)
     standin_only = args.impl == "nccl_cublas"
-    main_res = run_arm(args, comm, standin=standin_only, state="fp32", cap_rows=cap, K=K, W=W,
-                       sustained_s=args.sustained_sec)
-    # The headline is measured.  The extra arms must never cost it: if one of them wedges (a collective that
-    # never completes), the watchdog prints the line with what is known and leaves.
-    extra = {"secondary": None, "standin": None}
+    # As soon as the headline (K device-timed steps + the end-to-end loop) exists, a watchdog guards everything
+    # that follows -- sustained block, file e2e, secondary and stand-in arms: if any of it wedges (a collective
+    # that never completes), the line is printed with what is known and the process leaves.
+    extra = {"main": None, "secondary": None, "standin": None}
+    wd_box = []
 
-    def emit(final: bool):
-        if rank == 0:
-            print(json.dumps(_compose(args, n, K, W, main_res, extra["secondary"], extra["standin"])), flush=True)
+    def emit():
+        if rank == 0 and extra["main"] is not None:
+            print(json.dumps(_compose(args, n, K, W, extra["main"], extra["secondary"], extra["standin"])), flush=True)
 
     def on_timeout():
+        note = f"did not finish within {args.arm_timeout}s (abandoned)"
+        m = extra["main"]
+        if m.get("sustained") is None and args.sustained_sec > 0:
+            m["sustained"] = {"error": note}
         for k in ("secondary", "standin"):
             if extra[k] is None and not (k == "secondary" and n != 1):
-                extra[k] = {"error": f"arm did not finish within {args.arm_timeout}s (abandoned)"}
-        emit(False)
+                extra[k] = {"error": "arm " + note}
+        emit()
         sys.stdout.flush()
         os._exit(0)
-    wd = threading.Timer(args.arm_timeout, on_timeout)
-    wd.daemon = True
-    wd.start()
+
+    def on_partial(res):
+        extra["main"] = res
+        t = threading.Timer(args.arm_timeout, on_timeout)
+        t.daemon = True
+        t.start()
+        wd_box.append(t)
+    main_res = run_arm(args, comm, standin=standin_only, state="fp32", cap_rows=cap, K=K, W=W,
+                       sustained_s=args.sustained_sec, on_partial=on_partial)
+    extra["main"] = main_res
     secondary = None
     if n == 1 and not args.small and not args.cap_rows and not args.no_secondary and not standin_only:
         try:
@@ -595,8 +611,9 @@ def main():
             standin = {"impl": "nccl_cublas", "error": repr(e)[:300]}
 
     extra["standin"] = standin
-    wd.cancel()
-    emit(True)
+    for t in wd_box:
+        t.cancel()
+    emit()
     # orderly teardown: symmetric heap unmapped on every rank, process group destroyed, then a NORMAL interpreter
     # exit (atexit hooks and finalizers run).  The watchdog only fires if that exit wedges.
     sys.stdout.flush()
