@@ -86,8 +86,9 @@ class RawAsyncReader(IDataReader):
         # device-split mode (default on CUDA): workers move raw bytes with O_DIRECT into pinned slots, ONE H2D
         # per batch, a device kernel splits label / dense / keys.  HCTR_RAW_READER=host keeps the CPU split.
         import os
-        self.device_split = (model.device.type == "cuda" and os.environ.get("HCTR_RAW_READER", "device") == "device")
-        self.model_device = model.device
+        dev = getattr(model, "device", None) or torch.device("cpu")
+        self.device_split = (dev.type == "cuda" and os.environ.get("HCTR_RAW_READER", "device") == "device")
+        self.model_device = dev
         self.use_direct = os.environ.get("HCTR_RAW_ODIRECT", "1") == "1"
         L = self.lib
         L.hctr_rawd_open.restype = C.c_void_p
@@ -112,7 +113,7 @@ class RawAsyncReader(IDataReader):
             # from libaio (io_depth requests per thread) comes from a few more threads here
             self.threads = max(4, self._threads_cfg)
             self.split = RawSplit(b, self.label_dim, self.dense_dim, self.hot, self.key_in, self.key_dtype,
-                                  self.dense_float, model.device)
+                                  self.dense_float, dev)
         else:
             self._alloc()
 

@@ -55,6 +55,12 @@ def npz_member(path: str, name: str) -> np.ndarray:
 def write_records(out, label, dense, sparse, start: int, stop: int, chunk: int) -> int:
     """append samples [start, stop) as raw records; returns the number written"""
     lab2 = label.reshape(label.shape[0], -1)
+    if lab2.dtype.kind == "f":
+        # bytes are kept as they are (as the reference's converter does); the MLPerf numpy dumps carry int32
+        # labels, which is what the raw reader with is_dense_float expects (split_batch.cu:43-88)
+        import warnings
+        warnings.warn("float labels: read the raw file with DataReaderParams(float_label_dense=True), or store "
+                      "the labels as int32", stacklevel=2)
     parts = [lab2, dense.reshape(dense.shape[0], -1)] + [s.reshape(s.shape[0], -1) for s in sparse]
     widths = [p.shape[1] * p.dtype.itemsize for p in parts]
     rec_bytes = sum(widths)

@@ -68,7 +68,7 @@ def test_mlperf_numpy_days_to_raw(tmp_path, compressed):
     data = []
     for d in range(days):
         n = rows[d]
-        lab = rng.integers(0, 2, n).astype(np.float32)
+        lab = rng.integers(0, 2, n).astype(np.int32)       # the dtype of the MLPerf dumps
         den = rng.random((n, 13), dtype=np.float32)
         sp = {str(i): rng.integers(0, 1 << 20, (n, hot[i])).astype(np.int32) for i in range(26)}
         np.save(tmp_path / f"day_{d}_labels.npy", lab)
@@ -104,7 +104,7 @@ def test_converted_raw_data_trains_dlrm_dcnv2(tmp_path):
     for d in range(2):
         n = 256
         sp = {str(i): rng.integers(0, sizes[i], (n, hot[i])).astype(np.int32) for i in range(26)}
-        lab = (sp["2"][:, 0] % 2).astype(np.float32)            # learnable from the one-hot feature 2
+        lab = (sp["2"][:, 0] % 2).astype(np.int32)              # learnable from the one-hot feature 2
         np.save(tmp_path / f"day_{d}_labels.npy", lab)
         np.save(tmp_path / f"day_{d}_dense.npy", rng.random((n, 13), dtype=np.float32))
         np.savez(tmp_path / f"day_{d}_sparse_multi_hot.npz", **sp)
