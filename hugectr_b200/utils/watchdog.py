@@ -43,3 +43,53 @@ class StepWatchdog:
     def __exit__(self, *exc):
         self.disarm()
         return False
+
+
+class ExecWatchdog:
+    """GIL-independent deadline (csrc/host/exec_watchdog.cpp): unless disarmed in time, a native thread writes
+    ``message`` to ``message_fd`` and either replaces the process image (``argv`` given: ``execve`` with the
+    environment captured at arming time plus ``env`` overrides; the PID stays, so a launcher keeps supervising
+    the worker and the old CUDA context -- with whatever kernels were spinning in it -- is torn down) or leaves
+    with ``exit_code``.  One watchdog per process; arming again replaces the pending deadline."""
+
+    @staticmethod
+    def _lib():
+        import ctypes as C
+        from .. import _native
+        lib = _native.host_lib()
+        if not getattr(lib, "_hctr_wd_typed", False):
+            lib.hctr_exec_watchdog_arm.argtypes = [C.c_double, C.c_char_p, C.POINTER(C.c_char_p),
+                                                   C.POINTER(C.c_char_p), C.c_char_p, C.c_int, C.c_int]
+            lib.hctr_exec_watchdog_arm.restype = C.c_int
+            lib.hctr_exec_watchdog_disarm.restype = None
+            lib.hctr_exec_watchdog_armed.restype = C.c_int
+            lib._hctr_wd_typed = True
+        return lib
+
+    @classmethod
+    def arm(cls, seconds: float, argv=None, env=None, unset=(), message: str = "", message_fd: int = 2,
+            exit_code: int = 124):
+        import ctypes as C
+
+        def arr(items):
+            a = (C.c_char_p * (len(items) + 1))()
+            for i, s in enumerate(items):
+                a[i] = os.fsencode(s)
+            a[len(items)] = None
+            return a
+        e = dict(os.environ)
+        e.update(env or {})
+        for k in unset:
+            e.pop(k, None)
+        path = os.fsencode(argv[0]) if argv else None
+        cls._lib().hctr_exec_watchdog_arm(float(seconds), path, arr(list(argv or [])),
+                                          arr([f"{k}={v}" for k, v in e.items()]),
+                                          message.encode() if message else None, int(message_fd), int(exit_code))
+
+    @classmethod
+    def disarm(cls):
+        cls._lib().hctr_exec_watchdog_disarm()
+
+    @classmethod
+    def armed(cls) -> bool:
+        return bool(cls._lib().hctr_exec_watchdog_armed())

@@ -60,3 +60,72 @@ def test_reference_arm_unavailable_is_reported_not_raised():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference"
     assert "unavailable" in line or "value" in line       # no GPU here: unavailable; on a GPU box: the measurement
+
+
+# ----------------------------------------------------------------------------- headline watchdog / fallbacks
+_WD_SNIPPET = r'''
+import ctypes, os, sys
+sys.path.insert(0, {root!r})
+from hugectr_b200.utils.watchdog import ExecWatchdog as W
+if os.environ.get("REBORN"):
+    print("reborn", os.environ["REBORN"], os.environ.get("GONE"), flush=True)
+    sys.exit(0)
+W.arm(0.5, argv=[sys.executable, __file__], env={{"REBORN": "yes"}}, unset=("GONE",), message="firing\n")
+ctypes.PyDLL(None).sleep(60)          # a native call that never gives the GIL back
+print("not reached")
+'''
+
+
+def test_exec_watchdog_replaces_a_process_that_holds_the_gil(tmp_path):
+    f = tmp_path / "wd.py"
+    f.write_text(_WD_SNIPPET.format(root=ROOT))
+    r = subprocess.run([sys.executable, str(f)], capture_output=True, text=True, timeout=120,
+                       env={**os.environ, "GONE": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == "reborn yes None", (r.stdout, r.stderr[-500:])
+    assert "firing" in r.stderr and "not reached" not in r.stdout
+
+
+def test_exec_watchdog_disarm_and_exit_mode(tmp_path):
+    from hugectr_b200.utils.watchdog import ExecWatchdog as W
+    import time
+    W.arm(0.3, message="must not fire\n")
+    assert W.armed()
+    W.disarm()
+    time.sleep(0.6)
+    assert not W.armed()                 # (and this process is still here)
+    f = tmp_path / "wd2.py"
+    f.write_text("import sys, time\nsys.path.insert(0, %r)\n"
+                 "from hugectr_b200.utils.watchdog import ExecWatchdog as W\n"
+                 "W.arm(0.3, message='{\"value\": null}\\n', message_fd=1, exit_code=3)\ntime.sleep(30)\n" % ROOT)
+    r = subprocess.run([sys.executable, str(f)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and json.loads(r.stdout) == {"value": None}
+
+
+def test_fallback_schedule_list():
+    b = _bench()
+    env, unset = b.next_attempt_env(0, {"MASTER_PORT": "29500"})
+    assert env["HCTR_BENCH_ATTEMPT"] == "1" and env["MASTER_PORT"] != "29500" and env["HCTR_DISABLE_OVERLAP"] == "1"
+    assert "HCTR_DISABLE_P2P" not in env and "TORCHELASTIC_USE_AGENT_STORE" in unset
+    env2, _ = b.next_attempt_env(1, {**env})
+    assert env2["HCTR_DISABLE_P2P"] == "1" and env2["MASTER_PORT"] not in ("29500", env["MASTER_PORT"])
+    assert b.next_attempt_env(len(b.FALLBACKS) - 1, {}) is None
+    args = types.SimpleNamespace(per_gpu_batch=6912, plan="auto", no_graph=False, small=False, cap_rows=0,
+                                 fp8_mlp=False, impl="b200", attempt=1, headline_timeout=240.0)
+    line = b._compose(args, 8, 20, 5, _fake_result(), None, None)
+    assert line["config"]["fallback"]["attempt"] == 1 and line["config"]["fallback"]["env"] == b.FALLBACKS[1]
+
+
+def test_wedged_ranks_reexecute_with_the_next_schedule_under_torchrun():
+    """2 gloo ranks under torch.distributed.run (static rendezvous, as the driver launches bench.py): attempt 0
+    wedges, the watchdog re-executes both ranks, the new images rendezvous on a fresh port and finish"""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tests", "wd_worker.py")], capture_output=True, text=True, timeout=300,
+                       env={**{k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE")},
+                            "WD_SECONDS": "3"})
+    assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-2000:])
+    assert "OK attempt=1 sum=3.0 overlap_off=1 agent_store=None" in r.stdout and "NOT REACHED" not in r.stdout
