@@ -194,11 +194,43 @@ class EmbeddingCollection:
         self.is_train = is_train
         self.hotness = dict(hotness)
         self.seed = seed
+        self._unique_tables = self._resolve_unique_tables()
         self._kb = 8 if key_dtype == torch.int64 else 4
         self._abf = act_dtype == torch.bfloat16
         self._build_layout(hotness)
         self._build_storage(seed)
         self._alloc_buffers()
+
+    def _resolve_unique_tables(self):
+        """Tables whose lookups use CompressionStrategy.Unique (embedding/unique_exchange.py): named (or
+        indexed) in ``cfg.compression_strategy``, model parallel, static, not column-split -- and only on the
+        collective path: the peer-memory path moves pooled vectors with posted stores and keeps them."""
+        from ..enums import CompressionStrategy
+        req = None
+        for k, v in (self.cfg.compression_strategy or {}).items():
+            if k == CompressionStrategy.Unique or str(k).endswith("Unique"):
+                req = v
+        if not req or self.world == 1:
+            return set()
+        names = [t.name for t in self.tables]
+        want = {names[x] if isinstance(x, int) else str(x) for x in req}
+        unknown = want - set(names)
+        if unknown:
+            raise ValueError(f"compression_strategy names unknown tables: {sorted(unknown)}")
+        from ..utils import logger
+        if self.fused or self.hier:
+            logger.info("CompressionStrategy.Unique: %s exchange keeps pooled-vector transfers for tables %s"
+                        % ("peer-memory" if self.fused else "hierarchical", sorted(want)))
+            return set()
+        ok = set()
+        for n in want:
+            pl, t = self.placement[n], self.tmap[n]
+            if pl.kind == "mp" and pl.col_factor == 1 and not t.dynamic:
+                ok.add(n)
+            else:
+                logger.info(f"CompressionStrategy.Unique: table {n} ({pl.kind}, column factor {pl.col_factor}, "
+                            f"dynamic={t.dynamic}) stays on the Reduction exchange")
+        return ok
 
     def eval_clone(self, batch_per_gpu: int) -> "EmbeddingCollection":
         """Second plan (different batch, no grads) over the SAME tables -- the eval graph."""
@@ -248,6 +280,11 @@ class EmbeddingCollection:
             pl = self.placement[gl["table"]]
             k = len(pl.shard_gpus) // pl.col_factor if pl.kind == "mp" else 1
             gl["k"] = k
+            if gl["table"] in self._unique_tables:
+                # distinct keys travel once, rows come back once per distinct key (unique_exchange.py):
+                # no owner-side lookup descriptors, no per-shard partial blocks
+                gl["unique"], gl["unique_owners"] = True, list(pl.shard_gpus)
+                continue
             if getattr(self, "shard_split", False) and pl.kind == "mp" and k > 1 and pl.col_factor == 1 \
                     and gl["combiner"] == "sum":
                 # Requester-side split: every rank rewrites its bag of a row-sharded table into k
@@ -314,6 +351,9 @@ class EmbeddingCollection:
             for (kind, pitch), grp in groups.items():
                 for sl in grp.table_slices:
                     if sl["table"] != t.name:
+                        continue
+                    if gl.get("unique"):
+                        gl["unique_local"] = (grp, sl)
                         continue
                     H = gl["hotness"]
                     concat = gl["combiner"] == "concat"
@@ -454,6 +494,11 @@ class EmbeddingCollection:
                     self.grads_all = torch.zeros(W, max(self.grad_slab_elems, 1), dtype=self.act_dtype,
                                                  device=dev)
                 self._build_packed_exchange()
+        uq = [gi for gi, gl in enumerate(self.glookups) if gl.get("unique")]
+        self._uniq = None
+        if uq:
+            from .unique_exchange import UniqueExchange
+            self._uniq = UniqueExchange(self, uq)
         # named views
         self.key_views = {}
         for gl in self.glookups:
@@ -722,7 +767,7 @@ class EmbeddingCollection:
         else:
             self.send_out.zero_()
             for grp in self.groups:
-                if grp.kind == "mp":
+                if grp.kind == "mp" and grp.lookups:
                     E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch,
                               list(self.keys_all.unbind(0)), list(self.send_out.unbind(0)), b, self.rank,
                               nnz_bufs=self._nnz_bufs(grp))
@@ -751,6 +796,8 @@ class EmbeddingCollection:
                     if grp.kind == "dp":
                         E.forward(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, [self.key_slab],
                                   [self.out_slab], b)
+        if getattr(self, "_uniq", None) is not None:
+            self._uniq.forward()
         self._reduce_partials()
         self._rescale_mean(forward=True)
 
@@ -802,7 +849,7 @@ class EmbeddingCollection:
         """gradient-independent part of the backward (unique rows + bucket lists); may run on a
         side stream concurrently with the dense network once the keys are in place."""
         for grp in self.groups:
-            if grp.kind == "mp" and getattr(grp, "indexed", False):
+            if grp.kind == "mp" and getattr(grp, "indexed", False) and grp.lookups:
                 kb, _ = self._bwd_bufs(grp)
                 E.bwd_index(grp.lookups, grp.lookups_dev, grp.table, grp.pitch, kb, self.b, grp.ws,
                             self.rank, nnz_bufs=self._nnz_bufs(grp), key_bytes=self._kb)
@@ -853,6 +900,8 @@ class EmbeddingCollection:
         for grp in mp_groups:
             kb, gb = self._bwd_bufs(grp)
             self._accum_update(grp, kb, gb, lr_t, step_t)
+        if getattr(self, "_uniq", None) is not None:
+            self._uniq.backward(lr_t, step_t)
         if side:
             torch.cuda.current_stream().wait_stream(dp_stream)
         else:
@@ -873,6 +922,8 @@ class EmbeddingCollection:
 
     def _accum_update(self, grp, key_bufs, grad_bufs, lr_t, step_t):
         o = grp.opt
+        if not grp.lookups:
+            return            # (every lookup of this group travels through the Unique exchange)
         if grp.kind == "mp" and getattr(grp, "indexed", False):
             E.bwd_reduce_update(o.optimizer_type, grp.lookups, grp.lookups_dev, grp.table, grp.s0,
                                 grp.s1, grp.pitch, key_bufs, grad_bufs, self.b, grp.ws, self._hp(o),

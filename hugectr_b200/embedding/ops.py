@@ -503,8 +503,18 @@ def update(opt: Optimizer_t, table, s0, s1, ev_pitch, ws: UniqueWorkspace, hp: d
     if ws.ref_rows is None or ws.ref_rows.numel() == 0:
         ws.ref_rows = ws.ref_grads = None
         return
-    uniq, inv = torch.unique(ws.ref_rows, return_inverse=True)
-    g = torch.zeros(uniq.numel(), ev_pitch).index_add_(0, inv, ws.ref_grads)
+    update_rows(opt, table, s0, s1, ev_pitch, ws.ref_rows, ws.ref_grads, hp, lr_t, step_t)
+    ws.ref_rows = ws.ref_grads = None
+
+
+def update_rows(opt: Optimizer_t, table, s0, s1, ev_pitch, rows, grads, hp: dict, lr_t, step_t):
+    """One optimizer application per DISTINCT row (``rows`` [n] may repeat, ``grads`` [n, pitch] fp32 are
+    summed per row first).  Plain tensor ops on the tables' device: the CPU path of ``update`` and the
+    owner side of the Unique-compression exchange (embedding/unique_exchange.py)."""
+    if rows.numel() == 0:
+        return
+    uniq, inv = torch.unique(rows, return_inverse=True)
+    g = torch.zeros(uniq.numel(), ev_pitch, dtype=torch.float32, device=grads.device).index_add_(0, inv, grads.float())
     tab = table.view(-1, ev_pitch)
     w = tab[uniq].clone()
     a = None if s0 is None else s0.view(-1, ev_pitch)[uniq].float().clone()
@@ -515,7 +525,6 @@ def update(opt: Optimizer_t, table, s0, s1, ev_pitch, ws: UniqueWorkspace, hp: d
         s0.view(-1, ev_pitch)[uniq] = a.to(s0.dtype)
     if b is not None:
         s1.view(-1, ev_pitch)[uniq] = b.to(s1.dtype)
-    ws.ref_rows = ws.ref_grads = None
 
 
 def gather_rows(table, ev_pitch, rows, out):

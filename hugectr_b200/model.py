@@ -598,6 +598,8 @@ class Model:
         if any(getattr(e, "has_dynamic", False) and not getattr(e, "dynamic_graph_safe", False)
                for e in self.ebcs_train):
             return False
+        if any(getattr(e, "_uniq", None) is not None for e in self.ebcs_train):
+            return False          # Unique-compression exchange sizes its all-to-all on the host
         return True
 
     def close(self):

@@ -44,7 +44,7 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
                      mixed: bool = True, scaler: float = 1.0, source=None, shard_plan=None,
                      optimizer: str = "adagrad", bottom=(512, 256, 128),
                      top=(1024, 1024, 512, 256, 1), cross_layers: int = 3, projection_dim: int = 512,
-                     comm=None, comm_strategy=None, **solver_kw) -> "hugectr.Model":
+                     comm=None, comm_strategy=None, compression_strategy=None, **solver_kw) -> "hugectr.Model":
     table_sizes = list(table_sizes or CRITEO_TB_TABLE_SIZES)
     multi_hot = list(multi_hot or CRITEO_TB_MULTI_HOT)
     n = len(table_sizes)
@@ -76,7 +76,7 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
     if shard_plan is None:
         from hugectr_b200.tools.planner import generate_plan
         shard_plan = generate_plan(table_sizes, multi_hot, num_gpus, ev_size=max(evs))
-    ebc.shard(shard_matrix=shard_plan[0], shard_strategy=shard_plan[1])
+    ebc.shard(shard_matrix=shard_plan[0], shard_strategy=shard_plan[1], compression_strategy=compression_strategy)
     model.add(ebc)
     cc = hugectr.DenseLayerComputeConfig(async_wgrad=True, fuse_wb=False)
     model.add(hugectr.DenseLayer(hugectr.Layer_t.MLP, ["dense"], ["mlp1"], num_outputs=list(bottom),
@@ -94,7 +94,7 @@ def build_dlrm_dcnv2(batchsize: int = 55296, num_gpus: int = 8, table_sizes: Opt
 
 def build_dlrm(batchsize: int = 55296, num_gpus: int = 8, table_sizes=None, ev_size: int = 128,
                lr: float = 24.0, mixed: bool = True, scaler: float = 1.0, source=None,
-               shard_plan=None, comm=None, **solver_kw):
+               shard_plan=None, comm=None, compression_strategy=None, **solver_kw):
     """MLPerf-v1 DLRM: one-hot lookups, concat combiner, dot Interaction, SGD."""
     table_sizes = list(table_sizes or CRITEO_TB_TABLE_SIZES)
     n = len(table_sizes)
@@ -115,7 +115,7 @@ def build_dlrm(batchsize: int = 55296, num_gpus: int = 8, table_sizes=None, ev_s
     if shard_plan is None:
         from hugectr_b200.tools.planner import generate_plan
         shard_plan = generate_plan(table_sizes, [1] * n, num_gpus, ev_size=ev_size)
-    ebc.shard(shard_plan[0], shard_plan[1])
+    ebc.shard(shard_plan[0], shard_plan[1], compression_strategy=compression_strategy)
     model.add(ebc)
     model.add(hugectr.DenseLayer(hugectr.Layer_t.MLP, ["dense"], ["mlp1"], num_outputs=[512, 256, ev_size],
                                  act_type=hugectr.Activation_t.Relu))

@@ -562,8 +562,14 @@ def run_equiv(optimizer="sgd", gpus_per_node=0, comm=None):
         # logical nodes: hierarchical two-stage exchange (intra-node reduce, inter-node same-local-id)
         hkw = dict(gpus_per_node=gpus_per_node, comm_strategy=hugectr.CommunicationStrategy.Hierarchical,
                    fused_embedding_comm=False)
+    if os.environ.get("HCTR_TEST_UNIQUE"):
+        # every model-parallel table on the Unique-compression exchange (collective path)
+        mp_names = [x[0] if isinstance(x, tuple) else x for (k_, items) in plan[1] if k_ == "mp" for x in items]
+        hkw.update(compression_strategy={hugectr.CompressionStrategy.Unique: mp_names}, fused_embedding_comm=False)
     m = build_dlrm_dcnv2(batchsize=b * world, num_gpus=world, comm=comm, shard_plan=plan, **kw, **hkw)
     m.compile()
+    if os.environ.get("HCTR_TEST_UNIQUE"):
+        assert m.ebcs_train[0]._uniq is not None and not m._graph_safe()
     if gpus_per_node:
         assert m.ebcs_train[0].hier and comm.num_nodes == world // gpus_per_node
     if os.environ.get("HCTR_SHARD_SPLIT", "0") == "1":
@@ -706,8 +712,94 @@ def run_ckpt(tmpdir, comm=None):
         print("CKPT_OK", l_m, l_r)
 
 
+def run_unique(names="0,2", opt_name="adagrad", fused=False, comm=None):
+    """collective path with some tables on the Unique exchange (distinct keys travel once, rows return once per
+    distinct key, owners de-duplicate across requesters) against a single-process collection"""
+    c = comm or Comm.init_from_env()
+    world, device = c.world_size, c.device
+    unique_names = [x for x in str(names).split(",") if x]
+    from hugectr_b200.embedding.collection import (EmbeddingCollection, EmbeddingCollectionConfig,
+                                                   EmbeddingTableConfig)
+    from hugectr_b200.enums import CompressionStrategy, Optimizer_t
+    from hugectr_b200.solver import CreateOptimizer
+    b, ev = 6, 8
+    sizes = [40, 1000, 64, 300, 17, 90]
+    hot = [5, 3, 4, 2, 1, 6]
+    comb = ["sum", "mean", "concat", "sum", "sum", "mean"]
+    n = len(sizes)
+    # table 0: row-sharded over ranks {0, 1}; 1, 2, 3, 5: table-wise; 4: data parallel
+    sm = [[0] * n for _ in range(world)]
+    sm[0][0] = sm[1 % world][0] = 1
+    for i in (1, 2, 3, 5):
+        sm[i % world][i] = 1
+    for g in range(world):
+        sm[g][4] = 1
+    strat = [("mp", ["0", "1", "2", "3", "5"]), ("dp", ["4"])]
+
+    def cfg_for(sharded):
+        cfg = EmbeddingCollectionConfig()
+        cfg.embedding_lookup([EmbeddingTableConfig(str(i), sizes[i], ev) for i in range(n)],
+                             [f"d{i}" for i in range(n)], "emb", comb)
+        if sharded:
+            cfg.shard(sm, strat, compression_strategy={CompressionStrategy.Unique: list(unique_names),
+                                                       CompressionStrategy.Reduction: []})
+        return cfg
+    gen = torch.Generator().manual_seed(3)
+    full = {str(i): torch.randn(sizes[i], ev, generator=gen) * 0.1 for i in range(n)}
+    keys = [torch.randint(0, max(2, sizes[i] // 3), (b * world, hot[i]), generator=gen) for i in range(n)]
+    keys[1][::3, -1] = -1                               # short bags (mean over the actual bag)
+    keys[5][1::4, 2:] = -1
+    width = sum(ev * (hot[i] if comb[i] == "concat" else 1) for i in range(n))
+    grad = torch.randn(b * world, width, generator=gen) * 0.1
+    kind = {"adagrad": Optimizer_t.AdaGrad, "sgd": Optimizer_t.SGD, "adam": Optimizer_t.Adam}[opt_name]
+    opt = CreateOptimizer(kind, **({"initial_accu_value": 0.1, "epsilon": 1e-6} if opt_name == "adagrad" else {}))
+    hotd = {f"d{i}": hot[i] for i in range(n)}
+    cpu = torch.device("cpu")
+    ref = EmbeddingCollection(cfg_for(False), b * world, hotd, cpu, torch.float32, Comm.single(cpu), opt, seed=1)
+    for nm, w in full.items():
+        ref.load_table_rows(nm, torch.arange(w.shape[0]), w)
+    lr, st = torch.tensor([0.05]), torch.tensor([1], dtype=torch.int32)
+    steps = 2
+    ref_out = []
+    for it in range(steps):
+        ref.set_keys(torch.cat([k.roll(it, 0).reshape(-1) for k in keys]).int())
+        ref.forward()
+        ref_out.append(ref.top_data["emb"].clone())
+        ref.top_grad["emb"].copy_(grad)
+        ref.backward(lr, st + it)
+    e = EmbeddingCollection(cfg_for(True), b, hotd, device, torch.float32, c, opt, seed=1, fused=fused)
+    uq = {gl["table"] for gl in e.glookups if gl.get("unique")}
+    assert uq == (set(unique_names) if not fused else set()), uq
+    for nm, w in full.items():
+        e.load_table_rows(nm, torch.arange(w.shape[0]), w)
+    r = c.rank
+    for it in range(steps):
+        e.set_keys(torch.cat([k.roll(it, 0)[r * b:(r + 1) * b].reshape(-1) for k in keys]).int().to(device))
+        e.forward()
+        err = (e.top_data["emb"].float().cpu() - ref_out[it][r * b:(r + 1) * b]).abs().max().item()
+        assert err < 1e-5, ("forward", it, r, err)
+        if e._uniq is not None and it == 0:
+            sent, _ = e._uniq.wire_elems()
+            total = sum(b * hot[int(t)] for t in unique_names)
+            assert 0 < sent < total, (sent, total)        # repeated ids: fewer codes than key slots
+        e.top_grad["emb"].copy_(grad[r * b:(r + 1) * b].to(device))
+        e.backward(lr.to(device), (st + it).to(device))
+    for nm in full:
+        rk, rw = ref.dump_table_local(nm)[0][:2]
+        for (k, w, c0, sts, kind_) in e.dump_table_local(nm):
+            if len(k):
+                d = (w - rw[k][:, c0:c0 + w.shape[1]]).abs().max().item()
+                assert d < 2e-5, ("table", nm, r, d)
+    dsync(c)
+    c.barrier()
+    if c.rank == 0:
+        print("UNIQUE_OK", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
+    if what == "unique":
+        run_unique(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "adagrad")
     if what == "ckpt":
         run_ckpt(sys.argv[2])
     if what == "dynamic":

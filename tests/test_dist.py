@@ -207,3 +207,19 @@ def test_multi_rank_equals_single_process_random_plan_gloo(nproc, seed):
     out = _run(nproc, ["equiv", "adagrad"], 29800 + seed,
                env={"CUDA_VISIBLE_DEVICES": "", "HCTR_TEST_PLAN_SEED": str(seed)})
     assert "EQUIV_OK" in out, out[-2000:]
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc,names", [(2, "0,1,2,3,5"), (3, "0,2")])
+def test_unique_compression_exchange_gloo(nproc, names):
+    """CompressionStrategy.Unique on real processes: the count all-to-all and the variable all-to-alls of 64-bit
+    key codes / embedding rows / pre-reduced gradient rows over gloo"""
+    out = _run(nproc, ["unique", names, "adagrad"], 29741, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "UNIQUE_OK" in out
+
+
+@pytest.mark.dist
+def test_model_with_unique_compression_equals_single_process_gloo():
+    """whole model through the public API: ebc.shard(..., compression_strategy={Unique: [...]})"""
+    out = _run(2, ["equiv", "adagrad"], 29751, env={"CUDA_VISIBLE_DEVICES": "", "HCTR_TEST_UNIQUE": "1"})
+    assert "EQUIV_OK" in out

@@ -185,3 +185,15 @@ def test_emu_collective_benchmark_plan_cpu(world):
 @pytest.mark.parametrize("world", [4, 8])
 def test_emu_fused_benchmark_plan_gpu(world):
     _real_plan_body(world, torch.device("cuda"), True)
+
+
+# ----------------------------------------------------------------------------- CompressionStrategy.Unique
+@pytest.mark.parametrize("world,names,opt", [(2, "0,2", "adagrad"), (3, "0,1,2,3,5", "adagrad"),
+                                             (4, "1,5", "sgd"), (2, "0,1,2,3,5", "adam")])
+def test_emu_unique_compression_cpu(world, names, opt):
+    run_ranks(world, lambda c: W.run_unique(names, opt, comm=c), device=CPU, p2p=False)
+
+
+def test_emu_unique_is_left_to_the_peer_store_path_when_fused_cpu():
+    """fused (peer-memory) mode keeps pooled-vector transfers: Unique tables are not rerouted"""
+    run_ranks(2, lambda c: W.run_unique("0,2", "adagrad", fused=True, comm=c), device=CPU, p2p="force")
