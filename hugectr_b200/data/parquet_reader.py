@@ -46,6 +46,24 @@ def _csr_to_padded(offs, vals, n, H, add, blk, s, nz):
                          blk.ctypes.data + 8 * s * Hb, S * Hb, nz.ctypes.data + 4 * s * nz.shape[1])
 
 
+def _onehot_block(cols, add, lo, nloc, b, blk, nz):
+    """blk[i, s, 0] = cols[s][lo + i] + add[s] (i < nloc; -1 behind), nz[s, i] = 1 / 0 -- native, GIL released"""
+    import ctypes as C
+    from .. import _native
+    L = _native.host_lib()
+    L.hctr_onehot_block.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
+                                    C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
+    S = len(cols)
+    cols = [np.ascontiguousarray(c, dtype=np.int64) for c in cols]
+    ptrs = (C.c_void_p * S)(*[c.ctypes.data for c in cols])
+    addp = None
+    if add is not None:
+        add = np.ascontiguousarray(add, dtype=np.int64)
+        addp = add.ctypes.data
+    L.hctr_onehot_block(ptrs, addp, S, int(lo), int(nloc), int(b), blk.ctypes.data, blk.dtype.itemsize,
+                        nz.ctypes.data)
+
+
 class ParquetReader(IDataReader):
     def __init__(self, model, is_train: bool):
         rp = model.reader_params
@@ -184,35 +202,55 @@ class ParquetReader(IDataReader):
         return (lab[pos:], den[pos:], [self._slice_cat(c, pos, n) for c in cats], n - pos)
 
     def _emit_batch(self, chunk, nvalid_global):
+        self.q.put(self._assemble(chunk, nvalid_global))
+
+    def _assemble(self, chunk, nvalid_global):
+        """this rank's slice of one global batch -> HostBatch (label, dense, feature-major padded key blocks,
+        bag lengths).  Assembled with numpy into the final dtypes (torch CPU ops called from a side thread pay
+        for their own thread-pool start-up: 2 ms per ``torch.zeros`` here), wrapped zero-copy."""
         lab, den, cats, n = chunk
         b, r = self.b, self.rank
         lo, hi = r * b, min((r + 1) * b, n)
         nloc = max(0, hi - lo)
-        L = torch.zeros(b, self.inp.label_dim)
-        D = torch.zeros(b, self.inp.dense_dim)
+        L = np.zeros((b, self.inp.label_dim), dtype="float32")
+        D = np.zeros((b, self.inp.dense_dim), dtype="float32")
         if nloc > 0:
-            L[:nloc] = torch.from_numpy(lab[lo:hi])
-            D[:nloc] = torch.from_numpy(den[lo:hi])
-        blocks, nnzs = [], []
-        si = 0
-        for (name, S, H, fixed) in self.layout.blocks:
-            blk = np.full((b, S, H), -1, dtype="int64")
-            nz = np.zeros((S, b), dtype="int32")
-            for s in range(S):
-                offs, vals = self._slice_cat(cats[si], lo, hi) if nloc > 0 else (None, np.zeros(0, "int64"))
-                off_add = 0 if self.slot_offsets is None else self.slot_offsets[si]
-                if offs is None:
-                    blk[:nloc, s, 0] = vals[:nloc] + off_add
-                    nz[s, :nloc] = 1
-                else:
-                    _csr_to_padded(offs, vals, nloc, H, int(off_add), blk, s, nz)
-                si += 1
-            blocks.append(torch.from_numpy(blk.reshape(-1)))
-            nnzs.append(torch.from_numpy(nz.reshape(-1)))
-        keys = torch.cat(blocks).to(self.key_dtype) if blocks else torch.zeros(0, dtype=self.key_dtype)
-        nnz = torch.cat(nnzs) if nnzs else None
-        hb = HostBatch(L, D, keys, nnz, nloc).pin()
-        self.q.put((hb, nvalid_global))
+            L[:nloc] = lab[lo:hi]
+            D[:nloc] = den[lo:hi]
+        kdt = "int64" if self.key_dtype == torch.int64 else "int32"
+        blocks = self.layout.blocks
+        kelems = sum(b * S * H for (_, S, H, _) in blocks)
+        nelems = sum(S * b for (_, S, H, _) in blocks)
+        keys = np.full(kelems, -1, dtype=kdt)
+        nnz = np.zeros(nelems, dtype="int32")
+        si = ko = no = 0
+        for (name, S, H, fixed) in blocks:
+            blk = keys[ko:ko + b * S * H].reshape(b, S, H)
+            nz = nnz[no:no + S * b].reshape(S, b)
+            if H == 1 and all(cats[si + s][0] is None for s in range(S)):
+                # one-hot block: one strided store per slot, offsets added in the key dtype
+                _onehot_block([cats[si + s][1] for s in range(S)],
+                              None if self.slot_offsets is None else self.slot_offsets[si:si + S],
+                              lo, nloc, b, blk, nz)
+                si += S
+            else:
+                tmp = blk if kdt == "int64" else np.full((b, S, H), -1, dtype="int64")
+                for s in range(S):
+                    offs, vals = self._slice_cat(cats[si], lo, hi) if nloc > 0 else (None, np.zeros(0, "int64"))
+                    off_add = 0 if self.slot_offsets is None else self.slot_offsets[si]
+                    if offs is None:
+                        tmp[:nloc, s, 0] = vals[:nloc] + off_add
+                        nz[s, :nloc] = 1
+                    else:
+                        _csr_to_padded(offs, vals, nloc, H, int(off_add), tmp, s, nz)
+                    si += 1
+                if tmp is not blk:
+                    blk[...] = tmp
+            ko += b * S * H
+            no += S * b
+        hb = HostBatch(torch.from_numpy(L), torch.from_numpy(D), torch.from_numpy(keys),
+                       torch.from_numpy(nnz) if blocks else None, nloc).pin()
+        return (hb, nvalid_global)
 
     # -------------------------------------------------------------- consumer
     def start(self):
