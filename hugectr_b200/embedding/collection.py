@@ -166,8 +166,11 @@ class EmbeddingCollection:
                  scaler: float = 1.0, state_dtype=torch.float32, seed: int = 0,
                  fused: Optional[bool] = None, is_train: bool = True):
         self.cfg, self.b, self.device, self.act_dtype = cfg, batch_per_gpu, device, act_dtype
-        self.comm = comm
-        self.rank, self.world = comm.rank, comm.world_size
+        # who am I / whom do I talk to: through the backend-neutral interface (core.py; reference core.hpp)
+        from ..core import as_core
+        self.core = as_core(comm)
+        self.comm = comm = self.core.get_comm()
+        self.rank, self.world = self.core.get_global_gpu_id(), self.core.get_global_gpu_count()
         self.key_dtype = key_dtype
         self.scaler = scaler
         self.state_dtype = state_dtype

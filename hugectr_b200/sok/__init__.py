@@ -42,8 +42,14 @@ def _c() -> Comm:
     return _comm
 
 
-def rank(): return _c().rank
-def num_gpus(): return _c().world_size
+def core():
+    """the backend-neutral resource view SOK runs on (core.py; reference core::CoreResourceManager)"""
+    from ..core import as_core
+    return as_core(_c())
+
+
+def rank(): return core().get_global_gpu_id()
+def num_gpus(): return core().get_global_gpu_count()
 
 
 class Variable:
