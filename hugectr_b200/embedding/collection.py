@@ -283,7 +283,7 @@ class EmbeddingCollection:
             pl = self.placement[gl["table"]]
             k = len(pl.shard_gpus) // pl.col_factor if pl.kind == "mp" else 1
             gl["k"] = k
-            if gl["table"] in self._unique_tables:
+            if gl["table"] in getattr(self, "_unique_tables", ()):
                 # distinct keys travel once, rows come back once per distinct key (unique_exchange.py):
                 # no owner-side lookup descriptors, no per-shard partial blocks
                 gl["unique"], gl["unique_owners"] = True, list(pl.shard_gpus)
