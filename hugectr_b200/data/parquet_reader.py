@@ -111,17 +111,17 @@ class ParquetReader(IDataReader):
             tbl = tl.pf.read_row_group(rg)
         cols = [tbl.column(i) for i in range(tbl.num_columns)]
         n = tbl.num_rows
-        lab = np.stack([cols[i].to_numpy().astype("float32") for i in lab_i], 1) \
+        lab = np.stack([cols[i].to_numpy().astype("float32", copy=False) for i in lab_i], 1) \
             if lab_i else np.zeros((n, 0), "float32")
-        den = np.stack([cols[i].to_numpy().astype("float32") for i in con_i], 1) \
+        den = np.stack([cols[i].to_numpy().astype("float32", copy=False) for i in con_i], 1) \
             if con_i else np.zeros((n, 0), "float32")
         cats = []
         for i in cat_i:
             c = cols[i].combine_chunks()
             if pa.types.is_list(c.type) or pa.types.is_large_list(c.type):
-                cats.append((c.offsets.to_numpy(), c.values.to_numpy().astype("int64")))
+                cats.append((c.offsets.to_numpy(), c.values.to_numpy().astype("int64", copy=False)))
             else:
-                cats.append((None, c.to_numpy().astype("int64")))
+                cats.append((None, c.to_numpy().astype("int64", copy=False)))
         return (lab, den, cats, n)
 
     def _row_groups(self, files):
@@ -149,7 +149,9 @@ class ParquetReader(IDataReader):
             self._tls = threading.local()
             pending = deque()
             it = self._row_groups(files)
+            self._out = deque()
             with ThreadPoolExecutor(max_workers=self.num_workers) as ex:
+                self._ex = ex
                 while not self._stop.is_set():
                     while len(pending) < self.num_workers + 1:
                         nxt = next(it, None)
@@ -161,10 +163,15 @@ class ParquetReader(IDataReader):
                     carry = self._emit(pending.popleft().result(), carry, gb)
                 for f in pending:
                     f.cancel()
+                if not self._stop.is_set():
+                    if carry is not None and carry[3] > 0 and not self.drop_incomplete:
+                        self._emit_batch(carry, carry[3])
+                    self._drain(0)
+                for f in self._out:
+                    f.cancel()
+                self._ex = None
             if self._stop.is_set():
                 return
-            if carry is not None and carry[3] > 0 and not self.drop_incomplete:
-                self._emit_batch(carry, carry[3])
             self.q.put(None)
         except Exception as e:  # surface errors to the consumer
             self.q.put(e)
@@ -202,7 +209,19 @@ class ParquetReader(IDataReader):
         return (lab[pos:], den[pos:], [self._slice_cat(c, pos, n) for c in cats], n - pos)
 
     def _emit_batch(self, chunk, nvalid_global):
-        self.q.put(self._assemble(chunk, nvalid_global))
+        ex = getattr(self, "_ex", None)
+        if ex is None:
+            self.q.put(self._assemble(chunk, nvalid_global))
+            return
+        # assembly is native (GIL released): batches are built on the worker pool, leave in submission order
+        self._out.append(ex.submit(self._assemble, chunk, nvalid_global))
+        self._drain(self.num_workers)
+
+    def _drain(self, keep: int):
+        while self._out and (len(self._out) > keep or self._out[0].done()):
+            if self._stop.is_set():
+                return
+            self.q.put(self._out.popleft().result())
 
     def _assemble(self, chunk, nvalid_global):
         """this rank's slice of one global batch -> HostBatch (label, dense, feature-major padded key blocks,
