@@ -126,3 +126,74 @@ def test_converted_raw_data_trains_dlrm_dcnv2(tmp_path):
         assert m.eval()
     auc = dict(m.get_eval_metrics())["AUC"]
     assert auc > 0.85, auc
+
+
+def test_criteo_tsv_to_parquet_and_train(tmp_path):
+    """tools/criteo2parquet.py (the NVTabular preprocessing role): TSV -> categorified Parquet + metadata, ids equal
+    the raw converter's, and the Parquet reader trains a model from the result"""
+    import json
+    import pyarrow.parquet as pq
+    import torch
+    import hugectr_b200 as hugectr
+    from hugectr_b200.tools import criteo2parquet
+    rng = np.random.default_rng(4)
+    tr, va = str(tmp_path / "day_0"), str(tmp_path / "day_1")
+    _tsv(tr, 700, rng)
+    _tsv(va, 300, rng)
+    sizes = criteo2parquet.convert([tr], [va], str(tmp_path / "pq"), freq_limit=2, normalize_dense=True,
+                                   rows_per_file=256, threads=3, log=lambda *a: None)
+    meta = json.load(open(tmp_path / "pq" / "train" / "_metadata.json"))
+    assert sum(f["num_rows"] for f in meta["file_stats"]) == 700 and len(meta["file_stats"]) == 3
+    assert [c["index"] for c in meta["cats"]] == list(range(14, 40))
+    # same ids as the raw converter with the same vocabulary
+    pre = criteo2raw.CriteoPreprocessor(num_threads=2).fit(tr)
+    assert pre.finalize(2) == sizes
+    pre.transform(tr, str(tmp_path / "t.bin"))
+    raw = np.fromfile(tmp_path / "t.bin", dtype="<u4").reshape(700, 40)
+    files = open(tmp_path / "pq" / "train" / "_file_list.txt").read().split()[1:]
+    tbl = [pq.read_table(f).to_pandas() for f in files]
+    import pandas as pd
+    df = pd.concat(tbl, ignore_index=True)
+    assert (df[[f"C{j + 1}" for j in range(26)]].to_numpy() == raw[:, 14:]).all()
+    assert (df["label"].to_numpy() == raw[:, 0].view("<i4")).all()
+    assert np.allclose(df["I3"].to_numpy(), np.log1p(np.maximum(raw[:, 3].view("<i4"), 0)), atol=1e-6)
+    # train from it
+    solver = hugectr.CreateSolver(batchsize=64, batchsize_eval=64, lr=0.01, vvgpu=[[0]], repeat_dataset=True,
+                                  i64_input_key=True, use_cuda_graph=False, max_eval_batches=2)
+    rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.Parquet, source=[str(tmp_path / "pq" / "train" / "_file_list.txt")],
+                                  eval_source=str(tmp_path / "pq" / "val" / "_file_list.txt"),
+                                  check_type=hugectr.Check_t.Non, slot_size_array=sizes)
+    m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam))
+    m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=13, dense_name="dense",
+                        data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", 1, True, 26)]))
+    m.add(hugectr.SparseEmbedding(hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash, 8, 4, "sum", "emb", "data1",
+                                  slot_size_array=sizes))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.Reshape, ["emb"], ["r"], leading_dim=26 * 4))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["r", "dense"], ["c"]))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+    m.compile()
+    for _ in range(20):
+        assert m.train()
+    assert np.isfinite(m.get_current_loss())
+    assert m.eval()
+
+
+def test_criteo2predict_roundtrip(tmp_path):
+    """tools/criteo2predict.py: the reference's four-line inference input format, written and read back"""
+    import json
+    from hugectr_b200.tools import criteo2predict as P
+    rng = np.random.default_rng(2)
+    b, D, slots = 5, 3, [1, 2, 1]
+    rows = np.concatenate([rng.integers(0, 2, (b, 1)), rng.random((b, D)).round(4), rng.integers(0, 1000, (b, 4))], 1)
+    np.savetxt(tmp_path / "test.txt", rows, fmt="%g")
+    json.dump({"dense": D, "categorical": 4, "slot_size": slots}, open(tmp_path / "cfg.json", "w"))
+    n = P.main(["--src_csv_path", str(tmp_path / "test.txt"), "--src_config_path", str(tmp_path / "cfg.json"),
+                "--dst_path", str(tmp_path / "in.txt"), "--batch_size", "4"])
+    assert n == 4
+    lines = open(tmp_path / "in.txt").read().splitlines()
+    assert len(lines) == 4 and len(lines[0].split()) == 4 and len(lines[2].split()) == 16 and len(lines[3].split()) == 13
+    label, dense, keys, ptr = P.load(str(tmp_path / "in.txt"), D)
+    assert np.allclose(label.numpy(), rows[:4, 0]) and np.allclose(dense.numpy(), rows[:4, 1:4], atol=1e-6)
+    assert (keys.numpy() == rows[:4, 4:].astype(np.int64).reshape(-1)).all()
+    assert ptr.tolist() == [0, 1, 3, 4, 5, 7, 8, 9, 11, 12, 13, 15, 16]
