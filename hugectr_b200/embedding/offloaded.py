@@ -20,6 +20,8 @@ import os
 import numpy as np
 import torch
 
+from ..io import filesystem as FS
+
 from ..enums import Optimizer_t, TrainPSType_t
 from . import ops as E
 from .sparse_embedding import SparseEmbeddingRuntime
@@ -150,10 +152,10 @@ class CachedSparseEmbeddingRuntime(SparseEmbeddingRuntime):
         return self.comm.all_gather_object((keys, w, self._slot_ids(keys) if self.localized else None))
 
     def load_parameters(self, path: str):
-        keys = torch.from_numpy(np.fromfile(os.path.join(path, "key"), dtype="<i8").astype("int64"))
-        w = torch.from_numpy(np.fromfile(os.path.join(path, "emb_vector"), dtype="<f4")).view(-1, self.vec)
-        if self.localized and os.path.exists(os.path.join(path, "slot_id")):
-            slot = torch.from_numpy(np.fromfile(os.path.join(path, "slot_id"), dtype="<u8").astype("int64"))
+        keys = torch.from_numpy(FS.read_array(FS.path_join(path, "key"), "<i8").astype("int64"))
+        w = torch.from_numpy(FS.read_array(FS.path_join(path, "emb_vector"), "<f4")).view(-1, self.vec)
+        if self.localized and FS.path_exists(FS.path_join(path, "slot_id")):
+            slot = torch.from_numpy(FS.read_array(FS.path_join(path, "slot_id"), "<u8").astype("int64"))
             m = (slot % self.world) == self.rank
         else:
             m = (keys % self.world) == self.rank
@@ -169,13 +171,12 @@ class CachedSparseEmbeddingRuntime(SparseEmbeddingRuntime):
         st = [s[rows].clone() for s in self.ps.s]
         parts = self.comm.all_gather_object(st)
         if self.comm.rank == 0:
-            with open(path, "wb") as f:
-                for i in range(len(st)):
-                    f.write(torch.cat([p[i] for p in parts]).numpy().astype("<f4").tobytes())
+            FS.write_array(path, np.concatenate([torch.cat([p[i] for p in parts]).numpy().astype("<f4").reshape(-1)
+                                                 for i in range(len(st))]) if st else np.zeros(0, "<f4"))
         self.comm.barrier()
 
     def load_opt_states(self, path: str):
-        raw = np.fromfile(path, dtype="<f4")
+        raw = FS.read_array(path, "<f4")
         if not self.ps.s:
             return
         keys = getattr(self, "_loaded_keys", None)

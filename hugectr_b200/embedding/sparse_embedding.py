@@ -31,6 +31,8 @@ from typing import List
 import numpy as np
 import torch
 
+from ..io import filesystem as FS
+
 from ..enums import Embedding_t, Optimizer_t, Update_t
 from . import ops as E
 from .hashtable import HashTable
@@ -345,14 +347,13 @@ class SparseEmbeddingRuntime:
     def dump_parameters(self, path: str):
         parts = self._gather_all()
         if self.comm.rank == 0:
-            os.makedirs(path, exist_ok=True)
             keys = torch.cat([p[0] for p in parts])
             w = torch.cat([p[1] for p in parts])
-            keys.numpy().astype("<i8").tofile(os.path.join(path, "key"))
-            w.numpy().astype("<f4").tofile(os.path.join(path, "emb_vector"))
+            FS.write_array(FS.path_join(path, "key"), keys.numpy().astype("<i8"))
+            FS.write_array(FS.path_join(path, "emb_vector"), w.numpy().astype("<f4"))
             if self.localized:
                 slots = torch.cat([p[2] for p in parts])
-                slots.numpy().astype("<u8").tofile(os.path.join(path, "slot_id"))
+                FS.write_array(FS.path_join(path, "slot_id"), slots.numpy().astype("<u8"))
         self.comm.barrier()
 
     def _slot_ids(self, keys):
@@ -363,10 +364,10 @@ class SparseEmbeddingRuntime:
         return (torch.searchsorted(bounds, keys, right=True) - 1).clamp(0, len(ssa) - 1)
 
     def load_parameters(self, path: str):
-        keys = torch.from_numpy(np.fromfile(os.path.join(path, "key"), dtype="<i8").astype("int64"))
-        w = torch.from_numpy(np.fromfile(os.path.join(path, "emb_vector"), dtype="<f4")).view(-1, self.vec)
-        if self.localized and os.path.exists(os.path.join(path, "slot_id")):
-            slot = torch.from_numpy(np.fromfile(os.path.join(path, "slot_id"), dtype="<u8").astype("int64"))
+        keys = torch.from_numpy(FS.read_array(FS.path_join(path, "key"), "<i8").astype("int64"))
+        w = torch.from_numpy(FS.read_array(FS.path_join(path, "emb_vector"), "<f4")).view(-1, self.vec)
+        if self.localized and FS.path_exists(FS.path_join(path, "slot_id")):
+            slot = torch.from_numpy(FS.read_array(FS.path_join(path, "slot_id"), "<u8").astype("int64"))
             m = (slot % self.world) == self.rank
         else:
             m = (keys % self.world) == self.rank
@@ -375,7 +376,7 @@ class SparseEmbeddingRuntime:
         self.check_overflow()
         self.table.view(-1, self.vec)[rows] = w[m].to(self.device)
         self._loaded_keys = keys                 # file order: optimizer states are matched by key
-        if self.localized and self.slot_of_row is not None and os.path.exists(os.path.join(path, "slot_id")):
+        if self.localized and self.slot_of_row is not None and FS.path_exists(FS.path_join(path, "slot_id")):
             self.slot_of_row[rows] = slot[m].to(self.device)
 
     def dump_opt_states(self, path: str):
@@ -383,16 +384,15 @@ class SparseEmbeddingRuntime:
         st = [s.view(-1, self.vec)[rows.to(self.device)].cpu() for s in (self.s0, self.s1) if s is not None]
         parts = self.comm.all_gather_object(st)
         if self.comm.rank == 0:
-            with open(path, "wb") as f:
-                for i in range(len(st)):
-                    f.write(torch.cat([p[i] for p in parts]).numpy().astype("<f4").tobytes())
+            FS.write_array(path, np.concatenate([torch.cat([p[i] for p in parts]).numpy().astype("<f4").reshape(-1)
+                                                 for i in range(len(st))]) if st else np.zeros(0, "<f4"))
         self.comm.barrier()
 
     def load_opt_states(self, path: str):
         """States are stored in the order of the sparse model's ``key`` file (all ranks' rows concatenated).
         They are matched BY KEY: the hash table hands out rows in arbitrary order within a launch, so the
         row order of this process says nothing about the file order."""
-        raw = np.fromfile(path, dtype="<f4")
+        raw = FS.read_array(path, "<f4")
         states = [s for s in (self.s0, self.s1) if s is not None]
         if not states:
             return

@@ -70,9 +70,12 @@ class LocalFileSystem(FileSystem):
 class ArrowFileSystem(FileSystem):
     """HDFS / S3 / GCS through pyarrow.fs (same call surface as the local one)."""
 
-    def __init__(self, kind: FileSystemType_t, server: str = "", port: int = 0):
+    def __init__(self, kind: FileSystemType_t, server: str = "", port: int = 0, fs=None):
         import pyarrow.fs as pafs
         self.kind = kind
+        if fs is not None:          # an already constructed pyarrow FileSystem (custom endpoint, tests)
+            self.fs = fs
+            return
         try:
             if kind == FileSystemType_t.HDFS:
                 self.fs = pafs.HadoopFileSystem(server or "default", port or 0)
@@ -87,7 +90,7 @@ class ArrowFileSystem(FileSystem):
 
     @staticmethod
     def _strip(path):
-        for p in ("hdfs://", "s3://", "gs://", "https://"):
+        for p in ("hdfs://", "s3://", "gs://", "https://", "mock://"):
             if path.startswith(p):
                 return path[len(p):]
         return path
@@ -100,8 +103,23 @@ class ArrowFileSystem(FileSystem):
         import pyarrow.fs as pafs
         return self.fs.get_file_info(self._strip(path)).type != pafs.FileType.NotFound
 
+    def _out(self, path):
+        """output stream; back-ends with real directories (HDFS, local, in-memory) need the parent first,
+        object stores do not -- so the directory is only created when the open fails for its absence"""
+        p = self._strip(path)
+        try:
+            return self.fs.open_output_stream(p)
+        except (FileNotFoundError, OSError):
+            parent = p.rsplit("/", 1)[0] if "/" in p else ""
+            if not parent:
+                raise
+            self.fs.create_dir(parent, recursive=True)
+            return self.fs.open_output_stream(p)
+
     def write(self, path, data, overwrite=True):
-        with self.fs.open_output_stream(self._strip(path)) as f:
+        if not overwrite and self.exists(path):
+            data = self.read(path) + data            # (object stores have no append)
+        with self._out(path) as f:
             f.write(data)
         return len(data)
 
@@ -110,20 +128,55 @@ class ArrowFileSystem(FileSystem):
             f.seek(offset)
             return f.read() if size is None else f.read(size)
 
-    def copy(self, src, dst): self.fs.copy_file(self._strip(src), self._strip(dst))
+    def copy(self, src, dst):
+        try:
+            self.fs.copy_file(self._strip(src), self._strip(dst))
+        except (FileNotFoundError, OSError):
+            d = self._strip(dst)
+            if "/" not in d:
+                raise
+            self.fs.create_dir(d.rsplit("/", 1)[0], recursive=True)
+            self.fs.copy_file(self._strip(src), d)
+
+    def fetch(self, remote, local):
+        """remote -> local disk (filesystem.hpp fetch)"""
+        d = os.path.dirname(local)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        with open(local, "wb") as f:
+            f.write(self.read(remote))
+
+    def upload(self, local, remote):
+        with open(local, "rb") as f:
+            self.write(remote, f.read())
 
     def open(self, path, mode="rb"):
         if "r" in mode:
             return self.fs.open_input_file(self._strip(path))
-        return self.fs.open_output_stream(self._strip(path))
+        return self._out(path)
 
 
 class FileSystemBuilder:
+    _registered: dict = {}
+
+    @staticmethod
+    def register(scheme: str, arrow_fs) -> None:
+        """route paths starting with ``scheme`` (e.g. "mock://", "s3://my-minio/") to a constructed
+        ``pyarrow.fs.FileSystem`` -- custom endpoints / credentials, and the in-memory file system of the tests"""
+        FileSystemBuilder._registered[scheme] = arrow_fs
+
+    @staticmethod
+    def unregister(scheme: str) -> None:
+        FileSystemBuilder._registered.pop(scheme, None)
+
     @staticmethod
     def build_by_path(path: str, params=None) -> FileSystem:
         """FileSystemBuilder::build_unique_by_path: scheme decides the back-end."""
         server = getattr(params, "server", "") if params else ""
         port = getattr(params, "port", 0) if params else 0
+        for scheme, fs in FileSystemBuilder._registered.items():
+            if path.startswith(scheme):
+                return ArrowFileSystem(FileSystemType_t.Other, fs=fs)
         if path.startswith("hdfs://"):
             return ArrowFileSystem(FileSystemType_t.HDFS, server, port)
         if path.startswith("s3://") or ".s3." in path:
@@ -143,3 +196,39 @@ class FileSystemBuilder:
 
 
 FileSystemBuilder.build_unique_by_type = FileSystemBuilder.build_by_type
+
+
+# ---------------------------------------------------------------- array files on any back-end
+def is_remote(path: str) -> bool:
+    return not isinstance(FileSystemBuilder.build_by_path(path), LocalFileSystem) if "://" in path or ".s3." in path \
+        or "storage.googleapis.com" in path else False
+
+
+def write_array(path: str, arr, params=None) -> None:
+    """raw little-endian dump of ``arr`` (numpy) -- ``tofile`` locally, one object write remotely"""
+    import numpy as np
+    arr = np.ascontiguousarray(arr)
+    if not is_remote(path):
+        d = os.path.dirname(path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        arr.tofile(path)
+    else:
+        FileSystemBuilder.build_by_path(path, params).write(path, arr.tobytes())
+
+
+def read_array(path: str, dtype, params=None):
+    import numpy as np
+    if not is_remote(path):
+        return np.fromfile(path, dtype=dtype)
+    return np.frombuffer(FileSystemBuilder.build_by_path(path, params).read(path), dtype=dtype).copy()
+
+
+def path_exists(path: str, params=None) -> bool:
+    if not is_remote(path):
+        return os.path.exists(path)
+    return FileSystemBuilder.build_by_path(path, params).exists(path)
+
+
+def path_join(base: str, *names: str) -> str:
+    return "/".join([base.rstrip("/")] + list(names)) if "://" in base else os.path.join(base, *names)

@@ -248,3 +248,70 @@ def test_mixed_precision_single_output_fc_with_unaligned_input_width():
         losses.append(m.get_current_loss())
     assert np.isfinite(losses).all()
     assert m.eval()
+
+
+def test_checkpoint_round_trip_on_a_remote_filesystem(tmp_path):
+    """The non-local (pyarrow.fs) back-end end to end -- dense / optimizer / train-state files, the embedding
+    collection dump (gather mode, as for every remote path) and the legacy sparse model directories -- against
+    pyarrow's in-memory file system registered under a URI scheme, the way a custom S3 / HDFS endpoint is."""
+    import pyarrow.fs as pafs
+    from hugectr_b200.io import FileSystemBuilder
+    from hugectr_b200.models.legacy import build_deepfm
+    mem = pafs._MockFileSystem()
+    FileSystemBuilder.register("mock://", mem)
+    try:
+        fs = FileSystemBuilder.build_by_path("mock://bucket/x")
+        fs.write("mock://bucket/dir/a.bin", b"hello world")
+        assert fs.exists("mock://bucket/dir/a.bin") and fs.get_file_size("mock://bucket/dir/a.bin") == 11
+        assert fs.read("mock://bucket/dir/a.bin", 6, 5) == b"world"
+        fs.copy("mock://bucket/dir/a.bin", "mock://bucket/dir/b.bin")
+        fs.delete_file("mock://bucket/dir/a.bin")
+        assert not fs.exists("mock://bucket/dir/a.bin") and fs.read("mock://bucket/dir/b.bin") == b"hello world"
+        # ---- collection model
+        sizes, hot = [300, 40, 1000, 7], [3, 1, 5, 2]
+        kw = dict(batchsize=64, num_gpus=1, table_sizes=sizes, multi_hot=hot, ev_size=16, mixed=False,
+                  bottom=(32, 16), top=(32, 1), projection_dim=8, cross_layers=2, lr=0.05, comm=CPU())
+        m = build_dlrm_dcnv2(**kw)
+        m.compile()
+        for _ in range(5):
+            assert m.train()
+        prefix = "mock://bucket/run1/ck"
+        m.save_params_to_files(prefix, 5)
+        names = {i.path for i in mem.get_file_info(pafs.FileSelector("bucket/run1", recursive=True))}
+        assert "bucket/run1/ck_dense_5.model" in names and "bucket/run1/ck_opt_dense_5.model" in names
+        assert any(n.endswith("embedding_collection_0/meta_data") for n in names)
+        assert not os.path.exists("mock:")                      # nothing leaked to the local disk
+        hb = m.reader_train.read_a_batch()
+        m.train_on_host_batch(hb)
+        want = m.get_current_loss()
+        m2 = build_dlrm_dcnv2(**kw)
+        m2.compile()
+        m2.load_dense_weights(prefix + "_dense_5.model")
+        m2.load_dense_optimizer_states(prefix + "_opt_dense_5.model")
+        m2.embedding_load(prefix + "_ebc_5")
+        m2.step_t.fill_(5)
+        m2.train_on_host_batch(hb)
+        assert abs(m2.get_current_loss() - want) < 1e-4
+        # ---- legacy hash embeddings: sparse model directories (key / emb_vector) on the remote side
+        d = build_deepfm(batchsize=64, vvgpu=[[0]], slot_sizes=[50, 20, 30], workspace_mb=8, mixed=False, comm=CPU())
+        d.compile()
+        for _ in range(3):
+            d.train()
+        d.save_params_to_files("mock://bucket/run2/dfm", 3)
+        names = {i.path for i in mem.get_file_info(pafs.FileSelector("bucket/run2", recursive=True))}
+        assert any(n.endswith("/key") for n in names) and any(n.endswith("/emb_vector") for n in names)
+        hb = d.reader_train.read_a_batch()
+        d.train_on_host_batch(hb)
+        want = d.get_current_loss()
+        d2 = build_deepfm(batchsize=64, vvgpu=[[0]], slot_sizes=[50, 20, 30], workspace_mb=8, mixed=False, comm=CPU())
+        d2.compile()
+        d2.load_dense_weights("mock://bucket/run2/dfm_dense_3.model")
+        d2.load_dense_optimizer_states("mock://bucket/run2/dfm_opt_dense_3.model")
+        nl = len(d.legacy_train)
+        d2.load_sparse_weights([f"mock://bucket/run2/dfm{i}_sparse_3.model" for i in range(nl)])
+        d2.load_sparse_optimizer_states([f"mock://bucket/run2/dfm{i}_opt_sparse_3.model" for i in range(nl)])
+        d2.step_t.fill_(3)
+        d2.train_on_host_batch(hb)
+        assert abs(d2.get_current_loss() - want) < 1e-4
+    finally:
+        FileSystemBuilder.unregister("mock://")
