@@ -135,13 +135,17 @@ def save_train_state(model, prefix: str, it: int):
     _fs(prefix, model).write(train_state_path(prefix, it), json.dumps(st).encode())
 
 
-def latest_snapshot(prefix: str):
-    """largest <it> for which <prefix>_dense_<it>.model exists (local file systems), or None"""
-    import glob
+def latest_snapshot(prefix: str, model=None):
+    """largest <it> for which <prefix>_dense_<it>.model exists (any file system), or None"""
     import re
+    d, base = (prefix.rsplit("/", 1) + [""])[:2] if "/" in prefix else ("", prefix)
+    try:
+        names = _fs(prefix, model).list_dir(d)
+    except (FileNotFoundError, OSError):
+        return None
     its = []
-    for p in glob.glob(f"{glob.escape(prefix)}_dense_*.model"):
-        m = re.fullmatch(re.escape(prefix) + r"_dense_(\d+)\.model", p)
+    for n in names:
+        m = re.fullmatch(re.escape(base) + r"_dense_(\d+)\.model", n)
         if m:
             its.append(int(m.group(1)))
     return max(its) if its else None
@@ -152,7 +156,7 @@ def resume(model, prefix: str, it=None) -> int:
     legacy sparse models + their optimizer states, embedding collections (weights + optimizer state) and
     the training counters -- and return the iteration to continue from.  ``it=None``: latest snapshot."""
     if it is None:
-        it = latest_snapshot(prefix)
+        it = latest_snapshot(prefix, model)
         if it is None:
             raise FileNotFoundError(f"no snapshot with prefix {prefix}")
     fs = _fs(prefix, model)

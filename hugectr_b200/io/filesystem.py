@@ -21,6 +21,7 @@ class FileSystem:
     def delete_file(self, path: str): raise NotImplementedError
     def delete_dir(self, path: str): raise NotImplementedError
     def exists(self, path: str) -> bool: raise NotImplementedError
+    def list_dir(self, path: str): raise NotImplementedError          # base names of the entries of a directory
     def write(self, path: str, data: bytes, overwrite: bool = True) -> int: raise NotImplementedError
     def read(self, path: str, offset: int = 0, size: Optional[int] = None) -> bytes: raise NotImplementedError
     def copy(self, src: str, dst: str): raise NotImplementedError
@@ -40,6 +41,7 @@ class LocalFileSystem(FileSystem):
             os.remove(path)
     def delete_dir(self, path): shutil.rmtree(path, ignore_errors=True)
     def exists(self, path): return os.path.exists(path)
+    def list_dir(self, path): return sorted(os.listdir(path or "."))
 
     def write(self, path, data, overwrite=True):
         d = os.path.dirname(path)
@@ -102,6 +104,10 @@ class ArrowFileSystem(FileSystem):
     def exists(self, path):
         import pyarrow.fs as pafs
         return self.fs.get_file_info(self._strip(path)).type != pafs.FileType.NotFound
+
+    def list_dir(self, path):
+        import pyarrow.fs as pafs
+        return sorted(i.base_name for i in self.fs.get_file_info(pafs.FileSelector(self._strip(path), recursive=False)))
 
     def _out(self, path):
         """output stream; back-ends with real directories (HDFS, local, in-memory) need the parent first,

@@ -292,6 +292,11 @@ def test_checkpoint_round_trip_on_a_remote_filesystem(tmp_path):
         m2.step_t.fill_(5)
         m2.train_on_host_batch(hb)
         assert abs(m2.get_current_loss() - want) < 1e-4
+        m3 = build_dlrm_dcnv2(**kw)
+        m3.compile()
+        assert m3.resume(prefix) == 5                         # latest snapshot found by listing the remote directory
+        m3.train_on_host_batch(hb)
+        assert abs(m3.get_current_loss() - want) < 1e-4
         # ---- legacy hash embeddings: sparse model directories (key / emb_vector) on the remote side
         d = build_deepfm(batchsize=64, vvgpu=[[0]], slot_sizes=[50, 20, 30], workspace_mb=8, mixed=False, comm=CPU())
         d.compile()
