@@ -82,6 +82,7 @@ class ParquetReader(IDataReader):
         self.thread = None
         self._stop = threading.Event()
         self.drop_incomplete = model.solver.drop_incomplete_batch
+        self._device = getattr(model, "device", None)
 
     # -------------------------------------------------------------- producer
     def _columns(self, files):
@@ -136,6 +137,12 @@ class ParquetReader(IDataReader):
             if not self.repeat:
                 return
 
+    def _bind_device(self):
+        """reader threads pin host memory: bind them to this rank's GPU, not to device 0"""
+        d = self._device
+        if d is not None and d.type == "cuda":
+            torch.cuda.set_device(d)
+
     def _produce(self):
         """``num_workers`` threads decode row groups ahead of the batch assembler, which consumes them
         strictly in file order (so the stream of batches does not depend on the worker count)"""
@@ -150,7 +157,8 @@ class ParquetReader(IDataReader):
             pending = deque()
             it = self._row_groups(files)
             self._out = deque()
-            with ThreadPoolExecutor(max_workers=self.num_workers) as ex:
+            self._bind_device()
+            with ThreadPoolExecutor(max_workers=self.num_workers, initializer=self._bind_device) as ex:
                 self._ex = ex
                 while not self._stop.is_set():
                     while len(pending) < self.num_workers + 1:
