@@ -460,19 +460,21 @@ def run_secondary(args, comm):
     n, rank = args.gpus, comm.rank
     os.environ.setdefault("HCTR_SYNTH_POOL", "16")
     vv = [list(range(n))]
+    cuda = comm.device.type == "cuda"            # (CPU: logic smoke test of this path only, not a measurement)
+    bo = args.per_gpu_batch if args.per_gpu_batch != PER_GPU_BATCH else 0
     if args.model == "deepfm":
-        b = 16384
+        b = bo or 16384
         m = build_deepfm(batchsize=b * n, vvgpu=vv, slot_sizes=CRITEO_KAGGLE_SLOTS, workspace_mb=2000, mixed=True,
                          comm=comm, use_cuda_graph=not args.no_graph)
         desc = "DeepFM (samples/deepfm): 26 Criteo slots, vec 11, DistributedSlotSparseEmbeddingHash, 3x400 MLP, Adam"
     elif args.model == "dlrm":
-        b = 6912
+        b = bo or 6912
         tables = [min(t, args.cap_rows) for t in CRITEO_TB_TABLE_SIZES] if args.cap_rows else CRITEO_TB_TABLE_SIZES
         m = build_dlrm(batchsize=b * n, num_gpus=n, table_sizes=tables, mixed=True, lr=0.5, comm=comm,
                        use_cuda_graph=not args.no_graph)
         desc = "DLRM (MLPerf v1): 26 Criteo-TB tables, ev 128, one-hot, dot Interaction, top 1024-1024-512-256-1, SGD"
     elif args.model == "wdl_cache":
-        b = 16384
+        b = bo or 16384
         etc = hugectr.CreateETC(ps_types=[hugectr.TrainPSType_t.Cached] * 2, sparse_models=["", ""],
                                 host_capacity_rows=8 << 20)
         m = build_wdl(batchsize=b * n, vvgpu=vv, wide_slot_sizes=CRITEO_KAGGLE_SLOTS[:2],
@@ -485,18 +487,22 @@ def run_secondary(args, comm):
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W + 2):
         m.train()
-    torch.cuda.synchronize(); comm.barrier()
+    sync = torch.cuda.synchronize if cuda else (lambda: None)
+    sync(); comm.barrier()
     c0 = __import__("hugectr_b200.ops.dense", fromlist=["x"]).launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loss_host = torch.zeros(1).pin_memory()
-    e0.record()
+    loss_host = torch.zeros(1).pin_memory() if cuda else torch.zeros(1)
+    if cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    t0 = time.perf_counter()
     for _ in range(K):
         m.train()
         loss_host.copy_(m.net_train.loss_value(), non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize(); comm.barrier()
+    if cuda:
+        e1.record()
+    sync(); comm.barrier()
     launches = __import__("hugectr_b200.ops.dense", fromlist=["x"]).launch_count - c0
-    t = torch.tensor([e0.elapsed_time(e1)], device=m.device)
+    t = torch.tensor([e0.elapsed_time(e1) if cuda else (time.perf_counter() - t0) * 1e3], device=m.device)
     if n > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.item())
@@ -511,7 +517,7 @@ def run_secondary(args, comm):
             "metric": f"{args.model} training samples/sec (device-timed, max over ranks, end to end through model.train())",
             "value": v, "unit": "samples/s", "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "impl": "b200", "secondary": True,
+            "impl": "b200", "secondary": True, "device": str(m.device),
             "config": {"model": desc, "global_batch": b * n, "per_gpu_batch": b, "seq_len": None,
                        "parallelism": f"dp{n} dense + model-parallel embeddings",
                        "cuda_graph": bool(m._graph is not None), "final_loss": m.get_current_loss(), **extra},
