@@ -54,9 +54,11 @@ class EmbeddingTableConfig:
         self.init_param = kw.get("init_param", init_param_or_empty)
         # max_vocabulary_size < 0: dynamic table (embedding_storage/common.hpp:78) -- arbitrary 64-bit
         # keys, rows handed out on first sight by a per-shard hash table; ``init_capacity`` rows per
-        # shard are reserved (DynamicEmbeddingTable of the reference grows, this one is bounded)
+        # shard are reserved at first and doubled when a shard runs out (EmbeddingCollection.grow_dynamic)
         self.dynamic = self.max_vocabulary_size < 0
         self.init_capacity = int(kw.get("init_capacity", 1 << 20))
+        # rows per shard a dynamic table may grow to (0 = no limit but memory): see EmbeddingCollection.grow_dynamic
+        self.max_capacity = int(kw.get("max_capacity", 0))
 
 
 class EmbeddingCollectionConfig:
@@ -242,6 +244,7 @@ class EmbeddingCollection:
         c.b = batch_per_gpu
         c.is_train = False
         c._shared = self
+        self._clones = getattr(self, "_clones", []) + [c]
         c._build_layout(self.hotness)
         c._build_storage(self.seed, share_from=self)
         c._alloc_buffers()
@@ -373,6 +376,8 @@ class EmbeddingCollection:
                         split = ("split_off" in gl and pl.kind == "mp" and sl["k"] > 1) or sl["dynamic"]
                         grp.lookup_gl = getattr(grp, "lookup_gl", [])
                         grp.lookup_gl.append((gi, pl.kind == "mp" and sl["k"] > 1))
+                        grp.lookup_slices = getattr(grp, "lookup_slices", [])
+                        grp.lookup_slices.append(sl)
                         grp.lookups.append(E.LookupDesc(
                             table_row_off=sl["row_off"],
                             key_off=(gl["split_off"] + sl["s"] * b * H)
@@ -390,10 +395,10 @@ class EmbeddingCollection:
         gen = torch.Generator(device="cpu")
         if share_from is not None:
             for grp, src in zip(self.groups, share_from.groups):
-                assert (grp.kind, grp.pitch, grp.rows) == (src.kind, src.pitch, src.rows)
-                grp.table, grp.s0, grp.s1, grp.opt = src.table, src.s0, src.s1, src.opt
-                grp.lookups_dev = E.lookups_to_device(grp.lookups, dev)
+                assert (grp.kind, grp.pitch, len(grp.table_slices)) == (src.kind, src.pitch, len(src.table_slices))
+                grp.opt = src.opt
                 grp.ws = None
+            self._resync_storage(share_from)     # arrays + row windows (dynamic shards may have grown since)
             return
         for grp in self.groups:
             n = max(grp.rows, 1) * grp.pitch
@@ -752,6 +757,89 @@ class EmbeddingCollection:
                 raise RuntimeError(f"dynamic embedding table {name}: more than init_capacity="
                                    f"{ht.max_rows} distinct keys on one shard (shard {s_})")
 
+    def grow_dynamic(self, factor: float = 2.0):
+        """DynamicEmbeddingTable semantics (embedding_storage/dynamic_embedding.cu: the vocabulary is not bounded):
+        every shard whose hash table ran out of rows gets ``factor`` times the rows -- the group's weight and
+        optimizer-state arrays are re-laid out around the enlarged slice, the key -> row map is rebuilt with the same
+        rows, new rows start from the initializer.  Keys that found no row since the overflow read as empty and their
+        updates were dropped; they are admitted from the next step on.  Returns the grown (table, shard, old rows,
+        new rows) list; the caller re-captures its CUDA graphs (table pointers are baked into them).  Reads device
+        flags (host sync): call it where ``check_overflow`` is called.  Raises when ``max_capacity`` is reached."""
+        owner = getattr(self, "_shared", self)
+        grown = []
+        for (name, cpart, s_), ht in list(getattr(owner, "_dyn_tables", {}).items()):
+            if not ht.overflowed():
+                continue
+            old = ht.max_rows
+            new = owner._grow_to(name, cpart, s_, int(old * factor) + 1)
+            grown.append((name, s_, old, new))
+        return grown
+
+    def _grow_to(self, name, cpart, s_, want_rows: int) -> int:
+        """(owner plan) enlarge shard ``s_`` of dynamic table ``name`` to ``want_rows`` rows (capped by the
+        table's ``max_capacity``): storage, key -> row map with the same rows, every plan that shares the storage"""
+        t = self.tmap[name]
+        ht = self._dyn_tables[(name, cpart, s_)]
+        grp, sl = [(g, x) for g in self.groups for x in g.table_slices
+                   if x["table"] == name and x["cpart"] == cpart and x["s"] == s_][0]
+        old = sl["rows"]
+        new = min(want_rows, t.max_capacity) if t.max_capacity > 0 else want_rows
+        if new <= old:
+            raise RuntimeError(f"dynamic embedding table {name}: shard {s_} is full at max_capacity={old} rows")
+        self._grow_slice(grp, sl, new)
+        keys, rows = ht.dump()
+        from .hashtable import HashTable
+        nh = HashTable(new, self.device)
+        if keys.numel():
+            nh.set(keys, rows)
+        self._dyn_tables[(name, cpart, s_)] = nh
+        for c in [self] + list(getattr(self, "_clones", [])):
+            c._resync_storage(self)
+        return new
+
+    def _grow_slice(self, grp, sl, new_rows: int):
+        """re-layout ``grp``'s flat arrays with ``sl`` enlarged to ``new_rows`` (slices behind it shift)"""
+        pitch, dev = grp.pitch, self.device
+        delta = new_rows - sl["rows"]
+        cut = (sl["row_off"] + sl["rows"]) * pitch           # first element behind the slice
+
+        def relayout(a, fill):
+            if a is None:
+                return None
+            out = torch.empty(a.numel() + delta * pitch, dtype=a.dtype, device=dev)
+            out[:cut].copy_(a[:cut])
+            out[cut + delta * pitch:].copy_(a[cut:])
+            fill(out[cut:cut + delta * pitch])
+            return out
+        t = self.tmap[sl["table"]]
+        bound = math.sqrt(1.0 / max(t.init_capacity, 1))
+        if t.init_param is not None and t.init_param.up_bound > 0:
+            bound = t.init_param.up_bound
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(_stable_seed(self.seed, sl["table"], sl["cpart"], sl["s"], new_rows))
+        table = relayout(grp.table, lambda v: v.uniform_(-bound, bound, generator=gen))
+        accu = grp.opt.initial_accu_value if (grp.opt is not None and grp.opt.optimizer_type == Optimizer_t.AdaGrad) \
+            else 0.0
+        s0 = relayout(grp.s0, lambda v: v.fill_(accu))
+        s1 = relayout(grp.s1, lambda v: v.zero_())
+        grp.table, grp.s0, grp.s1 = table, s0, s1
+        old_end = sl["row_off"] + sl["rows"]
+        for other in grp.table_slices:
+            if other is not sl and other["row_off"] >= old_end:
+                other["row_off"] += delta
+        sl["rows"] = new_rows
+        grp.rows += delta
+
+    def _resync_storage(self, owner):
+        """after a growth: this plan's groups point at the owner's arrays and carry the new row windows"""
+        for grp, src in zip(self.groups, owner.groups):
+            grp.table, grp.s0, grp.s1, grp.rows = src.table, src.s0, src.s1, src.rows
+            for sl, so in zip(grp.table_slices, src.table_slices):
+                sl["row_off"], sl["rows"] = so["row_off"], so["rows"]
+            for d, sl in zip(grp.lookups, getattr(grp, "lookup_slices", [])):
+                d.table_row_off, d.rows = sl["row_off"], sl["rows"]
+            grp.lookups_dev = E.lookups_to_device(grp.lookups, self.device)
+
     def forward_compute(self):
         b = self.b
         if self.world == 1:
@@ -978,7 +1066,15 @@ class EmbeddingCollection:
                     if not bool(m.any()):
                         continue
                     ht = self._dyn_hash(name, dict(sl, cpart=0))
-                    rows = sl["row_off"] + ht.get_insert(keys[m].to(self.device)).to(grp.table.device).long()
+                    kk = keys[m].to(self.device)
+                    fresh = int((ht.get(kk) < 0).sum()) if ht.size() else int(kk.numel())
+                    if ht.size() + fresh > ht.max_rows:
+                        # a checkpoint with more keys than the shard currently holds: grow first (a failed insert
+                        # would hand back row -1)
+                        owner = getattr(self, "_shared", self)
+                        owner._grow_to(name, 0, sl["s"], max(2 * ht.max_rows, ht.size() + fresh))
+                        ht = self._dyn_hash(name, dict(sl, cpart=0))
+                    rows = sl["row_off"] + ht.get_insert(kk).to(grp.table.device).long()
                 else:
                     m = (keys % sl["k"] == sl["s"]) & (keys // sl["k"] < sl["rows"]) & (keys >= 0)
                     if not bool(m.any()):

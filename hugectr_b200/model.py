@@ -858,8 +858,7 @@ class Model:
                 continue
             it += 1
             if display > 0 and it % display == 0:
-                for e in self.ebcs_train:
-                    e.check_overflow()
+                self._dynamic_tables_checkpoint()
                 loss = self.get_current_loss()
                 if math.isnan(loss):
                     raise RuntimeError("Train Runtime error: Loss cannot converge")  # model.cpp:889
@@ -911,9 +910,34 @@ class Model:
         return stop
 
     # ------------------------------------------------------------------ checkpoints
+    def _dynamic_tables_checkpoint(self):
+        """Dynamic tables that ran out of rows grow (``HCTR_DYNAMIC_GROW=0``: raise instead, the round-1
+        behaviour).  Collective: every rank learns whether ANY shard grew, because the step graph holds table
+        pointers and its re-capture is a rendezvous."""
+        ebcs = [e for e in getattr(self, "ebcs_train", []) if getattr(e, "has_dynamic", False)]
+        if not ebcs:
+            return
+        if os.environ.get("HCTR_DYNAMIC_GROW", "1") == "0":
+            for e in ebcs:
+                e.check_overflow()
+            return
+        grown = []
+        for e in ebcs:
+            grown += e.grow_dynamic()
+        if self.world > 1:
+            grown_any = any(self.comm.all_gather_object(bool(grown)))
+        else:
+            grown_any = bool(grown)
+        for (name, shard, old, new) in grown:
+            logger.warning(f"dynamic embedding table {name} shard {shard}: {old} -> {new} rows "
+                           f"(keys seen while it was full were read as empty)")
+        if grown_any:
+            self._graph = None
+            self._graph_warm = 0
+            self._eval_pipe = None
+
     def save_params_to_files(self, prefix: str, iter: int = 0):
-        for e in getattr(self, "ebcs_train", []):
-            e.check_overflow()
+        self._dynamic_tables_checkpoint()
         from .io.checkpoint import save_model
         save_model(self, prefix, iter)
 

@@ -67,6 +67,9 @@ def run_ebc(plan, fused, comm=None):
     lr = torch.tensor([0.05])
     st = torch.tensor([1], dtype=torch.int32)
     lr_d, st_d = lr.to(dev), st.to(dev)
+    if os.environ.get("HCTR_TEST_DYN_CAP"):
+        assert max(sl["rows"] for g in e.groups for sl in g.table_slices if sl.get("dynamic")) > \
+            int(os.environ["HCTR_TEST_DYN_CAP"]), "no shard grew"
     for it in range(3):
         gk = [torch.randint(0, sizes[i], (b * world, h), generator=gen) for i, h in enumerate(hot.values())]
         keys_ref = torch.cat([k.reshape(-1) for k in gk]).int()
@@ -109,7 +112,9 @@ def run_dynamic(comm=None):
     scramble = lambda k: k * 1000003 + 17
 
     def cfg_for(w, dynamic):
-        ts = [EmbeddingTableConfig(str(i), -1 if (dynamic and i != 1) else sizes[i], ev, init_capacity=1024)
+        # HCTR_TEST_DYN_CAP: start far below the number of keys -- the shards grow while the tables are loaded
+        cap = int(os.environ.get("HCTR_TEST_DYN_CAP", "1024"))
+        ts = [EmbeddingTableConfig(str(i), -1 if (dynamic and i != 1) else sizes[i], ev, init_capacity=cap)
               for i in range(3)]
         cfg = EmbeddingCollectionConfig()
         cfg.embedding_lookup(ts, list(hot), "emb", ["sum", "sum", "mean"])
@@ -133,6 +138,9 @@ def run_dynamic(comm=None):
         ref.load_table_rows(n, k, w)
         e.load_table_rows(n, scramble(k) if n != "1" else k, w)
     lr, st = torch.tensor([0.05]), torch.tensor([1], dtype=torch.int32)
+    if os.environ.get("HCTR_TEST_DYN_CAP"):
+        assert max(sl["rows"] for g in e.groups for sl in g.table_slices if sl.get("dynamic")) > \
+            int(os.environ["HCTR_TEST_DYN_CAP"]), "no shard grew"
     for it in range(3):
         gk = [torch.randint(0, sizes[i], (b * world, h), generator=gen) for i, h in enumerate(hot.values())]
         keys_ref = torch.cat([k.reshape(-1) for k in gk])

@@ -99,6 +99,14 @@ def test_emu_dynamic_tables_cpu():
     run_ranks(2, lambda c: W.run_dynamic(comm=c), device=CPU)
 
 
+def test_emu_dynamic_tables_grow_while_loading_cpu(monkeypatch):
+    """shards start at 16 rows and grow as the (500 / 900-key) tables are loaded; results still equal the static
+    reference, in the collective and in the fused data flow"""
+    monkeypatch.setenv("HCTR_TEST_DYN_CAP", "16")
+    run_ranks(2, lambda c: W.run_dynamic(comm=c), device=CPU)
+    run_ranks(3, lambda c: W.run_dynamic(comm=c), device=CPU, p2p="force")
+
+
 def test_emu_legacy_embeddings_cpu():
     run_ranks(2, lambda c: W.run_legacy(comm=c), device=CPU)
 

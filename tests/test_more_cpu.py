@@ -276,3 +276,105 @@ def test_bucket_finality_out_of_order():
     assert f == 200 and pend == [(0, 100)]
     f, pend = advance_final(f, pend + [(100, 200)])      # bottom pass: B done -> everything final
     assert (f, pend) == (0, [])
+
+
+def test_dynamic_tables_grow_when_a_shard_runs_out_of_rows():
+    """DynamicEmbeddingTable semantics: no fixed vocabulary.  A shard that runs out of rows is doubled in place
+    (group arrays re-laid out around it), known keys keep their vectors and optimizer state, neighbours in the same
+    group are untouched, the evaluation plan follows, and the keys that were turned away are admitted afterwards."""
+    import torch
+    from hugectr_b200.embedding.collection import (EmbeddingCollection, EmbeddingCollectionConfig,
+                                                   EmbeddingTableConfig)
+    from hugectr_b200.enums import Optimizer_t
+    from hugectr_b200.parallel.comm import Comm
+    from hugectr_b200.solver import CreateOptimizer
+    cpu = torch.device("cpu")
+    b, ev = 4, 8
+    cfg = EmbeddingCollectionConfig()
+    tabs = [EmbeddingTableConfig("a", 50, ev), EmbeddingTableConfig("dyn", -1, ev, init_capacity=6, max_capacity=40),
+            EmbeddingTableConfig("c", 30, ev)]
+    cfg.embedding_lookup(tabs, ["ka", "kd", "kc"], "emb", ["sum", "sum", "sum"])
+    opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.1)
+    e = EmbeddingCollection(cfg, b, {"ka": 1, "kd": 2, "kc": 1}, cpu, torch.float32, Comm.single(cpu), opt, seed=3)
+    ev_plan = e.eval_clone(b)
+    lr, st = torch.tensor([0.1]), torch.tensor([1], dtype=torch.int32)
+
+    def step(plan, dyn_keys, train=True):
+        keys = torch.cat([torch.arange(b), torch.as_tensor(dyn_keys).reshape(-1), torch.arange(b) + 5]).int()
+        plan.set_keys(keys)
+        plan.forward(train)
+        out = plan.top_data["emb"].clone()
+        if train:
+            plan.top_grad["emb"].fill_(0.5)
+            plan.backward(lr, st)
+        return out
+    step(e, [[1000, 1001], [1002, 1003], [1004, 1005], [1000, 1003]])        # 6 distinct keys: table full
+    assert e.grow_dynamic() == []
+    snap_a = e.dump_table_local("a")[0][1].clone()
+    snap_c = e.dump_table_local("c")[0][1].clone()
+    kd, wd = e.dump_table_local("dyn")[0][:2]
+    known = {int(k): wd[i].clone() for i, k in enumerate(kd.tolist())}
+    assert len(known) == 6
+    out = step(e, [[2000, 2001], [1000, 2002], [2003, 2004], [2005, 1001]], train=False)      # new keys find no row
+    assert float(out[0, ev:2 * ev].abs().sum()) == 0.0                   # both keys of sample 0 read as empty
+    import pytest
+    old_rows = e.groups[0].rows
+    grown = e.grow_dynamic()
+    assert grown == [("dyn", 0, 6, 13)] and e.groups[0].rows == old_rows + 7
+    assert e.grow_dynamic() == []                                        # flag cleared with the new hash table
+    # neighbours and known keys are bit-identical, in the training and in the evaluation plan
+    assert torch.equal(e.dump_table_local("a")[0][1], snap_a) and torch.equal(e.dump_table_local("c")[0][1], snap_c)
+    kd2, wd2 = e.dump_table_local("dyn")[0][:2]
+    assert sorted(kd2.tolist()) == sorted(known) and all(torch.equal(wd2[i], known[int(k)]) for i, k in enumerate(kd2.tolist()))
+    o_tr = step(e, [[1000, 1001]] * b, train=False)
+    o_ev = step(ev_plan, [[1000, 1001]] * b, train=False)
+    assert torch.equal(o_tr, o_ev) and torch.allclose(o_tr[0, ev:2 * ev], known[1000] + known[1001])
+    # turned-away keys are admitted now, and train
+    out = step(e, [[2000, 2001], [1000, 2002], [2003, 2004], [2005, 1001]])
+    assert float(out[0, ev:2 * ev].abs().sum()) > 0.0
+    assert e._dyn_tables[("dyn", 0, 0)].size() == 12
+    # the cap: 13 -> 27 -> 40 (max_capacity), then the old error
+    step(e, [[3000 + 2 * i, 3001 + 2 * i] for i in range(b)])
+    assert e.grow_dynamic() == [("dyn", 0, 13, 27)]
+    for j in range(4):
+        step(e, [[4000 + 8 * j + 2 * i, 4001 + 8 * j + 2 * i] for i in range(b)])
+    assert e.grow_dynamic() == [("dyn", 0, 27, 40)]
+    for j in range(3):
+        step(e, [[5000 + 8 * j + 2 * i, 5001 + 8 * j + 2 * i] for i in range(b)])
+    with pytest.raises(RuntimeError, match="max_capacity"):
+        e.grow_dynamic()
+
+
+def test_model_fit_survives_a_growing_dynamic_table(monkeypatch):
+    """through `Model.fit`: the display checkpoint grows the table instead of raising (HCTR_DYNAMIC_GROW=0 raises)"""
+    import torch
+    import hugectr_b200 as hugectr
+    from hugectr_b200.parallel.comm import Comm
+
+    def build():
+        solver = hugectr.CreateSolver(batchsize=32, batchsize_eval=32, lr=0.05, vvgpu=[[0]], repeat_dataset=True,
+                                      max_eval_batches=2, use_cuda_graph=False)
+        rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.RawAsync, source=["synthetic:1.0"],
+                                      eval_source="synthetic:1.0", check_type=hugectr.Check_t.Non,
+                                      slot_size_array=[5000])          # key range of the synthetic batches
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.SGD), comm=Comm.single(torch.device("cpu")))
+        m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
+                            data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("k", 2, False, 1)]))
+        ebc = hugectr.EmbeddingCollectionConfig()
+        ebc.embedding_lookup(hugectr.EmbeddingTableConfig("t", -1, 8, init_capacity=16), "k", "emb", "sum")
+        m.add(ebc)
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Reshape, ["emb"], ["r"], leading_dim=8))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["r", "dense"], ["c"]))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+        m.compile()
+        return m
+    m = build()
+    m.fit(max_iter=30, display=5, eval_interval=15, snapshot=1000000)
+    rows = m.ebcs_train[0].groups[0].rows
+    assert rows > 16, rows
+    monkeypatch.setenv("HCTR_DYNAMIC_GROW", "0")
+    m2 = build()
+    import pytest
+    with pytest.raises(RuntimeError, match="init_capacity"):
+        m2.fit(max_iter=30, display=5, eval_interval=15, snapshot=1000000)
