@@ -595,3 +595,62 @@ def incremental_model_dump(variables: Sequence[DynamicVariable], time_threshold:
         _write(os.path.join(path, f"{v.name}-key"), k[m].numpy().astype("<i8"), 1)
         _write(os.path.join(path, f"{v.name}-weight"),
                v.weight[r[m].to(v.device)].float().cpu().numpy().astype("<f4"), 2)
+
+
+# ----------------------------------------------------------------------------- dynamic-variable utilities
+__version__ = "2.0.0.b200"
+
+
+def set_comm_tool(tool: str = "torch.distributed"):
+    """sok.set_comm_tool("horovod" | "tf.distribute") of the reference: there is one communication layer here
+    (torch.distributed, one process per GPU); the call is accepted so that scripts keep working."""
+    return "torch.distributed"
+
+
+def export(var):
+    """sok.export(var) -> (indices, values) of a DynamicVariable (dynamic_variable.py:465-491): the keys this rank
+    holds and their vectors, HBM tier and host tier, on the CPU"""
+    if not isinstance(var, DynamicVariable):
+        raise TypeError("sok.export takes a sok.DynamicVariable")
+    k, w, _ = var.export()
+    return k, w
+
+
+def assign(var, indices: torch.Tensor, values: torch.Tensor):
+    """sok.assign(var, indices, values) (dynamic_variable.py:494-517): insert or overwrite the rows of ``indices``
+    (this rank keeps the keys it owns, ``key % world == rank``)"""
+    if not isinstance(var, DynamicVariable):
+        raise TypeError("sok.assign takes a sok.DynamicVariable")
+    k = torch.as_tensor(indices).reshape(-1).to(torch.int64)
+    v = torch.as_tensor(values).reshape(k.numel(), var.dim)
+    mine = (k % var.world) == var.rank
+    if bool(mine.any()):
+        rows = var.local_rows(k[mine], create=True)
+        ok = rows >= 0
+        var.weight[rows[ok]] = v[mine][ok.cpu()].to(var.device, var.weight.dtype)
+    return var
+
+
+def sparse_read_and_evict(var, indices: torch.Tensor):
+    """sok.sparse_read_and_evict(var, indices) (lookup.py:75-80, hybrid variables only): the rows of ``indices`` with
+    unseen keys created; when the HBM tier is full the least recently / least frequently used rows are demoted to
+    the host tier first.  Local read: every key is served by this rank's table."""
+    if not isinstance(var, DynamicVariable) or var.var_type != "hybrid":
+        raise TypeError("sparse_read_and_evict only works on hybrid DynamicVariables")
+    k = torch.as_tensor(indices).to(torch.int64)
+    rows = var.local_rows(k.reshape(-1), create=True)
+    out = var.weight[rows.clamp(min=0)] * (rows >= 0).unsqueeze(-1).to(var.weight.dtype)
+    return out.view(*k.shape, var.dim)
+
+
+def group_lookup(params, indices):
+    """sok.group_lookup (lookup.py:83-96): several single-GPU embedding lookups in one call; every ``params[i]`` is a
+    local [rows, dim] tensor / Parameter or a sok.Variable whose rows live on this rank, gradients flow to it"""
+    single = not isinstance(params, (list, tuple))
+    ps = [params] if single else list(params)
+    ids = [indices] if not isinstance(indices, (list, tuple)) else list(indices)
+    outs = []
+    for p_, i_ in zip(ps, ids):
+        w = p_.weight if isinstance(p_, Variable) else p_
+        outs.append(torch.nn.functional.embedding(torch.as_tensor(i_).to(w.device).long(), w))
+    return outs[0] if single else outs

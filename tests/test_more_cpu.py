@@ -378,3 +378,40 @@ def test_model_fit_survives_a_growing_dynamic_table(monkeypatch):
     import pytest
     with pytest.raises(RuntimeError, match="init_capacity"):
         m2.fit(max_iter=30, display=5, eval_interval=15, snapshot=1000000)
+
+
+def test_sok_export_assign_read_and_evict_group_lookup():
+    """module-level SOK helpers of the reference: export / assign (dynamic_variable.py), sparse_read_and_evict
+    (lookup.py:75, hybrid variables), group_lookup, set_comm_tool"""
+    import pytest
+    from hugectr_b200 import sok
+    from hugectr_b200.parallel.comm import Comm
+    sok.init(Comm.single(torch.device("cpu")))
+    assert sok.set_comm_tool("horovod") == "torch.distributed" and sok.__version__
+    v = sok.DynamicVariable(4, var_type="hybrid", initializer=0.25, init_capacity=8, max_capacity=16)
+    keys = torch.tensor([5, 900000000007, 42])
+    vals = torch.arange(12, dtype=torch.float32).view(3, 4)
+    assert sok.assign(v, keys, vals) is v
+    k, w = sok.export(v)
+    order = torch.argsort(k)
+    assert k[order].tolist() == sorted(keys.tolist())
+    assert torch.equal(w[order], vals[torch.argsort(keys)])
+    # read-and-evict: known keys keep their values, unseen keys are created from the initializer; beyond the HBM
+    # capacity the oldest rows move to the host tier and still export
+    out = sok.sparse_read_and_evict(v, torch.tensor([[42, 7], [5, 8]]))
+    assert out.shape == (2, 2, 4) and torch.equal(out[0, 0], vals[2]) and torch.equal(out[1, 0], vals[0])
+    assert torch.allclose(out[0, 1].abs(), torch.full((4,), 0.25)) or float(out[0, 1].abs().max()) <= 0.25
+    sok.sparse_read_and_evict(v, torch.arange(1000, 1014))
+    assert v.size <= 16 and v.evictions > 0 and v.total_size == 5 + 14
+    k2, w2 = sok.export(v)
+    assert torch.equal(w2[(k2 == 900000000007).nonzero()[0, 0]], vals[1])         # wherever the row lives now
+    with pytest.raises(TypeError):
+        sok.sparse_read_and_evict(sok.DynamicVariable(4, var_type="hbm"), keys)
+    # group_lookup: plain local gathers with gradients
+    p1 = torch.nn.Parameter(torch.randn(10, 3))
+    p2 = sok.Variable(shape=[6, 2])
+    p2.weight.requires_grad_(True)
+    o1, o2 = sok.group_lookup([p1, p2], [torch.tensor([1, 1, 4]), torch.tensor([[0, 5]])])
+    assert o1.shape == (3, 3) and o2.shape == (1, 2, 2)
+    (o1.sum() + o2.sum()).backward()
+    assert float(p1.grad[1].sum()) == 6.0 and float(p2.weight.grad[5].sum()) == 2.0
