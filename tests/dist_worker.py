@@ -269,7 +269,14 @@ def run_fuzz(seed, comm=None):
         st = ([("mp", strat_mp)] if strat_mp else []) + ([("dp", strat_dp)] if strat_dp else [])
         if rnd.random() < 0.5:          # the reference's form: per GPU the list of table NAMES it holds
             sm = [[str(i) for i in range(nt) if row[i]] for row in sm]
-        cfg.shard(sm, st)
+        comp = None
+        if os.environ.get("HCTR_FUZZ_UNIQUE") and strat_mp:
+            # a random subset of the model-parallel tables on the Unique-compression exchange (column-split ones
+            # fall back to Reduction inside the collection; the fused data flow keeps its own exchange)
+            from hugectr_b200.enums import CompressionStrategy
+            names_mp = [x[0] if isinstance(x, tuple) else x for x in strat_mp]
+            comp = {CompressionStrategy.Unique: [n_ for n_ in names_mp if rnd.random() < 0.6]}
+        cfg.shard(sm, st, compression_strategy=comp)
     adagrad = rnd.random() < 0.5          # non-linear rule: exercises the reduce-then-update order and
     opt = CreateOptimizer(Optimizer_t.AdaGrad, initial_accu_value=0.0, epsilon=1e-7) if adagrad \
         else CreateOptimizer(Optimizer_t.SGD)    # the optimizer-state windows of column / row shards

@@ -205,3 +205,11 @@ def test_emu_unique_compression_cpu(world, names, opt):
 def test_emu_unique_is_left_to_the_peer_store_path_when_fused_cpu():
     """fused (peer-memory) mode keeps pooled-vector transfers: Unique tables are not rerouted"""
     run_ranks(2, lambda c: W.run_unique("0,2", "adagrad", fused=True, comm=c), device=CPU, p2p="force")
+
+
+def test_emu_fuzz_with_unique_subsets_cpu(monkeypatch):
+    """the randomised collection oracle with a random subset of the model-parallel tables on the Unique exchange"""
+    monkeypatch.setenv("HCTR_FUZZ_UNIQUE", "1")
+    for world, seeds in ((2, (9001, 9002, 9003)), (3, (9301, 9302)), (4, (9501,))):
+        for sd in seeds:
+            run_ranks(world, lambda c, sd=sd: W.run_fuzz(sd, comm=c), device=CPU, p2p=False)
