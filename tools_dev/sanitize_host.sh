@@ -23,7 +23,7 @@ fi
 g++ -O1 -g -std=c++17 -fPIC -pthread $OMP $FLAGS -shared -o "$OUT" hugectr_b200/csrc/host/*.cpp
 LD_PRELOAD=$RT HCTR_HOST_LIB=$OUT python -m pytest -q -m "not gpu and not dist" \
   tests/test_norm_reader_cpu.py tests/test_datagen_cpu.py tests/test_criteo_preprocess_cpu.py \
-  tests -k "norm or datagen or criteo or raw or hps or param_server or parquet or reader or csr" 2>&1 | tee /tmp/sanitize_${MODE}.log | tail -3
+  tests -k "norm or datagen or criteo or raw or hps or param_server or parquet or reader or csr or watchdog" 2>&1 | tee /tmp/sanitize_${MODE}.log | tail -3
 echo "sanitizer reports: $(cat /tmp/sanitize_${MODE}.log /tmp/tsan_report.* 2>/dev/null | grep -c 'ERROR: AddressSanitizer\|runtime error\|WARNING: ThreadSanitizer' || true)"
 if [ "$MODE" = tsan ]; then
   echo "in libhctr_host: $(cat /tmp/tsan_report.* 2>/dev/null | grep -c 'libhctr_host_tsan.so' || true) frames"
