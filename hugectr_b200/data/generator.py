@@ -72,10 +72,11 @@ class DataGenerator:
         p = self.p
         return p.alpha if p.power_law_type == PowerLaw_t.Specific else _ALPHA[p.power_law_type]
 
-    def _keys(self, n, vocab):
+    def _keys(self, n, vocab, gen=None):
+        gen = gen or self.gen
         if self.p.dist_type == Distribution_t.PowerLaw:
-            return power_law_keys(n, vocab, self.alpha, self.gen).numpy()
-        return torch.randint(0, max(1, vocab), (n,), generator=self.gen).numpy()
+            return power_law_keys(n, vocab, self.alpha, gen).numpy()
+        return torch.randint(0, max(1, vocab), (n,), generator=gen).numpy()
 
     def generate(self):
         p = self.p
@@ -101,31 +102,40 @@ class DataGenerator:
         d = os.path.join(root, sub)
         os.makedirs(d, exist_ok=True)
         n = p.num_samples_per_file
-        stats, paths = [], []
-        for f in range(num_files):
-            cols, names = [], []
+        names = []
+        for i in range(p.label_dim):
+            names.append(f"label{i}" if p.label_dim > 1 else "label")
+        names += [f"C{i + 1}" for i in range(p.dense_dim)] + [f"S{s + 1}" for s in range(p.num_slot)]
+
+        def one_file(f):
+            # every file has its own random stream (seeded by split and file index): files are written in
+            # parallel and the bytes do not depend on the number of writer threads
+            gen = torch.Generator()
+            gen.manual_seed(20260921 + 1000003 * (f + 1) + (0 if sub == "train" else 7919))
+            cols = []
             for i in range(p.label_dim):
-                cols.append(pa.array(torch.rand(n, generator=self.gen).round().numpy().astype("float32")))
-                names.append(f"label{i}" if p.label_dim > 1 else "label")
+                cols.append(pa.array(torch.rand(n, generator=gen).round().numpy().astype("float32")))
             for i in range(p.dense_dim):
-                cols.append(pa.array(torch.rand(n, generator=self.gen).numpy().astype("float32")))
-                names.append(f"C{i + 1}")
+                cols.append(pa.array(torch.rand(n, generator=gen).numpy().astype("float32")))
             for s in range(p.num_slot):
                 nnz = p.nnz_array[s] if p.nnz_array else 1
                 vocab = p.slot_size_array[s]
                 if nnz == 1:
-                    cols.append(pa.array(self._keys(n, vocab).astype("int64")))
+                    cols.append(pa.array(self._keys(n, vocab, gen).astype("int64")))
                 else:
-                    cnt = torch.randint(1, nnz + 1, (n,), generator=self.gen).numpy()
-                    flat = self._keys(int(cnt.sum()), vocab).astype("int64")
+                    cnt = torch.randint(1, nnz + 1, (n,), generator=gen).numpy()
+                    flat = self._keys(int(cnt.sum()), vocab, gen).astype("int64")
                     offs = np.concatenate([[0], np.cumsum(cnt)]).astype("int32")
                     cols.append(pa.ListArray.from_arrays(pa.array(offs), pa.array(flat)))
-                names.append(f"S{s + 1}")
             name = f"gen_{f}.parquet"
             path = os.path.join(d, name)
             pq.write_table(pa.Table.from_arrays(cols, names=names), path, row_group_size=min(n, 65536))
-            stats.append({"file_name": name, "num_rows": n})
-            paths.append(path)
+            return {"file_name": name, "num_rows": n}, path
+        from concurrent.futures import ThreadPoolExecutor
+        workers = max(1, min(int(getattr(p, "num_threads", 0) or 8), num_files, os.cpu_count() or 1))
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            done = list(ex.map(one_file, range(num_files)))
+        stats, paths = [x[0] for x in done], [x[1] for x in done]
         nl, nd = p.label_dim, p.dense_dim
         meta = {"file_stats": stats,
                 "labels": [{"col_name": names[i], "index": i} for i in range(nl)],
