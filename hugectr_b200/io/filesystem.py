@@ -206,8 +206,9 @@ FileSystemBuilder.build_unique_by_type = FileSystemBuilder.build_by_type
 
 # ---------------------------------------------------------------- array files on any back-end
 def is_remote(path: str) -> bool:
-    return not isinstance(FileSystemBuilder.build_by_path(path), LocalFileSystem) if "://" in path or ".s3." in path \
-        or "storage.googleapis.com" in path else False
+    """string test only (no back-end is constructed): a registered scheme, hdfs:// s3:// gs://, or an S3 / GCS URL"""
+    return any(path.startswith(sc) for sc in FileSystemBuilder._registered) or \
+        path.startswith(("hdfs://", "s3://", "gs://")) or ".s3." in path or "storage.googleapis.com" in path
 
 
 def write_array(path: str, arr, params=None) -> None:
