@@ -1,4 +1,5 @@
 """Drop-in compatibility of the ``hugectr`` module name with scripts written for the reference."""
+import json
 import os
 import subprocess
 import sys
@@ -261,3 +262,15 @@ def test_workspace_calculator_matches_the_reference_tool():
                     assert W.calculate(slots, vec, W._OPT[opt], W._UPD[upd], gpus,
                                        hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash) == \
                         ref.cal_workspace_size_per_gpu_from_vocabulary_size_per_gpu(vl, vec, gpus, opt, upd)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/HugeCTR/include/pybind"), reason="reference not mounted")
+def test_python_api_names_cover_the_reference_pybind_layer():
+    """every enum value, module function, class and bound member name of the reference's pybind headers exists here"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools_dev", "api_parity.py"), "--json"],
+                       capture_output=True, text=True, timeout=300)
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert rep["missing"] == [] and rep["enums"] >= 20 and rep["members"] >= 80, rep
