@@ -65,11 +65,31 @@ def main(argv):
     members = set(re.findall(r'\.def(?:_readonly|_readwrite|_property_readonly|_static)?\(\s*"([a-zA-Z_0-9]+)"', txt)) - DEAD
     rep["members"] = len(members)
     rep["missing"] += [f"member {n}" for n in sorted(members) if n not in have]
+    # keyword-argument names of the bound constructors / factory functions (pybind11::arg("...") lists)
+    ctor = {}
+    for m in re.finditer(r'm\.def\(\s*"(\w+)"(.*?)\);', txt, re.S):
+        ctor[m.group(1)] = re.findall(r'pybind11::arg\("(\w+)"\)', m.group(2))
+    for m in re.finditer(r'class_<[^;]*?>\s*(?:\w+\s*)?\(\s*\w+\s*,\s*"(\w+)"\)(.*?);\n', txt, re.S):
+        a = re.findall(r'pybind11::arg\("(\w+)"\)', m.group(2).split('.def("')[0])
+        if a:
+            ctor.setdefault(m.group(1), a)
+    rep["kwargs"] = 0
+    import hugectr_b200.tools as tools
+    for name, a in sorted(ctor.items()):
+        o = getattr(h, name, None) or getattr(tools, name, None)
+        if o is None:
+            continue
+        sig = inspect.signature(o.__init__ if isinstance(o, type) else o)
+        varkw = any(p_.kind == p_.VAR_KEYWORD for p_ in sig.parameters.values())
+        for x in a:
+            rep["kwargs"] += 1
+            if x not in sig.parameters and not (varkw and x == "lambda"):     # `lambda` is a Python keyword: via **kw
+                rep["missing"].append(f"{name}({x}=...)")
     if "--json" in argv:
         print(json.dumps(rep))
     else:
         print(f"{rep['enums']} enums / {rep['enum_values']} values, {rep['functions']} module functions, "
-              f"{rep['classes']} classes, {rep['members']} bound members: missing {rep['missing'] or 'none'}")
+              f"{rep['classes']} classes, {rep['members']} bound members, {rep['kwargs']} constructor keyword names: missing {rep['missing'] or 'none'}")
     return 1 if rep["missing"] else 0
 
 
