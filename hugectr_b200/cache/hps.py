@@ -103,6 +103,7 @@ class HostParameterServer:
             self.w = self.w.pin_memory()
             self.s = [t.pin_memory() for t in self.s]
         self.gen = torch.Generator().manual_seed(seed)
+        self._seed = (int(seed) * 0x9E3779B97F4A7C15 + 0x1234567) & 0xFFFFFFFFFFFFFFFF
         self.ssd = SparseModelFile(ssd_path, ev) if ssd_path else None
         # key -> row index: native sharded hash maps + OpenMP row movers (csrc/host/param_server.cpp);
         # a Python dict when the host library cannot be built
@@ -123,6 +124,7 @@ class HostParameterServer:
             lib.hctr_ps_dump.restype = ll
             lib.hctr_ps_gather.argtypes = [vp, vp, ll, ll, vp]
             lib.hctr_ps_scatter.argtypes = [vp, vp, ll, ll, vp]
+            lib.hctr_ps_init_rows.argtypes = [vp, vp, ll, C.c_int, C.c_float, C.c_ulonglong]
             self._lib = lib
             self._h = lib.hctr_ps_create()
         except Exception:  # pragma: no cover - no compiler available
@@ -147,14 +149,16 @@ class HostParameterServer:
             if created < 0:
                 raise RuntimeError("HostParameterServer capacity exceeded")
             if created > 0:
-                nr = rows[is_new.bool()]
-                init = (torch.rand(nr.numel(), self.ev, generator=self.gen) * 2 - 1) * self.bound
+                nr = rows[is_new.bool()].contiguous()
+                # counter-based initializer in the row movers' thread pool (value of a cell = f(seed, row, column))
+                self._lib.hctr_ps_init_rows(self.w.data_ptr(), nr.data_ptr(), nr.numel(), self.ev, float(self.bound),
+                                            int(self._seed) & 0xFFFFFFFFFFFFFFFF)
                 if self.ssd:
-                    loaded = self.ssd.load(keys[is_new.bool()].tolist())
-                    for j, k in enumerate(keys[is_new.bool()].tolist()):
+                    newk = keys[is_new.bool()].tolist()
+                    loaded = self.ssd.load(newk)
+                    for j, k in enumerate(newk):
                         if k in loaded:
-                            init[j] = loaded[k]
-                self.w[nr] = init
+                            self.w[nr[j]] = loaded[k]
             return rows
         rows = []
         for k in keys.tolist():
