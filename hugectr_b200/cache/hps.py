@@ -102,6 +102,7 @@ class HostParameterServer:
         if pin:
             self.w = self.w.pin_memory()
             self.s = [t.pin_memory() for t in self.s]
+        self._stage: Dict[int, torch.Tensor] = {}
         self.gen = torch.Generator().manual_seed(seed)
         self._seed = (int(seed) * 0x9E3779B97F4A7C15 + 0x1234567) & 0xFFFFFFFFFFFFFFFF
         self.ssd = SparseModelFile(ssd_path, ev) if ssd_path else None
@@ -173,11 +174,25 @@ class HostParameterServer:
             rows.append(-1 if r is None else r)
         return torch.tensor(rows, dtype=torch.int64)
 
-    def _gather(self, table: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    def _gather(self, table: torch.Tensor, rows: torch.Tensor, reuse: Optional[int] = None) -> torch.Tensor:
+        """out[i] = table[rows[i]] (rows[i] < 0 -> zeros).  ``reuse=<slot>``: gather into this server's reusable
+        (pinned on a GPU box) staging buffer ``slot`` and return a view of it -- no allocation / first-touch page
+        faults per step, fast H2D; the caller must be done with the previous result of the same slot."""
         if self._h is None:
-            return table[rows]
-        out = torch.empty(rows.numel(), self.ev)
-        self._lib.hctr_ps_gather(table.data_ptr(), rows.data_ptr(), rows.numel(), self.ev * 4, out.data_ptr())
+            return table[rows.clamp(min=0)] * (rows >= 0).unsqueeze(1)
+        n = rows.numel()
+        if reuse is None:
+            out = torch.empty(n, self.ev)
+        else:
+            buf = self._stage.get(reuse)
+            if buf is None or buf.shape[0] < n:
+                buf = torch.empty(max(n, 1024) * 5 // 4, self.ev)
+                if torch.cuda.is_available():
+                    buf = buf.pin_memory()
+                self._stage[reuse] = buf
+            out = buf[:n]
+        rows = rows.contiguous()
+        self._lib.hctr_ps_gather(table.data_ptr(), rows.data_ptr(), n, self.ev * 4, out.data_ptr())
         return out
 
     def _scatter(self, table: torch.Tensor, rows: torch.Tensor, src: torch.Tensor):

@@ -76,12 +76,11 @@ class CachedSparseEmbeddingRuntime(SparseEmbeddingRuntime):
         if mk.numel():
             mk_h = mk.cpu()
             rows = self.ps._rows(mk_h, create=create)
-            w = self.ps._gather(self.ps.w, rows.clamp(min=0))
             known = (rows >= 0)
-            w = w * known.unsqueeze(1)
-            vals[mi] = w.to(dev)
-            for t, src in zip(sts, self.ps.s):
-                t[mi] = (self.ps._gather(src, rows.clamp(min=0)) * known.unsqueeze(1)).to(dev)
+            # rows < 0 (unknown key in evaluation) gather as zeros; staging buffers are reused step after step
+            vals[mi] = self.ps._gather(self.ps.w, rows, reuse=0).to(dev)
+            for j, (t, src) in enumerate(zip(sts, self.ps.s)):
+                t[mi] = self.ps._gather(src, rows, reuse=1 + j).to(dev)
             if self.cache is not None and bool(known.any()):
                 kk = mk[known.to(dev)]
                 self.cache.replace(kk, vals[mi][known.to(dev)])
