@@ -665,6 +665,109 @@ def run_legacy(comm=None):
         print("LEGACY_OK")
 
 
+def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
+    """Legacy hash embeddings: N-rank training must equal single-process training on the concatenated batches, KEY BY
+    KEY (rows are handed out in arrival order, so tables are compared through their (key -> vector) dumps).  Both
+    models start from the same sparse model files and dense weights; random slots / bag lengths / combiner."""
+    import random
+    import tempfile
+    import numpy as np
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.batch import HostBatch
+    comm = comm or Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+    rnd = random.Random(int(seed))
+    S = rnd.randint(2, 5)
+    H = rnd.choice([1, 2, 4])
+    vec = rnd.choice([4, 8])
+    comb = rnd.choice(["sum", "mean"])
+    vocab = [rnd.randint(5, 40) for _ in range(S)]
+    offs = np.concatenate([[0], np.cumsum(vocab)[:-1]])
+    b = 16
+    et = hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash if kind == "localized" \
+        else hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash
+    opt_t = {"adam": hugectr.Optimizer_t.Adam, "sgd": hugectr.Optimizer_t.SGD, "adagrad": hugectr.Optimizer_t.AdaGrad}[optimizer]
+
+    def build(c, w):
+        solver = hugectr.CreateSolver(batchsize=b * world, batchsize_eval=b * world, lr=0.05, vvgpu=[list(range(w))],
+                                      repeat_dataset=True, i64_input_key=True, use_cuda_graph=False)
+        rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.Parquet, source=["synthetic"], eval_source="synthetic",
+                                      check_type=hugectr.Check_t.Non, slot_size_array=vocab)
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(opt_t, hugectr.Update_t.Local), comm=c)
+        m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
+                            data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", H, H == 1, S)]))
+        m.add(hugectr.SparseEmbedding(et, 1, vec, comb, "emb", "data1", slot_size_array=vocab))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Reshape, ["emb"], ["r"], leading_dim=S * vec))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["r", "dense"], ["c"]))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+        m.compile()
+        return m
+    m = build(comm, world)
+    ref = build(Comm.single(comm.device), 1) if rank == 0 else None
+    # identical start: every key of every slot with a known vector, identical dense weights
+    gen = torch.Generator().manual_seed(int(seed) + 1)
+    allk = torch.cat([torch.arange(vocab[s]) + int(offs[s]) for s in range(S)])
+    allv = torch.randn(allk.numel(), vec, generator=gen) * 0.1
+    slot_of = torch.cat([torch.full((vocab[s],), s) for s in range(S)])
+    d = comm.all_gather_object(tempfile.mkdtemp() if rank == 0 else None)[0]
+    if rank == 0:
+        sm = os.path.join(d, "init")
+        os.makedirs(sm, exist_ok=True)
+        allk.numpy().astype("<i8").tofile(os.path.join(sm, "key"))
+        allv.numpy().astype("<f4").tofile(os.path.join(sm, "emb_vector"))
+        if kind == "localized":
+            slot_of.numpy().astype("<u8").tofile(os.path.join(sm, "slot_id"))
+    comm.barrier()
+    m.load_sparse_weights([os.path.join(d, "init")])
+    w0 = m.arena.weights.clone()
+    comm.broadcast(w0, 0)
+    m.arena.weights.copy_(w0)
+    m.arena.sync_shadow()
+    if ref is not None:
+        ref.load_sparse_weights([os.path.join(d, "init")])
+        ref.arena.weights.copy_(w0)
+        ref.arena.sync_shadow()
+    for step in range(3):
+        lab = torch.randint(0, 2, (b * world, 1), generator=gen).float()
+        den = torch.rand(b * world, 2, generator=gen)
+        keys = torch.stack([torch.randint(0, vocab[s], (b * world, H), generator=gen) + int(offs[s]) for s in range(S)], 1)
+        if H > 1:                                   # shorter bags: padding -1 behind the first n keys
+            n = torch.randint(1, H + 1, (b * world, S), generator=gen)
+            keys = torch.where(torch.arange(H).view(1, 1, H) < n.unsqueeze(-1), keys, torch.full_like(keys, -1))
+        nnz = (keys >= 0).sum(-1).int()             # [B, S]
+
+        def batch(lo, hi):
+            k = keys[lo:hi].reshape(-1)
+            z = nnz[lo:hi].t().reshape(-1)          # [S, b] layout of the nnz block
+            return HostBatch(lab[lo:hi].clone(), den[lo:hi].clone(), k.clone(), z.clone(), hi - lo)
+        m.train_on_host_batch(batch(rank * b, (rank + 1) * b))
+        if ref is not None:
+            ref.train_on_host_batch(batch(0, b * world))
+    lm = m.get_current_loss()
+    out = os.path.join(d, "out_n")
+    m.legacy_train[0].dump_parameters(out)
+    if ref is not None:
+        lr_ = ref.get_current_loss()
+        assert abs(lm - lr_) < 1e-4 * max(1.0, abs(lr_)), (seed, kind, optimizer, lm, lr_)
+        err = float((m.arena.weights - ref.arena.weights).abs().max())
+        assert err < 1e-4, (seed, kind, optimizer, "dense", err)
+        ref.legacy_train[0].dump_parameters(os.path.join(d, "out_1"))
+        tabs = []
+        for o in ("out_n", "out_1"):
+            k = np.fromfile(os.path.join(d, o, "key"), dtype="<i8")
+            v = np.fromfile(os.path.join(d, o, "emb_vector"), dtype="<f4").reshape(-1, vec)
+            order = np.argsort(k)
+            tabs.append((k[order], v[order]))
+        assert (tabs[0][0] == tabs[1][0]).all() and len(tabs[0][0]) == allk.numel(), (seed, "key sets differ")
+        diff = float(np.abs(tabs[0][1] - tabs[1][1]).max())
+        moved = float(np.abs(tabs[1][1] - allv.numpy()[np.argsort(allk.numpy())]).max())
+        assert diff < 1e-4 and moved > 1e-6, (seed, kind, optimizer, "table", diff, moved)
+    comm.barrier()
+    if rank == 0:
+        print("LEGACY_EQUIV_OK", seed)
+
+
 def run_ckpt(tmpdir, comm=None):
     """train on N ranks (row-sharded + table-wise + dp tables), save dense + embedding-collection
     checkpoints, load them into a SINGLE-process model (different sharding) and compare weights,
@@ -833,6 +936,9 @@ if __name__ == "__main__":
             run_fuzz(sd)
     if what == "legacy":
         run_legacy()
+    if what == "legacy_equiv":
+        for sd in sys.argv[4].split(","):
+            run_legacy_equiv(sys.argv[2], sys.argv[3], sd)
     if what == "equiv":
         run_equiv(sys.argv[2] if len(sys.argv) > 2 else "sgd", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     if what == "model":

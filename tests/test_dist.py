@@ -223,3 +223,10 @@ def test_model_with_unique_compression_equals_single_process_gloo():
     """whole model through the public API: ebc.shard(..., compression_strategy={Unique: [...]})"""
     out = _run(2, ["equiv", "adagrad"], 29751, env={"CUDA_VISIBLE_DEVICES": "", "HCTR_TEST_UNIQUE": "1"})
     assert "EQUIV_OK" in out
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("kind", ["distributed", "localized"])
+def test_legacy_embeddings_equal_single_process_gloo(kind):
+    out = _run(2, ["legacy_equiv", kind, "adam", "11,12"], 29761, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert out.count("LEGACY_EQUIV_OK") == 2

@@ -213,3 +213,12 @@ def test_emu_fuzz_with_unique_subsets_cpu(monkeypatch):
     for world, seeds in ((2, (9001, 9002, 9003)), (3, (9301, 9302)), (4, (9501,))):
         for sd in seeds:
             run_ranks(world, lambda c, sd=sd: W.run_fuzz(sd, comm=c), device=CPU, p2p=False)
+
+
+@pytest.mark.parametrize("kind,opt,world,p2p", [("distributed", "adam", 2, False), ("localized", "adagrad", 3, False),
+                                                ("distributed", "adagrad", 3, "force"), ("localized", "adam", 4, "force")])
+def test_emu_legacy_embeddings_equal_single_process_cpu(kind, opt, world, p2p):
+    """legacy hash embeddings, N ranks == 1 process KEY BY KEY (same start from sparse model files, random slots / bag
+    lengths / combiner): collective exchange and the fused (peer-store) data flow"""
+    for sd in (world * 100 + 1, world * 100 + 2):
+        run_ranks(world, lambda c: W.run_legacy_equiv(kind, opt, sd, comm=c), device=CPU, p2p=p2p)
