@@ -693,7 +693,12 @@ def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
                                       repeat_dataset=True, i64_input_key=True, use_cuda_graph=False)
         rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.Parquet, source=["synthetic"], eval_source="synthetic",
                                       check_type=hugectr.Check_t.Non, slot_size_array=vocab)
-        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(opt_t, hugectr.Update_t.Local), comm=c)
+        etc = None
+        if w > 1 and os.environ.get("HCTR_TEST_ETC"):
+            # the N-rank model keeps its table on the host parameter server (behind the cache / staged)
+            ps_t = hugectr.TrainPSType_t.Cached if os.environ["HCTR_TEST_ETC"] == "cached" else hugectr.TrainPSType_t.Staged
+            etc = hugectr.CreateETC(ps_types=[ps_t], sparse_models=[""], host_capacity_rows=4096)
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(opt_t, hugectr.Update_t.Local), etc, comm=c)
         m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
                             data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", H, H == 1, S)]))
         m.add(hugectr.SparseEmbedding(et, 1, vec, comb, "emb", "data1", slot_size_array=vocab))
@@ -704,6 +709,8 @@ def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
         m.compile()
         return m
     m = build(comm, world)
+    if world > 1 and os.environ.get("HCTR_TEST_ETC"):
+        assert type(m.legacy_train[0]).__name__ == "CachedSparseEmbeddingRuntime", type(m.legacy_train[0])
     ref = build(Comm.single(comm.device), 1) if rank == 0 else None
     # identical start: every key of every slot with a known vector, identical dense weights
     gen = torch.Generator().manual_seed(int(seed) + 1)

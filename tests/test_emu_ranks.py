@@ -222,3 +222,11 @@ def test_emu_legacy_embeddings_equal_single_process_cpu(kind, opt, world, p2p):
     lengths / combiner): collective exchange and the fused (peer-store) data flow"""
     for sd in (world * 100 + 1, world * 100 + 2):
         run_ranks(world, lambda c: W.run_legacy_equiv(kind, opt, sd, comm=c), device=CPU, p2p=p2p)
+
+
+@pytest.mark.parametrize("mode", ["cached", "staged"])
+def test_emu_embedding_training_cache_multi_rank_equals_single_process_cpu(mode, monkeypatch):
+    """tables on the host parameter server (behind the cache / staged) on N ranks == resident tables on one process"""
+    monkeypatch.setenv("HCTR_TEST_ETC", mode)
+    run_ranks(2, lambda c: W.run_legacy_equiv("distributed", "adam", 201, comm=c), device=CPU, p2p=False)
+    run_ranks(3, lambda c: W.run_legacy_equiv("localized", "adagrad", 303, comm=c), device=CPU, p2p=False)
