@@ -770,6 +770,31 @@ def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
         diff = float(np.abs(tabs[0][1] - tabs[1][1]).max())
         moved = float(np.abs(tabs[1][1] - allv.numpy()[np.argsort(allk.numpy())]).max())
         assert diff < 1e-4 and moved > 1e-6, (seed, kind, optimizer, "table", diff, moved)
+    # ---- snapshot written by N ranks, loaded by ONE process (re-sharding + optimizer states matched by key), dumped
+    # again: (key -> vector, key -> states) must survive unchanged
+    ost = os.path.join(d, "out_n_opt")
+    m.legacy_train[0].dump_opt_states(ost)
+    comm.barrier()
+    if ref is not None:
+        fresh = build(Comm.single(comm.device), 1)
+        fresh.load_sparse_weights([out])
+        fresh.load_sparse_optimizer_states([ost])
+        fresh.legacy_train[0].dump_parameters(os.path.join(d, "re"))
+        fresh.legacy_train[0].dump_opt_states(os.path.join(d, "re_opt"))
+
+        def by_key(pd, po):
+            k = np.fromfile(os.path.join(d, pd, "key"), dtype="<i8")
+            v = np.fromfile(os.path.join(d, pd, "emb_vector"), dtype="<f4").reshape(-1, vec)
+            st = np.fromfile(os.path.join(d, po), dtype="<f4")
+            ns = st.size // max(1, k.size * vec)
+            st = st.reshape(ns, k.size, vec) if ns else st.reshape(0, k.size, vec)
+            o = np.argsort(k)
+            return k[o], v[o], st[:, o]
+        a_, b_ = by_key("out_n", "out_n_opt"), by_key("re", "re_opt")
+        assert (a_[0] == b_[0]).all() and np.array_equal(a_[1], b_[1]), (seed, "reloaded table differs")
+        assert a_[2].shape == b_[2].shape and np.array_equal(a_[2], b_[2]), (seed, "optimizer states scrambled on reload")
+        if optimizer != "sgd":
+            assert a_[2].shape[0] >= 1 and float(np.abs(a_[2]).max()) > 0, "no optimizer state was written"
     comm.barrier()
     if rank == 0:
         print("LEGACY_EQUIV_OK", seed)
