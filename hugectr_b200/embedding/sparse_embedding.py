@@ -74,7 +74,8 @@ class SparseEmbeddingRuntime:
             if self.s0 is not None and opt.optimizer_type == Optimizer_t.AdaGrad:
                 self.s0.fill_(opt.initial_accu_value)
             self.hash = HashTable(self.max_rows, device)
-            self.slot_of_row = torch.full((self.max_rows,), -1, dtype=torch.int64, device=device) \
+            # (one spare entry behind the table: the write target of batch entries this rank does not own)
+            self.slot_of_row = torch.full((self.max_rows + 1,), -1, dtype=torch.int64, device=device) \
                 if self.localized else None
         else:
             for k in ("max_rows", "table", "s0", "s1", "hash", "slot_of_row"):
@@ -186,7 +187,9 @@ class SparseEmbeddingRuntime:
             # remember the slot of every row (dumped as slot_id; the reference stores it per hash value)
             r = self.rows_all.reshape(-1)
             slot = (torch.arange(r.numel(), device=r.device) % n) // self.H % self.S
-            self.slot_of_row.index_put_((r.clamp(min=0),), torch.where(r >= 0, slot, self.slot_of_row[r.clamp(min=0)]))
+            # every occurrence of an owned row writes the same value (a Localized key lives in one slot); entries
+            # that are not mine go to the spare entry, so no write races with a row's real slot
+            self.slot_of_row.index_put_((torch.where(r >= 0, r, torch.full_like(r, self.max_rows)),), slot)
 
     def forward(self, is_train: bool):
         W, b, S, H, vec = self.world, self.b, self.S, self.H, self.vec
@@ -303,11 +306,13 @@ class SparseEmbeddingRuntime:
             alive = torch.arange(n, device=self.device) < self.hash.counter
         else:
             alive = torch.arange(n) < int(self.hash.size())
-        touched = torch.zeros(self.max_rows, dtype=torch.bool, device=self.device)
+        # rows of this step: every write stores True (entries that are not mine go to a spare slot behind the
+        # table) -- duplicates are harmless and no row's flag depends on the order of conflicting writes
+        touched = torch.zeros(self.max_rows + 1, dtype=torch.bool, device=self.device)
         r = self.rows_all.reshape(-1)
-        touched.index_put_((r.clamp(min=0),), (r >= 0), accumulate=False)
-        touched |= ~alive                       # never-allocated rows are left alone
-        unt = (~touched[:n]).unsqueeze(1)
+        touched.index_fill_(0, torch.where(r >= 0, r, torch.full_like(r, self.max_rows)), True)
+        touched = touched[:n] | ~alive          # never-allocated rows are left alone
+        unt = (~touched).unsqueeze(1)
         w = self.table.view(-1, vec)[:n]
         s0 = self.s0.view(-1, vec)[:n]
         lr = lr_t.reshape(()).float()

@@ -698,7 +698,9 @@ def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
             # the N-rank model keeps its table on the host parameter server (behind the cache / staged)
             ps_t = hugectr.TrainPSType_t.Cached if os.environ["HCTR_TEST_ETC"] == "cached" else hugectr.TrainPSType_t.Staged
             etc = hugectr.CreateETC(ps_types=[ps_t], sparse_models=[""], host_capacity_rows=4096)
-        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(opt_t, hugectr.Update_t.Local), etc, comm=c)
+        upd = {"global": hugectr.Update_t.Global, "lazy": hugectr.Update_t.LazyGlobal}.get(
+            os.environ.get("HCTR_TEST_UPDATE", ""), hugectr.Update_t.Local)
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(opt_t, upd), etc, comm=c)
         m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
                             data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", H, H == 1, S)]))
         m.add(hugectr.SparseEmbedding(et, 1, vec, comb, "emb", "data1", slot_size_array=vocab))
@@ -798,6 +800,76 @@ def run_legacy_equiv(kind="distributed", optimizer="adam", seed=0, comm=None):
     comm.barrier()
     if rank == 0:
         print("LEGACY_EQUIV_OK", seed)
+
+
+def run_resume(tmpdir, legacy=False, comm=None):
+    """multi-rank exact resume: N ranks train 3 steps, snapshot, train 2 more; a fresh N-rank model resumes from the
+    snapshot and trains the same 2 steps -- dense weights, embedding tables and the loss must be BIT-identical"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.models.legacy import build_deepfm
+    comm = comm or Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+
+    def mk():
+        if legacy:
+            m = build_deepfm(batchsize=32 * world, vvgpu=[list(range(world))], slot_sizes=[30, 12, 50, 7], workspace_mb=2,
+                             mixed=False, comm=comm, max_eval_batches=1, seed=5)
+            for c in m.dense_layers:
+                if c.layer_type == hugectr.Layer_t.Dropout:
+                    c.dropout_rate = 0.0
+        else:
+            sizes, hot = [400, 30, 50, 900, 120, 7], [3, 1, 1, 4, 2, 1]
+            sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]
+            sm[world - 1][3] = 1
+            plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+            m = build_dlrm_dcnv2(batchsize=32 * world, num_gpus=world, table_sizes=sizes, multi_hot=hot, ev_size=8, lr=0.02,
+                                 mixed=False, optimizer="adagrad", bottom=(16, 8), top=(16, 1), cross_layers=1,
+                                 projection_dim=4, use_cuda_graph=False, shard_plan=plan, comm=comm, seed=5)
+        m.compile()
+        return m
+    a = mk()
+    pool = a.reader_train.pool
+    for i in range(3):
+        a.train_on_host_batch(pool[i % len(pool)])
+    pre = os.path.join(tmpdir, "snap")
+    a.save_params_to_files(pre, 3)
+    comm.barrier()
+    for i in range(3, 5):
+        a.train_on_host_batch(pool[i % len(pool)])
+    b = mk()
+    assert b.resume(pre) == 3
+    for i in range(3, 5):
+        b.train_on_host_batch(pool[i % len(pool)])
+    # static tables: bit-identical.  Hash embeddings hand out rows in arrival order, which a reload does not reproduce;
+    # reductions over duplicate keys then add in another order -> equal to rounding, not to the bit
+    tol = 1e-5 if legacy else 0.0
+    err = float((a.arena.weights - b.arena.weights).abs().max())
+    assert err <= tol, f"dense weights differ after resume: {err}"
+    assert abs(a.get_current_loss() - b.get_current_loss()) <= tol
+    if legacy:
+        for ra, rb in zip(a.legacy_train, b.legacy_train):
+            da, db = os.path.join(tmpdir, f"a_{ra.name}"), os.path.join(tmpdir, f"b_{rb.name}")
+            ra.dump_parameters(da)
+            rb.dump_parameters(db)
+            if rank == 0:
+                import numpy as np
+                ka, kb = np.fromfile(da + "/key", "<i8"), np.fromfile(db + "/key", "<i8")
+                va = np.fromfile(da + "/emb_vector", "<f4").reshape(len(ka), -1)[np.argsort(ka)]
+                vb = np.fromfile(db + "/emb_vector", "<f4").reshape(len(kb), -1)[np.argsort(kb)]
+                assert np.array_equal(np.sort(ka), np.sort(kb)) and float(np.abs(va - vb).max()) <= 1e-5, \
+                    "legacy table differs after resume"
+    else:
+        for ea, eb in zip(a.ebcs_train, b.ebcs_train):
+            for name in ea.tmap:
+                for pa_, pb_ in zip(ea.dump_table_local(name), eb.dump_table_local(name)):
+                    assert torch.equal(pa_[0], pb_[0]) and torch.equal(pa_[1], pb_[1]), f"table {name} differs after resume"
+                    for sa, sb in zip(pa_[3] or [], pb_[3] or []):
+                        assert (sa is None and sb is None) or torch.equal(sa, sb), \
+                            f"optimizer state of table {name} differs after resume"
+    comm.barrier()
+    if rank == 0:
+        print("RESUME_OK")
 
 
 def run_ckpt(tmpdir, comm=None):
@@ -968,6 +1040,8 @@ if __name__ == "__main__":
             run_fuzz(sd)
     if what == "legacy":
         run_legacy()
+    if what == "resume":
+        run_resume(sys.argv[2], sys.argv[3] == "legacy")
     if what == "legacy_equiv":
         for sd in sys.argv[4].split(","):
             run_legacy_equiv(sys.argv[2], sys.argv[3], sd)

@@ -230,3 +230,10 @@ def test_model_with_unique_compression_equals_single_process_gloo():
 def test_legacy_embeddings_equal_single_process_gloo(kind):
     out = _run(2, ["legacy_equiv", kind, "adam", "11,12"], 29761, env={"CUDA_VISIBLE_DEVICES": ""})
     assert out.count("LEGACY_EQUIV_OK") == 2
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("legacy", ["ebc", "legacy"])
+def test_multi_rank_exact_resume_gloo(legacy, tmp_path):
+    out = _run(2, ["resume", str(tmp_path), legacy], 29771, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert "RESUME_OK" in out

@@ -230,3 +230,23 @@ def test_emu_embedding_training_cache_multi_rank_equals_single_process_cpu(mode,
     monkeypatch.setenv("HCTR_TEST_ETC", mode)
     run_ranks(2, lambda c: W.run_legacy_equiv("distributed", "adam", 201, comm=c), device=CPU, p2p=False)
     run_ranks(3, lambda c: W.run_legacy_equiv("localized", "adagrad", 303, comm=c), device=CPU, p2p=False)
+
+
+@pytest.mark.parametrize("update", ["global", "lazy"])
+def test_emu_legacy_global_update_equals_single_process_cpu(update, monkeypatch):
+    """Update_t.Global / LazyGlobal Adam on hash embeddings: N ranks == 1 process.  (Caught a real bug: batch entries a
+    rank does not own used to write `untouched` into row 0's flag, so row 0 was swept again after its real update.)"""
+    monkeypatch.setenv("HCTR_TEST_UPDATE", update)
+    run_ranks(2, lambda c: W.run_legacy_equiv("distributed", "adam", 201, comm=c), device=CPU, p2p=False)
+    run_ranks(3, lambda c: W.run_legacy_equiv("localized", "adam", 302, comm=c), device=CPU, p2p="force")
+    run_ranks(4, lambda c: W.run_legacy_equiv("distributed", "adam", 403, comm=c), device=CPU, p2p="force")
+
+
+@pytest.mark.parametrize("legacy", [False, True])
+def test_emu_multi_rank_exact_resume_cpu(legacy, tmp_path):
+    """N ranks: snapshot after 3 steps, 2 more steps == fresh N-rank model resumed from the snapshot + the same 2 steps
+    (bit-identical for static tables; to rounding for hash embeddings, whose row order a reload does not reproduce)"""
+    for i, (world, p2p) in enumerate(((2, False), (4, "force"))):
+        d = tmp_path / f"r{i}"
+        d.mkdir()
+        run_ranks(world, lambda c: W.run_resume(str(d), legacy, comm=c), device=CPU, p2p=p2p)
