@@ -250,3 +250,64 @@ def test_emu_multi_rank_exact_resume_cpu(legacy, tmp_path):
         d = tmp_path / f"r{i}"
         d.mkdir()
         run_ranks(world, lambda c: W.run_resume(str(d), legacy, comm=c), device=CPU, p2p=p2p)
+
+
+# ----------------------------------------------------------------------------- checkpoint re-sharding N -> M ranks
+def _reshard_case(n_save, n_load, tmpdir, p2p_load=False):
+    """train + snapshot on ``n_save`` ranks under plan A (row-sharded + table-wise + data-parallel tables); ``n_load``
+    ranks under plan B (everything model parallel, column x row split when the rank count is even) resume from it:
+    every table and its AdaGrad state must come back unchanged, key by key"""
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    cpu = CPU
+    d, saved = str(tmpdir), {}
+    sizes, hot = [400, 30, 50, 900, 120, 7], [3, 1, 1, 4, 2, 1]
+    def mk(comm, plan_kind):
+        world = comm.world_size
+        if plan_kind == "a":
+            sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]; sm[world - 1][3] = 1
+            plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+        else:       # everything model parallel: table 0 column+row split, 3 row split, rest table-wise
+            sm = [[1, 0, 0, 1, 0, 0] for _ in range(world)]
+            for i, t in enumerate((1, 2, 4, 5)): sm[i % world][t] = 1
+            plan = (sm, [("mp", [("0", 2) if world % 2 == 0 else "0", "1", "2", "3", "4", "5"])])
+        m = build_dlrm_dcnv2(batchsize=32 * world, num_gpus=world, table_sizes=sizes, multi_hot=hot, ev_size=8, lr=0.02,
+                             mixed=False, optimizer="adagrad", bottom=(16, 8), top=(16, 1), cross_layers=1,
+                             projection_dim=4, use_cuda_graph=False, shard_plan=plan, comm=comm, seed=5)
+        m.compile(); return m
+    def full_tables(m, comm):
+        """gather (key -> vector, state) of every table on every rank"""
+        out = {}
+        for e in m.ebcs_train:
+            for name in e.tmap:
+                parts = comm.all_gather_object([(k, w, c0, [None if s is None else s for s in (sts or [])], kind) for (k, w, c0, sts, kind) in e.dump_table_local(name)])
+                ev = e.tmap[name].ev_size; n = e.tmap[name].max_vocabulary_size
+                W = torch.zeros(n, ev); S = torch.zeros(n, ev)
+                for rp in parts:
+                    for (k, w, c0, sts, kind) in rp:
+                        if len(k):
+                            W[k, c0:c0 + w.shape[1]] = w
+                            if sts and sts[0] is not None: S[k, c0:c0 + w.shape[1]] = sts[0].float()
+                out[name] = (W, S)
+        return out
+    def save_body(comm):
+        m = mk(comm, "a"); pool = m.reader_train.pool
+        for i in range(3): m.train_on_host_batch(pool[i])
+        m.save_params_to_files(os.path.join(d, "s"), 3); comm.barrier()
+        t = full_tables(m, comm)
+        if comm.rank == 0: saved.update(t)
+    def load_body(comm):
+        m = mk(comm, "b"); m.resume(os.path.join(d, "s"))
+        t = full_tables(m, comm)
+        if comm.rank == 0:
+            for name in saved:
+                dw = float((t[name][0] - saved[name][0]).abs().max()); ds = float((t[name][1] - saved[name][1]).abs().max())
+                assert dw == 0.0 and ds == 0.0, (name, dw, ds)
+        return True
+
+    run_ranks(n_save, save_body, device=CPU, p2p=False)
+    run_ranks(n_load, load_body, device=CPU, p2p=p2p_load)
+
+
+@pytest.mark.parametrize("n_save,n_load,p2p", [(2, 3, False), (4, 2, "force"), (3, 4, False)])
+def test_emu_checkpoint_resharding_between_rank_counts_cpu(n_save, n_load, p2p, tmp_path):
+    _reshard_case(n_save, n_load, tmp_path, p2p)
