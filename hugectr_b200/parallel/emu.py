@@ -130,7 +130,31 @@ class EmuComm:
         pass
 
     def set_topology(self, gpus_per_node: int):
-        self.num_nodes, self.local_size = 1, self.world_size
+        """logical nodes (rank = node * gpus_per_node + local id, like ``Comm.set_topology``): one intra-node and
+        one inter-node emulated communicator per rank, so the hierarchical exchange runs on emulated ranks too"""
+        L = int(gpus_per_node)
+        if getattr(self, "_topo", None) == L:
+            return
+        self._topo = L
+        if self.world_size == 1 or L <= 0 or L >= self.world_size or self.world_size % L:
+            self.num_nodes, self.local_size = 1, self.world_size
+            return
+        nodes = self.world_size // L
+        node, lid = self.rank // L, self.rank % L
+        # the first member of every group creates its fabric; everybody learns all of them
+        made = (EmuFabric(L, self.device) if lid == 0 else None, EmuFabric(nodes, self.device) if node == 0 else None)
+        allf = self.fabric.exchange(self.rank, made)
+        self.intra = EmuComm(allf[node * L][0], lid, p2p=False)
+        self.inter = EmuComm(allf[lid][1], node, p2p=False)
+        self.num_nodes, self.local_size, self.node, self.local_id = nodes, L, node, lid
+
+    def hier_all_to_all_sum(self, send: torch.Tensor) -> torch.Tensor:
+        from .comm import Comm
+        return Comm.hier_all_to_all_sum(self, send)
+
+    def hier_all_gather(self, out: torch.Tensor, inp: torch.Tensor):
+        from .comm import Comm
+        return Comm.hier_all_gather(self, out, inp)
 
     # ---- symmetric heap look-alike (``comm.heap`` is the communicator itself)
     @property

@@ -311,3 +311,11 @@ def _reshard_case(n_save, n_load, tmpdir, p2p_load=False):
 @pytest.mark.parametrize("n_save,n_load,p2p", [(2, 3, False), (4, 2, "force"), (3, 4, False)])
 def test_emu_checkpoint_resharding_between_rank_counts_cpu(n_save, n_load, p2p, tmp_path):
     _reshard_case(n_save, n_load, tmp_path, p2p)
+
+
+@pytest.mark.parametrize("world,gpus_per_node,seed", [(4, 2, 501), (6, 3, 602), (6, 2, 703)])
+def test_emu_hierarchical_exchange_random_plans_cpu(world, gpus_per_node, seed, monkeypatch):
+    """node-aware two-stage exchange on logical nodes (emulated intra- / inter-node communicators): whole model ==
+    single process under a random placement (table / row / column-wise, dp)"""
+    monkeypatch.setenv("HCTR_TEST_PLAN_SEED", str(seed))
+    run_ranks(world, lambda c: W.run_equiv("adagrad" if seed % 2 else "sgd", gpus_per_node, comm=c), device=CPU, p2p=False)
