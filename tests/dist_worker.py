@@ -224,6 +224,77 @@ def run_sok(comm=None):
         print("SOK_OK")
 
 
+def run_sok_fuzz(seed, comm=None):
+    """sok.lookup_sparse over a random mix of variables (distributed / localized / dynamic with scrambled 64-bit keys),
+    random hotness, combiners, optional per-id weights, padded bags: forward, sparse backward and an AdaGrad step must
+    equal dense single-process embeddings"""
+    import random
+    import hugectr_b200 as hugectr
+    from hugectr_b200 import sok
+    comm = comm or Comm.init_from_env()
+    world, rank = comm.world_size, comm.rank
+    sok.init(comm)
+    rnd = random.Random(int(seed))
+    gen = torch.Generator().manual_seed(int(seed))
+    b = 5
+    nv = rnd.randint(1, 3)
+    scramble = lambda k: k * 1000003 + 17
+    vars_, fulls, kinds, ids_all, wts_all, combs = [], [], [], [], [], []
+    for i in range(nv):
+        vocab, dim = rnd.randint(6, 40), rnd.choice([4, 8])
+        full = torch.randn(vocab, dim, generator=gen)
+        kind = rnd.choice(["distributed", "localized", "dynamic"])
+        if kind == "distributed":
+            v = sok.Variable(initial_value=full.clone(), name=f"fz{seed}_{i}")
+        elif kind == "localized":
+            v = sok.Variable(initial_value=full.clone(), mode=f"localized:{rnd.randrange(world)}", name=f"fz{seed}_{i}")
+        else:
+            v = sok.DynamicVariable(dim, var_type="hbm", init_capacity=64, max_capacity=256, name=f"fz{seed}_{i}")
+            sok.assign(v, scramble(torch.arange(vocab)), full)
+        H = rnd.randint(1, 4)
+        ids = torch.randint(0, vocab, (b * world, H), generator=gen)
+        if H > 1:
+            n = torch.randint(1, H + 1, (b * world,), generator=gen)
+            ids = torch.where(torch.arange(H).view(1, -1) < n.view(-1, 1), ids, torch.full_like(ids, -1))
+        w = torch.rand(b * world, H, generator=gen) + 0.1 if rnd.random() < 0.4 else None
+        vars_.append(v); fulls.append(full); kinds.append(kind); ids_all.append(ids); wts_all.append(w)
+        combs.append(rnd.choice(["sum", "mean"]))
+    use_w = all(w is not None for w in wts_all)
+    loc = lambda t: t[rank * b:(rank + 1) * b]
+    feed = [loc(scramble(i_) * (i_ >= 0) + (-1) * (i_ < 0)) if k == "dynamic" else loc(i_) for i_, k in zip(ids_all, kinds)]
+    outs = sok.lookup_sparse(vars_, feed, sp_weights=[loc(w) for w in wts_all] if use_w else None, combiners=combs)
+    gouts = [torch.randn(b * world, f.shape[1], generator=gen) for f in fulls]
+    loss = sum((o * loc(g)).sum() for o, g in zip(outs, gouts))
+    loss.backward()
+    opt = sok.OptimizerWrapper(hugectr.Optimizer_t.AdaGrad, lr=0.1, initial_accu_value=0.0)
+    opt.apply_gradients(vars_)
+    for i in range(nv):
+        Wt = fulls[i].clone().requires_grad_(True)
+        ids = ids_all[i]
+        m = (ids >= 0).float()
+        wm = m * wts_all[i] if use_w else m
+        ref = (Wt[ids.clamp(min=0)] * wm.unsqueeze(-1)).sum(1)
+        if combs[i] == "mean":
+            ref = ref / wm.sum(1, keepdim=True).clamp(min=1e-12)
+        torch.testing.assert_close(outs[i].detach(), loc(ref).detach(), atol=1e-5, rtol=1e-5)
+        (ref * gouts[i]).sum().backward()
+        g = Wt.grad
+        W2 = Wt.detach() - 0.1 * g / ((g * g).sqrt() + 1e-7)        # first AdaGrad step from a zero accumulator
+        if kinds[i] == "dynamic":
+            k, wv = sok.export(vars_[i])
+            orig = (k - 17) // 1000003
+        else:
+            k = vars_[i].global_keys().cpu()
+            wv, orig = vars_[i].weight.float().cpu(), k
+        touched = (g.abs().sum(1) > 0)
+        sel = touched[orig]
+        torch.testing.assert_close(wv[sel], W2[orig][sel], atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(wv[~sel], fulls[i][orig][~sel], atol=0, rtol=0)       # untouched rows did not move
+    comm.barrier()
+    if rank == 0:
+        print("SOK_FUZZ_OK", seed)
+
+
 def run_fuzz(seed, comm=None):
     """randomised collection: random tables / hotness / combiners (sum, mean, concat) / batch- or
     feature-major tops / padded bags / random sharding plan (table-wise, row-wise, column-wise, dp),
@@ -1028,6 +1099,9 @@ if __name__ == "__main__":
         run_dynamic()
     if what == "sok":
         run_sok()
+    if what == "sok_fuzz":
+        for sd in sys.argv[2].split(","):
+            run_sok_fuzz(sd)
     if what == "ebcio":
         for sd in sys.argv[3].split(","):
             d = os.path.join(sys.argv[2], sd)

@@ -237,3 +237,11 @@ def test_legacy_embeddings_equal_single_process_gloo(kind):
 def test_multi_rank_exact_resume_gloo(legacy, tmp_path):
     out = _run(2, ["resume", str(tmp_path), legacy], 29771, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "RESUME_OK" in out
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_sok_randomised_lookups_against_dense_oracle_gloo(nproc):
+    """random mixes of distributed / localized / dynamic SOK variables, hotness, combiners, weights, padded bags"""
+    out = _run(nproc, ["sok_fuzz", "1001,1002,1003,1004,1005,1006"], 29781, env={"CUDA_VISIBLE_DEVICES": ""})
+    assert out.count("SOK_FUZZ_OK") == 6
