@@ -171,6 +171,20 @@ class RawAsyncReader(IDataReader):
         self.stop()
         self.start()
 
+    def _global_valid(self) -> int:
+        """valid samples of the GLOBAL batch just handed out -- the same number on every rank (a rank whose slice is
+        full cannot tell from its own count that the batch is the incomplete last one of the epoch; ranks disagreeing
+        on that would skip / train different steps and hang in the next collective)"""
+        gb = self.b * self.world
+        if getattr(self, "_nsamp", None) is None:          # (reset by stop(): a new handle starts a new epoch)
+            f = self.lib.hctr_rawd_num_samples if self.device_split else self.lib.hctr_raw_num_samples
+            f.restype, f.argtypes = C.c_longlong, [C.c_void_p]
+            self._nsamp, self._bi = int(f(self.h)), 0
+        bpe = max(1, -(-self._nsamp // gb))
+        i = self._bi % bpe
+        self._bi += 1
+        return int(min(gb, self._nsamp - i * gb))
+
     def read_a_batch(self):
         if self.h is None:
             self.start()
@@ -184,8 +198,7 @@ class RawAsyncReader(IDataReader):
             if valid.value < 0:
                 return None
             nv = valid.value
-            self.current_batchsize = self.b * self.world if nv == self.b else \
-                max(0, min(self.b * self.world, self.rank * self.b + nv)) if nv > 0 else self.rank * self.b
+            self.current_batchsize = self._global_valid()
             self._last = HostBatch(None, None, None, None, nv, raw=self.raw_slots[idx], raw_skew=skew.value,
                                    splitter=self.split)
             return self._last
@@ -194,9 +207,7 @@ class RawAsyncReader(IDataReader):
             return None
         lab, den, keys = self.slots[idx]
         nv = valid.value
-        # global batch size seen by all ranks (last batch may be incomplete)
-        self.current_batchsize = self.b * self.world if nv == self.b else \
-            max(0, min(self.b * self.world, self.rank * self.b + nv)) if nv > 0 else self.rank * self.b
+        self.current_batchsize = self._global_valid()
         self._last = HostBatch(lab, den, keys, None, nv)
         return self._last
 
@@ -205,6 +216,7 @@ class RawAsyncReader(IDataReader):
             (self.lib.hctr_rawd_close if self.device_split else self.lib.hctr_raw_close)(self.h)
             self.h = None
             self.started = False
+            self._nsamp = None
 
     def __del__(self):
         try:

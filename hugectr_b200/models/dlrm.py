@@ -32,7 +32,7 @@ def _solver(batchsize, num_gpus, lr, mixed, scaler, **kw):
     return hugectr.CreateSolver(
         model_name=kw.pop("model_name", "dlrm"), seed=kw.pop("seed", 0), max_eval_batches=kw.pop("max_eval_batches", 10),
         batchsize_eval=kw.pop("batchsize_eval", batchsize), batchsize=batchsize,
-        vvgpu=vvgpu, repeat_dataset=True, lr=lr, warmup_steps=kw.pop("warmup_steps", 1),
+        vvgpu=vvgpu, repeat_dataset=kw.pop("repeat_dataset", True), lr=lr, warmup_steps=kw.pop("warmup_steps", 1),
         use_mixed_precision=mixed, scaler=scaler, use_cuda_graph=kw.pop("use_cuda_graph", True),
         train_intra_iteration_overlap=True, train_inter_iteration_overlap=True,
         use_embedding_collection=True, grouped_all_reduce=True, gen_loss_summary=True,

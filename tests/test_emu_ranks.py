@@ -319,3 +319,48 @@ def test_emu_hierarchical_exchange_random_plans_cpu(world, gpus_per_node, seed, 
     single process under a random placement (table / row / column-wise, dp)"""
     monkeypatch.setenv("HCTR_TEST_PLAN_SEED", str(seed))
     run_ranks(world, lambda c: W.run_equiv("adagrad" if seed % 2 else "sgd", gpus_per_node, comm=c), device=CPU, p2p=False)
+
+
+# ----------------------------------------------------------------------------- epoch mode, data set not divisible by the batch
+@pytest.mark.parametrize("world", [2, 4])
+def test_emu_epoch_mode_with_incomplete_last_batch_equals_single_process_cpu(world, tmp_path):
+    """RawAsync file of 1000 training / 333 evaluation samples, global batch 64, two epochs + a full evaluation pass:
+    N ranks == 1 process (loss, AUC, dense weights).  (Caught a real bug: a rank whose own slice of the last batch was
+    full reported the batch as complete, the ranks then disagreed on dropping it and met in different collectives.)"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.generator import DataGenerator, DataGeneratorParams
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.parallel.comm import Comm
+    cpu, d = CPU, str(tmp_path)
+    sizes, hot = [300, 40, 1000, 7], [3, 1, 5, 2]
+    ntr, nev = 1000, 333                       # neither divisible by the global batch
+    gp = DataGeneratorParams(hugectr.DataReaderType_t.Raw, 1, 13, 4, False, os.path.join(d, "t.bin"), os.path.join(d, "v.bin"),
+                             sizes, nnz_array=hot, num_samples=ntr, eval_num_samples=nev, float_label_dense=True, num_threads=2)
+    DataGenerator(gp).generate()
+    def run(comm):
+        world = comm.world_size
+        m = build_dlrm_dcnv2(batchsize=64, batchsize_eval=64, num_gpus=world, table_sizes=sizes, multi_hot=hot, ev_size=8, mixed=False,
+                             bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1, lr=0.05, optimizer="sgd",
+                             source=[gp.source], comm=comm, use_cuda_graph=False, repeat_dataset=False, seed=2,
+                             max_eval_batches=100)
+        m.reader_params.eval_source = gp.eval_source
+        m.reader_params.num_samples, m.reader_params.eval_num_samples = ntr, nev
+        m.reader_params.float_label_dense = True
+        m.compile()
+        m.fit(num_epochs=2, display=1000, eval_interval=1000, snapshot=10**9)
+        m.eval_all = None
+        # full evaluation pass over the eval set
+        m.reader_eval.set_source(None)
+        n = 0
+        for mt in m.metrics: mt[2].reset() if hasattr(mt[2], "reset") else None
+        while m.eval():
+            n += 1
+            if n > 50: break
+        res = dict(m.get_eval_metrics())
+        return (round(m.get_current_loss(), 6), {k: round(float(v), 6) for k, v in res.items()}, n, float(m.arena.weights.double().sum()))
+
+    one = run(Comm.single(CPU))
+    res = run_ranks(world, run, device=CPU, p2p=False)
+    assert res[0][0] == one[0] and res[0][1] == one[1] and res[0][2] == one[2], (one, res[0])
+    assert abs(res[0][3] - one[3]) < 1e-5
+    assert one[2] == 6          # 333 samples / 64 -> 6 evaluation batches, the last one incomplete
