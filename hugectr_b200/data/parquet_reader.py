@@ -81,7 +81,9 @@ class ParquetReader(IDataReader):
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.thread = None
         self._stop = threading.Event()
-        self.drop_incomplete = model.solver.drop_incomplete_batch
+        # the incomplete last batch of an epoch is always DELIVERED (evaluation counts every sample; for training
+        # `Solver.drop_incomplete_batch` is applied by Model._train_step, like for the Raw / Norm readers)
+        self.drop_incomplete = False
         self._device = getattr(model, "device", None)
 
     # -------------------------------------------------------------- producer

@@ -364,3 +364,61 @@ def test_emu_epoch_mode_with_incomplete_last_batch_equals_single_process_cpu(wor
     assert res[0][0] == one[0] and res[0][1] == one[1] and res[0][2] == one[2], (one, res[0])
     assert abs(res[0][3] - one[3]) < 1e-5
     assert one[2] == 6          # 333 samples / 64 -> 6 evaluation batches, the last one incomplete
+
+
+@pytest.mark.parametrize("fmt", ["parquet", "norm"])
+def test_emu_file_readers_epoch_mode_equal_single_process_cpu(fmt, tmp_path):
+    """Parquet / Norm readers + Distributed hash embedding, 666 training and 333 evaluation samples at global batch 64
+    (incomplete last batches), two epochs and a full evaluation pass: 2 and 4 ranks == 1 process"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.generator import DataGenerator, DataGeneratorParams
+    from hugectr_b200.parallel.comm import Comm
+    cpu, d = CPU, str(tmp_path)
+    T = hugectr.DataReaderType_t
+    kind = {"parquet": T.Parquet, "norm": T.Norm}[fmt]
+    slots = [50, 20, 30]
+    src, ev = (os.path.join(d, "fl.txt"), os.path.join(d, "fl_test.txt"))
+    gp = DataGeneratorParams(kind, 1, 3, 3, True, src, ev, slots, nnz_array=[2, 1, 3], num_files=2, eval_num_files=1,
+                             num_samples_per_file=333, check_type=hugectr.Check_t.Sum, num_threads=2)
+    DataGenerator(gp).generate()
+    def run(comm):
+        world = comm.world_size
+        solver = hugectr.CreateSolver(batchsize=64, batchsize_eval=64, lr=0.05, vvgpu=[list(range(world))], repeat_dataset=False,
+                                      i64_input_key=True, use_cuda_graph=False, max_eval_batches=100, seed=4)
+        rp = hugectr.DataReaderParams(kind, source=[src], eval_source=ev, check_type=hugectr.Check_t.Sum if fmt == "norm" else hugectr.Check_t.Non,
+                                      slot_size_array=slots)
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.SGD), comm=comm)
+        m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=3, dense_name="dense",
+                            data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", [2, 1, 3], False, 3)]))
+        m.add(hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash, 1, 4, "sum", "emb", "data1",
+                                      slot_size_array=slots))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Reshape, ["emb"], ["r"], leading_dim=12))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["r", "dense"], ["c"]))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+        m.compile()
+        # same start for the hash embedding: all keys preloaded with fixed vectors
+        import numpy as np
+        allk = np.arange(sum(slots), dtype="<i8"); g = torch.Generator().manual_seed(1)
+        if comm.rank == 0:
+            os.makedirs(os.path.join(d, "init"), exist_ok=True)
+            allk.tofile(os.path.join(d, "init", "key")); (torch.randn(len(allk), 4, generator=g) * 0.1).numpy().astype("<f4").tofile(os.path.join(d, "init", "emb_vector"))
+        comm.barrier()
+        m.load_sparse_weights([os.path.join(d, "init")])
+        w0 = m.arena.weights.clone(); comm.broadcast(w0, 0); m.arena.weights.copy_(w0); m.arena.sync_shadow()
+        torch.save(w0, os.path.join(d, "w0.pt")) if comm.rank == 0 and world == 1 else None
+        if world > 1:
+            m.arena.weights.copy_(torch.load(os.path.join(d, "w0.pt"))); m.arena.sync_shadow()
+        m.fit(num_epochs=2, display=1000, eval_interval=1000, snapshot=10**9)
+        m.reader_eval.set_source(None)
+        n = 0
+        while m.eval():
+            n += 1
+            if n > 50: break
+        res = dict(m.get_eval_metrics())
+        return (round(m.get_current_loss(), 5), {k: round(float(v), 5) for k, v in res.items()}, n, round(float(m.arena.weights.double().sum()), 5))
+
+    one = run(Comm.single(CPU))
+    assert one[2] == 6                       # every evaluation sample is seen: ceil(333 / 64) batches
+    for w in (2, 4):
+        assert run_ranks(w, run, device=CPU, p2p=False)[0] == one
