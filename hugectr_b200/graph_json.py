@@ -201,16 +201,25 @@ def model_to_json(model) -> dict:
                        "top": se.sparse_embedding_name, "sparse_embedding_hparam": hp,
                        "optimizer": (se.optimizer or model.opt_params).to_json()})
     for cfg in model.ebc_configs:
-        tabs = [{"name": t.name, "max_vocabulary_size": t.max_vocabulary_size, "ev_size": t.ev_size,
-                 "optimizer": t.opt_params.to_json() if t.opt_params else None}
-                for t in cfg.tables()]
+        tabs = []
+        for t in cfg.tables():
+            tj = {"name": t.name, "max_vocabulary_size": t.max_vocabulary_size, "ev_size": t.ev_size,
+                  "optimizer": t.opt_params.to_json() if t.opt_params else None}
+            if t.dynamic:
+                tj.update(init_capacity=t.init_capacity, max_capacity=t.max_capacity)
+            if t.init_param is not None and getattr(t.init_param, "up_bound", 0) > 0:
+                tj["init_up_bound"] = float(t.init_param.up_bound)
+            tabs.append(tj)
         lks = [{"tables": [t.name for t in lk["tables"]], "bottoms": lk["bottoms"], "top": lk["top"],
                 "combiners": lk["combiners"], "batch_major": lk["batch_major"]} for lk in cfg.lookups]
         layers.append({"type": "EmbeddingCollection", "tables": tabs, "lookups": lks,
                        "shard_matrix": cfg.shard_matrix,
                        "shard_strategy": [[k, [list(i) if isinstance(i, tuple) else i for i in items]]
                                           for k, items in (cfg.shard_strategy or [])],
-                       "use_exclusive_keys": cfg.use_exclusive_keys})
+                       "use_exclusive_keys": cfg.use_exclusive_keys,
+                       "comm_strategy": cfg.comm_strategy.name,
+                       "compression_strategy": {getattr(k, "name", str(k)): [str(x) if not isinstance(x, int) else x for x in v]
+                                                for k, v in (cfg.compression_strategy or {}).items()}})
     for c in model.dense_layers:
         if getattr(c, "_auto", False):
             continue
@@ -242,11 +251,17 @@ def add_from_json(model, graph: dict, include_dense_network: bool = True):
                                       j["bottom"], hp.get("slot_size_array", []),
                                       OptParamsPy.from_json(j["optimizer"]) if "optimizer" in j else None))
         elif t == "EmbeddingCollection":
-            tabs = {tt["name"]: EmbeddingTableConfig(
-                tt["name"], tt["max_vocabulary_size"], tt["ev_size"],
-                OptParamsPy.from_json(tt["optimizer"]) if tt.get("optimizer") else None)
-                for tt in j["tables"]}
-            cfg = EmbeddingCollectionConfig(j.get("use_exclusive_keys", False))
+            from .enums import CommunicationStrategy, CompressionStrategy
+            from .embedding.collection import InitParams
+            tabs = {}
+            for tt in j["tables"]:
+                kw = {k: tt[k] for k in ("init_capacity", "max_capacity") if k in tt}
+                ip = InitParams(up_bound=tt["init_up_bound"]) if "init_up_bound" in tt else None
+                tabs[tt["name"]] = EmbeddingTableConfig(
+                    tt["name"], tt["max_vocabulary_size"], tt["ev_size"],
+                    OptParamsPy.from_json(tt["optimizer"]) if tt.get("optimizer") else None, ip, **kw)
+            cfg = EmbeddingCollectionConfig(j.get("use_exclusive_keys", False),
+                                            CommunicationStrategy[j.get("comm_strategy", "Uniform")])
             for lk in j["lookups"]:
                 if lk["batch_major"]:
                     cfg.embedding_lookup([tabs[n] for n in lk["tables"]], lk["bottoms"], lk["top"],
@@ -257,7 +272,8 @@ def add_from_json(model, graph: dict, include_dense_network: bool = True):
             if j.get("shard_matrix") is not None:
                 ss = [(k, [tuple(i) if isinstance(i, list) else i for i in items])
                       for k, items in j["shard_strategy"]]
-                cfg.shard(j["shard_matrix"], ss)
+                comp = {CompressionStrategy[k]: v for k, v in (j.get("compression_strategy") or {}).items()}
+                cfg.shard(j["shard_matrix"], ss, comp or None)
             model.add(cfg)
         elif include_dense_network:
             model.add(dense_layer_from_json(j))

@@ -415,3 +415,47 @@ def test_sok_export_assign_read_and_evict_group_lookup():
     assert o1.shape == (3, 3) and o2.shape == (1, 2, 2)
     (o1.sum() + o2.sum()).backward()
     assert float(p1.grad[1].sum()) == 6.0 and float(p2.weight.grad[5].sum()) == 2.0
+
+
+def test_graph_json_round_trips_collection_extras(tmp_path):
+    """dynamic-table capacities, the initializer bound, the communication strategy and the per-table compression
+    strategy of an embedding collection survive graph_to_json -> construct_from_json"""
+    import json
+    import hugectr_b200 as hugectr
+    from hugectr_b200.embedding.collection import InitParams
+    from hugectr_b200.parallel.comm import Comm
+    cpu = Comm.single(torch.device("cpu"))
+
+    def solver():
+        return hugectr.CreateSolver(batchsize=16, batchsize_eval=16, lr=0.01, vvgpu=[[0]], use_cuda_graph=False)
+    rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.RawAsync, source=["synthetic"], eval_source="synthetic",
+                                  check_type=hugectr.Check_t.Non, slot_size_array=[100, 100])
+    m = hugectr.Model(solver(), rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.SGD), comm=cpu)
+    m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
+                        data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("a", 2, False, 1),
+                                                        hugectr.DataReaderSparseParam("b", 1, True, 1)]))
+    ebc = hugectr.EmbeddingCollectionConfig(comm_strategy=hugectr.CommunicationStrategy.Hierarchical)
+    ebc.embedding_lookup([hugectr.EmbeddingTableConfig("dyn", -1, 8, init_capacity=77, max_capacity=999),
+                          hugectr.EmbeddingTableConfig("st", 100, 8, init_param=InitParams(up_bound=0.25))],
+                         ["a", "b"], "emb", ["sum", "sum"])
+    ebc.shard([["dyn", "st"]], [("mp", ["dyn", "st"])],
+              compression_strategy={hugectr.CompressionStrategy.Unique: ["st"], hugectr.CompressionStrategy.Reduction: ["dyn"]})
+    m.add(ebc)
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["emb", "dense"], ["c"]))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+    m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+    m.compile()
+    p = str(tmp_path / "g.json")
+    m.graph_to_json(p)
+    j = [l for l in json.load(open(p))["layers"] if l["type"] == "EmbeddingCollection"][0]
+    assert j["comm_strategy"] == "Hierarchical" and j["compression_strategy"] == {"Unique": ["st"], "Reduction": ["dyn"]}
+    m2 = hugectr.Model(solver(), rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.SGD), comm=cpu)
+    m2.construct_from_json(p)
+    m2.compile()
+    c2 = m2.ebc_configs[0]
+    t = {x.name: x for x in c2.tables()}
+    assert t["dyn"].dynamic and (t["dyn"].init_capacity, t["dyn"].max_capacity) == (77, 999)
+    assert t["st"].init_param.up_bound == 0.25 and c2.comm_strategy == hugectr.CommunicationStrategy.Hierarchical
+    assert c2.compression_strategy == {hugectr.CompressionStrategy.Unique: ["st"], hugectr.CompressionStrategy.Reduction: ["dyn"]}
+    m2.train()
+    assert m2.get_current_loss() == m2.get_current_loss()
