@@ -422,3 +422,36 @@ def test_emu_file_readers_epoch_mode_equal_single_process_cpu(fmt, tmp_path):
     assert one[2] == 6                       # every evaluation sample is seen: ceil(333 / 64) batches
     for w in (2, 4):
         assert run_ranks(w, run, device=CPU, p2p=False)[0] == one
+
+
+def test_emu_dynamic_table_grows_on_one_rank_while_all_ranks_agree_cpu():
+    """`Model.fit` with a dynamic table that lives on rank 0 only and starts far too small: the display checkpoints grow
+    it, every rank learns about it (the graph re-capture is a rendezvous) and training continues in lock step"""
+    import hugectr_b200 as hugectr
+    cpu = CPU
+    def run(comm):
+        world = comm.world_size
+        solver = hugectr.CreateSolver(batchsize=32 * world, batchsize_eval=32 * world, lr=0.05, vvgpu=[list(range(world))], repeat_dataset=True,
+                                      max_eval_batches=2, use_cuda_graph=False)
+        rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.RawAsync, source=["synthetic:1.0"], eval_source="synthetic:1.0",
+                                      check_type=hugectr.Check_t.Non, slot_size_array=[5000, 300])
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.AdaGrad), comm=comm)
+        m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense",
+                            data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("k", 2, False, 1), hugectr.DataReaderSparseParam("q", 1, True, 1)]))
+        ebc = hugectr.EmbeddingCollectionConfig()
+        ebc.embedding_lookup([hugectr.EmbeddingTableConfig("t", -1, 8, init_capacity=16), hugectr.EmbeddingTableConfig("u", 300, 8)], ["k", "q"], "emb", ["sum", "sum"])
+        sm = [["t"] if g == 0 else [] for g in range(world)]; sm[world - 1] = sm[world - 1] + ["u"]
+        ebc.shard(sm, [("mp", ["t", "u"])])
+        m.add(ebc)
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["emb", "dense"], ["c"]))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+        m.compile()
+        m.fit(max_iter=40, display=5, eval_interval=20, snapshot=10**9)
+        rows = [sl["rows"] for g in m.ebcs_train[0].groups for sl in g.table_slices if sl["table"] == "t"]
+        return rows, round(m.get_current_loss(), 4)
+
+    for w, p2p in ((2, False), (3, "force")):
+        res = run_ranks(w, run, device=CPU, p2p=p2p)
+        assert res[0][0][0] > 16 and all(r[0] == [] for r in res[1:])
+        assert len({r[1] for r in res}) == 1
