@@ -113,7 +113,20 @@ def resolve_placement(cfg: EmbeddingCollectionConfig, num_gpus: int) -> Dict[str
             place[n] = TablePlacement("mp", [i % num_gpus])
         return place
     sm = cfg.shard_matrix
-    assert len(sm) == num_gpus, "shard_matrix must have one row per GPU"
+    if len(sm) != num_gpus:
+        # a plan written for another GPU count (a graph JSON of an 8-GPU training run opened by a single-GPU
+        # inference session, or a job restarted on a different machine): keep which tables are data parallel, place
+        # the model-parallel ones table-wise round robin.  Checkpoints load under any sharding, so nothing is lost.
+        from ..utils import logger
+        logger.warning(f"sharding plan has {len(sm)} GPU rows, the job runs {num_gpus}: re-planned "
+                       "(data-parallel tables kept, model-parallel tables table-wise round robin)")
+        dp = set()
+        for kind, items in (cfg.shard_strategy or []):
+            if kind == "dp":
+                dp |= {str(it[0] if isinstance(it, (tuple, list)) else it) for it in items}
+        for i, n in enumerate(names):
+            place[n] = TablePlacement("dp", list(range(num_gpus))) if n in dp else TablePlacement("mp", [i % num_gpus])
+        return place
     if any(isinstance(x, str) for row in sm for x in row):
         # the reference's form (embedding_collection.hpp:55-90, samples/dlrm/sharding/generate_plan.py):
         # row g lists the NAMES of the tables GPU g holds -> 0/1 matrix over the table order

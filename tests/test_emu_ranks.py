@@ -455,3 +455,39 @@ def test_emu_dynamic_table_grows_on_one_rank_while_all_ranks_agree_cpu():
         res = run_ranks(w, run, device=CPU, p2p=p2p)
         assert res[0][0][0] > 16 and all(r[0] == [] for r in res[1:])
         assert len({r[1] for r in res}) == 1
+
+
+def test_emu_checkpoint_of_a_multi_rank_run_serves_single_process_inference_cpu(tmp_path):
+    """graph JSON + snapshot of a 2-rank run (row-sharded + data-parallel tables) opened by a single-process inference
+    session: the stored 2-GPU plan is re-planned for one GPU and the predictions equal the training model's exactly"""
+    import numpy as np
+    import hugectr_b200 as hugectr
+    from hugectr_b200.inference import CreateInferenceSession, InferenceParams
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    cpu, d = CPU, str(tmp_path)
+    sizes, hot = [400, 30, 50, 900, 120, 7], [3, 1, 1, 4, 2, 1]
+    def run(comm):
+        world = comm.world_size
+        sm = [[1, 1, 1, 0, 1, 1] for _ in range(world)]; sm[world - 1][3] = 1
+        plan = (sm, [("mp", ["0", "3"]), ("dp", ["1", "2", "4", "5"])])
+        m = build_dlrm_dcnv2(batchsize=32 * world, batchsize_eval=32 * world, num_gpus=world, table_sizes=sizes, multi_hot=hot, ev_size=8, lr=0.02,
+                             mixed=False, optimizer="adagrad", bottom=(16, 8), top=(16, 1), cross_layers=1, projection_dim=4,
+                             use_cuda_graph=False, shard_plan=plan, comm=comm, seed=5)
+        m.compile()
+        for _ in range(4): m.train()
+        m.save_params_to_files(os.path.join(d, "m"), 4)
+        if comm.rank == 0: m.graph_to_json(os.path.join(d, "g.json"))
+        # predictions of this rank's slice of one eval batch
+        hb = m.reader_eval.read_a_batch(); m._load_batch(hb, False)
+        for e in m.ebcs_eval: e.forward(False)
+        m.net_eval.fprop(False)
+        pred = m.net_eval.loss_layers[0].pred.float().clone()
+        return hb.dense.clone(), hb.keys.clone(), pred
+
+    res = run_ranks(2, run, device=CPU, p2p=False)
+    sess = CreateInferenceSession(os.path.join(d, "g.json"), InferenceParams(
+        model_name="x", max_batchsize=32, dense_model_file=os.path.join(d, "m_dense_4.model"),
+        embedding_collection_path=os.path.join(d, "m_ebc_4")))
+    for dense, keys, pred in res:
+        p = sess.predict(dense.numpy(), keys.numpy())
+        assert float(np.abs(p.reshape(-1) - pred.numpy().reshape(-1)).max()) == 0.0
