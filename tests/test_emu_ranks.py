@@ -491,3 +491,47 @@ def test_emu_checkpoint_of_a_multi_rank_run_serves_single_process_inference_cpu(
     for dense, keys, pred in res:
         p = sess.predict(dense.numpy(), keys.numpy())
         assert float(np.abs(p.reshape(-1) - pred.numpy().reshape(-1)).max()) == 0.0
+
+
+@pytest.mark.parametrize("n_save,n_load", [(2, 3), (4, 2)])
+def test_emu_legacy_snapshot_resharding_between_rank_counts_cpu(n_save, n_load, tmp_path):
+    """Distributed hash embedding (DeepFM): snapshot of N ranks resumed on M ranks -- (key -> vector) and the Adam moments
+    (matched by key) are identical, and training continues"""
+    import numpy as np
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.legacy import build_deepfm
+    cpu, d, kind = CPU, str(tmp_path), "distributed"
+    def mk(comm):
+        world = comm.world_size
+        kw = {"embedding_type": hugectr.Embedding_t.LocalizedSlotSparseEmbeddingHash} if kind == "localized" else {}
+        m = build_deepfm(batchsize=24 * world, vvgpu=[list(range(world))], slot_sizes=[30, 12, 50, 7], workspace_mb=2, mixed=False, comm=comm, max_eval_batches=1, seed=5, **kw)
+        m.compile(); return m
+    def dump(m, comm, tag):
+        out = {}
+        for rt in m.legacy_train:
+            p, o = os.path.join(d, f"{tag}_{rt.name}"), os.path.join(d, f"{tag}_{rt.name}_opt")
+            rt.dump_parameters(p); rt.dump_opt_states(o)
+            if comm.rank == 0:
+                k = np.fromfile(p + "/key", "<i8"); v = np.fromfile(p + "/emb_vector", "<f4").reshape(len(k), -1)
+                st = np.fromfile(o, "<f4"); ns = st.size // max(1, v.size); st = st.reshape(ns, len(k), -1)
+                idx = np.argsort(k); out[rt.name] = (k[idx], v[idx], st[:, idx])
+        return out
+    saved = {}
+    def save_body(comm):
+        m = mk(comm)
+        for _ in range(3): m.train()
+        m.save_params_to_files(os.path.join(d, "s"), 3); comm.barrier()
+        t = dump(m, comm, "a")
+        if comm.rank == 0: saved.update(t)
+    def load_body(comm):
+        m = mk(comm); assert m.resume(os.path.join(d, "s")) == 3
+        t = dump(m, comm, "b")
+        if comm.rank == 0:
+            for n in saved:
+                assert np.array_equal(saved[n][0], t[n][0]) and np.array_equal(saved[n][1], t[n][1]), (n, "table")
+                assert saved[n][2].shape == t[n][2].shape and np.array_equal(saved[n][2], t[n][2]), (n, "opt states")
+                assert saved[n][2].shape[0] >= 1 and np.abs(saved[n][2]).max() > 0
+        m.train(); return True
+
+    run_ranks(n_save, save_body, device=CPU, p2p=False)
+    run_ranks(n_load, load_body, device=CPU, p2p=False)
