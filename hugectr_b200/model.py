@@ -731,6 +731,7 @@ class Model:
         self._load_batch(hb, False)
         self._eval_pipeline().run_graph() if self._eval_graph_ok() else self._eval_pipeline().run()
         raw = self._raw_metrics()
+        self._eval_pending = getattr(self, "_eval_pending", 0) + 1
         for (_, _, m) in self.metrics:
             m.set_current_batch_size(self.reader_eval.get_current_batchsize())
             m.local_reduce(raw)
@@ -775,7 +776,14 @@ class Model:
                 MetricsRawType.Label: label[:nvalid]}
 
     def get_eval_metrics(self):
-        return [(k.name, m.finalize_metric()) for (k, _, m) in self.metrics]
+        """(name, value) of every metric over the evaluation batches since the previous call (collective on several
+        ranks).  Called again without new ``eval()`` batches -- e.g. after ``fit`` -- it returns the values of the
+        last evaluation instead of finalising empty accumulators."""
+        if getattr(self, "_eval_pending", 0) == 0 and getattr(self, "_last_eval_metrics", None) is not None:
+            return list(self._last_eval_metrics)
+        res = [(k.name, m.finalize_metric()) for (k, _, m) in self.metrics]
+        self._last_eval_metrics, self._eval_pending = res, 0
+        return res
 
     def get_current_loss(self) -> float:
         v = self.net_train.loss_value().detach().float().clone()

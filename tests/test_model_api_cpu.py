@@ -91,3 +91,22 @@ def test_compile_with_loss_weights():
     total = m.get_current_loss()
     parts = [float(l.outputs[0].data) for l in m.net_train.loss_layers]
     assert abs(total - sum(parts)) < 1e-5
+
+
+def test_get_eval_metrics_after_fit_returns_the_last_evaluation():
+    """`fit` finalises the metrics at every evaluation; asking again afterwards returns those values rather than the
+    result of finalising empty accumulators; new `eval()` batches start a new evaluation"""
+    import torch
+    from hugectr_b200.models.dlrm import build_dlrm_dcnv2
+    from hugectr_b200.parallel.comm import Comm
+    m = build_dlrm_dcnv2(batchsize=32, batchsize_eval=48, num_gpus=1, table_sizes=[50, 20], multi_hot=[2, 1], ev_size=8,
+                         mixed=False, bottom=(16, 8), top=(16, 1), projection_dim=4, cross_layers=1, use_cuda_graph=False,
+                         comm=Comm.single(torch.device("cpu")), max_eval_batches=3)
+    m.compile()
+    m.fit(max_iter=4, display=2, eval_interval=2, snapshot=10**9)
+    a = dict(m.get_eval_metrics())
+    assert 0.0 < a["AUC"] < 1.0 and dict(m.get_eval_metrics()) == a          # stable until new batches arrive
+    for _ in range(2):
+        assert m.eval()
+    b = dict(m.get_eval_metrics())
+    assert 0.0 < b["AUC"] < 1.0 and b != a
