@@ -308,10 +308,10 @@ class SparseEmbeddingRuntime:
             alive = torch.arange(n) < int(self.hash.size())
         # rows of this step: every write stores True (entries that are not mine go to a spare slot behind the
         # table) -- duplicates are harmless and no row's flag depends on the order of conflicting writes
-        touched = torch.zeros(self.max_rows + 1, dtype=torch.bool, device=self.device)
+        touched = torch.zeros(self.max_rows + 1, dtype=torch.int32, device=self.device)
         r = self.rows_all.reshape(-1)
-        touched.index_fill_(0, torch.where(r >= 0, r, torch.full_like(r, self.max_rows)), True)
-        touched = touched[:n] | ~alive          # never-allocated rows are left alone
+        touched.index_fill_(0, torch.where(r >= 0, r, torch.full_like(r, self.max_rows)), 1)
+        touched = (touched[:n] > 0) | ~alive    # never-allocated rows are left alone
         unt = (~touched).unsqueeze(1)
         w = self.table.view(-1, vec)[:n]
         s0 = self.s0.view(-1, vec)[:n]
