@@ -125,7 +125,7 @@ class HostParameterServer:
             lib.hctr_ps_dump.restype = ll
             lib.hctr_ps_gather.argtypes = [vp, vp, ll, ll, vp]
             lib.hctr_ps_scatter.argtypes = [vp, vp, ll, ll, vp]
-            lib.hctr_ps_init_rows.argtypes = [vp, vp, ll, C.c_int, C.c_float, C.c_ulonglong]
+            lib.hctr_ps_init_rows.argtypes = [vp, vp, vp, ll, C.c_int, C.c_float, C.c_ulonglong]
             self._lib = lib
             self._h = lib.hctr_ps_create()
         except Exception:  # pragma: no cover - no compiler available
@@ -151,9 +151,10 @@ class HostParameterServer:
                 raise RuntimeError("HostParameterServer capacity exceeded")
             if created > 0:
                 nr = rows[is_new.bool()].contiguous()
-                # counter-based initializer in the row movers' thread pool (value of a cell = f(seed, row, column))
-                self._lib.hctr_ps_init_rows(self.w.data_ptr(), nr.data_ptr(), nr.numel(), self.ev, float(self.bound),
-                                            int(self._seed) & 0xFFFFFFFFFFFFFFFF)
+                nk = keys[is_new.bool()].contiguous()
+                # counter-based initializer in the row movers' thread pool (value of a cell = f(seed, key, column))
+                self._lib.hctr_ps_init_rows(self.w.data_ptr(), nr.data_ptr(), nk.data_ptr(), nr.numel(), self.ev,
+                                            float(self.bound), int(self._seed) & 0xFFFFFFFFFFFFFFFF)
                 if self.ssd:
                     newk = keys[is_new.bool()].tolist()
                     loaded = self.ssd.load(newk)

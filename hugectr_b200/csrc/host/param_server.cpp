@@ -110,16 +110,18 @@ void hctr_ps_scatter(char* table, const long long* rows, long long n, long long 
     if (rows[i] >= 0) memcpy(table + rows[i] * row_bytes, in + i * row_bytes, row_bytes);
 }
 
-// table[rows[i], :] = U(-bound, bound), counter-based: the value of (row, column) depends on (seed, row, column)
-// only -- independent of the thread count and of the order in which rows are created.  (The embedding initializer
+// table[rows[i], :] = U(-bound, bound), counter-based: the value of a cell depends on (seed, key, column) only --
+// independent of the thread count and of the order in which rows are created.  (The embedding initializer
 // of rows seen for the first time; a single-threaded generator made first-epoch steps creation-bound.)
-void hctr_ps_init_rows(float* table, const long long* rows, long long n, int ev, float bound,
+void hctr_ps_init_rows(float* table, const long long* rows, const long long* keys, long long n, int ev, float bound,
                        unsigned long long seed) {
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < n; ++i) {
     if (rows[i] < 0) continue;
     float* dst = table + rows[i] * static_cast<long long>(ev);
-    unsigned long long x = seed ^ (static_cast<unsigned long long>(rows[i]) * 0x9E3779B97F4A7C15ull);
+    // keyed by the KEY (not the row it happened to get): a key's first-sight vector does not depend on arrival order,
+    // sharding or a resume in between
+    unsigned long long x = seed ^ (static_cast<unsigned long long>(keys ? keys[i] : rows[i]) * 0x9E3779B97F4A7C15ull);
     for (int c = 0; c < ev; ++c) {
       x += 0x9E3779B97F4A7C15ull;                       // splitmix64 stream per row
       unsigned long long z = x;

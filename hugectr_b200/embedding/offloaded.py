@@ -46,7 +46,7 @@ class CachedSparseEmbeddingRuntime(SparseEmbeddingRuntime):
         cap = int(host_capacity or max(vocab // max(1, self.world) + 1024, 4 * self.max_rows))
         bound = float(np.sqrt(1.0 / max(1.0, vocab / max(1, len(cfg.slot_size_array) or 1)))) if vocab else 0.05
         self.ps = HostParameterServer(self.vec, self.nstates, init_bound=bound, ssd_path=local_path,
-                                      capacity_rows=cap, seed=seed * 7919 + self.rank + 13)
+                                      capacity_rows=cap, seed=seed * 7919 + 13)      # (rank independent: first-sight vectors are keyed by key)
         if self.nstates and self.opt.optimizer_type == Optimizer_t.AdaGrad and self.opt.initial_accu_value:
             self.ps.s[0].fill_(self.opt.initial_accu_value)
         # half of the workspace rows cache hot rows, the other half (self.table of the base class) stages
