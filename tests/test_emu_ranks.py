@@ -535,3 +535,38 @@ def test_emu_legacy_snapshot_resharding_between_rank_counts_cpu(n_save, n_load, 
 
     run_ranks(n_save, save_body, device=CPU, p2p=False)
     run_ranks(n_load, load_body, device=CPU, p2p=False)
+
+
+def test_emu_embedding_training_cache_snapshot_resumes_exactly_cpu(tmp_path):
+    """W&D with both tables on the host parameter server (cached + staged): snapshot after 3 steps, 2 more steps == a
+    fresh cached model resumed from the snapshot + the same steps, on 1 and 2 ranks (first-sight vectors are keyed by
+    key, so rows created after the resume match too); a resident model resumes from the same files"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.models.legacy import build_wdl
+    from hugectr_b200.parallel.comm import Comm
+    cpu, d = CPU, str(tmp_path)
+    def mk(comm, cached):
+        world = comm.world_size
+        etc = hugectr.CreateETC(ps_types=[hugectr.TrainPSType_t.Cached, hugectr.TrainPSType_t.Staged], sparse_models=["", ""], host_capacity_rows=8192) if cached else None
+        m = build_wdl(batchsize=32 * world, vvgpu=[list(range(world))], wide_slot_sizes=[30, 12], deep_slot_sizes=[30, 12, 50, 7], workspace_mb=(1, 2), mixed=False,
+                      comm=comm, max_eval_batches=1, seed=5, etc=etc)
+        for c in m.dense_layers:
+            if c.layer_type == hugectr.Layer_t.Dropout: c.dropout_rate = 0.0
+        m.compile(); return m
+    def body(comm):
+        a = mk(comm, True); pool = a.reader_train.pool
+        for i in range(3): a.train_on_host_batch(pool[i])
+        a.save_params_to_files(os.path.join(d, "s"), 3); comm.barrier()
+        for i in range(3, 5): a.train_on_host_batch(pool[i])
+        # resume into a RESIDENT (no ETC) model and into another cached model: both must continue like `a`
+        out = {}
+        for tag, cached in (("resident", False), ("cached", True)):
+            b = mk(comm, cached); assert b.resume(os.path.join(d, "s")) == 3
+            for i in range(3, 5): b.train_on_host_batch(pool[i])
+            out[tag] = (abs(a.get_current_loss() - b.get_current_loss()), float((a.arena.weights - b.arena.weights).abs().max()))
+        return out
+
+    one = body(Comm.single(CPU))
+    assert one["cached"] == (0.0, 0.0) and one["resident"][1] < 1e-3
+    two = run_ranks(2, body, device=CPU, p2p=False)[0]
+    assert two["cached"][0] == 0.0 and two["cached"][1] < 1e-8 and two["resident"][1] < 1e-3
