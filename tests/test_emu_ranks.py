@@ -570,3 +570,51 @@ def test_emu_embedding_training_cache_snapshot_resumes_exactly_cpu(tmp_path):
     assert one["cached"] == (0.0, 0.0) and one["resident"][1] < 1e-3
     two = run_ranks(2, body, device=CPU, p2p=False)[0]
     assert two["cached"][0] == 0.0 and two["cached"][1] < 1e-8 and two["resident"][1] < 1e-3
+
+
+def test_emu_embedding_training_cache_from_scratch_is_rank_count_independent_cpu(tmp_path):
+    """tables on the host parameter server, NO preloaded keys: the same global batches train to the same loss trace and
+    dense weights on 1, 2 and 4 ranks (a key's first-sight vector depends on the key only)"""
+    import hugectr_b200 as hugectr
+    from hugectr_b200.data.batch import HostBatch
+    from hugectr_b200.parallel.comm import Comm
+    cpu, W0 = CPU, str(tmp_path / "w0.pt")
+    S, H, vec, b = 3, 2, 4, 16
+    vocab = [40, 25, 60]
+    def build(c, world_total):
+        w = c.world_size
+        solver = hugectr.CreateSolver(batchsize=b * world_total, batchsize_eval=b * world_total, lr=0.05, vvgpu=[list(range(w))], repeat_dataset=True,
+                                      i64_input_key=True, use_cuda_graph=False, seed=9)
+        rp = hugectr.DataReaderParams(hugectr.DataReaderType_t.Parquet, source=["synthetic"], eval_source="synthetic", check_type=hugectr.Check_t.Non, slot_size_array=vocab)
+        etc = hugectr.CreateETC(ps_types=[hugectr.TrainPSType_t.Cached], sparse_models=[""], host_capacity_rows=4096)
+        m = hugectr.Model(solver, rp, hugectr.CreateOptimizer(hugectr.Optimizer_t.Adam, hugectr.Update_t.Local), etc, comm=c)
+        m.add(hugectr.Input(label_dim=1, label_name="label", dense_dim=2, dense_name="dense", data_reader_sparse_param_array=[hugectr.DataReaderSparseParam("data1", H, False, S)]))
+        m.add(hugectr.SparseEmbedding(hugectr.Embedding_t.DistributedSlotSparseEmbeddingHash, 1, vec, "sum", "emb", "data1", slot_size_array=vocab))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Reshape, ["emb"], ["r"], leading_dim=S * vec))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.Concat, ["r", "dense"], ["c"]))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.InnerProduct, ["c"], ["fc"], num_output=1))
+        m.add(hugectr.DenseLayer(hugectr.Layer_t.BinaryCrossEntropyLoss, ["fc", "label"], ["loss"]))
+        m.compile(); return m
+    def run(comm, W):
+        m = build(comm, W)
+        w0 = torch.load(W0) if os.path.exists(W0) else None
+        if w0 is None:
+            torch.save(m.arena.weights.clone(), W0); w0 = m.arena.weights.clone()
+        m.arena.weights.copy_(w0); m.arena.sync_shadow()
+        gen = torch.Generator().manual_seed(5); import numpy as np
+        offs = np.concatenate([[0], np.cumsum(vocab)[:-1]])
+        L = []
+        for step in range(4):
+            lab = torch.randint(0, 2, (b * W, 1), generator=gen).float(); den = torch.rand(b * W, 2, generator=gen)
+            keys = torch.stack([torch.randint(0, vocab[s], (b * W, H), generator=gen) + int(offs[s]) for s in range(S)], 1)
+            nnz = (keys >= 0).sum(-1).int()
+            r, ws = comm.rank, comm.world_size; per = b * W // ws
+            sl = slice(r * per, (r + 1) * per)
+            m.train_on_host_batch(HostBatch(lab[sl].clone(), den[sl].clone(), keys[sl].reshape(-1).clone(), nnz[sl].t().reshape(-1).clone(), per))
+            L.append(round(m.get_current_loss(), 6))
+        return L, round(float(m.arena.weights.double().sum()), 6)
+
+    W = 4
+    one = run(Comm.single(CPU), W)
+    for w in (2, 4):
+        assert run_ranks(w, lambda c: run(c, W), device=CPU, p2p=False)[0] == one
