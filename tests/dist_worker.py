@@ -1089,43 +1089,58 @@ def run_unique(names="0,2", opt_name="adagrad", fused=False, comm=None):
         print("UNIQUE_OK", flush=True)
 
 
-if __name__ == "__main__":
-    what = sys.argv[1]
+def dispatch(what, a):
+    """one worker mode with its positional arguments (strings)"""
     if what == "unique":
-        run_unique(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "adagrad")
-    if what == "ckpt":
-        run_ckpt(sys.argv[2])
-    if what == "dynamic":
+        run_unique(a[0], a[1] if len(a) > 1 else "adagrad")
+    elif what == "ckpt":
+        run_ckpt(a[0])
+    elif what == "dynamic":
         run_dynamic()
-    if what == "sok":
+    elif what == "sok":
         run_sok()
-    if what == "sok_fuzz":
-        for sd in sys.argv[2].split(","):
+    elif what == "sok_fuzz":
+        for sd in a[0].split(","):
             run_sok_fuzz(sd)
-    if what == "ebcio":
-        for sd in sys.argv[3].split(","):
-            d = os.path.join(sys.argv[2], sd)
+    elif what == "ebcio":
+        for sd in a[1].split(","):
+            d = os.path.join(a[0], sd)
             os.makedirs(d, exist_ok=True)
             run_ebcio(d, sd)
-    if what == "symmfail":
+    elif what == "symmfail":
         run_symmfail()
-    if what == "fuzz":
-        for sd in sys.argv[2].split(","):
+    elif what == "fuzz":
+        for sd in a[0].split(","):
             run_fuzz(sd)
-    if what == "legacy":
+    elif what == "legacy":
         run_legacy()
-    if what == "resume":
-        run_resume(sys.argv[2], sys.argv[3] == "legacy")
-    if what == "legacy_equiv":
-        for sd in sys.argv[4].split(","):
-            run_legacy_equiv(sys.argv[2], sys.argv[3], sd)
-    if what == "equiv":
-        run_equiv(sys.argv[2] if len(sys.argv) > 2 else "sgd", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
-    if what == "model":
+    elif what == "resume":
+        run_resume(a[0], a[1] == "legacy")
+    elif what == "legacy_equiv":
+        for sd in a[2].split(","):
+            run_legacy_equiv(a[0], a[1], sd)
+    elif what == "equiv":
+        run_equiv(a[0] if a else "sgd", int(a[1]) if len(a) > 1 else 0)
+    elif what == "model":
         run_model()
-    if what == "ebc":
-        run_ebc(sys.argv[2], {"fused": True, "collective": False}[sys.argv[3]])
+    elif what == "ebc":
+        run_ebc(a[0], {"fused": True, "collective": False}[a[1]])
     elif what == "allreduce":
         run_allreduce()
+    else:
+        raise SystemExit(f"unknown worker mode {what}")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "multi":
+        # several modes in ONE process group (interpreter start-up dominates a gloo test): "mode;arg;arg" each;
+        # a failing mode stops the session, the markers printed so far tell which ones passed
+        for spec in sys.argv[2:]:
+            parts = spec.split(";")
+            dispatch(parts[0], parts[1:])
+            if int(os.environ.get("RANK", "0")) == 0:
+                print("MULTI_DONE", spec, flush=True)
+    else:
+        dispatch(sys.argv[1], sys.argv[2:])
     if dist.is_initialized():
         dist.destroy_process_group()

@@ -20,11 +20,45 @@ def _run(nproc, args, port, env=None, timeout=300):
     return r.stdout
 
 
+# ----------------------------------------------------------------------------- one 2-rank session for the plain cases
+# Interpreter start-up dominates a gloo test (two workers importing torch ~ 6 s): the world-2 cases that need no
+# special environment share ONE torchrun session (dist_worker.py `multi`); every test below checks its own marker.
+W2_FUZZ = ",".join(str(200 + i) for i in range(6))
+
+
+@pytest.fixture(scope="module")
+def world2(tmp_path_factory):
+    d = tmp_path_factory.mktemp("world2")
+    specs = ["ebc;mixed;collective", "ebc;column;collective", "model", "equiv;sgd", "equiv;adagrad", "legacy",
+             f"ckpt;{d / 'ckpt'}", "dynamic", "sok", f"fuzz;{W2_FUZZ}", "unique;0,1,2,3,5;adagrad",
+             "legacy_equiv;distributed;adam;11,12", "legacy_equiv;localized;adam;11,12",
+             f"resume;{d / 'r_ebc'};ebc", f"resume;{d / 'r_leg'};legacy", "sok_fuzz;1001,1002,1003,1004,1005,1006"]
+    for sub in ("ckpt", "r_ebc", "r_leg"):
+        (d / sub).mkdir()
+    return _run(2, ["multi"] + specs, 29611, env={"CUDA_VISIBLE_DEVICES": ""}, timeout=1500)
+
+
+def _in_process(what, args):
+    """single-rank cases need no process group: run the worker mode right here"""
+    sys.path.insert(0, HERE)
+    import dist_worker as W
+    from hugectr_b200.parallel.comm import Comm
+    comm = Comm.single(torch.device("cpu"))
+    fn = {"dynamic": lambda: W.run_dynamic(comm=comm),
+          "fuzz": lambda: [W.run_fuzz(sd, comm=comm) for sd in args[0].split(",")],
+          "ebcio": lambda: [(os.makedirs(os.path.join(args[0], sd), exist_ok=True),
+                             W.run_ebcio(os.path.join(args[0], sd), sd, comm=comm)) for sd in args[1].split(",")]}[what]
+    fn()
+
+
+def _done(out, spec_prefix):
+    return any(l.startswith("MULTI_DONE " + spec_prefix) for l in out.splitlines())
+
+
 @pytest.mark.dist
 @pytest.mark.parametrize("plan", ["mixed", "column"])
-def test_ebc_collective_gloo(plan):
-    out = _run(2, ["ebc", plan, "collective"], 29611, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "EBC_OK" in out
+def test_ebc_collective_gloo(plan, world2):
+    assert f"EBC_OK plan={plan}" in world2 and _done(world2, f"ebc;{plan}")
 
 
 @pytest.mark.gpu
@@ -48,9 +82,8 @@ def test_p2p_allreduce():
 
 
 @pytest.mark.dist
-def test_model_data_parallel_gloo():
-    out = _run(2, ["model"], 29641, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "MODEL_OK" in out
+def test_model_data_parallel_gloo(world2):
+    assert "MODEL_OK" in world2 and _done(world2, "model")
 
 
 @pytest.mark.gpu
@@ -64,9 +97,8 @@ def test_model_multi_gpu_overlap_paths():
 
 @pytest.mark.dist
 @pytest.mark.parametrize("opt", ["sgd", "adagrad"])
-def test_multi_rank_equals_single_process_gloo(opt):
-    out = _run(2, ["equiv", opt], 29661, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "EQUIV_OK" in out
+def test_multi_rank_equals_single_process_gloo(opt, world2):
+    assert world2.count("EQUIV_OK") >= 2 and _done(world2, f"equiv;{opt}")
 
 
 @pytest.mark.gpu
@@ -81,9 +113,8 @@ def test_multi_gpu_equals_single_gpu():
 
 
 @pytest.mark.dist
-def test_legacy_embeddings_gloo():
-    out = _run(2, ["legacy"], 29681, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "LEGACY_OK" in out
+def test_legacy_embeddings_gloo(world2):
+    assert "LEGACY_OK" in world2 and _done(world2, "legacy")
 
 
 @pytest.mark.gpu
@@ -123,30 +154,38 @@ def test_requester_side_shard_split_multi_gpu():
 
 
 @pytest.mark.dist
-def test_checkpoint_resharding_gloo(tmp_path):
+def test_checkpoint_resharding_gloo(world2):
     """2-rank checkpoint (dense + embedding collection) loads into a single-process model"""
-    out = _run(2, ["ckpt", str(tmp_path)], 29731, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "CKPT_OK" in out
+    assert "CKPT_OK" in world2 and _done(world2, "ckpt;")
 
 
 @pytest.mark.dist
 @pytest.mark.parametrize("nproc", [1, 2])
-def test_dynamic_tables_in_collection_gloo(nproc):
-    out = _run(nproc, ["dynamic"], 29741, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "DYNAMIC_OK" in out
+def test_dynamic_tables_in_collection_gloo(nproc, world2, capsys):
+    if nproc == 2:
+        assert "DYNAMIC_OK" in world2 and _done(world2, "dynamic")
+        return
+    _in_process("dynamic", [])
+    assert "DYNAMIC_OK" in capsys.readouterr().out
 
 
 @pytest.mark.dist
-def test_sok_distributed_lookup_gloo():
-    out = _run(2, ["sok"], 29751, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "SOK_OK" in out
+def test_sok_distributed_lookup_gloo(world2):
+    assert "SOK_OK" in world2 and _done(world2, "sok")
 
 
 @pytest.mark.parametrize("nproc", [1, 2, 3])
-def test_randomised_collection_against_bruteforce_oracle_gloo(nproc):
+def test_randomised_collection_against_bruteforce_oracle_gloo(nproc, world2, capsys):
     """random tables / hotness / combiners / layouts / padded bags / sharding plans vs gather+scatter oracle"""
     seeds = ",".join(str(100 * nproc + i) for i in range(6))
-    out = _run(nproc, ["fuzz", seeds], 29751 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
+    if nproc == 1:
+        _in_process("fuzz", [seeds])
+        out = capsys.readouterr().out
+    elif nproc == 2:
+        out, seeds = "\n".join(l for l in world2.splitlines() if l.startswith("FUZZ_OK 20")), W2_FUZZ
+        assert _done(world2, "fuzz;")
+    else:
+        out = _run(nproc, ["fuzz", seeds], 29751 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
     assert out.count("FUZZ_OK") == 6, out[-2000:]
 
 
@@ -162,10 +201,14 @@ def test_randomised_collection_against_bruteforce_oracle_gpu():
 
 @pytest.mark.dist
 @pytest.mark.parametrize("nproc", [1, 3])
-def test_parallel_collection_dump_equals_gather_dump_gloo(nproc, tmp_path):
+def test_parallel_collection_dump_equals_gather_dump_gloo(nproc, tmp_path, capsys):
     """every rank writes its own windows of key / weight / opt files; chunked streamed load restores them"""
     seeds = ",".join(str(40 * nproc + i) for i in range(4))
-    out = _run(nproc, ["ebcio", str(tmp_path), seeds], 29771 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
+    if nproc == 1:
+        _in_process("ebcio", [str(tmp_path), seeds])
+        out = capsys.readouterr().out
+    else:
+        out = _run(nproc, ["ebcio", str(tmp_path), seeds], 29771 + nproc, env={"CUDA_VISIBLE_DEVICES": ""})
     assert out.count("EBCIO_OK") == 4, out[-2000:]
 
 
@@ -211,9 +254,12 @@ def test_multi_rank_equals_single_process_random_plan_gloo(nproc, seed):
 
 @pytest.mark.dist
 @pytest.mark.parametrize("nproc,names", [(2, "0,1,2,3,5"), (3, "0,2")])
-def test_unique_compression_exchange_gloo(nproc, names):
+def test_unique_compression_exchange_gloo(nproc, names, world2):
     """CompressionStrategy.Unique on real processes: the count all-to-all and the variable all-to-alls of 64-bit
     key codes / embedding rows / pre-reduced gradient rows over gloo"""
+    if nproc == 2:
+        assert "UNIQUE_OK" in world2 and _done(world2, "unique;")
+        return
     out = _run(nproc, ["unique", names, "adagrad"], 29741, env={"CUDA_VISIBLE_DEVICES": ""})
     assert "UNIQUE_OK" in out
 
@@ -227,21 +273,23 @@ def test_model_with_unique_compression_equals_single_process_gloo():
 
 @pytest.mark.dist
 @pytest.mark.parametrize("kind", ["distributed", "localized"])
-def test_legacy_embeddings_equal_single_process_gloo(kind):
-    out = _run(2, ["legacy_equiv", kind, "adam", "11,12"], 29761, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert out.count("LEGACY_EQUIV_OK") == 2
+def test_legacy_embeddings_equal_single_process_gloo(kind, world2):
+    assert world2.count("LEGACY_EQUIV_OK") == 4 and _done(world2, f"legacy_equiv;{kind}")
 
 
 @pytest.mark.dist
 @pytest.mark.parametrize("legacy", ["ebc", "legacy"])
-def test_multi_rank_exact_resume_gloo(legacy, tmp_path):
-    out = _run(2, ["resume", str(tmp_path), legacy], 29771, env={"CUDA_VISIBLE_DEVICES": ""})
-    assert "RESUME_OK" in out
+def test_multi_rank_exact_resume_gloo(legacy, world2):
+    assert world2.count("RESUME_OK") == 2 and any(l.startswith("MULTI_DONE resume;") and l.endswith(";" + legacy)
+                                                   for l in world2.splitlines())
 
 
 @pytest.mark.dist
 @pytest.mark.parametrize("nproc", [2, 3])
-def test_sok_randomised_lookups_against_dense_oracle_gloo(nproc):
+def test_sok_randomised_lookups_against_dense_oracle_gloo(nproc, world2):
     """random mixes of distributed / localized / dynamic SOK variables, hotness, combiners, weights, padded bags"""
+    if nproc == 2:
+        assert world2.count("SOK_FUZZ_OK") == 6 and _done(world2, "sok_fuzz;")
+        return
     out = _run(nproc, ["sok_fuzz", "1001,1002,1003,1004,1005,1006"], 29781, env={"CUDA_VISIBLE_DEVICES": ""})
     assert out.count("SOK_FUZZ_OK") == 6
