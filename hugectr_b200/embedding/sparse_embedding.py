@@ -301,16 +301,17 @@ class SparseEmbeddingRuntime:
         update mathematically identical to the dense optimizer.  LazyGlobal (the reference's cheaper
         approximation of the same thing) takes this exact path too."""
         vec = self.vec
-        n = self.max_rows                      # (allocated rows only, masked on the device: no host sync)
         if self.device.type == "cuda":
+            n = self.max_rows                  # (allocated rows only, masked on the device: no host sync)
             alive = torch.arange(n, device=self.device) < self.hash.counter
         else:
-            alive = torch.arange(n) < int(self.hash.size())
+            n = max(1, int(self.hash.size()))  # the host knows the size: sweep the allocated prefix only
+            alive = torch.ones(n, dtype=torch.bool)
         # rows of this step: every write stores True (entries that are not mine go to a spare slot behind the
         # table) -- duplicates are harmless and no row's flag depends on the order of conflicting writes
-        touched = torch.zeros(self.max_rows + 1, dtype=torch.int32, device=self.device)
+        touched = torch.zeros(n + 1, dtype=torch.int32, device=self.device)
         r = self.rows_all.reshape(-1)
-        touched.index_fill_(0, torch.where(r >= 0, r, torch.full_like(r, self.max_rows)), 1)
+        touched.index_fill_(0, torch.where(r >= 0, r, torch.full_like(r, n)), 1)
         touched = (touched[:n] > 0) | ~alive    # never-allocated rows are left alone
         unt = (~touched).unsqueeze(1)
         w = self.table.view(-1, vec)[:n]

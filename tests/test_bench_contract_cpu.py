@@ -139,13 +139,13 @@ def test_secondary_configurations_run_through_the_public_api(model):
     """`bench.py --model ...` (BASELINE configurations 2, 3 and 5) on CPU with a small batch: a logic smoke test of the
     builders, the ETC wiring and the JSON line -- the value itself means nothing here"""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--model", model, "--steps", "2", "--warmup", "3",
-                        "--per-gpu-batch", "128", "--cap-rows", "20000"], capture_output=True, text=True, timeout=600,
+                        "--per-gpu-batch", "64", "--cap-rows", "20000"], capture_output=True, text=True, timeout=600,
                        env={**{k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE")},
                             "CUDA_VISIBLE_DEVICES": ""})
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["secondary"] is True and line["device"] == "cpu" and line["value"] > 0
-    assert line["config"]["global_batch"] == 128 and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert line["config"]["global_batch"] == 64 and line["e2e"]["h2d_bytes_per_step"] > 0
     assert abs(line["config"]["final_loss"]) < 50
     if model == "wdl_cache":
         assert 0.0 <= line["config"]["cache_hit_rate"] <= 1.0 and line["config"]["host_rows"] > 0
