@@ -464,7 +464,7 @@ def run_secondary(args, comm):
     bo = args.per_gpu_batch if args.per_gpu_batch != PER_GPU_BATCH else 0
     if args.model == "deepfm":
         b = bo or 16384
-        m = build_deepfm(batchsize=b * n, vvgpu=vv, slot_sizes=CRITEO_KAGGLE_SLOTS, workspace_mb=2000, mixed=True,
+        m = build_deepfm(batchsize=b * n, vvgpu=vv, slot_sizes=CRITEO_KAGGLE_SLOTS, workspace_mb=400, mixed=True,   # 3.2 M rows incl. Adam moments (2.1 M keys exist)
                          comm=comm, use_cuda_graph=not args.no_graph)
         desc = "DeepFM (samples/deepfm): 26 Criteo slots, vec 11, DistributedSlotSparseEmbeddingHash, 3x400 MLP, Adam"
     elif args.model == "dlrm":
